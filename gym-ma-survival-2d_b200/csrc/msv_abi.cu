@@ -1,0 +1,616 @@
+// msv_abi.cu -- the C ABI of libmasurv.so (include/masurv.h): handle life
+// cycle, config -> device constants, SoA allocation, AoS<->SoA state
+// exchange, DLPack export, launches.  There is NO CPU fallback: every entry
+// point that computes fails with MSV_ERR_NO_DEVICE when no CUDA device exists.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/masurv.h"
+#include "msv_launch.h"
+
+// ---- minimal DLPack (dlpack.h v0.8 layout) --------------------------------
+extern "C" {
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void* data; DLDevice device; int32_t ndim; DLDataType dtype;
+  int64_t* shape; int64_t* strides; uint64_t byte_offset;
+} DLTensor;
+typedef struct DLManagedTensor {
+  DLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct DLManagedTensor*);
+} DLManagedTensor;
+}
+
+struct TensorInfo { void* ptr; int ndim; int64_t shape[4]; int dtype; /*0 f32, 1 u8, 2 i32*/ };
+
+struct msv_handle {
+  msv_config cfg;
+  DevConst C;
+  DevState S;
+  DevOut O;
+  int cap, AC, BC, HC, P, PW;
+  int device;
+  std::vector<void*> allocs;
+  std::map<std::string, TensorInfo> tensors;
+  uint8_t* d_actions;       // staging for msv_step_host
+  double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
+  int64_t launches;
+  int64_t exported;          // live DLPack exports
+  std::string err;
+};
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t _e = (call);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
+      return MSV_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+static thread_local std::string g_err;
+
+// ---- host float32 helpers (same arithmetic as the reference's pybox2d calls)
+static void h_rot(float angle, float* s, float* c) { *s = (float)sin((double)angle); *c = (float)cos((double)angle); }
+// sim.from_polar (simulation.py:20-23)
+static void h_from_polar(double length, double angle, float out[2]) {
+  float s, c; h_rot((float)angle, &s, &c);
+  float L = (float)length;
+  out[0] = c * L + (-s) * 0.0f; out[1] = s * L + c * 0.0f;
+}
+// b2PolygonShape::Set for the 4-vertex camera cone (simulation.py:321-328)
+static void h_polygon_set4(const float vin[4][2], float vout[4][2], float nout[4][2]) {
+  int n = 4, i0 = 0; float x0 = vin[0][0];
+  for (int i = 1; i < n; ++i) {
+    float x = vin[i][0];
+    if (x > x0 || (x == x0 && vin[i][1] < vin[i0][1])) { i0 = i; x0 = x; }
+  }
+  int hull[8], m = 0, ih = i0;
+  for (;;) {
+    hull[m] = ih;
+    int ie = 0;
+    for (int j = 1; j < n; ++j) {
+      if (ie == ih) { ie = j; continue; }
+      float rx = vin[ie][0] - vin[hull[m]][0], ry = vin[ie][1] - vin[hull[m]][1];
+      float vx = vin[j][0] - vin[hull[m]][0], vy = vin[j][1] - vin[hull[m]][1];
+      float c = rx * vy - ry * vx;
+      if (c < 0.0f) ie = j;
+      if (c == 0.0f && vx * vx + vy * vy > rx * rx + ry * ry) ie = j;
+    }
+    ++m; ih = ie;
+    if (ie == i0 || m >= 4) break;
+  }
+  for (int i = 0; i < 4; ++i) { int k = i < m ? i : m - 1; vout[i][0] = vin[hull[k]][0]; vout[i][1] = vin[hull[k]][1]; }
+  for (int i = 0; i < 4; ++i) {
+    int i2 = i + 1 < 4 ? i + 1 : 0;
+    float ex = vout[i2][0] - vout[i][0], ey = vout[i2][1] - vout[i][1];
+    float nx = 1.0f * ey, ny = -1.0f * ex;
+    float len = sqrtf(nx * nx + ny * ny);
+    if (!(len < 1.1920929e-7f)) { float inv = 1.0f / len; nx *= inv; ny *= inv; }
+    nout[i][0] = nx; nout[i][1] = ny;
+  }
+}
+
+static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_offset, DevConst* D) {
+  memset(D, 0, sizeof *D);
+  D->N = N; D->A = c->n_agents; D->B0 = c->n_boxes; D->H0 = c->n_heals;
+  D->S = 8 + (c->teams ? 1 : 0);
+  D->teams = c->teams; D->omniscient = c->omniscient; D->gameover_mode = c->gameover_mode;
+  D->health = c->health; D->melee_damage = c->melee_damage; D->melee_cooldown = c->melee_cooldown;
+  D->box_ownership = c->box_ownership; D->box_randomized = c->box_randomized; D->box_health = c->box_health;
+  D->healing = c->healing; D->inv_slots = c->inv_slots;
+  D->zone_phases = c->zone_phases; D->zone_cooldown = c->zone_cooldown; D->zone_damage = c->zone_damage;
+  D->n_zones = c->zone_n_radiuses + 1; D->zone_centers_random = c->zone_centers_random;
+  D->lidar_n = c->lidar_n; D->auto_reset = c->auto_reset; D->grid_n = c->grid_size * c->grid_size;
+  D->r_alive = c->r_alive; D->r_dead = c->r_dead; D->r_kill = c->r_kill; D->r_death = c->r_death;
+  D->agent_r = (float)(c->agent_size / 2);          // semantics.py:16-18
+  D->heal_r = (float)(c->heal_item_size / 2);       // semantics.py:24-25
+  D->item_r = (float)(c->box_item_size / 2);
+  D->box_h = (float)(c->box_size / 2.);             // semantics.py:20-22
+  {  // b2CircleShape::ComputeMass + b2Body::ResetMassData, density 1
+    const float b2_pi = 3.14159265359f;
+    float r = D->agent_r, density = 1.0f;
+    float mass = density * b2_pi * r * r;
+    float I = mass * (0.5f * r * r + 0.0f);
+    D->inv_mass = 1.0f / mass;
+    I -= mass * 0.0f;
+    D->inv_I = 1.0f / I;
+  }
+  D->friction = sqrtf(0.2f * 0.2f);                  // b2MixFriction of the fixture default
+  D->dt = (float)(1.0 / 60);                         // simulation.py:219
+  D->dt_ratio1 = (1.0f / D->dt) * D->dt;
+  D->damp = 1.0f / (1.0f + D->dt * (float)0.8);      // simulation.py:118, Pade damping
+  static const double dtab[3] = {-1., 0., 1.};       // env:742
+  for (int a = 0; a < 3; ++a) {
+    D->imp_par[a] = (float)(dtab[a] * c->motor_impulse[0]);
+    D->imp_nor[a] = (float)(dtab[a] * c->motor_impulse[1]);
+    D->imp_ang[a] = (float)(dtab[a] * c->motor_impulse[2]);
+  }
+  D->melee_range = (float)c->melee_range; D->box_item_offset = (float)c->box_item_offset;
+  D->drop_radius = (float)c->drop_radius; D->pickup_r = (float)c->pickup_radius; D->give_r = (float)c->give_radius;
+  D->cam_k1 = (float)(1 + 1e-6);                     // simulation.py:349
+  D->lidar_depth = (float)c->lidar_depth;
+  {
+    float vin[4][2] = {{0.0f, 0.0f}, {0, 0}, {(float)c->cam_depth, 0.0f}, {0, 0}};
+    h_from_polar(c->cam_depth, +c->cam_fov / 2, vin[1]);
+    h_from_polar(c->cam_depth, -c->cam_fov / 2, vin[3]);
+    h_polygon_set4(vin, D->cone_v, D->cone_n);
+  }
+  {  // ThickRoomWalls, semantics.py:685-695
+    double height = c->floor_size, width = height / 100;
+    D->wall_hx = (float)(width / 2.); D->wall_hy = (float)(height / 2.);
+    float o = (float)(c->floor_size / 2), hp = (float)(M_PI / 2);
+    float wx[4] = {-o, 0.0f, o, 0.0f}, wy[4] = {0.0f, o, 0.0f, -o}, wa[4] = {0.0f, hp, 0.0f, hp};
+    for (int k = 0; k < 4; ++k) {
+      WallC& w = D->walls[k];
+      w.px = wx[k]; w.py = wy[k]; w.ang = wa[k]; h_rot(wa[k], &w.qs, &w.qc);
+      float hx = D->wall_hx, hy = D->wall_hy;
+      float vs[4][2] = {{-hx, -hy}, {hx, -hy}, {hx, hy}, {-hx, hy}};
+      float lx = 0, ly = 0, ux = 0, uy = 0;
+      for (int v = 0; v < 4; ++v) {
+        float x = (w.qc * vs[v][0] - w.qs * vs[v][1]) + w.px, y = (w.qs * vs[v][0] + w.qc * vs[v][1]) + w.py;
+        if (v == 0) { lx = ux = x; ly = uy = y; }
+        else { lx = x < lx ? x : lx; ly = y < ly ? y : ly; ux = x > ux ? x : ux; uy = y > uy ? y : uy; }
+      }
+      const float pr = 2.0f * 0.005f, ext = 0.1f;
+      w.fat[0] = (lx - pr) - ext; w.fat[1] = (ly - pr) - ext; w.fat[2] = (ux + pr) + ext; w.fat[3] = (uy + pr) + ext;
+    }
+  }
+  {  // square_grid, semantics.py:987-992
+    int g = c->grid_size;
+    for (int k = 0; k < g * g; ++k) {
+      int i = k % g, j = k / g;
+      double ci = (double)i / g + 0.5 / g, cj = (double)j / g + 0.5 / g;
+      D->grid_px[k] = (float)(c->floor_size * ci - c->floor_size / 2.);
+      D->grid_py[k] = (float)(c->floor_size * cj - c->floor_size / 2.);
+    }
+  }
+  for (int z = 0; z < MSV_MAX_ZONES; ++z) {
+    double r = z < c->zone_n_radiuses ? c->zone_radiuses[z] : 0.0;   // semantics.py:726-727
+    D->zone_radiuses[z] = r; D->zone_r32[z] = (float)r;
+    if (z < c->zone_n_radiuses) { D->zone_centers[z][0] = c->zone_centers[z][0]; D->zone_centers[z][1] = c->zone_centers[z][1]; }
+  }
+  D->floor_size = c->floor_size;
+  D->box_avg_w = c->box_avg_w; D->box_std_w = c->box_std_w; D->box_avg_h = c->box_avg_h; D->box_std_h = c->box_std_h;
+  D->box_min_w = c->box_min_w; D->box_min_h = c->box_min_h;
+  for (int r = 0; r < c->lidar_n && r < MSV_MAX_LASERS; ++r)     // simulation.py:385-392
+    D->lidar_ang[r] = c->lidar_n > 1 ? r * (c->lidar_fov / (c->lidar_n - 1)) - c->lidar_fov / 2. : 0.0;
+  D->seed_lo = (uint32_t)seed; D->seed_hi = (uint32_t)(seed >> 32);
+  D->env_offset = (uint32_t)env_offset;
+  return 0;
+}
+
+template <typename T> static int dalloc(msv_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return MSV_ERR_ALLOC; }
+  cudaMemset(q, 0, bytes);
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+static void reg(msv_handle* h, const char* name, void* ptr, int dtype, std::initializer_list<int64_t> shape) {
+  TensorInfo t; t.ptr = ptr; t.ndim = (int)shape.size(); t.dtype = dtype;
+  int i = 0; for (auto s : shape) t.shape[i++] = s;
+  h->tensors[name] = t;
+}
+
+// ---- AoS <-> SoA -----------------------------------------------------------
+struct Mirror {
+  std::vector<float4> akin0, akin1, afat, ainv, box0, item0, pend0, zonecur;
+  std::vector<int4> aint, box1, zoneint, hdr0, hdr1, smisc;
+  std::vector<int> boxseq, healseq, pend1, skills;
+  std::vector<int2> item1;
+  std::vector<float2> heal, zonec, pimp;
+  std::vector<unsigned long long> pex, ptc, pen;
+  std::vector<uint32_t> pseq;
+  std::vector<float> sreward;
+};
+template <typename T> static cudaError_t dl(std::vector<T>& v, const T* d, size_t n) {
+  v.resize(n); return cudaMemcpy(v.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost);
+}
+template <typename T> static cudaError_t ul(const std::vector<T>& v, T* d) {
+  return cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+static int download(msv_handle* h, Mirror& m) {
+  const size_t N = h->C.N, AC = h->AC, BC = h->BC, HC = h->HC, P = h->P, PW = h->PW;
+  DevState& S = h->S;
+  CK(cudaSetDevice(h->device)); CK(cudaDeviceSynchronize());
+  CK(dl(m.akin0, S.akin0, AC * N)); CK(dl(m.akin1, S.akin1, AC * N)); CK(dl(m.afat, S.afat, AC * N));
+  CK(dl(m.aint, S.aint, AC * N)); CK(dl(m.ainv, S.ainv, AC * 4 * N));
+  CK(dl(m.box0, S.box0, BC * N)); CK(dl(m.box1, S.box1, BC * N)); CK(dl(m.boxseq, S.boxseq, BC * N));
+  CK(dl(m.item0, S.item0, BC * N)); CK(dl(m.item1, S.item1, BC * N));
+  CK(dl(m.heal, S.heal, HC * N)); CK(dl(m.healseq, S.healseq, HC * N));
+  CK(dl(m.pend0, S.pend0, BC * N)); CK(dl(m.pend1, S.pend1, BC * N));
+  CK(dl(m.zonec, S.zonec, (size_t)MSV_MAX_ZONES * N)); CK(dl(m.zonecur, S.zonecur, N)); CK(dl(m.zoneint, S.zoneint, N));
+  CK(dl(m.hdr0, S.hdr0, N)); CK(dl(m.hdr1, S.hdr1, N));
+  CK(dl(m.pex, S.pex, PW * N)); CK(dl(m.ptc, S.ptc, PW * N)); CK(dl(m.pen, S.pen, PW * N));
+  CK(dl(m.pseq, S.pseq, P * N)); CK(dl(m.pimp, S.pimp, P * N));
+  CK(dl(m.sreward, S.sreward, AC * N)); CK(dl(m.skills, S.skills, AC * N)); CK(dl(m.smisc, S.smisc, N));
+  return MSV_OK;
+}
+static int upload(msv_handle* h, const Mirror& m) {
+  DevState& S = h->S;
+  CK(ul(m.akin0, S.akin0)); CK(ul(m.akin1, S.akin1)); CK(ul(m.afat, S.afat)); CK(ul(m.aint, S.aint)); CK(ul(m.ainv, S.ainv));
+  CK(ul(m.box0, S.box0)); CK(ul(m.box1, S.box1)); CK(ul(m.boxseq, S.boxseq)); CK(ul(m.item0, S.item0)); CK(ul(m.item1, S.item1));
+  CK(ul(m.heal, S.heal)); CK(ul(m.healseq, S.healseq)); CK(ul(m.pend0, S.pend0)); CK(ul(m.pend1, S.pend1));
+  CK(ul(m.zonec, S.zonec)); CK(ul(m.zonecur, S.zonecur)); CK(ul(m.zoneint, S.zoneint)); CK(ul(m.hdr0, S.hdr0)); CK(ul(m.hdr1, S.hdr1));
+  CK(ul(m.pex, S.pex)); CK(ul(m.ptc, S.ptc)); CK(ul(m.pen, S.pen)); CK(ul(m.pseq, S.pseq)); CK(ul(m.pimp, S.pimp));
+  CK(ul(m.sreward, S.sreward)); CK(ul(m.skills, S.skills)); CK(ul(m.smisc, S.smisc));
+  return MSV_OK;
+}
+static inline int f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline bool gbit(const std::vector<unsigned long long>& v, size_t N, size_t e, int p) { return (v[(p >> 6) * N + e] >> (p & 63)) & 1ull; }
+static inline void sbit(std::vector<unsigned long long>& v, size_t N, size_t e, int p, bool on) {
+  unsigned long long& w = v[(p >> 6) * N + e];
+  if (on) w |= 1ull << (p & 63); else w &= ~(1ull << (p & 63));
+}
+
+
+extern "C" {
+
+int msv_abi_version(void) { return MSV_ABI_VERSION; }
+int64_t msv_sizeof_config(void) { return (int64_t)sizeof(msv_config); }
+int64_t msv_sizeof_env_state(void) { return (int64_t)sizeof(msv_env_state); }
+int64_t msv_sizeof_stats(void) { return (int64_t)sizeof(msv_stats); }
+
+int msv_default_config(msv_config* c) {  // env:140-238
+  if (!c) return MSV_ERR_INVALID;
+  memset(c, 0, sizeof *c);
+  c->n_agents = 2; c->n_boxes = 4; c->n_heals = 4; c->teams = 0; c->omniscient = 1;
+  c->gameover_mode = MSV_GAMEOVER_ALLDEAD; c->grid_size = 4; c->floor_size = 20;
+  c->health = 100; c->melee_range = 2; c->melee_damage = 20; c->melee_cooldown = 40;
+  c->box_ownership = 0; c->box_randomized = 0; c->box_health = 20; c->box_size = 1;
+  c->box_item_size = 0.5; c->box_item_offset = 0.75; c->heal_item_size = 0.5; c->healing = 50;
+  c->inv_slots = 4; c->pickup_radius = 0.5; c->give_radius = 2; c->drop_radius = 0.5;
+  c->zone_phases = 5; c->zone_cooldown = 100; c->zone_damage = 1; c->zone_n_radiuses = 4;
+  c->zone_radiuses[0] = 10; c->zone_radiuses[1] = 5; c->zone_radiuses[2] = 2.5; c->zone_radiuses[3] = 1;
+  c->zone_centers_random = 1;
+  c->r_alive = 1; c->r_dead = -1; c->r_kill = 0; c->r_death = 0;
+  c->agent_size = 1; c->cam_fov = 0.4 * M_PI; c->cam_depth = 10;
+  c->motor_impulse[0] = 0.25; c->motor_impulse[1] = 0.25; c->motor_impulse[2] = 0.0125;
+  c->box_min_w = 0.1; c->box_min_h = 0.1;
+  c->lidar_n = 0; c->lidar_fov = 0.8 * M_PI; c->lidar_depth = 10;
+  return MSV_OK;
+}
+
+int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t seed, int64_t env_offset,
+               msv_handle** out) {
+  if (!cfg || !out || num_envs <= 0) return MSV_ERR_INVALID;
+  if (cfg->n_agents < 1 || cfg->n_agents > MSV_MAX_AGENTS || cfg->n_boxes < 0 || cfg->n_boxes > MSV_MAX_BOXES ||
+      cfg->n_heals < 0 || cfg->n_heals > MSV_MAX_HEALS || cfg->grid_size < 1 || cfg->grid_size > 8 ||
+      cfg->n_agents + cfg->n_boxes + cfg->n_heals > cfg->grid_size * cfg->grid_size ||
+      cfg->inv_slots < 1 || cfg->inv_slots > MSV_MAX_SLOTS || cfg->zone_n_radiuses + 1 > MSV_MAX_ZONES ||
+      cfg->zone_phases > cfg->zone_n_radiuses + 1 || cfg->lidar_n < 0 || cfg->lidar_n > MSV_MAX_LASERS)
+    return MSV_ERR_INVALID;
+  if (!cfg->omniscient) return MSV_ERR_INVALID;  // not built yet
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
+    g_err = "no CUDA device: libmasurv has no CPU fallback";
+    return MSV_ERR_NO_DEVICE;
+  }
+  msv_handle* h = new msv_handle();
+  h->cfg = *cfg; h->device = device; h->launches = 0; h->exported = 0;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return MSV_ERR_CUDA; }
+  build_const(cfg, num_envs, seed, env_offset, &h->C);
+  h->cap = (cfg->n_agents <= 2 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 0
+         : (cfg->n_agents <= 4 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 1 : 2;
+  msv_capacity(h->cap, &h->AC, &h->BC, &h->HC, &h->P, &h->PW);
+  const size_t N = (size_t)num_envs, AC = h->AC, BC = h->BC, HC = h->HC, P = h->P, PW = h->PW;
+  DevState& S = h->S; DevOut& O = h->O;
+  int rc = 0;
+  rc |= dalloc(h, &S.akin0, AC * N); rc |= dalloc(h, &S.akin1, AC * N); rc |= dalloc(h, &S.afat, AC * N);
+  rc |= dalloc(h, &S.aint, AC * N); rc |= dalloc(h, &S.ainv, AC * 4 * N);
+  rc |= dalloc(h, &S.box0, BC * N); rc |= dalloc(h, &S.box1, BC * N); rc |= dalloc(h, &S.boxseq, BC * N);
+  rc |= dalloc(h, &S.item0, BC * N); rc |= dalloc(h, &S.item1, BC * N);
+  rc |= dalloc(h, &S.heal, HC * N); rc |= dalloc(h, &S.healseq, HC * N);
+  rc |= dalloc(h, &S.pend0, BC * N); rc |= dalloc(h, &S.pend1, BC * N);
+  rc |= dalloc(h, &S.zonec, (size_t)MSV_MAX_ZONES * N); rc |= dalloc(h, &S.zonecur, N); rc |= dalloc(h, &S.zoneint, N);
+  rc |= dalloc(h, &S.hdr0, N); rc |= dalloc(h, &S.hdr1, N);
+  rc |= dalloc(h, &S.pex, PW * N); rc |= dalloc(h, &S.ptc, PW * N); rc |= dalloc(h, &S.pen, PW * N);
+  rc |= dalloc(h, &S.pseq, P * N); rc |= dalloc(h, &S.pimp, P * N);
+  rc |= dalloc(h, &S.sreward, AC * N); rc |= dalloc(h, &S.skills, AC * N); rc |= dalloc(h, &S.smisc, N);
+  const size_t A = cfg->n_agents, B = cfg->n_boxes, H = cfg->n_heals, Sw = h->C.S, L = cfg->lidar_n;
+  rc |= dalloc(h, &O.agent, N * A * Sw); rc |= dalloc(h, &O.others, N * A * (A - 1) * Sw);
+  rc |= dalloc(h, &O.others_mask, N * A * (A - 1)); rc |= dalloc(h, &O.zone, N * 6);
+  rc |= dalloc(h, &O.heals, N * H * 2); rc |= dalloc(h, &O.heals_mask, N * A * H);
+  rc |= dalloc(h, &O.heal_slot, N * A); rc |= dalloc(h, &O.heal_slot_mask, N * A);
+  rc |= dalloc(h, &O.boxes, N * B * 11); rc |= dalloc(h, &O.boxes_mask, N * A * B);
+  rc |= dalloc(h, &O.box_items, N * B * 10); rc |= dalloc(h, &O.box_items_mask, N * A * B);
+  rc |= dalloc(h, &O.box_slot, N * A * 8); rc |= dalloc(h, &O.box_slot_mask, N * A);
+  rc |= dalloc(h, &O.lidar_frac, N * A * L); rc |= dalloc(h, &O.lidar_hit, N * A * L);
+  rc |= dalloc(h, &O.rewards, N * A); rc |= dalloc(h, &O.dones, N);
+  rc |= dalloc(h, &h->d_actions, N * A * 6);
+  rc |= dalloc(h, &h->d_stat_reward, (size_t)MSV_MAX_AGENTS); rc |= dalloc(h, &h->d_stat_kills, (size_t)MSV_MAX_AGENTS);
+  rc |= dalloc(h, &h->d_stat_misc, (size_t)4);
+  if (rc) { g_err = h->err; msv_destroy(h); return MSV_ERR_ALLOC; }
+  {  // episode counter starts at -1 so that the first reset is episode 0
+    std::vector<int4> hd(N, make_int4(0, 0, -1, 0));
+    cudaMemcpy(S.hdr0, hd.data(), N * sizeof(int4), cudaMemcpyHostToDevice);
+  }
+  const int64_t n = num_envs, a = A, b = B, hh = H, s = Sw, l = L;
+  reg(h, "agent", O.agent, 0, {n, a, s});
+  reg(h, "others", O.others, 0, {n, a, a - 1, s});
+  reg(h, "others_mask", O.others_mask, 0, {n, a, a - 1});
+  reg(h, "zone", O.zone, 0, {n, 6});
+  if (H > 0) {
+    reg(h, "heals", O.heals, 0, {n, hh, 2}); reg(h, "heals_mask", O.heals_mask, 0, {n, a, hh});
+    reg(h, "heal_slot", O.heal_slot, 0, {n, a, 1, 1}); reg(h, "heal_slot_mask", O.heal_slot_mask, 0, {n, a, 1});
+  }
+  if (B > 0) {
+    reg(h, "boxes", O.boxes, 0, {n, b, 11}); reg(h, "boxes_mask", O.boxes_mask, 0, {n, a, b});
+    reg(h, "box_items", O.box_items, 0, {n, b, 10}); reg(h, "box_items_mask", O.box_items_mask, 0, {n, a, b});
+    reg(h, "box_slot", O.box_slot, 0, {n, a, 1, 8}); reg(h, "box_slot_mask", O.box_slot_mask, 0, {n, a, 1});
+  }
+  if (L > 0) { reg(h, "lidar_frac", O.lidar_frac, 0, {n, a, l}); reg(h, "lidar_hit", O.lidar_hit, 2, {n, a, l}); }
+  reg(h, "rewards", O.rewards, 0, {n, a});
+  reg(h, "dones", O.dones, 1, {n});
+  *out = h;
+  return MSV_OK;
+}
+
+int msv_destroy(msv_handle* h) {
+  if (!h) return MSV_ERR_INVALID;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return MSV_OK;
+}
+
+const char* msv_last_error(msv_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream) {
+  CK(cudaSetDevice(h->device));
+  CK(msv_launch(h->cap, which, h->C, h->S, h->O, actions, (cudaStream_t)stream));
+  h->launches++;
+  return MSV_OK;
+}
+
+int msv_reset(msv_handle* h, void* stream) { return h ? launch(h, 1, nullptr, stream) : MSV_ERR_INVALID; }
+int msv_observe(msv_handle* h, void* stream) { return h ? launch(h, 2, nullptr, stream) : MSV_ERR_INVALID; }
+int msv_step(msv_handle* h, const uint8_t* actions_dev, void* stream) {
+  if (!h || !actions_dev) return MSV_ERR_INVALID;
+  return launch(h, 0, actions_dev, stream);
+}
+
+int msv_step_host(msv_handle* h, const uint8_t* actions_host, float* rewards_host, uint8_t* dones_host, void* stream) {
+  if (!h || !actions_host) return MSV_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t N = h->C.N, A = h->C.A;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_actions, actions_host, N * A * 6, cudaMemcpyHostToDevice, st));
+  int rc = launch(h, 0, h->d_actions, stream);
+  if (rc) return rc;
+  if (rewards_host) CK(cudaMemcpyAsync(rewards_host, h->O.rewards, N * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (dones_host) CK(cudaMemcpyAsync(dones_host, h->O.dones, N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MSV_OK;
+}
+
+int msv_tensor_info(msv_handle* h, const char* name, void** dev_ptr, int32_t* ndim, int64_t shape[4],
+                    int64_t strides[4], int32_t* dtype_code) {
+  if (!h || !name) return MSV_ERR_INVALID;
+  auto it = h->tensors.find(name);
+  if (it == h->tensors.end()) { h->err = std::string("unknown tensor: ") + name; return MSV_ERR_NAME; }
+  const TensorInfo& t = it->second;
+  if (dev_ptr) *dev_ptr = t.ptr;
+  if (ndim) *ndim = t.ndim;
+  int64_t st = 1;
+  for (int i = t.ndim - 1; i >= 0; --i) { if (shape) shape[i] = t.shape[i]; if (strides) strides[i] = st; st *= t.shape[i]; }
+  if (dtype_code) *dtype_code = t.dtype;
+  return MSV_OK;
+}
+
+struct DLCtx { msv_handle* h; int64_t shape[4]; int64_t strides[4]; };
+static void dl_deleter(DLManagedTensor* m) {
+  if (!m) return;
+  DLCtx* c = (DLCtx*)m->manager_ctx;
+  // the library owns the memory for the handle's lifetime: only drop the count
+  if (c) { c->h->exported--; delete c; }
+  delete m;
+}
+
+int msv_tensor(msv_handle* h, const char* name, struct DLManagedTensor** out) {
+  if (!h || !name || !out) return MSV_ERR_INVALID;
+  auto it = h->tensors.find(name);
+  if (it == h->tensors.end()) { h->err = std::string("unknown tensor: ") + name; return MSV_ERR_NAME; }
+  const TensorInfo& t = it->second;
+  DLCtx* c = new DLCtx(); c->h = h;
+  int64_t st = 1;
+  for (int i = t.ndim - 1; i >= 0; --i) { c->shape[i] = t.shape[i]; c->strides[i] = st; st *= t.shape[i]; }
+  DLManagedTensor* m = new DLManagedTensor();
+  m->dl_tensor.data = t.ptr;
+  m->dl_tensor.device.device_type = 2;  // kDLCUDA
+  m->dl_tensor.device.device_id = h->device;
+  m->dl_tensor.ndim = t.ndim;
+  m->dl_tensor.dtype.code = t.dtype == 0 ? 2 : (t.dtype == 1 ? 1 : 0);  // kDLFloat / kDLUInt / kDLInt
+  m->dl_tensor.dtype.bits = t.dtype == 1 ? 8 : 32;
+  m->dl_tensor.dtype.lanes = 1;
+  m->dl_tensor.shape = c->shape; m->dl_tensor.strides = c->strides; m->dl_tensor.byte_offset = 0;
+  m->manager_ctx = c; m->deleter = dl_deleter;
+  h->exported++;
+  *out = m;
+  return MSV_OK;
+}
+
+int msv_get_state(msv_handle* h, int32_t first, int32_t count, msv_env_state* out) {
+  if (!h || !out || first < 0 || count < 0 || first + count > h->C.N) return MSV_ERR_INVALID;
+  Mirror m; int rc = download(h, m); if (rc) return rc;
+  const size_t N = h->C.N; const int AC = h->AC, BC = h->BC, A = h->C.A, NAA = AC * (AC - 1) / 2;
+  for (int q = 0; q < count; ++q) {
+    size_t e = (size_t)first + q; msv_env_state& s = out[q];
+    memset(&s, 0, sizeof s);
+    for (int i = 0; i < A; ++i) {
+      float4 k0 = m.akin0[i * N + e], k1 = m.akin1[i * N + e], ft = m.afat[i * N + e]; int4 ai = m.aint[i * N + e];
+      int fl = f2i(k1.w);
+      s.alive[i] = fl & 1; s.cooldown[i] = ai.z; s.cause[i] = MSV_CAUSE_NONE;
+      if (!s.alive[i]) continue;
+      s.awake[i] = (fl >> 1) & 1;
+      s.x[i] = k0.x; s.y[i] = k0.y; s.angle[i] = k0.z; s.vx[i] = k0.w; s.vy[i] = k1.x; s.omega[i] = k1.y; s.sleep_time[i] = k1.z;
+      s.fat[i][0] = ft.x; s.fat[i][1] = ft.y; s.fat[i][2] = ft.z; s.fat[i][3] = ft.w;
+      s.health[i] = ai.x; s.cause[i] = ai.y;
+      s.inv_n[i] = ai.w & 7;
+      for (int k = 0; k < s.inv_n[i]; ++k) {
+        s.inv_kind[i][k] = (ai.w >> (4 + 2 * k)) & 3;
+        s.inv_owner[i][k] = MSV_CAUSE_NONE;
+        if (s.inv_kind[i][k] == MSV_ITEM_BOX) {
+          float4 pl = m.ainv[(i * 4 + k) * N + e];
+          s.inv_shape[i][k].hx = pl.x; s.inv_shape[i][k].hy = pl.y; s.inv_owner[i][k] = f2i(pl.z); s.inv_shape[i][k].rehulled = f2i(pl.w) & 1;
+        }
+      }
+    }
+    int4 h0 = m.hdr0[e], h1 = m.hdr1[e];
+    s.n_boxes = h0.x & 255; s.n_items = (h0.x >> 8) & 255; s.n_heals = (h0.x >> 16) & 255; s.n_pending = (h0.x >> 24) & 255;
+    for (int k = 0; k < s.n_boxes; ++k) {
+      float4 b0 = m.box0[k * N + e]; int4 b1 = m.box1[k * N + e];
+      s.box_x[k] = b0.x; s.box_y[k] = b0.y; s.box_shape[k].hx = b0.z; s.box_shape[k].hy = b0.w; s.box_shape[k].rehulled = (b1.y >> 1) & 1;
+      s.box_health[k] = b1.x; s.box_has_health[k] = b1.y & 1; s.box_cause[k] = b1.z; s.box_owner[k] = b1.w; s.box_seq[k] = m.boxseq[k * N + e];
+    }
+    for (int k = 0; k < s.n_items; ++k) {
+      float4 i0 = m.item0[k * N + e]; int2 i1 = m.item1[k * N + e];
+      s.item_x[k] = i0.x; s.item_y[k] = i0.y; s.item_shape[k].hx = i0.z; s.item_shape[k].hy = i0.w; s.item_shape[k].rehulled = 1;
+      s.item_owner[k] = i1.x; s.item_seq[k] = i1.y;
+    }
+    for (int k = 0; k < s.n_heals; ++k) { float2 hh = m.heal[k * N + e]; s.heal_x[k] = hh.x; s.heal_y[k] = hh.y; s.heal_seq[k] = m.healseq[k * N + e]; }
+    for (int k = 0; k < s.n_pending; ++k) {
+      float4 p0 = m.pend0[k * N + e];
+      s.pend_x[k] = p0.x; s.pend_y[k] = p0.y; s.pend_shape[k].hx = p0.z; s.pend_shape[k].hy = p0.w; s.pend_shape[k].rehulled = 1;
+      s.pend_owner[k] = m.pend1[k * N + e];
+    }
+    for (int z = 0; z < h->C.n_zones; ++z) { float2 zc = m.zonec[z * N + e]; s.zone_cx[z] = zc.x; s.zone_cy[z] = zc.y; }
+    int4 zi = m.zoneint[e]; float4 zc = m.zonecur[e];
+    s.zone_phase = zi.x; s.zone_t_cooldown = zi.y; s.zone_t_shrink = zi.z; s.zone_endgame = zi.w;
+    s.zone_cur_x = zc.x; s.zone_cur_y = zc.y; s.zone_cur_r = zc.z;
+    auto get_pair = [&](int p, msv_pair& pr) {
+      if (!gbit(m.pex, N, e, p)) return;
+      pr.seq = (int32_t)m.pseq[p * N + e];
+      pr.flags = (gbit(m.ptc, N, e, p) ? MSV_PAIR_TOUCHING : 0) | (gbit(m.pen, N, e, p) ? MSV_PAIR_ENABLED : 0);
+      float2 im = m.pimp[p * N + e]; pr.normal_impulse = im.x; pr.tangent_impulse = im.y;
+    };
+    for (int j = 1; j < A; ++j) for (int i = 0; i < j; ++i) get_pair(j * (j - 1) / 2 + i, s.pair_aa[j * (j - 1) / 2 + i]);
+    for (int i = 0; i < A; ++i) {
+      for (int k = 0; k < s.n_boxes; ++k) get_pair(NAA + i * BC + k, s.pair_ab[i][k]);
+      for (int k = 0; k < 4; ++k) get_pair(NAA + AC * BC + i * 4 + k, s.pair_aw[i][k]);
+    }
+    s.first_step = h1.y; s.steps = h0.y; s.episode = h0.z; s.body_seq = h0.w; s.contact_seq = h1.x;
+    for (int i = 0; i < AC; ++i) { s.stat_reward[i] = m.sreward[i * N + e]; s.stat_kills[i] = m.skills[i * N + e]; }
+    int4 sm = m.smisc[e]; s.stat_steps = sm.x; s.stat_heals_used = sm.y; s.stat_boxes_placed = sm.z;
+  }
+  return MSV_OK;
+}
+
+int msv_set_state(msv_handle* h, int32_t first, int32_t count, const msv_env_state* in) {
+  if (!h || !in || first < 0 || count < 0 || first + count > h->C.N) return MSV_ERR_INVALID;
+  Mirror m; int rc = download(h, m); if (rc) return rc;
+  const size_t N = h->C.N; const int AC = h->AC, BC = h->BC, HC = h->HC, A = h->C.A, NAA = AC * (AC - 1) / 2;
+  for (int q = 0; q < count; ++q) {
+    size_t e = (size_t)first + q; const msv_env_state& s = in[q];
+    if (s.n_boxes > BC || s.n_items > BC || s.n_heals > HC || s.n_pending > BC) return MSV_ERR_INVALID;
+    for (int i = 0; i < A; ++i) {
+      int fl = (s.alive[i] ? 1 : 0) | (s.alive[i] && s.awake[i] ? 2 : 0);
+      m.akin0[i * N + e] = make_float4(s.x[i], s.y[i], s.angle[i], s.vx[i]);
+      m.akin1[i * N + e] = make_float4(s.vy[i], s.omega[i], s.sleep_time[i], i2f(fl));
+      m.afat[i * N + e] = make_float4(s.fat[i][0], s.fat[i][1], s.fat[i][2], s.fat[i][3]);
+      int inv = s.alive[i] ? s.inv_n[i] : 0;
+      for (int k = 0; k < (s.alive[i] ? s.inv_n[i] : 0); ++k) {
+        inv |= s.inv_kind[i][k] << (4 + 2 * k);
+        m.ainv[(i * 4 + k) * N + e] = make_float4(s.inv_shape[i][k].hx, s.inv_shape[i][k].hy, i2f(s.inv_owner[i][k]), i2f(s.inv_shape[i][k].rehulled));
+      }
+      m.aint[i * N + e] = make_int4(s.health[i], s.cause[i], s.cooldown[i], inv);
+    }
+    m.hdr0[e] = make_int4(s.n_boxes | (s.n_items << 8) | (s.n_heals << 16) | (s.n_pending << 24), s.steps, s.episode, s.body_seq);
+    m.hdr1[e] = make_int4(s.contact_seq, s.first_step, 0, 0);
+    for (int k = 0; k < s.n_boxes; ++k) {
+      m.box0[k * N + e] = make_float4(s.box_x[k], s.box_y[k], s.box_shape[k].hx, s.box_shape[k].hy);
+      m.box1[k * N + e] = make_int4(s.box_health[k], (s.box_has_health[k] ? 1 : 0) | (s.box_shape[k].rehulled ? 2 : 0), s.box_cause[k], s.box_owner[k]);
+      m.boxseq[k * N + e] = s.box_seq[k];
+    }
+    for (int k = 0; k < s.n_items; ++k) {
+      m.item0[k * N + e] = make_float4(s.item_x[k], s.item_y[k], s.item_shape[k].hx, s.item_shape[k].hy);
+      m.item1[k * N + e] = make_int2(s.item_owner[k], s.item_seq[k]);
+    }
+    for (int k = 0; k < s.n_heals; ++k) { m.heal[k * N + e] = make_float2(s.heal_x[k], s.heal_y[k]); m.healseq[k * N + e] = s.heal_seq[k]; }
+    for (int k = 0; k < s.n_pending; ++k) {
+      m.pend0[k * N + e] = make_float4(s.pend_x[k], s.pend_y[k], s.pend_shape[k].hx, s.pend_shape[k].hy);
+      m.pend1[k * N + e] = s.pend_owner[k];
+    }
+    for (int z = 0; z < h->C.n_zones; ++z) m.zonec[z * N + e] = make_float2(s.zone_cx[z], s.zone_cy[z]);
+    m.zoneint[e] = make_int4(s.zone_phase, s.zone_t_cooldown, s.zone_t_shrink, s.zone_endgame);
+    m.zonecur[e] = make_float4(s.zone_cur_x, s.zone_cur_y, s.zone_cur_r, 0.0f);
+    for (int p = 0; p < h->P; ++p) { sbit(m.pex, N, e, p, false); sbit(m.ptc, N, e, p, false); sbit(m.pen, N, e, p, false); }
+    auto set_pair = [&](int p, const msv_pair& pr) {
+      if (!pr.seq) return;
+      sbit(m.pex, N, e, p, true); sbit(m.ptc, N, e, p, pr.flags & MSV_PAIR_TOUCHING); sbit(m.pen, N, e, p, pr.flags & MSV_PAIR_ENABLED);
+      m.pseq[p * N + e] = (uint32_t)pr.seq; m.pimp[p * N + e] = make_float2(pr.normal_impulse, pr.tangent_impulse);
+    };
+    for (int j = 1; j < A; ++j) for (int i = 0; i < j; ++i)
+      if (s.alive[i] && s.alive[j]) set_pair(j * (j - 1) / 2 + i, s.pair_aa[j * (j - 1) / 2 + i]);
+    for (int i = 0; i < A; ++i) {
+      if (!s.alive[i]) continue;
+      for (int k = 0; k < s.n_boxes; ++k) set_pair(NAA + i * BC + k, s.pair_ab[i][k]);
+      for (int k = 0; k < 4; ++k) set_pair(NAA + AC * BC + i * 4 + k, s.pair_aw[i][k]);
+    }
+    for (int i = 0; i < AC; ++i) { m.sreward[i * N + e] = s.stat_reward[i]; m.skills[i * N + e] = s.stat_kills[i]; }
+    m.smisc[e] = make_int4(s.stat_steps, s.stat_heals_used, s.stat_boxes_placed, 0);
+  }
+  return upload(h, m);
+}
+
+int msv_flush_stats(msv_handle* h, msv_stats* out) {
+  if (!h || !out) return MSV_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemset(h->d_stat_reward, 0, sizeof(double) * MSV_MAX_AGENTS));
+  CK(cudaMemset(h->d_stat_kills, 0, sizeof(unsigned long long) * MSV_MAX_AGENTS));
+  CK(cudaMemset(h->d_stat_misc, 0, sizeof(unsigned long long) * 4));
+  CK(msv_launch_stats(h->C.N, h->AC, h->S.sreward, h->S.skills, h->S.smisc, h->d_stat_reward, h->d_stat_kills, h->d_stat_misc, 0));
+  h->launches++;
+  double r[MSV_MAX_AGENTS]; unsigned long long k[MSV_MAX_AGENTS], mm[4];
+  CK(cudaMemcpy(r, h->d_stat_reward, sizeof r, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(k, h->d_stat_kills, sizeof k, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(mm, h->d_stat_misc, sizeof mm, cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof *out);
+  for (int i = 0; i < MSV_MAX_AGENTS; ++i) { out->reward[i] = r[i]; out->kills[i] = (int64_t)k[i]; }
+  out->steps = (int64_t)mm[0]; out->heals_used = (int64_t)mm[1]; out->boxes_placed = (int64_t)mm[2]; out->episodes = (int64_t)mm[3];
+  return MSV_OK;
+}
+
+// Algorithmic HBM bytes of one step for one env: every live state word is read
+// once, the words a step can change are written once, plus actions in and
+// observations / rewards / dones out.  (DESIGN.md "roofline numerator".)
+int64_t msv_bytes_per_env_step(msv_handle* h) {
+  if (!h) return 0;
+  const int64_t A = h->C.A, B = h->C.B0, H = h->C.H0, S = h->C.S, L = h->C.lidar_n, Z = h->C.n_zones, PW = h->PW;
+  int64_t agents_rw = A * (16 + 16 + 16 + 16);            // akin0, akin1, afat, aint
+  int64_t boxes_r = B * (16 + 16), items_r = 0, heals_r = H * 8;  // static geometry read for ray casts
+  int64_t zone_rw = 16 + 16, zone_r = Z * 8 > 16 ? 16 : Z * 8;     // current + next centre
+  int64_t hdr_rw = 16 + 16 + PW * 8 * 3, stats_rw = A * 8 + 16;
+  int64_t state_r = agents_rw + boxes_r + items_r + heals_r + zone_rw + zone_r + hdr_rw + stats_rw;
+  int64_t state_w = agents_rw + zone_rw + hdr_rw + stats_rw;
+  int64_t obs = 4 * (A * S + A * (A - 1) * S + A * (A - 1) + 6);
+  if (H > 0) obs += 4 * (H * 2 + A * H + 2 * A);
+  if (B > 0) obs += 4 * (B * 11 + A * B + B * 10 + A * B + A * 8 + A);
+  if (L > 0) obs += 8 * A * L;
+  return state_r + state_w + A * 6 + obs + 4 * A + 1;
+}
+int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }
+
+void msv_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+}  // extern "C"

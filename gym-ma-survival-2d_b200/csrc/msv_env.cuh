@@ -1,0 +1,1238 @@
+// msv_env.cuh -- one environment's step, executed by ONE thread of a block
+// whose threads hold consecutive environments (coalesced SoA traffic).  The
+// dynamically-indexed hot state (agent sweeps/velocities/fat AABBs, boxes)
+// lives in a bank-conflict-free shared-memory column per thread
+// (word w of thread t at sm[w * blockDim + t]).
+//
+// Reference behaviour being reproduced (citations into /root/reference):
+//   env  = masurvival/envs/masurvival_env.py   sim = masurvival/simulation.py
+//   sem  = masurvival/semantics.py
+// and, for the physics, the Box2D v2.3.x routines named at each function.
+#pragma once
+#include "msv_device.cuh"
+#include "msv_types.cuh"
+
+// shared-memory agent fields
+enum { F_CX, F_CY, F_A, F_VX, F_VY, F_W, F_C0X, F_C0Y, F_A0, F_ALPHA0, F_SLEEP,
+       F_FAT0, F_FAT1, F_FAT2, F_FAT3, F_FLAGS, F_COUNT };
+// shared-memory box fields
+enum { G_X, G_Y, G_HX, G_HY, G_AX, G_AY, G_ROT, G_COUNT };
+
+#define FL_ALIVE 1
+#define FL_AWAKE 2
+#define FL_ISLAND 4
+#define FL_MOVED 8
+
+#define KIND_NONE 0
+#define KIND_AGENT 1
+#define KIND_BOX 2
+#define KIND_ITEM 3
+#define KIND_HEAL 4
+#define KIND_WALL 5
+
+#define STREAM_SHUFFLE 0
+#define STREAM_BOX 1
+#define STREAM_ZONE 2
+#define STREAM_DEATH 3
+
+template <int AC, int BC> struct PairLayout {
+  static constexpr int NAA = AC * (AC - 1) / 2;
+  static constexpr int NAB = AC * BC;
+  static constexpr int P = NAA + NAB + AC * 4;
+  static constexpr int PW = (P + 63) / 64;
+};
+
+// one touching contact, with its solver scratch (b2ContactVelocityConstraint /
+// b2ContactPositionConstraint for a single manifold point)
+struct TCon {
+  int p, seq;
+  int a;     // agent index of body A, or -1 when A is static
+  int sid;   // static id of body A (box k, or BC + wall k) when a < 0
+  int b;     // agent index of body B
+  int flags; // 1 = in island
+  Manifold m;
+  float ni, ti;
+  f2 normal, rA, rB;
+  float normalMass, tangentMass;
+};
+
+struct BodyS { f2 c; float a; f2 v; float w; float invM, invI; };
+
+template <int AC, int BC, int HC>
+struct Env {
+  using PL = PairLayout<AC, BC>;
+  static constexpr int P = PL::P, PW = PL::PW, NAA = PL::NAA;
+  static constexpr int MAXC = AC <= 4 ? 16 : 24;
+  static constexpr int SM_WORDS = F_COUNT * AC + G_COUNT * BC;
+
+  const DevConst& C;
+  const DevState& S;
+  float* sm;
+  int T, tid, e, N;
+
+  int health[AC], cause[AC], cooldown[AC], inv[AC];
+  int nb, ni, nh, np, steps, episode, body_seq, contact_seq, first_step, overflow;
+  unsigned long long ex[PW], tc[PW], en[PW];
+  float zx, zy, zr; int zphase, ztcool, ztshrink, zend;
+  float st_reward[AC]; int st_kills[AC]; int st_steps, st_heals, st_boxes, st_episodes;
+  // per-step trackers
+  int use_heal, use_box;
+  int new_box;
+  TCon tcs[MAXC]; int ntc;
+  // sensors
+  unsigned seenA[AC];  // by PRE-death rank: bit j = agent j seen
+  unsigned pre_alive;
+
+  __device__ Env(const DevConst& c, const DevState& s, float* smem, int T_, int tid_, int e_)
+      : C(c), S(s), sm(smem), T(T_), tid(tid_), e(e_), N(c.N) {}
+
+  // ---- shared-memory accessors
+  DEV float& AG(int f, int i) { return sm[(f * AC + i) * T + tid]; }
+  DEV int& AGF(int i) { return reinterpret_cast<int*>(sm)[(F_FLAGS * AC + i) * T + tid]; }
+  DEV float& BX(int g, int k) { return sm[(F_COUNT * AC + g * BC + k) * T + tid]; }
+  DEV int& BXROT(int k) { return reinterpret_cast<int*>(sm)[(F_COUNT * AC + G_ROT * BC + k) * T + tid]; }
+  DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
+  DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
+  DEV f2 apos(int i) { return mk2(AG(F_CX, i), AG(F_CY, i)); }
+
+  // ---- pair bit helpers
+  DEV static bool bit(const unsigned long long* m, int p) { return (m[p >> 6] >> (p & 63)) & 1ull; }
+  DEV static void setb(unsigned long long* m, int p) { m[p >> 6] |= 1ull << (p & 63); }
+  DEV static void clrb(unsigned long long* m, int p) { m[p >> 6] &= ~(1ull << (p & 63)); }
+  DEV static int p_aa(int i, int j) { return j * (j - 1) / 2 + i; }  // i < j
+  DEV static int p_ab(int i, int k) { return NAA + i * BC + k; }
+  DEV static int p_aw(int i, int k) { return NAA + AC * BC + i * 4 + k; }
+  // decode pair -> (a, sid, b)
+  DEV static void decode(int p, int& a, int& sid, int& b) {
+    if (p < NAA) {
+      int j = 1; while (j * (j + 1) / 2 <= p) ++j;
+      a = p - j * (j - 1) / 2; b = j; sid = -1;
+    } else if (p < NAA + AC * BC) {
+      int q = p - NAA; a = -1; b = q / BC; sid = q % BC;
+    } else {
+      int q = p - NAA - AC * BC; a = -1; b = q >> 2; sid = BC + (q & 3);
+    }
+  }
+
+  // ---- global state I/O -------------------------------------------------
+  __device__ void load() {
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      if (i < C.A) {
+        float4 k0 = S.akin0[i * N + e], k1 = S.akin1[i * N + e], ft = S.afat[i * N + e];
+        int4 ai = S.aint[i * N + e];
+        AG(F_CX, i) = k0.x; AG(F_CY, i) = k0.y; AG(F_A, i) = k0.z; AG(F_VX, i) = k0.w;
+        AG(F_VY, i) = k1.x; AG(F_W, i) = k1.y; AG(F_SLEEP, i) = k1.z; AGF(i) = __float_as_int(k1.w) & 3;
+        AG(F_FAT0, i) = ft.x; AG(F_FAT1, i) = ft.y; AG(F_FAT2, i) = ft.z; AG(F_FAT3, i) = ft.w;
+        AG(F_C0X, i) = k0.x; AG(F_C0Y, i) = k0.y; AG(F_A0, i) = k0.z; AG(F_ALPHA0, i) = 0.0f;
+        health[i] = ai.x; cause[i] = ai.y; cooldown[i] = ai.z; inv[i] = ai.w;
+      } else { AGF(i) = 0; health[i] = 0; cause[i] = MSV_CAUSE_NONE; cooldown[i] = 0; inv[i] = 0; }
+      st_reward[i] = S.sreward[i * N + e]; st_kills[i] = S.skills[i * N + e];
+    }
+    int4 h0 = S.hdr0[e], h1 = S.hdr1[e];
+    nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; np = (h0.x >> 24) & 255;
+    steps = h0.y; episode = h0.z; body_seq = h0.w;
+    contact_seq = h1.x; first_step = h1.y; overflow = h1.z;
+#pragma unroll
+    for (int k = 0; k < BC; ++k) {
+      if (k < nb) load_box(k, k);
+    }
+#pragma unroll
+    for (int w = 0; w < PW; ++w) { ex[w] = S.pex[w * N + e]; tc[w] = S.ptc[w * N + e]; en[w] = S.pen[w * N + e]; }
+    float4 zc = S.zonecur[e]; int4 zi = S.zoneint[e];
+    zx = zc.x; zy = zc.y; zr = zc.z; zphase = zi.x; ztcool = zi.y; ztshrink = zi.z; zend = zi.w;
+    int4 sm_ = S.smisc[e];
+    st_steps = sm_.x; st_heals = sm_.y; st_boxes = sm_.z; st_episodes = sm_.w;
+  }
+  // read box at global slot `src` into shared slot `dst`
+  DEV void load_box(int dst, int src) {
+    float4 b0 = S.box0[src * N + e]; int4 b1 = S.box1[src * N + e];
+    BX(G_X, dst) = b0.x; BX(G_Y, dst) = b0.y;
+    SBox t; sb_set_shape(t, b0.z, b0.w, (b1.y >> 1) & 1);
+    BX(G_HX, dst) = t.hx; BX(G_HY, dst) = t.hy; BX(G_AX, dst) = t.ax; BX(G_AY, dst) = t.ay; BXROT(dst) = t.rot;
+  }
+  __device__ void store() {
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      if (i < C.A) {
+        S.akin0[i * N + e] = make_float4(AG(F_CX, i), AG(F_CY, i), AG(F_A, i), AG(F_VX, i));
+        S.akin1[i * N + e] = make_float4(AG(F_VY, i), AG(F_W, i), AG(F_SLEEP, i), __int_as_float(AGF(i) & 3));
+        S.afat[i * N + e] = make_float4(AG(F_FAT0, i), AG(F_FAT1, i), AG(F_FAT2, i), AG(F_FAT3, i));
+        S.aint[i * N + e] = make_int4(health[i], cause[i], cooldown[i], inv[i]);
+      }
+      S.sreward[i * N + e] = st_reward[i]; S.skills[i * N + e] = st_kills[i];
+    }
+    S.hdr0[e] = make_int4(nb | (ni << 8) | (nh << 16) | (np << 24), steps, episode, body_seq);
+    S.hdr1[e] = make_int4(contact_seq, first_step, overflow, 0);
+    // box positions/shapes only change on spawn/despawn, which write through
+#pragma unroll
+    for (int w = 0; w < PW; ++w) { S.pex[w * N + e] = ex[w]; S.ptc[w * N + e] = tc[w]; S.pen[w * N + e] = en[w]; }
+    S.zonecur[e] = make_float4(zx, zy, zr, 0.0f);
+    S.zoneint[e] = make_int4(zphase, ztcool, ztshrink, zend);
+    S.smisc[e] = make_int4(st_steps, st_heals, st_boxes, st_episodes);
+  }
+
+  // ---- geometry helpers ---------------------------------------------------
+  DEV SBox static_box(int sid) {
+    SBox b;
+    if (sid < BC) {
+      b.px = BX(G_X, sid); b.py = BX(G_Y, sid); b.qs = 0.0f; b.qc = 1.0f; b.ang = 0.0f;
+      b.hx = BX(G_HX, sid); b.hy = BX(G_HY, sid); b.ax = BX(G_AX, sid); b.ay = BX(G_AY, sid); b.rot = BXROT(sid);
+    } else {
+      const WallC& w = C.walls[sid - BC];
+      b.px = w.px; b.py = w.py; b.qs = w.qs; b.qc = w.qc; b.ang = w.ang;
+      b.hx = C.wall_hx; b.hy = C.wall_hy; b.ax = 1.0f; b.ay = 1.0f; b.rot = 0;
+    }
+    return b;
+  }
+  DEV void static_fat(int sid, float out[4]) {
+    if (sid < BC) { SBox b = static_box(sid); sb_fat(b, out); }
+    else { const WallC& w = C.walls[sid - BC]; out[0] = w.fat[0]; out[1] = w.fat[1]; out[2] = w.fat[2]; out[3] = w.fat[3]; }
+  }
+  DEV void agent_fat(int i, float out[4]) {
+    out[0] = AG(F_FAT0, i); out[1] = AG(F_FAT1, i); out[2] = AG(F_FAT2, i); out[3] = AG(F_FAT3, i);
+  }
+  DEV int static_seq(int sid) { return sid < BC ? S.boxseq[sid * N + e] : C.B0 + C.H0 + (sid - BC); }
+  DEV int agent_seq(int i) { return C.B0 + C.H0 + 4 + i; }
+  DEV void wake(int i) {  // b2Body::SetAwake(true)
+    int f = AGF(i);
+    if (!(f & FL_AWAKE)) { AGF(i) = f | FL_AWAKE; AG(F_SLEEP, i) = 0.0f; }
+  }
+  DEV void sleep_body(int i) {  // b2Body::SetAwake(false)
+    AGF(i) &= ~FL_AWAKE; AG(F_SLEEP, i) = 0.0f; AG(F_VX, i) = 0.0f; AG(F_VY, i) = 0.0f; AG(F_W, i) = 0.0f;
+  }
+  DEV int team_of(int i) { return i < C.A / 2 ? 0 : 1; }  // sem:957-966
+
+  // closest hit of the segment p1->p2 over every fixture except agent `self`
+  // (whose own circle contains p1 and therefore always misses); minimum
+  // fraction over independent b2Shape::RayCast tests (sim:431-439, 471-484)
+  __device__ __noinline__ int raycast(f2 p1, f2 p2, int self, int& idx, float& frac) {
+    int kind = KIND_NONE; idx = -1; frac = 0.0f; float f;
+    for (int k = 0; k < nb; ++k)
+      if (ray_box(static_box(k), p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_BOX; idx = k; frac = f; }
+    for (int k = 0; k < ni; ++k) {
+      float4 it = S.item0[k * N + e];
+      if (ray_circle(mk2(it.x, it.y), C.item_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_ITEM; idx = k; frac = f; }
+    }
+    for (int k = 0; k < nh; ++k) {
+      float2 h = S.heal[k * N + e];
+      if (ray_circle(mk2(h.x, h.y), C.heal_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_HEAL; idx = k; frac = f; }
+    }
+    for (int k = 0; k < 4; ++k)
+      if (ray_box(static_box(BC + k), p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_WALL; idx = k; frac = f; }
+    for (int j = 0; j < C.A; ++j) {
+      if (j == self || !alive(j)) continue;
+      if (ray_circle(apos(j), C.agent_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_AGENT; idx = j; frac = f; }
+    }
+    return kind;
+  }
+
+  // Health._change_health (sem:490-500)
+  DEV void agent_change_health(int i, int delta, int cz) {
+    if (!alive(i)) return;
+    if (C.teams && cz == MSV_CAUSE_TEAM0 + team_of(i)) return;  // immunities sem:942-946
+#pragma unroll
+    for (int j = 0; j < AC; ++j) if (j == i) { health[j] += delta; cause[j] = cz; }
+  }
+  DEV void box_change_health(int k, int delta, int cz) {
+    int4 b1 = S.box1[k * N + e];
+    if (!(b1.y & 1)) return;                                      // Q9 sem:491-492
+    if (b1.w != MSV_CAUSE_NONE && cz != b1.w) return;             // sem:497-498
+    b1.x += delta; b1.z = cz;
+    S.box1[k * N + e] = b1;
+  }
+  DEV int inv_n(int i) { return inv[i] & 7; }
+  DEV int inv_kind(int i, int s) { return (inv[i] >> (4 + 2 * s)) & 3; }
+  DEV void inv_push(int i, int kind, float4 payload) {
+    int n = inv_n(i);
+    inv[i] = (inv[i] & ~(3 << (4 + 2 * n)) & ~7) | (kind << (4 + 2 * n)) | (n + 1);
+    if (kind == MSV_ITEM_BOX) S.ainv[(i * 4 + n) * N + e] = payload;
+  }
+  DEV int inv_pop(int i, float4& payload) {  // list.pop(-1)
+    int n = inv_n(i) - 1;
+    int kind = inv_kind(i, n);
+    if (kind == MSV_ITEM_BOX) payload = S.ainv[(i * 4 + n) * N + e];
+    inv[i] = (inv[i] & ~7) | n;
+    return kind;
+  }
+
+  // ---- list maintenance (stable compaction, sim:185-189) -----------------
+  // shift the AB pair column k+1.. down by one for every agent
+  __device__ void remove_box(int k) {
+    for (int i = 0; i < C.A; ++i) {   // b2World::DestroyBody -> contacts die, touching ones wake
+      int p = p_ab(i, k);
+      if (bit(ex, p) && bit(tc, p)) wake(i);
+      for (int q = k; q + 1 < nb; ++q) {
+        int pd = p_ab(i, q), ps = p_ab(i, q + 1);
+        if (bit(ex, ps)) { setb(ex, pd); S.pseq[pd * N + e] = S.pseq[ps * N + e]; S.pimp[pd * N + e] = S.pimp[ps * N + e]; } else clrb(ex, pd);
+        if (bit(tc, ps)) setb(tc, pd); else clrb(tc, pd);
+        if (bit(en, ps)) setb(en, pd); else clrb(en, pd);
+      }
+      int pl = p_ab(i, nb - 1);
+      clrb(ex, pl); clrb(tc, pl); clrb(en, pl);
+    }
+    for (int q = k; q + 1 < nb; ++q) {
+      S.box0[q * N + e] = S.box0[(q + 1) * N + e];
+      S.box1[q * N + e] = S.box1[(q + 1) * N + e];
+      S.boxseq[q * N + e] = S.boxseq[(q + 1) * N + e];
+      BX(G_X, q) = BX(G_X, q + 1); BX(G_Y, q) = BX(G_Y, q + 1); BX(G_HX, q) = BX(G_HX, q + 1);
+      BX(G_HY, q) = BX(G_HY, q + 1); BX(G_AX, q) = BX(G_AX, q + 1); BX(G_AY, q) = BX(G_AY, q + 1);
+      BXROT(q) = BXROT(q + 1);
+    }
+    nb--;
+  }
+  DEV void remove_item(int k) {
+    for (int q = k; q + 1 < ni; ++q) { S.item0[q * N + e] = S.item0[(q + 1) * N + e]; S.item1[q * N + e] = S.item1[(q + 1) * N + e]; }
+    ni--;
+  }
+  DEV void remove_heal(int k) {
+    for (int q = k; q + 1 < nh; ++q) { S.heal[q * N + e] = S.heal[(q + 1) * N + e]; S.healseq[q * N + e] = S.healseq[(q + 1) * N + e]; }
+    nh--;
+  }
+  DEV void add_item(float x, float y, float hx, float hy, int owner) {  // Item.drop sem:143-148
+    if (ni >= BC) { overflow++; return; }
+    S.item0[ni * N + e] = make_float4(x, y, hx, hy);
+    S.item1[ni * N + e] = make_int2(owner, body_seq++);
+    ni++;
+  }
+  DEV void add_heal(float x, float y) {
+    if (nh >= HC) { overflow++; return; }
+    S.heal[nh * N + e] = make_float2(x, y);
+    S.healseq[nh * N + e] = body_seq++;
+    nh++;
+  }
+  DEV void kill_agent(int i) {  // b2World::DestroyBody for an agent
+    for (int j = 0; j < C.A; ++j) {
+      if (j == i) continue;
+      int p = i < j ? p_aa(i, j) : p_aa(j, i);
+      if (bit(ex, p) && bit(tc, p)) wake(j);
+      clrb(ex, p); clrb(tc, p); clrb(en, p);
+    }
+    for (int k = 0; k < BC + 4; ++k) {
+      int p = k < BC ? p_ab(i, k) : p_aw(i, k - BC);
+      clrb(ex, p); clrb(tc, p); clrb(en, p);
+    }
+    AGF(i) = 0;
+  }
+
+  // ======================================================================
+  //                               PHYSICS
+  // ======================================================================
+  // b2ContactManager::FindNewContacts + AddPair over every body pair whose
+  // fat AABBs overlap and that has no contact yet; new contacts are numbered
+  // in ascending (proxyIdA, proxyIdB) order (creation sequence surrogate).
+  __device__ __noinline__ void find_new_contacts() {
+    unsigned long long cand[PW];
+#pragma unroll
+    for (int w = 0; w < PW; ++w) cand[w] = 0ull;
+    bool any = false;
+    for (int i = 0; i < C.A; ++i) {
+      if (!alive(i)) continue;
+      float fi[4]; agent_fat(i, fi);
+      for (int j = i + 1; j < C.A; ++j) {
+        if (!alive(j)) continue;
+        int p = p_aa(i, j);
+        if (bit(ex, p)) continue;
+        float fj[4]; agent_fat(j, fj);
+        if (aabb_overlap(fi, fj)) { setb(cand, p); any = true; }
+      }
+      for (int k = 0; k < BC + 4; ++k) {
+        if (k < BC && k >= nb) continue;
+        int p = k < BC ? p_ab(i, k) : p_aw(i, k - BC);
+        if (bit(ex, p)) continue;
+        float fs[4]; static_fat(k, fs);
+        if (aabb_overlap(fi, fs)) { setb(cand, p); any = true; }
+      }
+    }
+    while (any) {
+      int best = -1; unsigned bestKey = 0xFFFFFFFFu;
+      for (int w = 0; w < PW; ++w) {
+        unsigned long long m = cand[w];
+        while (m) {
+          int p = w * 64 + __ffsll((long long)m) - 1; m &= m - 1;
+          int a, sid, b; decode(p, a, sid, b);
+          int s1 = a >= 0 ? agent_seq(a) : static_seq(sid), s2 = agent_seq(b);
+          int lo = s1 < s2 ? s1 : s2, hi = s1 < s2 ? s2 : s1;
+          unsigned key = ((unsigned)lo << 16) | (unsigned)hi;
+          if (key < bestKey) { bestKey = key; best = p; }
+        }
+      }
+      if (best < 0) break;
+      clrb(cand, best);
+      setb(ex, best); setb(en, best); clrb(tc, best);
+      S.pseq[best * N + e] = (uint32_t)(++contact_seq);
+      S.pimp[best * N + e] = make_float2(0.0f, 0.0f);
+    }
+  }
+
+  // evaluate the manifold of pair (a|sid, b) at the bodies' current transforms
+  DEV bool evaluate(int a, int sid, int b, Manifold& m) {
+    if (a >= 0) return collide_circles(apos(a), apos(b), C.agent_r, C.agent_r, m);
+    return collide_box_circle(static_box(sid), apos(b), C.agent_r, m);
+  }
+
+  DEV void tcon_add(int p, int a, int sid, int b, const Manifold& m, float nimp, float timp) {
+    if (ntc >= MAXC) { overflow++; return; }
+    TCon& t = tcs[ntc++];
+    t.p = p; t.seq = (int)S.pseq[p * N + e]; t.a = a; t.sid = sid; t.b = b; t.flags = 0; t.m = m; t.ni = nimp; t.ti = timp;
+  }
+
+  // b2Contact::Update for one pair; returns touching.  Appends to tcs.
+  DEV bool contact_update(int p, int a, int sid, int b, bool list) {
+    Manifold m; bool touching = evaluate(a, sid, b, m);
+    bool was = bit(tc, p);
+    setb(en, p);
+    float2 imp = make_float2(0.0f, 0.0f);
+    if (touching && was) imp = S.pimp[p * N + e];
+    else if (was || touching) S.pimp[p * N + e] = imp;
+    if (touching != was) { if (a >= 0) wake(a); wake(b); }
+    if (touching) setb(tc, p); else clrb(tc, p);
+    if (touching && list) tcon_add(p, a, sid, b, m, imp.x, imp.y);
+    return touching;
+  }
+
+  // b2ContactManager::Collide
+  __device__ __noinline__ void collide() {
+    ntc = 0;
+    for (int w = 0; w < PW; ++w) {
+      unsigned long long mbits = ex[w];
+      while (mbits) {
+        int p = w * 64 + __ffsll((long long)mbits) - 1; mbits &= mbits - 1;
+        int a, sid, b; decode(p, a, sid, b);
+        bool activeA = a >= 0 && awake(a), activeB = awake(b);
+        if (!activeA && !activeB) {
+          // both asleep/static: Box2D keeps the stale manifold; it is only ever
+          // used if the island DFS wakes one of them -> evaluate it lazily now
+          if (bit(tc, p)) { Manifold m; if (evaluate(a, sid, b, m)) { float2 imp = S.pimp[p * N + e]; tcon_add(p, a, sid, b, m, imp.x, imp.y); } }
+          continue;
+        }
+        float fa[4], fb[4];
+        if (a >= 0) agent_fat(a, fa); else static_fat(sid, fa);
+        agent_fat(b, fb);
+        if (!aabb_overlap(fa, fb)) {  // b2ContactManager::Destroy
+          if (bit(tc, p)) { if (a >= 0) wake(a); wake(b); }
+          clrb(ex, p); clrb(tc, p); clrb(en, p);
+          continue;
+        }
+        contact_update(p, a, sid, b, true);
+      }
+    }
+  }
+
+  // ---- contact solver (single manifold point) ----------------------------
+  DEV BodyS body_of(int a, int sid) {
+    BodyS s;
+    if (a >= 0) {
+      s.c = apos(a); s.a = AG(F_A, a); s.v = mk2(AG(F_VX, a), AG(F_VY, a)); s.w = AG(F_W, a);
+      s.invM = C.inv_mass; s.invI = C.inv_I;
+    } else {
+      SBox bx = static_box(sid);
+      s.c = mk2(bx.px, bx.py); s.a = bx.ang; s.v = mk2(0.0f, 0.0f); s.w = 0.0f; s.invM = 0.0f; s.invI = 0.0f;
+    }
+    return s;
+  }
+  DEV void put_vel(int a, const BodyS& s) { if (a >= 0) { AG(F_VX, a) = s.v.x; AG(F_VY, a) = s.v.y; AG(F_W, a) = s.w; } }
+  DEV void put_pos(int a, const BodyS& s) { if (a >= 0) { AG(F_CX, a) = s.c.x; AG(F_CY, a) = s.c.y; AG(F_A, a) = s.a; } }
+
+  // b2ContactSolver::InitializeVelocityConstraints + b2WorldManifold::Initialize
+  DEV void init_velocity(TCon& t) {
+    BodyS A = body_of(t.a, t.sid), B = body_of(t.b, -1);
+    f2 normal, point;
+    if (t.m.type == 0) {
+      normal = mk2(1.0f, 0.0f);
+      f2 pointA = A.c, pointB = B.c;
+      if (vlen2(vsub(pointA, pointB)) > B2_EPS * B2_EPS) { normal = vsub(pointB, pointA); vnormalize(normal); }
+      f2 pA = vadd(pointA, vmul(C.agent_r, normal));
+      f2 pB = vsub(pointB, vmul(C.agent_r, normal));
+      point = vmul(0.5f, vadd(pA, pB));
+    } else {
+      SBox bx = static_box(t.sid);
+      normal = qmul(bx.qs, bx.qc, t.m.localNormal);
+      f2 planePoint = sb_mul(bx, t.m.localPoint);
+      f2 clipPoint = B.c;
+      f2 pA = vadd(clipPoint, vmul(B2_POLY_RADIUS - vdot(vsub(clipPoint, planePoint), normal), normal));
+      f2 pB = vsub(clipPoint, vmul(C.agent_r, normal));
+      point = vmul(0.5f, vadd(pA, pB));
+    }
+    t.normal = normal;
+    t.rA = vsub(point, A.c); t.rB = vsub(point, B.c);
+    float rnA = vcross(t.rA, normal), rnB = vcross(t.rB, normal);
+    float kNormal = A.invM + B.invM + A.invI * rnA * rnA + B.invI * rnB * rnB;
+    t.normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+    f2 tangent = cross_vs(normal, 1.0f);
+    float rtA = vcross(t.rA, tangent), rtB = vcross(t.rB, tangent);
+    float kTangent = A.invM + B.invM + A.invI * rtA * rtA + B.invI * rtB * rtB;
+    t.tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+    // restitution 0: velocityBias stays 0
+  }
+  DEV void apply_impulse(BodyS& A, BodyS& B, const TCon& t, f2 Pv) {
+    A.v = vsub(A.v, vmul(A.invM, Pv)); A.w -= A.invI * vcross(t.rA, Pv);
+    B.v = vadd(B.v, vmul(B.invM, Pv)); B.w += B.invI * vcross(t.rB, Pv);
+  }
+  DEV void warm_start(TCon& t) {
+    BodyS A = body_of(t.a, t.sid), B = body_of(t.b, -1);
+    f2 tangent = cross_vs(t.normal, 1.0f);
+    f2 Pv = vadd(vmul(t.ni, t.normal), vmul(t.ti, tangent));
+    A.w -= A.invI * vcross(t.rA, Pv); A.v = vsub(A.v, vmul(A.invM, Pv));
+    B.w += B.invI * vcross(t.rB, Pv); B.v = vadd(B.v, vmul(B.invM, Pv));
+    put_vel(t.a, A); put_vel(t.b, B);
+  }
+  // b2ContactSolver::SolveVelocityConstraints, one contact
+  DEV void solve_velocity(TCon& t) {
+    BodyS A = body_of(t.a, t.sid), B = body_of(t.b, -1);
+    f2 normal = t.normal, tangent = cross_vs(normal, 1.0f);
+    {
+      f2 dv = vsub(vsub(vadd(B.v, cross_sv(B.w, t.rB)), A.v), cross_sv(A.w, t.rA));
+      float vt = vdot(dv, tangent) - 0.0f;
+      float lambda = t.tangentMass * (-vt);
+      float maxFriction = C.friction * t.ni;
+      float newImpulse = fclamp_(t.ti + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - t.ti; t.ti = newImpulse;
+      apply_impulse(A, B, t, vmul(lambda, tangent));
+    }
+    {
+      f2 dv = vsub(vsub(vadd(B.v, cross_sv(B.w, t.rB)), A.v), cross_sv(A.w, t.rA));
+      float vn = vdot(dv, normal);
+      float lambda = -t.normalMass * (vn - 0.0f);
+      float newImpulse = fmax_(t.ni + lambda, 0.0f);
+      lambda = newImpulse - t.ni; t.ni = newImpulse;
+      apply_impulse(A, B, t, vmul(lambda, normal));
+    }
+    put_vel(t.a, A); put_vel(t.b, B);
+  }
+  // b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints, one contact
+  DEV float solve_position(const TCon& t, bool toi, int toiAgent) {
+    BodyS A = body_of(t.a, t.sid), B = body_of(t.b, -1);
+    float mA = A.invM, iA = A.invI, mB = B.invM, iB = B.invI;
+    if (toi) {  // only the two TOI bodies move; the static one has no mass anyway
+      if (t.a != toiAgent) { mA = 0.0f; iA = 0.0f; }
+      if (t.b != toiAgent) { mB = 0.0f; iB = 0.0f; }
+    }
+    f2 normal, point; float separation;
+    if (t.m.type == 0) {
+      normal = vsub(B.c, A.c); vnormalize(normal);
+      point = vmul(0.5f, vadd(A.c, B.c));
+      separation = vdot(vsub(B.c, A.c), normal) - C.agent_r - C.agent_r;
+    } else {
+      SBox bx = static_box(t.sid);
+      normal = qmul(bx.qs, bx.qc, t.m.localNormal);
+      f2 planePoint = sb_mul(bx, t.m.localPoint);
+      separation = vdot(vsub(B.c, planePoint), normal) - B2_POLY_RADIUS - C.agent_r;
+      point = B.c;
+    }
+    f2 rA = vsub(point, A.c), rB = vsub(point, B.c);
+    float Cc = fclamp_((toi ? B2_TOI_BAUMGARTE : B2_BAUMGARTE) * (separation + B2_LINEAR_SLOP), -B2_MAX_LIN_CORR, 0.0f);
+    float rnA = vcross(rA, normal), rnB = vcross(rB, normal);
+    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    float impulse = K > 0.0f ? -Cc / K : 0.0f;
+    f2 Pv = vmul(impulse, normal);
+    A.c = vsub(A.c, vmul(mA, Pv)); A.a -= iA * vcross(rA, Pv);
+    B.c = vadd(B.c, vmul(mB, Pv)); B.a += iB * vcross(rB, Pv);
+    put_pos(t.a, A); put_pos(t.b, B);
+    return separation;
+  }
+  DEV void integrate_position(int i, float h) {  // b2Island::Solve "Integrate positions"
+    f2 v = mk2(AG(F_VX, i), AG(F_VY, i)); float w = AG(F_W, i);
+    f2 translation = vmul(h, v);
+    if (vdot(translation, translation) > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) {
+      float ratio = B2_MAX_TRANSLATION / vlen(translation);
+      v = vmul(ratio, v);
+    }
+    float rotation = h * w;
+    if (rotation * rotation > B2_MAX_ROTATION * B2_MAX_ROTATION) {
+      float ratio = B2_MAX_ROTATION / fabsf(rotation);
+      w *= ratio;
+    }
+    AG(F_CX, i) += h * v.x; AG(F_CY, i) += h * v.y; AG(F_A, i) += h * w;
+    AG(F_VX, i) = v.x; AG(F_VY, i) = v.y; AG(F_W, i) = w;
+  }
+
+  // b2Body::SynchronizeFixtures + b2DynamicTree::MoveProxy for agent i
+  DEV void synchronize_fixtures(int i) {
+    float r = C.agent_r;
+    float c0x = AG(F_C0X, i), c0y = AG(F_C0Y, i), cx = AG(F_CX, i), cy = AG(F_CY, i);
+    float a1[4] = {c0x - r, c0y - r, c0x + r, c0y + r};
+    float a2[4] = {cx - r, cy - r, cx + r, cy + r};
+    float ab[4] = {fmin_(a1[0], a2[0]), fmin_(a1[1], a2[1]), fmax_(a1[2], a2[2]), fmax_(a1[3], a2[3])};
+    float f0 = AG(F_FAT0, i), f1 = AG(F_FAT1, i), f2_ = AG(F_FAT2, i), f3 = AG(F_FAT3, i);
+    if (f0 <= ab[0] && f1 <= ab[1] && ab[2] <= f2_ && ab[3] <= f3) return;
+    float n0 = ab[0] - B2_AABB_EXT, n1 = ab[1] - B2_AABB_EXT, n2 = ab[2] + B2_AABB_EXT, n3 = ab[3] + B2_AABB_EXT;
+    float dx = B2_AABB_MULT * (cx - c0x), dy = B2_AABB_MULT * (cy - c0y);
+    if (dx < 0.0f) n0 += dx; else n2 += dx;
+    if (dy < 0.0f) n1 += dy; else n3 += dy;
+    AG(F_FAT0, i) = n0; AG(F_FAT1, i) = n1; AG(F_FAT2, i) = n2; AG(F_FAT3, i) = n3;
+    AGF(i) |= FL_MOVED;
+  }
+
+  // b2World::Solve: islands by DFS over touching contacts, seeds in body-list
+  // order (newest body first = highest agent index first), contact edges
+  // newest first; each island solved by b2Island::Solve.
+  __device__ __noinline__ void solve(float h, float dtRatio) {
+    for (int i = 0; i < C.A; ++i) AGF(i) &= ~(FL_ISLAND | FL_MOVED);
+    for (int k = 0; k < ntc; ++k) tcs[k].flags = 0;
+    int stack[AC], members[AC], order[MAXC];
+    for (int seed = C.A - 1; seed >= 0; --seed) {
+      int fs = AGF(seed);
+      if (!(fs & FL_ALIVE) || (fs & FL_ISLAND) || !(fs & FL_AWAKE)) continue;
+      int sc = 0, nm = 0, nc = 0;
+      stack[sc++] = seed; AGF(seed) |= FL_ISLAND;
+      while (sc > 0) {
+        int bI = stack[--sc];
+        members[nm++] = bI;
+        wake(bI);
+        for (;;) {  // contact edges of bI, newest (largest seq) first
+          int best = -1, bestSeq = -1;
+          for (int k = 0; k < ntc; ++k) {
+            const TCon& t = tcs[k];
+            if (t.flags & 1) continue;
+            if (t.a != bI && t.b != bI) continue;
+            if (!bit(en, t.p) || !bit(tc, t.p)) continue;
+            if (t.seq > bestSeq) { bestSeq = t.seq; best = k; }
+          }
+          if (best < 0) break;
+          tcs[best].flags |= 1;
+          order[nc++] = best;
+          const TCon& t = tcs[best];
+          if (t.a >= 0) {
+            int other = t.a == bI ? t.b : t.a;
+            if (!(AGF(other) & FL_ISLAND)) { stack[sc++] = other; AGF(other) |= FL_ISLAND; }
+          }
+        }
+      }
+      // ---- b2Island::Solve
+      for (int m = 0; m < nm; ++m) {
+        int i = members[m];
+        AG(F_C0X, i) = AG(F_CX, i); AG(F_C0Y, i) = AG(F_CY, i); AG(F_A0, i) = AG(F_A, i);
+        AG(F_VX, i) = C.damp * AG(F_VX, i); AG(F_VY, i) = C.damp * AG(F_VY, i);  // v *= 1/(1+h*damping)
+        AG(F_W, i) *= C.damp;
+      }
+      for (int k = 0; k < nc; ++k) { TCon& t = tcs[order[k]]; t.ni = dtRatio * t.ni; t.ti = dtRatio * t.ti; }
+      for (int k = 0; k < nc; ++k) init_velocity(tcs[order[k]]);
+      for (int k = 0; k < nc; ++k) warm_start(tcs[order[k]]);
+      for (int it = 0; it < 10; ++it)
+        for (int k = 0; k < nc; ++k) solve_velocity(tcs[order[k]]);
+      for (int k = 0; k < nc; ++k) { const TCon& t = tcs[order[k]]; S.pimp[t.p * N + e] = make_float2(t.ni, t.ti); }
+      for (int m = 0; m < nm; ++m) integrate_position(members[m], h);
+      bool positionSolved = false;
+      for (int it = 0; it < 10; ++it) {
+        float minSep = 0.0f;
+        for (int k = 0; k < nc; ++k) minSep = fmin_(minSep, solve_position(tcs[order[k]], false, -1));
+        if (minSep >= -3.0f * B2_LINEAR_SLOP) { positionSolved = true; break; }
+      }
+      float minSleep = FLT_MAX;
+      const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
+      for (int m = 0; m < nm; ++m) {
+        int i = members[m];
+        float w = AG(F_W, i); f2 v = mk2(AG(F_VX, i), AG(F_VY, i));
+        if (w * w > angTol || vdot(v, v) > linTol) { AG(F_SLEEP, i) = 0.0f; minSleep = 0.0f; }
+        else { AG(F_SLEEP, i) += h; minSleep = fmin_(minSleep, AG(F_SLEEP, i)); }
+      }
+      if (minSleep >= B2_TIME_TO_SLEEP && positionSolved)
+        for (int m = 0; m < nm; ++m) sleep_body(members[m]);
+    }
+    bool moved = false;
+    for (int i = 0; i < C.A; ++i)
+      if (AGF(i) & FL_ISLAND) { synchronize_fixtures(i); moved |= (AGF(i) & FL_MOVED) != 0; }
+    if (moved) find_new_contacts();
+  }
+
+  // b2Body::Advance for agent i
+  DEV void advance(int i, float alpha) {
+    float a0 = AG(F_ALPHA0, i);
+    float beta = (alpha - a0) / (1.0f - a0);
+    AG(F_C0X, i) += beta * (AG(F_CX, i) - AG(F_C0X, i));
+    AG(F_C0Y, i) += beta * (AG(F_CY, i) - AG(F_C0Y, i));
+    AG(F_A0, i) += beta * (AG(F_A, i) - AG(F_A0, i));
+    AG(F_ALPHA0, i) = alpha;
+    AG(F_CX, i) = AG(F_C0X, i); AG(F_CY, i) = AG(F_C0Y, i); AG(F_A, i) = AG(F_A0, i);
+  }
+
+  // b2World::SolveTOI: continuous collision of agents against static boxes
+  // and walls (agent-agent pairs are "two non-bullet dynamic bodies": skipped)
+  __device__ __noinline__ void solve_toi(float dt) {
+    for (int i = 0; i < C.A; ++i) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
+    // per-contact toiCount: only contacts that produced events carry one
+    int evP[8], evN[8], nev = 0;
+    for (int guard = 0; guard < 64; ++guard) {
+      int minP = -1, minSeq = -1; float minAlpha = 1.0f;
+      for (int i = 0; i < C.A; ++i) {
+        if (!alive(i) || !awake(i)) continue;
+        for (int k = 0; k < BC + 4; ++k) {
+          if (k < BC && k >= nb) continue;
+          int p = k < BC ? p_ab(i, k) : p_aw(i, k - BC);
+          if (!bit(ex, p) || !bit(en, p)) continue;
+          int cnt = 0; for (int q = 0; q < nev; ++q) if (evP[q] == p) cnt = evN[q];
+          if (cnt > B2_MAX_SUBSTEPS) continue;
+          float beta;
+          int state = time_of_impact(static_box(k), mk2(AG(F_C0X, i), AG(F_C0Y, i)), apos(i), C.agent_r, beta);
+          float alpha0 = AG(F_ALPHA0, i);
+          float alpha = 1.0f;
+          if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+          if (alpha < minAlpha || (alpha == minAlpha && minP >= 0 && alpha < 1.0f && (int)S.pseq[p * N + e] > minSeq)) {
+            minAlpha = alpha; minP = p; minSeq = (int)S.pseq[p * N + e];
+          }
+        }
+      }
+      if (minP < 0 || 1.0f - 10.0f * B2_EPS < minAlpha) break;
+      int a, sid, b; decode(minP, a, sid, b);
+      // backup the agent's sweep, advance to the TOI, re-evaluate the contact
+      float bk[7] = {AG(F_C0X, b), AG(F_C0Y, b), AG(F_CX, b), AG(F_CY, b), AG(F_A0, b), AG(F_A, b), AG(F_ALPHA0, b)};
+      advance(b, minAlpha);
+      int save_ntc = ntc;
+      bool touching = contact_update(minP, a, sid, b, false);
+      {
+        int q = 0; for (; q < nev; ++q) if (evP[q] == minP) break;
+        if (q == nev && nev < 8) { evP[nev] = minP; evN[nev] = 0; nev++; }
+        if (q < nev) evN[q]++;
+      }
+      if (!touching) {
+        clrb(en, minP);
+        AG(F_C0X, b) = bk[0]; AG(F_C0Y, b) = bk[1]; AG(F_CX, b) = bk[2]; AG(F_CY, b) = bk[3];
+        AG(F_A0, b) = bk[4]; AG(F_A, b) = bk[5]; AG(F_ALPHA0, b) = bk[6];
+        continue;
+      }
+      wake(b);
+      // mini island: the TOI contact first, then the agent's other touching
+      // contacts against statics, newest first
+      TCon isl[8]; int nisl = 0;
+      {
+        Manifold m; evaluate(a, sid, b, m);
+        TCon& t = isl[nisl++];
+        t.p = minP; t.seq = 0; t.a = -1; t.sid = sid; t.b = b; t.flags = 0; t.m = m; t.ni = 0.0f; t.ti = 0.0f;
+      }
+      {
+        unsigned long long done[PW];
+#pragma unroll
+        for (int w = 0; w < PW; ++w) done[w] = 0ull;
+        setb(done, minP);
+        for (;;) {
+          int best = -1, bestSeq = -1;
+          for (int k = 0; k < BC + 4; ++k) {
+            if (k < BC && k >= nb) continue;
+            int p = k < BC ? p_ab(b, k) : p_aw(b, k - BC);
+            if (!bit(ex, p) || bit(done, p)) continue;
+            int sq = (int)S.pseq[p * N + e];
+            if (sq > bestSeq) { bestSeq = sq; best = p; }
+          }
+          if (best < 0) break;
+          setb(done, best);
+          if (nisl >= 8) { overflow++; break; }
+          int a2, sid2, b2; decode(best, a2, sid2, b2);
+          bool t2 = contact_update(best, a2, sid2, b2, false);
+          if (!t2) continue;
+          Manifold m; evaluate(a2, sid2, b2, m);
+          TCon& t = isl[nisl++];
+          t.p = best; t.seq = 0; t.a = -1; t.sid = sid2; t.b = b; t.flags = 0; t.m = m; t.ni = 0.0f; t.ti = 0.0f;
+        }
+      }
+      ntc = save_ntc;
+      float subdt = (1.0f - minAlpha) * dt;
+      // b2Island::SolveTOI
+      for (int it = 0; it < 20; ++it) {
+        float minSep = 0.0f;
+        for (int k = 0; k < nisl; ++k) minSep = fmin_(minSep, solve_position(isl[k], true, b));
+        if (minSep >= -1.5f * B2_LINEAR_SLOP) break;
+      }
+      AG(F_C0X, b) = AG(F_CX, b); AG(F_C0Y, b) = AG(F_CY, b); AG(F_A0, b) = AG(F_A, b);
+      for (int k = 0; k < nisl; ++k) init_velocity(isl[k]);
+      for (int it = 0; it < 10; ++it)
+        for (int k = 0; k < nisl; ++k) solve_velocity(isl[k]);
+      integrate_position(b, subdt);
+      AGF(b) &= ~FL_MOVED;
+      synchronize_fixtures(b);
+      if (AGF(b) & FL_MOVED) find_new_contacts();
+    }
+  }
+
+  // b2World::Step(dt, 10, 10)
+  __device__ void world_step(bool first_sub) {
+    if (first_sub) find_new_contacts();   // newFixture (boxes placed in pre_step)
+    float dtRatio = first_step ? 0.0f : C.dt_ratio1;
+    collide();
+    solve(C.dt, dtRatio);
+    solve_toi(C.dt);
+    first_step = 0;
+  }
+
+  // ======================================================================
+  //                      SEMANTICS (pre_step / post_step)
+  // ======================================================================
+  __device__ __noinline__ void pre_step(const uint8_t* act) {
+    use_heal = 0; use_box = 0; new_box = 0;
+    // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
+    for (int q = 0; q < np; ++q) {
+      float4 p0 = S.pend0[q * N + e];
+      add_item(p0.x, p0.y, p0.z, p0.w, S.pend1[q * N + e]);
+    }
+    np = 0;
+    float qs[AC], qc[AC];
+    // agents/DynamicMotors.pre_step (sim:407-424)
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      qs[i] = 0.0f; qc[i] = 1.0f;
+      if (i >= C.A || !alive(i)) continue;
+      rot_set(AG(F_A, i), qs[i], qc[i]);
+      const uint8_t* a = act + 6 * i;
+      float par = C.imp_par[a[0]], nor = C.imp_nor[a[1]];
+      float ix = qc[i] * par + (-qs[i]) * nor, iy = qs[i] * par + qc[i] * nor;
+      wake(i);
+      AG(F_VX, i) += C.inv_mass * ix; AG(F_VY, i) += C.inv_mass * iy;
+      AG(F_W, i) += C.inv_I * C.imp_ang[a[2]];
+    }
+    // agents/UseLast.pre_step (sem:300-309) -> Inventory.use (sem:206-213)
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      if (i >= C.A || !alive(i) || !act[6 * i + 4] || inv_n(i) == 0) continue;
+      float4 pl; int kind = inv_pop(i, pl);
+      if (kind == MSV_ITEM_HEAL) { use_heal++; agent_change_health(i, C.healing, MSV_CAUSE_NONE); }  // sem:646-649
+      else {  // ObjectItem.use (sem:830-836, 876-884)
+        use_box++;
+        if (nb >= BC) { overflow++; continue; }
+        float L = C.box_item_offset;
+        f2 off = mk2(qc[i] * L + (-qs[i]) * 0.0f, qs[i] * L + qc[i] * 0.0f);
+        float x = AG(F_CX, i) + off.x, y = AG(F_CY, i) + off.y;
+        int reh = __float_as_int(pl.w) & 1;
+        S.box0[nb * N + e] = make_float4(x, y, pl.x, pl.y);
+        S.box1[nb * N + e] = make_int4(0, reh << 1, MSV_CAUSE_NONE, C.box_ownership ? __float_as_int(pl.z) : MSV_CAUSE_NONE);
+        S.boxseq[nb * N + e] = body_seq++;
+        load_box(nb, nb);
+        for (int j = 0; j < C.A; ++j) { int p = p_ab(j, nb); clrb(ex, p); clrb(tc, p); clrb(en, p); }
+        nb++; new_box = 1;
+      }
+    }
+    // agents/GiveLast.pre_step (sem:335-370): taker = nearest body of any kind
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      if (i >= C.A || !alive(i) || !act[6 * i + 5] || inv_n(i) == 0) continue;
+      f2 me = apos(i); float r2 = C.give_r * C.give_r;
+      float minDist = INFINITY; int tkind = KIND_NONE, tidx = -1;
+      auto consider = [&](f2 o, int kind, int idx) {
+        f2 d = vsub(o, me);
+        if (!(vdot(d, d) <= r2)) return;                 // b2CircleShape::TestPoint
+        f2 dd = vsub(me, o);
+        float dist = sqrtf(dd.x * dd.x + dd.y * dd.y);
+        if (dist < minDist) { minDist = dist; tkind = kind; tidx = idx; }
+      };
+      for (int k = 0; k < nb; ++k) consider(mk2(BX(G_X, k), BX(G_Y, k)), KIND_BOX, k);
+      for (int k = 0; k < ni; ++k) { float4 it = S.item0[k * N + e]; consider(mk2(it.x, it.y), KIND_ITEM, k); }
+      for (int k = 0; k < nh; ++k) { float2 h = S.heal[k * N + e]; consider(mk2(h.x, h.y), KIND_HEAL, k); }
+      for (int k = 0; k < 4; ++k) consider(mk2(C.walls[k].px, C.walls[k].py), KIND_WALL, k);
+      for (int j = 0; j < C.A; ++j) if (j != i && alive(j)) consider(apos(j), KIND_AGENT, j);
+      if (tkind != KIND_AGENT) continue;                               // sem:196-198
+      if (C.teams && team_of(tidx) != team_of(i)) continue;            // strangers sem:344-349
+      float4 pl = make_float4(0.f, 0.f, 0.f, 0.f); int kind = inv_pop(i, pl);
+      if (inv_n(tidx) + 1 <= C.inv_slots) {
+#pragma unroll
+        for (int j = 0; j < AC; ++j) if (j == tidx) inv_push(j, kind, pl);
+      }                                                                // else lost (Q6)
+    }
+    // agents/Melee.pre_step (sem:584-617) / ContinuousMelee (sem:531-554)
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      if (i >= C.A || !alive(i)) continue;
+      bool on_cd = C.melee_cooldown >= 0 && cooldown[i] > 0;
+      if (!act[6 * i + 3] || on_cd) continue;
+      f2 me = apos(i);
+      float L = C.melee_range;
+      f2 hand = mk2(qc[i] * L + (-qs[i]) * 0.0f, qs[i] * L + qc[i] * 0.0f);
+      int tidx; float frac;
+      int kind = raycast(me, vadd(me, hand), i, tidx, frac);
+      if (kind == KIND_NONE) continue;
+      int cz = C.teams ? MSV_CAUSE_TEAM0 + team_of(i) : i;
+      if (kind == KIND_AGENT) agent_change_health(tidx, -C.melee_damage, cz);
+      else if (kind == KIND_BOX) box_change_health(tidx, -C.melee_damage, cz);
+      if (C.melee_cooldown >= 0) cooldown[i] = C.melee_cooldown;
+    }
+    if (C.melee_cooldown >= 0) {
+#pragma unroll
+      for (int i = 0; i < AC; ++i) if (cooldown[i] > 0) cooldown[i]--;
+    }
+  }
+
+  DEV double philox_uniform(uint32_t step, uint32_t stream, uint32_t k) {
+    uint32_t o[4];
+    philox4x32(C.env_offset + (uint32_t)e, (uint32_t)episode, step, (stream << 16) | (k >> 1), C.seed_lo, C.seed_hi, o);
+    uint32_t a = o[(k & 1) * 2], b = o[(k & 1) * 2 + 1];
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+  }
+
+  // Cameras._update_seen (sim:336-354), agent targets (the only ones the
+  // omniscient observation reads, env:692-703)
+  __device__ __noinline__ void cameras() {
+    pre_alive = 0; int row = 0;
+    for (int i = 0; i < AC; ++i) seenA[i] = 0;
+    for (int i = 0; i < C.A; ++i) {
+      if (!alive(i)) continue;
+      pre_alive |= 1u << i;
+      f2 me = apos(i); float s, c; rot_set(AG(F_A, i), s, c);
+      unsigned seen = 0;
+      for (int j = 0; j < C.A; ++j) {
+        if (j == i || !alive(j)) continue;
+        f2 o = apos(j);
+        f2 pl = qmulT(s, c, vsub(o, me));      // b2PolygonShape::TestPoint(cone)
+        bool inside = true;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float d = vdot(mk2(C.cone_n[v][0], C.cone_n[v][1]), vsub(pl, mk2(C.cone_v[v][0], C.cone_v[v][1])));
+          if (d > 0.0f) inside = false;
+        }
+        if (!inside) continue;
+        f2 d = vsub(o, me);
+        f2 end = mk2(me.x + C.cam_k1 * d.x, me.y + C.cam_k1 * d.y);
+        int idx; float fr;
+        int kind = raycast(me, end, i, idx, fr);
+        if (kind == KIND_AGENT && idx == j) seen |= 1u << j;
+      }
+      seenA[row++] = seen;
+    }
+  }
+
+  // Lidars._update (sim:377-392): extension block, see DESIGN.md
+  __device__ __noinline__ void lidar(DevOut& O) {
+    int L = C.lidar_n;
+    for (int i = 0; i < C.A; ++i) {
+      for (int r = 0; r < L; ++r) {
+        float fr = 1.0f; int hit = 0;
+        if (alive(i)) {
+          f2 me = apos(i);
+          double ang = C.lidar_ang[r] + (double)AG(F_A, i);
+          f2 off = from_polar(C.lidar_depth, (float)ang);
+          int idx; float f;
+          int kind = raycast(me, vadd(me, off), i, idx, f);
+          if (kind != KIND_NONE) { fr = f; hit = (kind << 8) | idx; }
+        }
+        O.lidar_frac[((size_t)e * C.A + i) * L + r] = fr;
+        O.lidar_hit[((size_t)e * C.A + i) * L + r] = hit;
+      }
+    }
+  }
+
+  int n_deaths, deaths[AC], n_kills, kill_cause[AC];
+
+  __device__ __noinline__ void post_step(DevOut& O) {
+    // boxes/Health.post_step (sem:429-435) + Object.pre_despawn (sem:858-861, 911-912)
+    for (int k = 0; k < nb;) {
+      int4 b1 = S.box1[k * N + e];
+      if (!(b1.y & 1)) { b1.y |= 1; b1.x = C.box_health; S.box1[k * N + e] = b1; }
+      if (b1.x <= 0) {
+        if (np < BC) {
+          S.pend0[np * N + e] = make_float4(BX(G_X, k), BX(G_Y, k), BX(G_HX, k), BX(G_HY, k));
+          S.pend1[np * N + e] = C.box_ownership ? b1.z : MSV_CAUSE_NONE;
+          np++;
+        } else overflow++;
+        remove_box(k);
+      } else ++k;
+    }
+    // agents/Cameras.post_step (sim:333-334)
+    cameras();
+    if (C.lidar_n > 0) lidar(O);
+    // agents/Health.post_step -> despawn(dead) (sem:429-448)
+    n_deaths = 0; n_kills = 0;
+    {
+      int total = 0;
+      for (int i = 0; i < C.A; ++i) if (alive(i) && health[i] <= 0) { deaths[n_deaths++] = i; total += inv_n(i); }
+      if (n_deaths > 0) {
+        int top = total;
+        for (int d = 0; d < n_deaths; ++d) {  // DeathDrop.pre_despawn (sem:387-396)
+          int i = deaths[d];
+          f2 me = apos(i);
+          int n = inv_n(i);
+          for (int j = 0; j < n; ++j) {
+            double ang = 2 * 3.141592653589793 * philox_uniform((uint32_t)steps, STREAM_DEATH, (uint32_t)(--top));
+            f2 off = from_polar(C.drop_radius, (float)ang);
+            float x = me.x + off.x, y = me.y + off.y;
+            int kind = inv_kind(i, j);
+            if (kind == MSV_ITEM_HEAL) add_heal(x, y);
+            else { float4 pl = S.ainv[(i * 4 + j) * N + e]; add_item(x, y, pl.x, pl.y, __float_as_int(pl.z)); }
+          }
+          inv[i] = 0;
+        }
+        for (int d = 0; d < n_deaths; ++d) kill_cause[n_kills++] = cause[deaths[d]];  // TrackKills sem:628-629
+        for (int d = 0; d < n_deaths; ++d) kill_agent(deaths[d]);
+      }
+    }
+    // agents/AutoPickup.post_step (sem:278-283): bodies in creation order
+    {
+      float r2 = C.pickup_r * C.pickup_r;
+      for (int i = 0; i < C.A; ++i) {
+        if (!alive(i)) continue;
+        f2 me = apos(i);
+        int lastSeq = -1;
+        for (;;) {
+          int bestSeq = 0x7FFFFFFF, bkind = KIND_NONE, bidx = -1;
+          for (int k = 0; k < ni; ++k) {
+            float4 it = S.item0[k * N + e]; f2 d = vsub(mk2(it.x, it.y), me);
+            if (!(vdot(d, d) <= r2)) continue;
+            int sq = S.item1[k * N + e].y;
+            if (sq > lastSeq && sq < bestSeq) { bestSeq = sq; bkind = KIND_ITEM; bidx = k; }
+          }
+          for (int k = 0; k < nh; ++k) {
+            float2 h = S.heal[k * N + e]; f2 d = vsub(mk2(h.x, h.y), me);
+            if (!(vdot(d, d) <= r2)) continue;
+            int sq = S.healseq[k * N + e];
+            if (sq > lastSeq && sq < bestSeq) { bestSeq = sq; bkind = KIND_HEAL; bidx = k; }
+          }
+          if (bkind == KIND_NONE) break;
+          lastSeq = bestSeq;
+          if (inv_n(i) + 1 > C.inv_slots) continue;  // sem:184-185
+          if (bkind == KIND_HEAL) { inv_push(i, MSV_ITEM_HEAL, make_float4(0.f, 0.f, 0.f, 0.f)); remove_heal(bidx); }
+          else {
+            float4 it = S.item0[bidx * N + e]; int2 i1 = S.item1[bidx * N + e];
+            inv_push(i, MSV_ITEM_BOX, make_float4(it.z, it.w, __int_as_float(i1.x), __int_as_float(1)));
+            remove_item(bidx);
+          }
+        }
+      }
+    }
+    // agents/SafeZone.post_step (sem:758-768) + tick (sem:776-811)
+    for (int i = 0; i < C.A; ++i) {
+      if (!alive(i)) continue;
+      float dx = AG(F_CX, i) - zx, dy = AG(F_CY, i) - zy;
+      bool inside = dx * dx + dy * dy <= zr * zr;
+      if (zend || !inside) agent_change_health(i, -C.zone_damage, MSV_CAUSE_ZONE);
+    }
+    if (ztcool == 0) {
+      if (!zend) {
+        ztshrink -= 1;
+        if (ztshrink > 0) {
+          double t = (double)ztshrink / C.zone_cooldown;
+          double r1 = C.zone_radiuses[zphase], r2 = C.zone_radiuses[zphase + 1];
+          zr = (float)(t * r1 + (1 - t) * r2);
+          float t1 = (float)t, t2 = (float)(1 - t);
+          float2 c1 = S.zonec[zphase * N + e], c2 = S.zonec[(zphase + 1) * N + e];
+          zx = t1 * c1.x + t2 * c2.x; zy = t1 * c1.y + t2 * c2.y;
+        } else {
+          ztcool = C.zone_cooldown; zphase += 1;
+          zr = C.zone_r32[zphase];
+          float2 cc = S.zonec[zphase * N + e]; zx = cc.x; zy = cc.y;
+          if (zphase == C.zone_phases - 1) zend = 1;
+        }
+      }
+    } else {
+      ztcool -= 1;
+      if (ztcool <= 0) ztshrink = C.zone_cooldown;
+    }
+  }
+
+  // ======================================================================
+  //                 OBSERVATIONS / REWARDS / DONE / STATS
+  // ======================================================================
+  // fetch_observations (env:510-657); layout notes in msv_types.cuh
+  __device__ __noinline__ void observe(DevOut& O) {
+    const int A = C.A, B = C.B0, H = C.H0, Sw = C.S;
+    float rows[AC][9];
+    int rank[AC]; int r = 0;
+    for (int i = 0; i < A; ++i) {
+      int s = 0;
+      rows[i][s++] = (float)i;
+      if (C.teams) rows[i][s++] = (float)team_of(i);
+      if (alive(i)) {
+        rows[i][s++] = (float)health[i];
+        rows[i][s++] = AG(F_CX, i); rows[i][s++] = AG(F_CY, i); rows[i][s++] = AG(F_A, i);
+        rows[i][s++] = AG(F_VX, i); rows[i][s++] = AG(F_VY, i); rows[i][s++] = AG(F_W, i);
+        rank[i] = r++;
+      } else { for (int k = 0; k < 7; ++k) rows[i][s++] = 0.0f; rank[i] = -1; }
+    }
+    float* oa = O.agent + (size_t)e * A * Sw;
+    for (int i = 0; i < A; ++i) for (int s = 0; s < Sw; ++s) oa[i * Sw + s] = rows[i][s];
+    float* oo = O.others + (size_t)e * A * (A - 1) * Sw;
+    float* om = O.others_mask + (size_t)e * A * (A - 1);
+    for (int i = 0; i < A; ++i) {
+      int k = 0;
+      for (int j = 0; j < A; ++j) {
+        if (j == i) continue;
+        for (int s = 0; s < Sw; ++s) oo[(i * (A - 1) + k) * Sw + s] = rows[j][s];
+        // Q1: the seen-list is looked up by the POST-death list position
+        float m = 1.0f;
+        if (alive(i) && alive(j) && ((seenA[rank[i]] >> j) & 1u)) m = 0.0f;
+        om[i * (A - 1) + k] = m;
+        k++;
+      }
+    }
+    float* oz = O.zone + (size_t)e * 6;
+    oz[0] = zx; oz[1] = zy; oz[2] = zr;
+    if (zphase < C.zone_phases - 1) {
+      float2 nc = S.zonec[(zphase + 1) * N + e];
+      oz[3] = nc.x; oz[4] = nc.y; oz[5] = C.zone_r32[zphase + 1];
+    } else { oz[3] = 0.0f; oz[4] = 0.0f; oz[5] = 0.0f; }
+    if (H > 0) {
+      float* oh = O.heals + (size_t)e * H * 2;
+      for (int k = 0; k < H; ++k) {
+        float2 h = k < nh ? S.heal[k * N + e] : make_float2(0.0f, 0.0f);
+        oh[2 * k] = h.x; oh[2 * k + 1] = h.y;
+      }
+      float* ohm = O.heals_mask + (size_t)e * A * H;
+      for (int i = 0; i < A; ++i) for (int k = 0; k < H; ++k) ohm[i * H + k] = k < nh ? 0.0f : 1.0f;
+      float* hs = O.heal_slot + (size_t)e * A; float* hsm = O.heal_slot_mask + (size_t)e * A;
+      for (int i = 0; i < A; ++i) {
+        bool has = alive(i) && inv_n(i) > 0 && inv_kind(i, inv_n(i) - 1) == MSV_ITEM_HEAL;
+        hs[i] = has ? (float)C.healing : 0.0f; hsm[i] = has ? 0.0f : 1.0f;
+      }
+    }
+    if (B > 0) {
+      float* ob = O.boxes + (size_t)e * B * 11;
+      for (int k = 0; k < B; ++k) {
+        float* d = ob + k * 11;
+        if (k < nb) {
+          SBox bx = static_box(k);
+          for (int v = 0; v < 4; ++v) { f2 p = sb_vert(bx, v); d[2 * v] = p.x; d[2 * v + 1] = p.y; }
+          d[8] = bx.px; d[9] = bx.py; d[10] = 0.0f;
+        } else for (int v = 0; v < 11; ++v) d[v] = 0.0f;
+      }
+      float* obm = O.boxes_mask + (size_t)e * A * B;
+      for (int i = 0; i < A; ++i) for (int k = 0; k < B; ++k) obm[i * B + k] = k < nb ? 0.0f : 1.0f;
+      float* oi = O.box_items + (size_t)e * B * 10;
+      for (int k = 0; k < B; ++k) {
+        float* d = oi + k * 10;
+        if (k < ni) {
+          float4 it = S.item0[k * N + e];
+          SBox bx; sb_set_shape(bx, it.z, it.w, 1);
+          for (int v = 0; v < 4; ++v) { f2 p = sb_vert(bx, v); d[2 * v] = p.x; d[2 * v + 1] = p.y; }
+          d[8] = it.x; d[9] = it.y;
+        } else for (int v = 0; v < 10; ++v) d[v] = 0.0f;
+      }
+      float* oim = O.box_items_mask + (size_t)e * A * B;
+      for (int i = 0; i < A; ++i) for (int k = 0; k < B; ++k) oim[i * B + k] = k < ni ? 0.0f : 1.0f;
+      float* bs = O.box_slot + (size_t)e * A * 8; float* bsm = O.box_slot_mask + (size_t)e * A;
+      for (int i = 0; i < A; ++i) {
+        bool has = alive(i) && inv_n(i) > 0 && inv_kind(i, inv_n(i) - 1) == MSV_ITEM_BOX;
+        if (has) {
+          float4 pl = S.ainv[(i * 4 + inv_n(i) - 1) * N + e];
+          SBox bx; sb_set_shape(bx, pl.x, pl.y, __float_as_int(pl.w) & 1);
+          for (int v = 0; v < 4; ++v) { f2 p = sb_vert(bx, v); bs[i * 8 + 2 * v] = p.x; bs[i * 8 + 2 * v + 1] = p.y; }
+        } else for (int v = 0; v < 8; ++v) bs[i * 8 + v] = 0.0f;
+        bsm[i] = has ? 0.0f : 1.0f;
+      }
+    }
+  }
+
+  DEV bool team_alive(int t) {
+    int split = C.A / 2; bool any = false;
+    for (int i = (t ? split : 0); i < (t ? C.A : split); ++i) any |= alive(i);
+    return any;
+  }
+
+  // compute_rewards (env:757-803), is_done (env:810-831), _update_stats (env:483-508)
+  __device__ __noinline__ bool rewards_done(DevOut& O) {
+    const int A = C.A;
+    float rew[AC]; int lk[AC];
+    for (int i = 0; i < AC; ++i) { rew[i] = 0.0f; lk[i] = 0; }
+    if (!C.teams) {
+      for (int i = 0; i < A; ++i) rew[i] += alive(i) ? C.r_alive : C.r_dead;
+      for (int k = 0; k < n_kills; ++k) {
+        int killer = kill_cause[k];
+        if (killer >= 0 && killer < A && alive(killer)) { rew[killer] += C.r_kill; lk[killer]++; }
+      }
+      for (int k = 0; k < n_deaths; ++k) rew[deaths[k]] += C.r_death;
+    } else {
+      int split = A / 2;
+      for (int t = 0; t < 2; ++t) {
+        float rr = team_alive(t) ? C.r_alive : C.r_dead;
+        for (int i = (t ? split : 0); i < (t ? A : split); ++i) rew[i] += rr;
+      }
+      for (int k = 0; k < n_kills; ++k) {
+        int cz = kill_cause[k];
+        if (cz != MSV_CAUSE_TEAM0 && cz != MSV_CAUSE_TEAM0 + 1) continue;
+        int t = cz - MSV_CAUSE_TEAM0;
+        for (int i = (t ? split : 0); i < (t ? A : split); ++i) rew[i] += C.r_kill;
+        lk[t]++;
+      }
+      for (int k = 0; k < n_deaths; ++k) {
+        int t = team_of(deaths[k]);
+        for (int i = (t ? split : 0); i < (t ? A : split); ++i) rew[i] += C.r_death;
+      }
+    }
+    int n_alive = 0;
+    if (C.teams) n_alive = (int)team_alive(0) + (int)team_alive(1);
+    else for (int i = 0; i < A; ++i) n_alive += alive(i);
+    bool done = C.gameover_mode == MSV_GAMEOVER_ALLDEAD ? n_alive == 0 : n_alive <= 1;
+    steps += 1;
+    if (!C.teams) for (int i = 0; i < A; ++i) st_reward[i] += rew[i];
+    else { st_reward[0] += rew[0]; st_reward[1] += rew[A / 2]; }
+    for (int i = 0; i < (C.teams ? 2 : A); ++i) st_kills[i] += lk[i];
+    st_steps += 1; st_heals += use_heal; st_boxes += use_box;
+    for (int i = 0; i < A; ++i) O.rewards[(size_t)e * A + i] = rew[i];
+    O.dones[e] = done ? 1 : 0;
+    return done;
+  }
+
+  // ======================================================================
+  //                               RESET
+  // ======================================================================
+  // BaseEnv.reset (env:59-74): SpawnGrid (sem:59-79), ResetSpawns (sem:82-94),
+  // RandomizeBoxShapes (sem:97-120), ThickRoomWalls, SafeZone.post_reset
+  // (sem:739-756).  The numpy Generator is replaced by counter-based
+  // Philox4x32-10 keyed by (seed, global env id, episode).
+  __device__ __noinline__ void reset() {
+    episode += 1; steps = 0;
+    int n = C.grid_n;
+    unsigned char perm[64];
+    for (int k = 0; k < n; ++k) perm[k] = (unsigned char)k;
+    for (int i = n - 1; i >= 1; --i) {
+      double u = philox_uniform(0u, STREAM_SHUFFLE, (uint32_t)(n - 1 - i));
+      int j = (int)(u * (i + 1));
+      unsigned char t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    }
+    int top = n;
+    body_seq = 0; contact_seq = 0; first_step = 1;
+    nb = 0; ni = 0; nh = 0; np = 0;
+#pragma unroll
+    for (int w = 0; w < PW; ++w) { ex[w] = 0ull; tc[w] = 0ull; en[w] = 0ull; }
+    for (int b = 0; b < C.B0; ++b) {
+      float hx = C.box_h, hy = C.box_h;
+      if (C.box_randomized) {
+        double z[2];
+        for (int q = 0; q < 2; ++q) {
+          double u1 = philox_uniform(0u, STREAM_BOX, (uint32_t)(2 * (2 * b + q)));
+          double u2 = philox_uniform(0u, STREAM_BOX, (uint32_t)(2 * (2 * b + q) + 1));
+          z[q] = sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);
+        }
+        double w = C.box_avg_w + C.box_std_w * z[0]; if (!(w > C.box_min_w)) w = C.box_min_w;
+        double h = C.box_avg_h + C.box_std_h * z[1]; if (!(h > C.box_min_h)) h = C.box_min_h;
+        hx = (float)(w / 2.); hy = (float)(h / 2.);
+      }
+      int cell = perm[--top];
+      S.box0[b * N + e] = make_float4(C.grid_px[cell], C.grid_py[cell], hx, hy);
+      S.box1[b * N + e] = make_int4(C.box_health, 1, MSV_CAUSE_NONE, MSV_CAUSE_NONE);
+      S.boxseq[b * N + e] = body_seq++;
+      load_box(b, b);
+      nb++;
+    }
+    for (int h = 0; h < C.H0; ++h) {
+      int cell = perm[--top];
+      S.heal[h * N + e] = make_float2(C.grid_px[cell], C.grid_py[cell]);
+      S.healseq[h * N + e] = body_seq++;
+      nh++;
+    }
+    body_seq += 4;  // walls
+    for (int i = 0; i < AC; ++i) {
+      if (i < C.A) {
+        int cell = perm[--top];
+        float x = C.grid_px[cell], y = C.grid_py[cell], r = C.agent_r;
+        AG(F_CX, i) = x; AG(F_CY, i) = y; AG(F_A, i) = 0.0f; AG(F_VX, i) = 0.0f; AG(F_VY, i) = 0.0f; AG(F_W, i) = 0.0f;
+        AG(F_C0X, i) = x; AG(F_C0Y, i) = y; AG(F_A0, i) = 0.0f; AG(F_ALPHA0, i) = 0.0f; AG(F_SLEEP, i) = 0.0f;
+        AG(F_FAT0, i) = (x - r) - B2_AABB_EXT; AG(F_FAT1, i) = (y - r) - B2_AABB_EXT;
+        AG(F_FAT2, i) = (x + r) + B2_AABB_EXT; AG(F_FAT3, i) = (y + r) + B2_AABB_EXT;
+        AGF(i) = FL_ALIVE | FL_AWAKE;
+        health[i] = C.health; body_seq++;
+      } else { AGF(i) = 0; health[i] = 0; }
+      cause[i] = MSV_CAUSE_NONE; cooldown[i] = 0; inv[i] = 0;
+    }
+    if (C.zone_centers_random) {
+      int d = 0;
+      for (int z = C.n_zones - 1; z >= 0; --z) {
+        double L = C.floor_size - 2 * C.zone_radiuses[z];
+        double ux = philox_uniform(0u, STREAM_ZONE, (uint32_t)d); d++;
+        double uy = philox_uniform(0u, STREAM_ZONE, (uint32_t)d); d++;
+        S.zonec[z * N + e] = make_float2((float)((ux * L) - L / 2), (float)((uy * L) - L / 2));
+      }
+    } else {
+      for (int z = 0; z < C.n_zones; ++z)
+        S.zonec[z * N + e] = make_float2((float)C.zone_centers[z][0], (float)C.zone_centers[z][1]);
+    }
+    ztcool = C.zone_cooldown; ztshrink = 0; zphase = 0; zend = 0;
+    zr = C.zone_r32[0];
+    float2 c0 = S.zonec[e]; zx = c0.x; zy = c0.y;
+    n_deaths = 0; n_kills = 0; use_heal = 0; use_box = 0;
+  }
+};

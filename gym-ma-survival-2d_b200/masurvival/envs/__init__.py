@@ -1,0 +1,1 @@
+from .masurvival_env import MaSurvival, MaSurvivalVec  # noqa: F401

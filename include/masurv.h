@@ -206,6 +206,11 @@ typedef struct msv_handle msv_handle;
 struct DLManagedTensor;
 
 int msv_abi_version(void);
+/* sizeof() of the PODs above as the library was compiled (layout check for
+ * bindings that mirror the structs). */
+int64_t msv_sizeof_config(void);
+int64_t msv_sizeof_env_state(void);
+int64_t msv_sizeof_stats(void);
 
 /* Fill `cfg` with the reference's class default, env:140-238 (1v1, A=2). */
 int msv_default_config(msv_config* cfg);

@@ -894,8 +894,11 @@ void orc_set_state(oracle_env* e, const msv_env_state* s) {
       e->inv[i][k].owner = s->inv_owner[i][k];
     }
   }
-  for (int i = 0; i < B2L_MAX_BODIES; ++i) w->bodies[i].moved = 0;
-  w->newFixture = 0;
+  /* every proxy counts as freshly created: the next Step starts with a full
+   * FindNewContacts, exactly what an injected state needs (no-op on any state
+   * reachable by stepping, where contact <=> fat-AABB overlap already holds) */
+  for (int i = 0; i < B2L_MAX_BODIES; ++i) w->bodies[i].moved = w->bodies[i].used;
+  w->newFixture = 1;
   e->n_pending = s->n_pending;
   for (int k = 0; k < s->n_pending; ++k) {
     e->pend_x[k] = s->pend_x[k]; e->pend_y[k] = s->pend_y[k];
