@@ -603,6 +603,16 @@ int64_t msv_bytes_per_env_step(msv_handle* h) {
 }
 int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }
 
+/* debug: enable / read the per-phase cycle profile of k_step (not part of
+ * the stable ABI; used by tests/gpu_quickbench.py) */
+int msv_debug_profile(msv_handle* h, int enable, unsigned long long out[16]) {
+  if (!h) return MSV_ERR_INVALID;
+  CK(cudaSetDevice(h->device)); CK(cudaDeviceSynchronize());
+  if (out) CK(msv_read_profile(out, 1));
+  h->C.profile = enable;
+  return MSV_OK;
+}
+
 void msv_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
   for (int r = 0; r < 10; ++r) {

@@ -744,16 +744,6 @@ struct Env {
     }
   }
 
-  // b2World::Step(dt, 10, 10)
-  __device__ void world_step(bool first_sub) {
-    if (first_sub) find_new_contacts();   // newFixture (boxes placed in pre_step)
-    float dtRatio = first_step ? 0.0f : C.dt_ratio1;
-    collide();
-    solve(C.dt, dtRatio);
-    solve_toi(C.dt);
-    first_step = 0;
-  }
-
   // ======================================================================
   //                      SEMANTICS (pre_step / post_step)
   // ======================================================================
@@ -909,7 +899,7 @@ struct Env {
 
   int n_deaths, deaths[AC], n_kills, kill_cause[AC];
 
-  __device__ __noinline__ void post_step(DevOut& O) {
+  __device__ __noinline__ void post_step_boxes() {
     // boxes/Health.post_step (sem:429-435) + Object.pre_despawn (sem:858-861, 911-912)
     for (int k = 0; k < nb;) {
       int4 b1 = S.box1[k * N + e];
@@ -923,9 +913,9 @@ struct Env {
         remove_box(k);
       } else ++k;
     }
-    // agents/Cameras.post_step (sim:333-334)
-    cameras();
-    if (C.lidar_n > 0) lidar(O);
+  }
+  // agents/Cameras.post_step (sim:333-334) runs between the two halves
+  __device__ __noinline__ void post_step_rest() {
     // agents/Health.post_step -> despawn(dead) (sem:429-448)
     n_deaths = 0; n_kills = 0;
     {

@@ -9,6 +9,11 @@
 #include "msv_env.cuh"
 #include "msv_launch.h"
 
+// debug phase profile (enabled by msv_debug_profile): sum over threads of the
+// clock64() cycles spent in each phase of k_step
+__device__ unsigned long long g_prof[16];
+#define PROF(k) do { if (C.profile) { long long _t = clock64(); atomicAdd(&g_prof[k], (unsigned long long)(_t - t_last)); t_last = _t; } } while (0)
+
 template <int AC, int BC, int HC>
 __global__ void __launch_bounds__(MSV_TPB)
 k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
@@ -18,17 +23,36 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   if (e >= C.N) return;
   DevOut O = Oc;
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
+  long long t_last = C.profile ? clock64() : 0;
   env.load();
   uint8_t act[AC * 6];
   {
     const uint8_t* src = actions + (size_t)e * C.A * 6;
     for (int k = 0; k < AC * 6; ++k) act[k] = k < C.A * 6 ? src[k] : 0;
   }
+  PROF(0);
   env.pre_step(act);                       // sim:234-235
-  env.world_step(true);                    // sim:236-239, substep 1
-  env.world_step(false);                   //              substep 2
-  env.post_step(O);                        // sim:241-242
+  PROF(1);
+  for (int sub = 0; sub < 2; ++sub) {      // sim:236-239: b2World::Step x2
+    if (sub == 0) env.find_new_contacts(); // newFixture (boxes placed in pre_step)
+    PROF(2);
+    env.collide();
+    PROF(3);
+    env.solve(C.dt, env.first_step ? 0.0f : C.dt_ratio1);
+    PROF(4);
+    env.solve_toi(C.dt);
+    env.first_step = 0;
+    PROF(5);
+  }
+  env.post_step_boxes();
+  PROF(6);
+  env.cameras();
+  if (C.lidar_n > 0) env.lidar(O);
+  PROF(7);
+  env.post_step_rest();                    // sim:241-242
+  PROF(8);
   env.observe(O);                          // env:84
+  PROF(9);
   bool done = env.rewards_done(O);         // env:85-89
   if (done && C.auto_reset) {              // vector-env extension
     env.st_episodes++;
@@ -37,7 +61,9 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     if (C.lidar_n > 0) env.lidar(O);
     env.observe(O);
   }
+  PROF(10);
   env.store();
+  PROF(11);
 }
 
 template <int AC, int BC, int HC>
@@ -138,4 +164,11 @@ cudaError_t msv_launch_stats(int N, int AC, float* sreward, int* skills, int4* s
                              unsigned long long* out_kills, unsigned long long* out_misc, cudaStream_t st) {
   k_stats<<<(N + 127) / 128, 128, 0, st>>>(N, AC, sreward, skills, smisc, out_reward, out_kills, out_misc);
   return cudaPeekAtLastError();
+}
+
+cudaError_t msv_read_profile(unsigned long long out[16], int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return e;
+  if (reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof z); }
+  return e;
 }

@@ -34,6 +34,7 @@ struct DevConst {
   double lidar_ang[MSV_MAX_LASERS];       // i*(fov/(n-1)) - fov/2, as Python doubles
   uint32_t seed_lo, seed_hi;
   uint32_t env_offset;
+  int profile;           // debug: accumulate per-phase clock64() deltas into g_prof
 };
 
 // All per-environment state, structure-of-arrays: every array is

@@ -35,8 +35,8 @@
 extern "C" {
 #endif
 
-#define B2L_MAX_BODIES 160
-#define B2L_MAX_CONTACTS 1024
+#define B2L_MAX_BODIES 64
+#define B2L_MAX_CONTACTS 192
 #define B2L_MAX_VERTS 8
 
 #define B2L_STATIC 0

@@ -989,3 +989,51 @@ int64_t orc_rollout(const msv_config* cfg, uint64_t seed, int32_t n_envs, int32_
   for (int t = 0; t < used; ++t) { pthread_join(th[t], 0); total += jobs[t].done_steps; }
   return total;
 }
+
+/* ------------------------------------------------------------ batch API --- */
+struct orc_batch { msv_config cfg; int n, n_threads; oracle_env** envs; orc_out* outs; };
+typedef struct { orc_batch* b; int first, count; const uint8_t* actions; float* rewards; uint8_t* dones; int op; } batch_job;
+
+static void* batch_thread(void* arg) {
+  batch_job* j = (batch_job*)arg;
+  int A = j->b->cfg.n_agents;
+  for (int k = j->first; k < j->first + j->count; ++k) {
+    orc_out* o = &j->b->outs[k - j->first + j->first];
+    if (j->op == 0) orc_reset(j->b->envs[k], o);
+    else {
+      orc_step(j->b->envs[k], j->actions + (size_t)k * A * 6, o);
+      if (j->rewards) for (int i = 0; i < A; ++i) j->rewards[(size_t)k * A + i] = o->rewards[i];
+      if (j->dones) j->dones[k] = (uint8_t)o->done;
+    }
+  }
+  return 0;
+}
+static void batch_run(orc_batch* b, int op, const uint8_t* actions, float* rewards, uint8_t* dones) {
+  pthread_t th[256]; batch_job jobs[256];
+  int nt = b->n_threads, per = (b->n + nt - 1) / nt, first = 0, used = 0;
+  for (int t = 0; t < nt && first < b->n; ++t) {
+    int cnt = per < b->n - first ? per : b->n - first;
+    batch_job jj = {b, first, cnt, actions, rewards, dones, op};
+    jobs[t] = jj;
+    pthread_create(&th[t], 0, batch_thread, &jobs[t]);
+    first += cnt; used++;
+  }
+  for (int t = 0; t < used; ++t) pthread_join(th[t], 0);
+}
+orc_batch* orc_batch_create(const msv_config* cfg, uint64_t seed, int32_t n_envs, int32_t n_threads) {
+  orc_batch* b = (orc_batch*)calloc(1, sizeof *b);
+  b->cfg = *cfg; b->n = n_envs;
+  b->n_threads = n_threads < 1 ? 1 : (n_threads > 256 ? 256 : n_threads);
+  b->envs = (oracle_env**)calloc((size_t)n_envs, sizeof(oracle_env*));
+  b->outs = (orc_out*)calloc((size_t)n_envs, sizeof(orc_out));
+  for (int k = 0; k < n_envs; ++k) b->envs[k] = orc_create(cfg, seed, k);
+  return b;
+}
+void orc_batch_destroy(orc_batch* b) {
+  for (int k = 0; k < b->n; ++k) orc_destroy(b->envs[k]);
+  free(b->envs); free(b->outs); free(b);
+}
+void orc_batch_reset(orc_batch* b) { batch_run(b, 0, 0, 0, 0); }
+void orc_batch_step(orc_batch* b, const uint8_t* actions, float* rewards, uint8_t* dones) {
+  batch_run(b, 1, actions, rewards, dones);
+}

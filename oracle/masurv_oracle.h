@@ -78,6 +78,15 @@ void orc_flush_stats(oracle_env* e, msv_stats* out);
 int64_t orc_rollout(const msv_config* cfg, uint64_t seed, int32_t n_envs,
                     int32_t steps, int32_t n_threads);
 
+/* batch of n envs stepped together by n_threads host threads: the CPU arm of
+ * bench.py (`--impl reference` / cpu_baseline). */
+typedef struct orc_batch orc_batch;
+orc_batch* orc_batch_create(const msv_config* cfg, uint64_t seed, int32_t n_envs, int32_t n_threads);
+void orc_batch_destroy(orc_batch* b);
+void orc_batch_reset(orc_batch* b);
+/* actions uint8[n][A][6] -> rewards float[n][A], dones uint8[n] */
+void orc_batch_step(orc_batch* b, const uint8_t* actions, float* rewards, uint8_t* dones);
+
 void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* uniform double for (env, episode, step, stream, k) */
 double orc_philox_uniform(uint64_t seed, uint32_t env, uint32_t episode,

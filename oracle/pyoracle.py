@@ -50,6 +50,11 @@ def lib():
         L.orc_flush_stats.argtypes = [vp, vp]
         L.orc_rollout.restype = i64
         L.orc_rollout.argtypes = [vp, u64, i32, i32, i32]
+        L.orc_batch_create.restype = vp
+        L.orc_batch_create.argtypes = [vp, u64, i32, i32]
+        L.orc_batch_destroy.argtypes = [vp]
+        L.orc_batch_reset.argtypes = [vp]
+        L.orc_batch_step.argtypes = [vp, vp, vp, vp]
         L.orc_philox_uniform.restype = ctypes.c_double
         L.orc_philox_uniform.argtypes = [u64] + [ctypes.c_uint32] * 5
         L.orc_philox4x32.argtypes = [vp, vp, vp]
@@ -159,3 +164,28 @@ def rollout(cfg, seed, n_envs, steps, n_threads):
 
 def philox_uniform(seed, env, episode, step, stream, k):
     return lib().orc_philox_uniform(seed, env, episode, step, stream, k)
+
+
+class OracleBatch:
+    """n reference-equivalent envs stepped together on `n_threads` host
+    threads (the CPU arm of bench.py)."""
+
+    def __init__(self, cfg, seed, n_envs, n_threads):
+        self._cfgbuf = np.ascontiguousarray(np.array(cfg, dtype=CONFIG_DT).reshape(1))
+        self.n, self.A = int(n_envs), int(self._cfgbuf[0]['n_agents'])
+        self.h = lib().orc_batch_create(self._cfgbuf.ctypes.data, seed, n_envs, n_threads)
+        self.rewards = np.zeros((self.n, self.A), dtype=np.float32)
+        self.dones = np.zeros(self.n, dtype=np.uint8)
+
+    def reset(self):
+        lib().orc_batch_reset(self.h)
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        lib().orc_batch_step(self.h, a.ctypes.data, self.rewards.ctypes.data, self.dones.ctypes.data)
+        return self.rewards, self.dones
+
+    def close(self):
+        if self.h:
+            lib().orc_batch_destroy(self.h)
+            self.h = None

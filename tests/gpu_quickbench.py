@@ -7,7 +7,7 @@ from parity import make_config
 import torch
 from masurvival import _lib
 
-def run(variant, N, steps=200, warm=50):
+def run(variant, N, steps=200, warm=50, prof=True):
     rec = make_config(variant, auto_reset=True)
     A = int(rec['n_agents'])
     h = _lib.Handle(rec, N, 0, 1, 0)
@@ -25,6 +25,17 @@ def run(variant, N, steps=200, warm=50):
     st = h.flush_stats()
     print(f'{variant} N={N}: {ms*1e3:.1f} us/step, {N/ms*1e3:.3e} env-steps/s, {N*A/ms*1e3:.3e} agent-steps/s, '
           f'{bps} B/env-step -> {N*bps/ms/1e6:.1f} GB/s, episodes={int(st["episodes"])}')
+    if prof:
+        import ctypes
+        L = _lib.load()
+        L.msv_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        buf = (ctypes.c_ulonglong * 16)()
+        L.msv_debug_profile(h.h, 1, buf)
+        for t in range(20): h.step(acts[t % 8].data_ptr())
+        L.msv_debug_profile(h.h, 0, buf)
+        names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'observe', 'rewards+reset', 'store']
+        tot = sum(buf[:12])
+        print('   phase cycles/thread/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(names)))
     h.close()
 
 if __name__ == '__main__':

@@ -100,3 +100,89 @@ def compare_obs(a, b, rel_tol=REL_TOL):
             if not np.array_equal(x[..., :ncol], y[..., :ncol]):
                 fail.append((k + '[discrete cols]', d))
     return exact, fail
+
+
+def scramble_state(s, rec, rng):
+    """Turn a freshly reset msv_env_state into a dense-interaction scenario:
+    agents are teleported next to random entities / each other, get random
+    health, inventories and melee cooldowns.  Fat AABBs are rebuilt tight+0.1
+    and all contact pairs cleared, so both implementations start by running
+    FindNewContacts on the injected world."""
+    s = s.copy()
+    A, B, H = int(rec['n_agents']), int(s['n_boxes']), int(s['n_heals'])
+    r = np.float32(rec['agent_size'] / 2)
+    ext = np.float32(0.1)
+    for i in range(A):
+        kind = rng.integers(0, 5)
+        if kind == 0 and B > 0:
+            k = rng.integers(0, B); cx, cy = s['box_x'][k], s['box_y'][k]; d = rng.uniform(0.9, 1.6)
+        elif kind == 1 and H > 0:
+            k = rng.integers(0, H); cx, cy = s['heal_x'][k], s['heal_y'][k]; d = rng.uniform(0.0, 1.0)
+        elif kind == 2 and i > 0:
+            k = rng.integers(0, i); cx, cy = s['x'][k], s['y'][k]; d = rng.uniform(0.95, 1.8)
+        elif kind == 3:
+            w = rng.integers(0, 4); t = rng.uniform(-9, 9); off = rng.uniform(9.2, 9.45)
+            cx, cy = [(-off, t), (t, off), (off, t), (t, -off)][w]; d = 0.0
+        else:
+            cx, cy, d = s['x'][i], s['y'][i], 0.0
+        ang = rng.uniform(0, 2 * np.pi)
+        x = np.float32(np.clip(cx + d * np.cos(ang), -9.45, 9.45))
+        y = np.float32(np.clip(cy + d * np.sin(ang), -9.45, 9.45))
+        s['x'][i], s['y'][i] = x, y
+        s['angle'][i] = np.float32(rng.uniform(-np.pi, np.pi))
+        s['vx'][i], s['vy'][i] = np.float32(rng.normal(0, 4)), np.float32(rng.normal(0, 4))
+        s['omega'][i] = np.float32(rng.normal(0, 2))
+        s['fat'][i] = [(x - r) - ext, (y - r) - ext, (x + r) + ext, (y + r) + ext]
+        s['health'][i] = int(rng.choice([1, 2, 19, 20, 21, 40, 100]))
+        s['cooldown'][i] = int(rng.choice([0, 0, 1, 2, 39]))
+        n = int(rng.integers(0, int(rec['inv_slots']) + 1))
+        s['inv_n'][i] = n
+        for k in range(n):
+            if B > 0 and rng.random() < 0.5:
+                s['inv_kind'][i][k] = 2
+                s['inv_shape'][i][k]['hx'] = np.float32(rng.uniform(0.2, 0.9))
+                s['inv_shape'][i][k]['hy'] = np.float32(rng.uniform(0.2, 0.9))
+                s['inv_shape'][i][k]['rehulled'] = 1
+                s['inv_owner'][i][k] = int(rng.integers(0, A)) if not rec['teams'] else 100 + int(rng.integers(0, 2))
+            else:
+                s['inv_kind'][i][k] = 1
+                s['inv_owner'][i][k] = -1
+    # conservation: live + floor + carried boxes (heals) never exceed what a
+    # reset created, so free some floor entities for what the agents carry
+    bcap = 4 if A <= 4 and B <= 4 else 8
+    hcap = 4 if A <= 4 and H <= 4 else 16
+    drop_b = int(rng.integers(0, min(B, 3) + 1)) if B > 0 else 0
+    drop_h = int(rng.integers(0, min(H, 3) + 1)) if H > 0 else 0
+    s['n_boxes'] = B - drop_b
+    s['n_heals'] = H - drop_h
+    room_b, room_h = bcap - int(s['n_boxes']), hcap - int(s['n_heals'])
+    for i in range(A):
+        keep = 0
+        for k in range(int(s['inv_n'][i])):
+            kind = int(s['inv_kind'][i][k])
+            if kind == 2 and room_b > 0:
+                room_b -= 1
+            elif kind == 1 and room_h > 0:
+                room_h -= 1
+            else:
+                continue
+            for f in ('inv_kind', 'inv_owner'):
+                s[f][i][keep] = s[f][i][k]
+            s['inv_shape'][i][keep] = s['inv_shape'][i][k]
+            keep += 1
+        s['inv_n'][i] = keep
+    for i in range(A):  # canonical form: nothing beyond the list lengths
+        for k in range(s['inv_kind'].shape[1]):
+            if k >= int(s['inv_n'][i]):
+                s['inv_kind'][i][k] = 0; s['inv_owner'][i][k] = 0
+            if k >= int(s['inv_n'][i]) or int(s['inv_kind'][i][k]) == 1:
+                s['inv_shape'][i][k] = np.zeros((), dtype=s['inv_shape'].dtype)
+    for k in range(int(s['n_boxes']), s['box_x'].shape[0]):
+        for f in ('box_x', 'box_y', 'box_health', 'box_has_health', 'box_cause', 'box_owner', 'box_seq'):
+            s[f][k] = 0
+        s['box_shape'][k] = np.zeros((), dtype=s['box_shape'].dtype)
+    for k in range(int(s['n_heals']), s['heal_x'].shape[0]):
+        s['heal_x'][k] = 0; s['heal_y'][k] = 0; s['heal_seq'][k] = 0
+    for name in ('pair_aa', 'pair_ab', 'pair_aw'):
+        s[name] = np.zeros_like(s[name])
+    return s

@@ -1,0 +1,158 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on identical seeded inputs.  Discrete outputs (health, inventories,
+alive/done flags, masks, rewards, lidar hit ids, contact bookkeeping) must be
+bit-exact; continuous outputs within 1e-4 relative (BASELINE.json north_star).
+In practice every field is bit-exact and the tests also assert that."""
+import numpy as np
+import pytest
+
+import parity
+from parity import compare_obs, compare_states, make_config, random_actions, scramble_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_clean(r, need_exact=True):
+    assert r['state_fail'] == 0 and r['obs_fail'] == 0, r['details']
+    if need_exact:
+        assert r['state_exact_mismatch'] == 0 and r['obs_exact_mismatch'] == 0, r['details']
+    assert r['stats_gpu'] == r['stats_oracle']
+
+
+@pytest.mark.parametrize('variant,n,steps', [('2v2', 64, 150), ('1v1', 64, 150), ('1v1_heal_only', 64, 100),
+                                             ('ffa', 16, 80), ('ffa_lidar', 8, 40)])
+def test_lockstep_rollout(variant, n, steps):
+    import gpu_lockstep
+    r = gpu_lockstep.run(variant, n, steps, verbose=False)
+    _assert_clean(r)
+
+
+def test_lockstep_fast_zone_and_resets():
+    """short safe-zone phases: every env runs through shrink, endgame, death,
+    death-drop and in-kernel auto-reset several times"""
+    import gpu_lockstep
+    r = gpu_lockstep.run('2v2', 48, 260, verbose=False, safe_zone={'cooldown': 8}, health={'health': 12})
+    _assert_clean(r)
+    assert r['dones'] > 40
+
+
+def test_lockstep_ownership():
+    import gpu_lockstep
+    r = gpu_lockstep.run('2v2', 32, 120, verbose=False, boxes={'ownership': True}, p_attack=0.9)
+    _assert_clean(r)
+
+
+def _scenario(variant, n, steps, seed, **over):
+    """dense-interaction scenario: scrambled states injected on both sides"""
+    import torch
+    import pyoracle as po
+    from masurvival import _lib
+    rec = make_config(variant, auto_reset=False, **over)
+    A = int(rec['n_agents'])
+    h = _lib.Handle(rec, n, 0, seed, 0)
+    orcs = [po.OracleEnv(rec, seed=seed, env_id=e) for e in range(n)]
+    h.reset()
+    rng = np.random.default_rng(seed)
+    states = []
+    for e in range(n):
+        orcs[e].reset()
+        s = scramble_state(orcs[e].get_state(), rec, rng)
+        orcs[e].set_state(s)
+        states.append(s)
+    h.set_state(np.array(states))
+    keys = list(po.obs_dims(rec).keys())
+    bad = []
+    events = {'toi': 0, 'deaths': 0, 'pick': 0}
+    for t in range(steps):
+        act = random_actions(rng, n, A, 0.6, 0.5, 0.3)
+        a_dev = torch.as_tensor(act).cuda()
+        h.step(a_dev.data_ptr())
+        torch.cuda.synchronize()
+        sg = h.get_state()
+        g = {k: h.tensor(k).cpu().numpy() for k in keys + ['rewards', 'dones']}
+        for e in range(n):
+            oo = orcs[e].step(act[e])
+            events['toi'] += oo['n_toi_events']
+            so = orcs[e].get_state()
+            ex, fl = compare_states(sg[e], so)
+            og = {k: (np.broadcast_to(g[k][e][None], (A,) + g[k][e].shape) if k in ('zone', 'heals', 'boxes', 'box_items') else g[k][e]) for k in keys}
+            og['rewards'] = g['rewards'][e]; og['done'] = bool(g['dones'][e])
+            oex, ofl = compare_obs(og, oo)
+            if ex or oex:
+                bad.append((t, e, ex[:4], oex[:4]))
+                h.set_state(np.array([so]), first=e)
+            events['deaths'] += int((so['alive'][:A] == 0).sum())
+            events['pick'] += int(so['inv_n'][:A].sum())
+    h.close()
+    return bad, events
+
+
+@pytest.mark.parametrize('variant,n,steps,over', [
+    ('2v2', 96, 40, {}), ('1v1', 96, 40, {}), ('ffa', 24, 30, {}),
+    ('2v2', 64, 40, {'boxes': {'ownership': True}}),
+])
+def test_scrambled_scenarios(variant, n, steps, over):
+    bad, events = _scenario(variant, n, steps, seed=11, **over)
+    assert not bad, bad[:5]
+    assert events['toi'] > 0
+
+
+def test_step_host_matches_step_and_dlpack_views():
+    """msv_step_host (host buffers) and msv_step (device buffer) are the same
+    computation; DLPack views alias library memory with reference shapes."""
+    import torch
+    from masurvival.envs import MaSurvivalVec
+    from masurvival.config import variant
+    N = 256
+    e1 = MaSurvivalVec(variant('2v2'), N, seed=3)
+    e2 = MaSurvivalVec(variant('2v2'), N, seed=3)
+    o1 = e1.reset(); e2.reset()
+    assert o1['agent'].shape == (N, 4, 9) and o1['zone'].shape == (N, 4, 6)
+    assert o1['boxes'].shape == (N, 4, 4, 11) and o1['boxes'].stride(1) == 0
+    assert o1['others'].shape == (N, 4, 3, 9) and o1['heal_slot'].shape == (N, 4, 1, 1)
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        a = random_actions(rng, N, 4)
+        obs, rew, done, info = e1.step(torch.as_tensor(a).cuda())
+        rh, dh = e2.step_host(a)
+        torch.cuda.synchronize()
+        assert np.array_equal(rew.cpu().numpy(), rh) and np.array_equal(done.cpu().numpy().astype(np.uint8), dh)
+    s1, s2 = e1.get_state(), e2.get_state()
+    assert s1.tobytes() == s2.tobytes()
+    p = obs['agent'].data_ptr()
+    obs2, *_ = e1.step(torch.as_tensor(a).cuda())
+    assert obs2['agent'].data_ptr() == p  # zero-copy: same HBM every step
+    e1.close(); e2.close()
+
+
+def test_full_size_properties():
+    """BASELINE size (16384 envs): determinism and domain invariants."""
+    import torch
+    from masurvival.envs import MaSurvivalVec
+    from masurvival.config import variant
+    N = 16384
+    envs = [MaSurvivalVec(variant('2v2'), N, seed=5) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    g = torch.Generator(device='cuda'); g.manual_seed(0)
+    tot_done = 0
+    for t in range(120):
+        a = torch.empty((N, 4, 6), dtype=torch.uint8, device='cuda')
+        a[..., :3] = torch.randint(0, 3, (N, 4, 3), dtype=torch.uint8, device='cuda', generator=g)
+        a[..., 3:] = torch.randint(0, 2, (N, 4, 3), dtype=torch.uint8, device='cuda', generator=g)
+        outs = [e.step(a) for e in envs]
+        tot_done += int(outs[0][2].sum())
+    o0, r0, d0, _ = outs[0]; o1, r1, d1, _ = outs[1]
+    for k in o0:
+        assert torch.equal(o0[k], o1[k]), k          # same seed + actions -> identical (no atomics, no races)
+    assert torch.equal(r0, r1) and torch.equal(d0, d1)
+    ag = o0['agent']
+    assert torch.all(ag[..., 3:5].abs() <= 10.0)      # nobody tunnels through the walls (TOI)
+    hp = ag[..., 2]
+    assert torch.all(hp == hp.round()) and torch.all(hp >= 0)
+    assert torch.all((o0['others_mask'] == 0) | (o0['others_mask'] == 1))
+    assert torch.all((r0 == 1) | (r0 == -1))
+    st = envs[0].flush_stats()
+    assert st['steps'] == N * 120 and st['episodes'] == tot_done
+    for e in envs:
+        e.close()
