@@ -128,6 +128,7 @@ def pack_config(cfg, continuous_melee=False, auto_reset=False):
     rec['box_ownership'] = int(bool(boxes.get('ownership', False)))
     rec['box_health'] = boxes['health']
     rec['box_size'] = brs.get('box_size', 1)
+    rec['box_min_w'] = 0.1; rec['box_min_h'] = 0.1
     if 'randomized_shape' in boxes:
         rs = boxes['randomized_shape']
         rec['box_randomized'] = 1

@@ -76,7 +76,6 @@ typedef struct b2l_body {
   int islandFlag, islandIndex;
   float fat[4];
   int moved;
-  void* user;
 } b2l_body;
 
 typedef struct b2l_contact {

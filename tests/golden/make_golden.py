@@ -1,0 +1,230 @@
+#!/usr/bin/env python
+"""Generate the golden input/output vectors under tests/golden/ by running the
+reference's OWN, UNMODIFIED `masurvival` package (imported from
+/root/reference) on the Box2D/gym shims of oracle/shim/.
+
+    python tests/golden/make_golden.py        # needs /root/reference (this container only)
+
+For every case it drives the reference env with a scripted + random policy,
+feeding its numpy-Generator call sites (SpawnGrid shuffle, RandomizeBoxShapes
+normal, SafeZone/DeathDrop random) from the same counter-based Philox streams
+the oracle and the CUDA kernel use, and records actions, observations, rewards
+and dones.  While generating it also steps the C oracle in lock-step and
+asserts bit-equality, so a committed fixture is by construction one the oracle
+reproduces.  The fixtures pin layers L1-L3 (reference Python semantics) on the
+restated L0 (b2lite); see DESIGN.md "Parity status".
+"""
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'shim'))
+
+import parity  # noqa: E402  (product config helpers: variant/make_config)
+import pyoracle as po  # noqa: E402
+import Box2D  # noqa: E402,F401  (the shim)
+import gym  # noqa: E402,F401
+
+# switch `masurvival` from the product package to the reference package
+for m in [k for k in sys.modules if k == 'masurvival' or k.startswith('masurvival.')]:
+    del sys.modules[m]
+sys.path = [p for p in sys.path if 'gym-ma-survival-2d_b200' not in p]
+sys.path.insert(0, '/root/reference')
+from masurvival.envs.masurvival_env import MaSurvival  # noqa: E402
+import masurvival  # noqa: E402
+assert masurvival.__file__.startswith('/root/reference'), masurvival.__file__
+
+STREAM_SHUFFLE, STREAM_BOX, STREAM_ZONE, STREAM_DEATH = 0, 1, 2, 3
+
+
+class PhiloxGenerator:
+    """Stands in for `np.random.default_rng()` inside the reference env
+    (env:50,67,455-465): same three methods, draws from Philox4x32-10 keyed by
+    (seed, env id, episode, step) exactly like oracle/masurv_oracle.c."""
+
+    def __init__(self, seed, env_id):
+        self.seed, self.env_id, self.episode, self.step = seed, env_id, -1, 0
+        self._zone = self._box = 0
+
+    def begin_episode(self):
+        self.episode += 1
+        self.step = 0
+        self._zone = self._box = 0
+
+    def _u(self, stream, k, step=0):
+        return po.philox_uniform(self.seed, self.env_id, self.episode, step, stream, k)
+
+    def shuffle(self, x):                      # semantics.py:74
+        n = len(x)
+        for i in range(n - 1, 0, -1):
+            j = int(self._u(STREAM_SHUFFLE, n - 1 - i) * (i + 1))
+            x[i], x[j] = x[j], x[i]
+
+    def normal(self, loc=0.0, scale=1.0):      # semantics.py:111-118
+        k = self._box
+        self._box += 1
+        u1, u2 = self._u(STREAM_BOX, 2 * k), self._u(STREAM_BOX, 2 * k + 1)
+        z = math.sqrt(-2.0 * math.log(1.0 - u1)) * math.cos(6.283185307179586 * u2)
+        return loc + scale * z
+
+    def random(self, n=None):
+        if n is None:                          # semantics.py:745-746
+            k = self._zone
+            self._zone += 1
+            return self._u(STREAM_ZONE, k)
+        return np.array([self._u(STREAM_DEATH, k, self.step) for k in range(int(n))])  # semantics.py:391
+
+
+def ref_config(name, over):
+    user = parity.apply_overrides(parity.variant(name), over)
+    user.pop('lidars', None)
+    return user
+
+
+def scripted_actions(obs, t, rng, A):
+    """seek-and-interact policy so that pickups, heals, box placement, melee
+    kills, death drops and gives all happen within a few hundred steps"""
+    acts = np.zeros((A, 6), dtype=np.uint8)
+    off = obs['agent'].shape[1] - 6
+    for i in range(A):
+        row = obs['agent'][i]
+        x, y, ang = row[off], row[off + 1], row[off + 2]
+        mode = (t // 40 + i) % 4
+        target = None
+        if mode == 0 and 'heals' in obs:
+            m = obs['heals_mask'][i] == 0
+            if m.any():
+                p = obs['heals'][i][m]
+                target = p[np.argmin(((p - [x, y]) ** 2).sum(1))]
+        elif mode == 1 and 'boxes' in obs:
+            m = obs['boxes_mask'][i] == 0
+            if m.any():
+                p = obs['boxes'][i][m][:, 8:10]
+                target = p[np.argmin(((p - [x, y]) ** 2).sum(1))]
+        elif mode == 2 and 'box_items' in obs:
+            m = obs['box_items_mask'][i] == 0
+            if m.any():
+                p = obs['box_items'][i][m][:, 8:10]
+                target = p[np.argmin(((p - [x, y]) ** 2).sum(1))]
+        if target is None:
+            others = obs['others'][i]
+            alive = others[:, off - 1] > 0
+            if alive.any():
+                p = others[alive][:, off:off + 2]
+                target = p[np.argmin(((p - [x, y]) ** 2).sum(1))]
+        if target is None or rng.random() < 0.15:
+            acts[i, 0:3] = rng.integers(0, 3, 3)
+        else:
+            bearing = math.atan2(target[1] - y, target[0] - x) - ang
+            bearing = (bearing + math.pi) % (2 * math.pi) - math.pi
+            acts[i, 0] = 2 if abs(bearing) < 1.0 else 1
+            acts[i, 1] = 1
+            acts[i, 2] = 2 if bearing > 0.05 else (0 if bearing < -0.05 else 1)
+        acts[i, 3] = rng.random() < 0.6
+        has_heal = 'heal_slot_mask' in obs and obs['heal_slot_mask'][i][0] == 0
+        has_box = 'box_slot_mask' in obs and obs['box_slot_mask'][i][0] == 0
+        hp = row[off - 1]
+        acts[i, 4] = (has_heal and hp < 70 and rng.random() < 0.5) or (has_box and rng.random() < 0.2) or rng.random() < 0.03
+        acts[i, 5] = rng.random() < 0.08
+    return acts
+
+
+def run_case(name, over, seed, env_id, steps, policy='scripted'):
+    rec = parity.make_config(name, auto_reset=False, **{k: dict(v) for k, v in over.items() if k != 'lidars'})
+    A = int(rec['n_agents'])
+    env = MaSurvival(ref_config(name, over))
+    gen = PhiloxGenerator(seed, env_id)
+    env.np_random = gen
+    orc = po.OracleEnv(rec, seed=seed, env_id=env_id)
+    rng = np.random.default_rng(seed * 1000 + env_id)
+    keys = [k for k in po.obs_dims(rec) if not k.startswith('lidar')]
+    log = {k: [] for k in keys}
+    log.update(kind=[], rewards=[], done=[], actions=[])
+
+    def record(kind, obs, rew, done, act):
+        for k in keys:
+            log[k].append(np.asarray(obs[k], dtype=np.float32))
+        log['kind'].append(kind); log['rewards'].append(np.asarray(rew, dtype=np.float32))
+        log['done'].append(done); log['actions'].append(act)
+
+    def check(tag, obs, oo, rew=None, done=None):
+        for k in keys:
+            a, b = np.asarray(obs[k]), oo[k]
+            assert a.dtype == np.float32 and a.shape == b.shape, (tag, k, a.shape, b.shape)
+            if not np.array_equal(a, b):
+                idx = np.argwhere(a != b)[:4]
+                raise AssertionError(f'{name} {tag}: key {k} differs at {idx.tolist()}: ref {a[tuple(idx[0])]} oracle {b[tuple(idx[0])]}')
+        if rew is not None:
+            assert np.array_equal(np.asarray(rew, dtype=np.float32), oo['rewards']), (tag, rew, oo['rewards'])
+            assert bool(done) == oo['done'], (tag, done, oo['done'])
+
+    def reset():
+        gen.begin_episode()
+        obs = env.reset()
+        oo = orc.reset()
+        check('reset', obs, oo)
+        record(0, obs, np.zeros(A, np.float32), False, np.zeros((A, 6), np.uint8))
+        return obs
+
+    obs = reset()
+    counters = dict(dones=0, heals_used=0, boxes_placed=0, kills=0, toi=0)
+    for t in range(steps):
+        act = scripted_actions(obs, t, rng, A) if policy == 'scripted' else parity.random_actions(rng, 1, A)[0]
+        gen.step = env.steps
+        obs, rew, done, _ = env.step(tuple(tuple(int(v) for v in a) for a in act))
+        oo = orc.step(act)
+        check(f'step {t}', obs, oo, rew, done)
+        counters['toi'] += oo['n_toi_events']
+        record(1, obs, rew, done, act)
+        if done:
+            counters['dones'] += 1
+            st = env.flush_stats()
+            so = orc.flush_stats()
+            n = 2 if rec['teams'] else A
+            assert st['steps'] == so['steps'] and st['heals_used'] == so['heals_used'] and st['boxes_placed'] == so['boxes_placed'], (st, so)
+            for i in range(n):
+                assert st[f'kills{i}'] == so['kills'][i] and abs(st[f'reward{i}'] - so['reward'][i]) < 1e-3, (st, so)
+            counters['heals_used'] += st['heals_used']; counters['boxes_placed'] += st['boxes_placed']
+            counters['kills'] += sum(st[f'kills{i}'] for i in range(n))
+            obs = reset()
+    st = env.flush_stats()
+    n = 2 if rec['teams'] else A
+    counters['heals_used'] += st['heals_used']; counters['boxes_placed'] += st['boxes_placed']
+    counters['kills'] += sum(st[f'kills{i}'] for i in range(n))
+    out = {k: np.stack(v) for k, v in log.items()}
+    out['kind'] = np.array(log['kind'], dtype=np.uint8)
+    out['done'] = np.array(log['done'], dtype=np.uint8)
+    out['meta'] = np.array([seed, env_id, steps], dtype=np.int64)
+    return out, counters
+
+
+CASES = [
+    # file, variant, overrides, seed, env_id, steps, policy
+    ('g_1v1_default', '1v1', {}, 11, 0, 1200, 'scripted'),
+    ('g_1v1_random', '1v1', {}, 12, 3, 300, 'random'),
+    ('g_1v1_heal_only', '1v1_heal_only', {}, 13, 1, 800, 'scripted'),
+    ('g_2v2_teams', '2v2', {}, 14, 2, 1200, 'scripted'),
+    ('g_2v2_owned_fastzone', '2v2', {'boxes': {'ownership': True}, 'safe_zone': {'cooldown': 12}, 'health': {'health': 40}}, 15, 5, 1000, 'scripted'),
+    ('g_2v2_lastalive_kills', '2v2', {'gameover': {'mode': 'lastalive'}, 'reward_scheme': {'r_kill': 5, 'r_death': -3},
+                                      'melee': {'damage': 50}}, 16, 7, 1000, 'scripted'),
+    ('g_ffa_randomized', 'ffa', {'health': {'health': 60}}, 17, 4, 500, 'scripted'),
+    ('g_1v1_continuous_melee', '1v1', {'melee': {'cooldown': None}}, 18, 6, 600, 'scripted'),
+]
+
+
+def main():
+    for fname, name, over, seed, env_id, steps, policy in CASES:
+        out, counters = run_case(name, over, seed, env_id, steps, policy)
+        path = os.path.join(HERE, fname + '.npz')
+        np.savez_compressed(path, **out)
+        print(f'{fname}: {len(out["kind"])} records, {os.path.getsize(path) / 1024:.0f} KiB, {counters}')
+
+
+if __name__ == '__main__':
+    main()

@@ -14,10 +14,21 @@ from masurvival.config import merge_config, pack_config, variant  # noqa: E402
 REL_TOL = 1e-4  # BASELINE.json north_star: continuous outputs within 1e-4 relative
 
 
-def make_config(name, auto_reset=False, **over):
-    user = variant(name)
+def apply_overrides(user, over):
+    """user-config dict + overrides; a value of None deletes the key (e.g.
+    {'melee': {'cooldown': None}} selects ContinuousMelee, env:309-312)."""
     for k, v in over.items():
-        user.setdefault(k, {}).update(v)
+        sub = user.setdefault(k, {})
+        for kk, vv in v.items():
+            if vv is None:
+                sub.pop(kk, None)
+            else:
+                sub[kk] = vv
+    return user
+
+
+def make_config(name, auto_reset=False, **over):
+    user = apply_overrides(variant(name), over)
     cfg, cm = merge_config(user)
     return pack_config(cfg, cm, auto_reset=auto_reset)
 

@@ -156,3 +156,35 @@ def test_full_size_properties():
     assert st['steps'] == N * 120 and st['episodes'] == tot_done
     for e in envs:
         e.close()
+
+
+def test_golden_fixtures_on_gpu():
+    """the committed golden vectors (recorded from the reference's own Python,
+    tests/golden/make_golden.py) replayed through the C ABI on the GPU"""
+    import torch
+    import test_cpu_golden as tg
+    from masurvival import _lib
+    import pyoracle as po
+    for path in tg.GOLDEN:
+        g = np.load(path)
+        rec = tg.case_config(path)
+        A = int(rec['n_agents'])
+        seed, env_id, _ = [int(v) for v in g['meta']]
+        h = _lib.Handle(rec, 1, 0, seed, env_id)
+        keys = list(po.obs_dims(rec).keys())
+        for r in range(len(g['kind'])):
+            if g['kind'][r] == 0:
+                h.reset()
+            else:
+                a = torch.as_tensor(g['actions'][r][None]).cuda()
+                h.step(a.data_ptr())
+            torch.cuda.synchronize()
+            for k in keys:
+                v = h.tensor(k).cpu().numpy()[0]
+                if k in ('zone', 'heals', 'boxes', 'box_items'):
+                    v = np.broadcast_to(v[None], (A,) + v.shape)
+                assert np.array_equal(v, g[k][r]), (path, r, k)
+            if g['kind'][r] == 1:
+                assert np.array_equal(h.tensor('rewards').cpu().numpy()[0], g['rewards'][r]), (path, r)
+                assert bool(h.tensor('dones').cpu().numpy()[0]) == bool(g['done'][r]), (path, r)
+        h.close()
