@@ -205,23 +205,38 @@ struct Env {
 
   // closest hit of the segment p1->p2 over every fixture except agent `self`
   // (whose own circle contains p1 and therefore always misses); minimum
-  // fraction over independent b2Shape::RayCast tests (sim:431-439, 471-484)
+  // fraction over independent b2Shape::RayCast tests (sim:431-439, 471-484).
+  // Every exact test is preceded by a conservative reject (segment AABB vs a
+  // bound of the shape): it can only skip shapes the exact test would miss.
   __device__ __noinline__ int raycast(f2 p1, f2 p2, int self, int& idx, float& frac) {
     int kind = KIND_NONE; idx = -1; frac = 0.0f; float f;
-    for (int k = 0; k < nb; ++k)
+    const float lx = fmin_(p1.x, p2.x), ly = fmin_(p1.y, p2.y), ux = fmax_(p1.x, p2.x), uy = fmax_(p1.y, p2.y);
+    auto far_from = [&](float cx, float cy, float rad) {  // rad already includes slack
+      return cx + rad < lx || cx - rad > ux || cy + rad < ly || cy - rad > uy;
+    };
+    for (int k = 0; k < nb; ++k) {
+      float bxr = BX(G_HX, k) + BX(G_HY, k) + 0.01f;     // |hx|+|hy| >= circumradius
+      if (far_from(BX(G_X, k), BX(G_Y, k), bxr)) continue;
       if (ray_box(static_box(k), p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_BOX; idx = k; frac = f; }
+    }
     for (int k = 0; k < ni; ++k) {
       float4 it = S.item0[k * N + e];
+      if (far_from(it.x, it.y, C.item_r + 0.01f)) continue;
       if (ray_circle(mk2(it.x, it.y), C.item_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_ITEM; idx = k; frac = f; }
     }
     for (int k = 0; k < nh; ++k) {
       float2 h = S.heal[k * N + e];
+      if (far_from(h.x, h.y, C.heal_r + 0.01f)) continue;
       if (ray_circle(mk2(h.x, h.y), C.heal_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_HEAL; idx = k; frac = f; }
     }
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k) {
+      const WallC& w = C.walls[k];                        // fat AABB = tight AABB + 0.11
+      if (w.fat[2] < lx || w.fat[0] > ux || w.fat[3] < ly || w.fat[1] > uy) continue;
       if (ray_box(static_box(BC + k), p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_WALL; idx = k; frac = f; }
+    }
     for (int j = 0; j < C.A; ++j) {
       if (j == self || !alive(j)) continue;
+      if (far_from(AG(F_CX, j), AG(F_CY, j), C.agent_r + 0.01f)) continue;
       if (ray_circle(apos(j), C.agent_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_AGENT; idx = j; frac = f; }
     }
     return kind;
@@ -566,20 +581,26 @@ struct Env {
 
   // b2World::Solve: islands by DFS over touching contacts, seeds in body-list
   // order (newest body first = highest agent index first), contact edges
-  // newest first; each island solved by b2Island::Solve.
+  // newest first; each island solved by b2Island::Solve.  Islands touch
+  // disjoint bodies, so all islands are built first and then advanced
+  // together (per-island contact order, position-iteration early-out and sleep
+  // decision are kept): a thread loops over ITS contacts once, not per seed.
   __device__ __noinline__ void solve(float h, float dtRatio) {
     for (int i = 0; i < C.A; ++i) AGF(i) &= ~(FL_ISLAND | FL_MOVED);
     for (int k = 0; k < ntc; ++k) tcs[k].flags = 0;
-    int stack[AC], members[AC], order[MAXC];
+    int stack[AC], isl_of[AC];
+    unsigned char order[MAXC], cisl[MAXC];
+    int nisl = 0, nc = 0;
     for (int seed = C.A - 1; seed >= 0; --seed) {
       int fs = AGF(seed);
       if (!(fs & FL_ALIVE) || (fs & FL_ISLAND) || !(fs & FL_AWAKE)) continue;
-      int sc = 0, nm = 0, nc = 0;
+      int sc = 0;
       stack[sc++] = seed; AGF(seed) |= FL_ISLAND;
       while (sc > 0) {
         int bI = stack[--sc];
-        members[nm++] = bI;
+        isl_of[bI] = nisl;
         wake(bI);
+        if (ntc == 0) continue;
         for (;;) {  // contact edges of bI, newest (largest seq) first
           int best = -1, bestSeq = -1;
           for (int k = 0; k < ntc; ++k) {
@@ -591,7 +612,7 @@ struct Env {
           }
           if (best < 0) break;
           tcs[best].flags |= 1;
-          order[nc++] = best;
+          order[nc] = (unsigned char)best; cisl[nc] = (unsigned char)nisl; nc++;
           const TCon& t = tcs[best];
           if (t.a >= 0) {
             int other = t.a == bI ? t.b : t.a;
@@ -599,36 +620,52 @@ struct Env {
           }
         }
       }
-      // ---- b2Island::Solve
-      for (int m = 0; m < nm; ++m) {
-        int i = members[m];
-        AG(F_C0X, i) = AG(F_CX, i); AG(F_C0Y, i) = AG(F_CY, i); AG(F_A0, i) = AG(F_A, i);
-        AG(F_VX, i) = C.damp * AG(F_VX, i); AG(F_VY, i) = C.damp * AG(F_VY, i);  // v *= 1/(1+h*damping)
-        AG(F_W, i) *= C.damp;
-      }
+      nisl++;
+    }
+    // ---- b2Island::Solve, all islands
+    for (int i = 0; i < C.A; ++i) {
+      if (!(AGF(i) & FL_ISLAND)) continue;
+      AG(F_C0X, i) = AG(F_CX, i); AG(F_C0Y, i) = AG(F_CY, i); AG(F_A0, i) = AG(F_A, i);
+      AG(F_VX, i) = C.damp * AG(F_VX, i); AG(F_VY, i) = C.damp * AG(F_VY, i);  // v *= 1/(1+h*damping)
+      AG(F_W, i) *= C.damp;
+    }
+    unsigned solved = 0;                       // per-island positionSolved
+    const unsigned all_isl = nisl >= 32 ? 0xFFFFFFFFu : ((1u << nisl) - 1u);
+    if (nc > 0) {
       for (int k = 0; k < nc; ++k) { TCon& t = tcs[order[k]]; t.ni = dtRatio * t.ni; t.ti = dtRatio * t.ti; }
       for (int k = 0; k < nc; ++k) init_velocity(tcs[order[k]]);
       for (int k = 0; k < nc; ++k) warm_start(tcs[order[k]]);
       for (int it = 0; it < 10; ++it)
         for (int k = 0; k < nc; ++k) solve_velocity(tcs[order[k]]);
       for (int k = 0; k < nc; ++k) { const TCon& t = tcs[order[k]]; S.pimp[t.p * N + e] = make_float2(t.ni, t.ti); }
-      for (int m = 0; m < nm; ++m) integrate_position(members[m], h);
-      bool positionSolved = false;
-      for (int it = 0; it < 10; ++it) {
-        float minSep = 0.0f;
-        for (int k = 0; k < nc; ++k) minSep = fmin_(minSep, solve_position(tcs[order[k]], false, -1));
-        if (minSep >= -3.0f * B2_LINEAR_SLOP) { positionSolved = true; break; }
+    }
+    for (int i = 0; i < C.A; ++i) if (AGF(i) & FL_ISLAND) integrate_position(i, h);
+    if (nc > 0) {
+      for (int it = 0; it < 10 && solved != all_isl; ++it) {
+        unsigned bad = 0;                      // islands whose minSeparation < -3 slop this pass
+        for (int k = 0; k < nc; ++k) {
+          unsigned ib = 1u << cisl[k];
+          if (solved & ib) continue;
+          float sep = solve_position(tcs[order[k]], false, -1);
+          if (!(fmin_(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) bad |= ib;
+        }
+        solved |= all_isl & ~bad;
       }
-      float minSleep = FLT_MAX;
+    } else solved = all_isl;
+    {
       const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
-      for (int m = 0; m < nm; ++m) {
-        int i = members[m];
+      unsigned can_sleep = solved;             // islands with minSleepTime >= timeToSleep && positionSolved
+      for (int i = 0; i < C.A; ++i) {
+        if (!(AGF(i) & FL_ISLAND)) continue;
         float w = AG(F_W, i); f2 v = mk2(AG(F_VX, i), AG(F_VY, i));
-        if (w * w > angTol || vdot(v, v) > linTol) { AG(F_SLEEP, i) = 0.0f; minSleep = 0.0f; }
-        else { AG(F_SLEEP, i) += h; minSleep = fmin_(minSleep, AG(F_SLEEP, i)); }
+        float st;
+        if (w * w > angTol || vdot(v, v) > linTol) st = 0.0f; else st = AG(F_SLEEP, i) + h;
+        AG(F_SLEEP, i) = st;
+        if (!(st >= B2_TIME_TO_SLEEP)) can_sleep &= ~(1u << isl_of[i]);
       }
-      if (minSleep >= B2_TIME_TO_SLEEP && positionSolved)
-        for (int m = 0; m < nm; ++m) sleep_body(members[m]);
+      if (can_sleep)
+        for (int i = 0; i < C.A; ++i)
+          if ((AGF(i) & FL_ISLAND) && ((can_sleep >> isl_of[i]) & 1u)) sleep_body(i);
     }
     bool moved = false;
     for (int i = 0; i < C.A; ++i)
@@ -655,12 +692,14 @@ struct Env {
     int evP[8], evN[8], nev = 0;
     for (int guard = 0; guard < 64; ++guard) {
       int minP = -1, minSeq = -1; float minAlpha = 1.0f;
-      for (int i = 0; i < C.A; ++i) {
-        if (!alive(i) || !awake(i)) continue;
-        for (int k = 0; k < BC + 4; ++k) {
-          if (k < BC && k >= nb) continue;
-          int p = k < BC ? p_ab(i, k) : p_aw(i, k - BC);
-          if (!bit(ex, p) || !bit(en, p)) continue;
+      for (int w = 0; w < PW; ++w) {
+        // existing, enabled agent-vs-static contacts (pair index >= NAA), ascending
+        unsigned long long mbits = ex[w] & en[w];
+        if (w == 0) mbits &= ~((1ull << NAA) - 1ull);
+        while (mbits) {
+          int p = w * 64 + __ffsll((long long)mbits) - 1; mbits &= mbits - 1;
+          int a_, k, i; decode(p, a_, k, i);
+          if (!alive(i) || !awake(i)) continue;
           int cnt = 0; for (int q = 0; q < nev; ++q) if (evP[q] == p) cnt = evN[q];
           if (cnt > B2_MAX_SUBSTEPS) continue;
           float beta;
@@ -850,30 +889,40 @@ struct Env {
   // omniscient observation reads, env:692-703)
   __device__ __noinline__ void cameras() {
     pre_alive = 0; int row = 0;
+    int rowof[AC];
     for (int i = 0; i < AC; ++i) seenA[i] = 0;
+    // pass 1: which (observer i, target j) pairs have the target inside the cone
+    unsigned long long incone = 0ull;                 // bit i*AC + j
     for (int i = 0; i < C.A; ++i) {
+      rowof[i] = -1;
       if (!alive(i)) continue;
-      pre_alive |= 1u << i;
+      pre_alive |= 1u << i; rowof[i] = row++;
       f2 me = apos(i); float s, c; rot_set(AG(F_A, i), s, c);
-      unsigned seen = 0;
       for (int j = 0; j < C.A; ++j) {
         if (j == i || !alive(j)) continue;
-        f2 o = apos(j);
-        f2 pl = qmulT(s, c, vsub(o, me));      // b2PolygonShape::TestPoint(cone)
+        f2 pl = qmulT(s, c, vsub(apos(j), me));      // b2PolygonShape::TestPoint(cone)
         bool inside = true;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           float d = vdot(mk2(C.cone_n[v][0], C.cone_n[v][1]), vsub(pl, mk2(C.cone_v[v][0], C.cone_v[v][1])));
           if (d > 0.0f) inside = false;
         }
-        if (!inside) continue;
-        f2 d = vsub(o, me);
-        f2 end = mk2(me.x + C.cam_k1 * d.x, me.y + C.cam_k1 * d.y);
-        int idx; float fr;
-        int kind = raycast(me, end, i, idx, fr);
-        if (kind == KIND_AGENT && idx == j) seen |= 1u << j;
+        if (inside) incone |= 1ull << (i * AC + j);
       }
-      seenA[row++] = seen;
+    }
+    // pass 2: one line-of-sight ray per in-cone pair (a thread walks ITS list)
+    while (incone) {
+      int q = __ffsll((long long)incone) - 1; incone &= incone - 1;
+      int i = q / AC, j = q % AC;
+      f2 me = apos(i), o = apos(j);
+      f2 d = vsub(o, me);
+      f2 end = mk2(me.x + C.cam_k1 * d.x, me.y + C.cam_k1 * d.y);
+      int idx; float fr;
+      int kind = raycast(me, end, i, idx, fr);
+      if (kind == KIND_AGENT && idx == j) {
+#pragma unroll
+        for (int r = 0; r < AC; ++r) if (r == rowof[i]) seenA[r] |= 1u << j;
+      }
     }
   }
 
