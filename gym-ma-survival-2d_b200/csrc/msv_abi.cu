@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <algorithm>
 
 #include "../../include/masurv.h"
 #include "msv_launch.h"
@@ -40,6 +41,7 @@ struct msv_handle {
   uint8_t* d_actions;       // staging for msv_step_host
   double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
   int64_t launches;
+  ObsTable obs;
   int64_t exported;          // live DLPack exports
   std::string err;
 };
@@ -98,7 +100,7 @@ static void h_polygon_set4(const float vin[4][2], float vout[4][2], float nout[4
 
 static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_offset, DevConst* D) {
   memset(D, 0, sizeof *D);
-  D->N = N; D->A = c->n_agents; D->B0 = c->n_boxes; D->H0 = c->n_heals;
+  D->N = (N + MSV_TPB - 1) / MSV_TPB * MSV_TPB; D->n_real = N; D->A = c->n_agents; D->B0 = c->n_boxes; D->H0 = c->n_heals;
   D->S = 8 + (c->teams ? 1 : 0);
   D->teams = c->teams; D->omniscient = c->omniscient; D->gameover_mode = c->gameover_mode;
   D->health = c->health; D->melee_damage = c->melee_damage; D->melee_cooldown = c->melee_cooldown;
@@ -304,7 +306,10 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   h->cap = (cfg->n_agents <= 2 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 0
          : (cfg->n_agents <= 4 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 1 : 2;
   msv_capacity(h->cap, &h->AC, &h->BC, &h->HC, &h->P, &h->PW);
-  const size_t N = (size_t)num_envs, AC = h->AC, BC = h->BC, HC = h->HC, P = h->P, PW = h->PW;
+  if (msv_launch(h->cap, 3, h->C, h->S, h->O, nullptr, 0) != cudaSuccess) {
+    g_err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; delete h; return MSV_ERR_CUDA;
+  }
+  const size_t N = (size_t)h->C.N, AC = h->AC, BC = h->BC, HC = h->HC, P = h->P, PW = h->PW;  // padded
   DevState& S = h->S; DevOut& O = h->O;
   int rc = 0;
   rc |= dalloc(h, &S.akin0, AC * N); rc |= dalloc(h, &S.akin1, AC * N); rc |= dalloc(h, &S.afat, AC * N);
@@ -328,6 +333,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   rc |= dalloc(h, &O.box_slot, N * A * 8); rc |= dalloc(h, &O.box_slot_mask, N * A);
   rc |= dalloc(h, &O.lidar_frac, N * A * L); rc |= dalloc(h, &O.lidar_hit, N * A * L);
   rc |= dalloc(h, &O.rewards, N * A); rc |= dalloc(h, &O.dones, N);
+  rc |= dalloc(h, &S.obm, N);
   rc |= dalloc(h, &h->d_actions, N * A * 6);
   rc |= dalloc(h, &h->d_stat_reward, (size_t)MSV_MAX_AGENTS); rc |= dalloc(h, &h->d_stat_kills, (size_t)MSV_MAX_AGENTS);
   rc |= dalloc(h, &h->d_stat_misc, (size_t)4);
@@ -335,6 +341,52 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   {  // episode counter starts at -1 so that the first reset is episode 0
     std::vector<int4> hd(N, make_int4(0, 0, -1, 0));
     cudaMemcpy(S.hdr0, hd.data(), N * sizeof(int4), cudaMemcpyHostToDevice);
+  }
+  {  // observation element table for k_obs (env:391-447 shapes, env:510-657 contents)
+    std::vector<ObsDesc> D;
+    const int Ai = (int)A, Bi = (int)B, Hi = (int)H, Si = (int)Sw;
+    auto add = [&](int key, int off, int src, int slot, int comp, int aux) {
+      ObsDesc d; d.src = (uint8_t)src; d.slot = (uint8_t)slot; d.comp = (uint8_t)comp; d.aux = (uint8_t)aux;
+      d.key = (uint16_t)key; d.off = (uint16_t)off; D.push_back(d);
+    };
+    auto agent_row = [&](int key, int off, int i) {
+      int o = off;
+      add(key, o++, OS_AGENT_ID, i, 0, 0);
+      if (cfg->teams) add(key, o++, OS_AGENT_TEAM, i, 0, i < Ai / 2 ? 0 : 1);
+      add(key, o++, OS_AGENT_HEALTH, i, 0, 0);
+      add(key, o++, OS_AKIN0, i, 0, 0); add(key, o++, OS_AKIN0, i, 1, 0); add(key, o++, OS_AKIN0, i, 2, 0);
+      add(key, o++, OS_AKIN0, i, 3, 0); add(key, o++, OS_AKIN1, i, 0, 0); add(key, o++, OS_AKIN1, i, 1, 0);
+    };
+    ObsKey* K = h->obs.keys;
+    K[0] = {O.agent, Ai * Si}; K[1] = {O.others, Ai * (Ai - 1) * Si}; K[2] = {O.others_mask, Ai * (Ai - 1)}; K[3] = {O.zone, 6};
+    K[4] = {O.heals, Hi * 2}; K[5] = {O.heals_mask, Ai * Hi}; K[6] = {O.heal_slot, Ai}; K[7] = {O.heal_slot_mask, Ai};
+    K[8] = {O.boxes, Bi * 11}; K[9] = {O.boxes_mask, Ai * Bi}; K[10] = {O.box_items, Bi * 10}; K[11] = {O.box_items_mask, Ai * Bi};
+    K[12] = {O.box_slot, Ai * 8}; K[13] = {O.box_slot_mask, Ai};
+    for (int i = 0; i < Ai; ++i) agent_row(0, i * Si, i);
+    for (int i = 0; i < Ai; ++i) { int k = 0; for (int j = 0; j < Ai; ++j) { if (j == i) continue; agent_row(1, (i * (Ai - 1) + k) * Si, j); add(2, i * (Ai - 1) + k, OS_OTHERS_MASK, i, j, 0); k++; } }
+    for (int c2 = 0; c2 < 3; ++c2) { add(3, c2, OS_ZONE_CUR, 0, c2, 0); add(3, 3 + c2, OS_ZONE_NEXT, 0, c2, 0); }
+    if (Hi > 0) {
+      for (int k = 0; k < Hi; ++k) { add(4, 2 * k, OS_HEAL, k, 0, 0); add(4, 2 * k + 1, OS_HEAL, k, 1, 0); }
+      for (int i = 0; i < Ai; ++i) { for (int k = 0; k < Hi; ++k) add(5, i * Hi + k, OS_LIST_MASK, k, 0, 2); add(6, i, OS_HEAL_SLOT, i, 0, 0); add(7, i, OS_HEAL_SLOT_MASK, i, 0, 0); }
+    }
+    if (Bi > 0) {
+      for (int k = 0; k < Bi; ++k) {
+        for (int c2 = 0; c2 < 8; ++c2) { add(8, k * 11 + c2, OS_BOX_VERT, k, c2, 0); add(10, k * 10 + c2, OS_ITEM_VERT, k, c2, 0); }
+        for (int c2 = 0; c2 < 3; ++c2) add(8, k * 11 + 8 + c2, OS_BOX_POS, k, c2, 0);
+        for (int c2 = 0; c2 < 2; ++c2) add(10, k * 10 + 8 + c2, OS_ITEM_POS, k, c2, 0);
+      }
+      for (int i = 0; i < Ai; ++i) {
+        for (int k = 0; k < Bi; ++k) { add(9, i * Bi + k, OS_LIST_MASK, k, 0, 0); add(11, i * Bi + k, OS_LIST_MASK, k, 0, 1); }
+        for (int c2 = 0; c2 < 8; ++c2) add(12, i * 8 + c2, OS_BOX_SLOT, i, c2, 0);
+        add(13, i, OS_BOX_SLOT_MASK, i, 0, 0);
+      }
+    }
+    // group the table by key so that consecutive threads write consecutive floats
+    std::stable_sort(D.begin(), D.end(), [](const ObsDesc& x, const ObsDesc& y) { return x.key != y.key ? x.key < y.key : x.off < y.off; });
+    ObsDesc* dd = nullptr;
+    if (dalloc(h, &dd, D.size())) { g_err = h->err; msv_destroy(h); return MSV_ERR_ALLOC; }
+    cudaMemcpy(dd, D.data(), D.size() * sizeof(ObsDesc), cudaMemcpyHostToDevice);
+    h->obs.desc = dd; h->obs.n_elems = (int)D.size();
   }
   const int64_t n = num_envs, a = A, b = B, hh = H, s = Sw, l = L;
   reg(h, "agent", O.agent, 0, {n, a, s});
@@ -369,9 +421,11 @@ int msv_destroy(msv_handle* h) {
 const char* msv_last_error(msv_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
 static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream) {
-  CK(cudaSetDevice(h->device));
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) CK(cudaSetDevice(h->device));
   CK(msv_launch(h->cap, which, h->C, h->S, h->O, actions, (cudaStream_t)stream));
-  h->launches++;
+  CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, (cudaStream_t)stream));   // fetch_observations
+  h->launches += 2;
   return MSV_OK;
 }
 
@@ -385,8 +439,9 @@ int msv_step(msv_handle* h, const uint8_t* actions_dev, void* stream) {
 int msv_step_host(msv_handle* h, const uint8_t* actions_host, float* rewards_host, uint8_t* dones_host, void* stream) {
   if (!h || !actions_host) return MSV_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  size_t N = h->C.N, A = h->C.A;
-  CK(cudaSetDevice(h->device));
+  size_t N = h->C.n_real, A = h->C.A;
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(h->d_actions, actions_host, N * A * 6, cudaMemcpyHostToDevice, st));
   int rc = launch(h, 0, h->d_actions, stream);
   if (rc) return rc;
@@ -443,7 +498,7 @@ int msv_tensor(msv_handle* h, const char* name, struct DLManagedTensor** out) {
 }
 
 int msv_get_state(msv_handle* h, int32_t first, int32_t count, msv_env_state* out) {
-  if (!h || !out || first < 0 || count < 0 || first + count > h->C.N) return MSV_ERR_INVALID;
+  if (!h || !out || first < 0 || count < 0 || first + count > h->C.n_real) return MSV_ERR_INVALID;
   Mirror m; int rc = download(h, m); if (rc) return rc;
   const size_t N = h->C.N; const int AC = h->AC, BC = h->BC, A = h->C.A, NAA = AC * (AC - 1) / 2;
   for (int q = 0; q < count; ++q) {
@@ -509,7 +564,7 @@ int msv_get_state(msv_handle* h, int32_t first, int32_t count, msv_env_state* ou
 }
 
 int msv_set_state(msv_handle* h, int32_t first, int32_t count, const msv_env_state* in) {
-  if (!h || !in || first < 0 || count < 0 || first + count > h->C.N) return MSV_ERR_INVALID;
+  if (!h || !in || first < 0 || count < 0 || first + count > h->C.n_real) return MSV_ERR_INVALID;
   Mirror m; int rc = download(h, m); if (rc) return rc;
   const size_t N = h->C.N; const int AC = h->AC, BC = h->BC, HC = h->HC, A = h->C.A, NAA = AC * (AC - 1) / 2;
   for (int q = 0; q < count; ++q) {
@@ -571,7 +626,7 @@ int msv_flush_stats(msv_handle* h, msv_stats* out) {
   CK(cudaMemset(h->d_stat_reward, 0, sizeof(double) * MSV_MAX_AGENTS));
   CK(cudaMemset(h->d_stat_kills, 0, sizeof(unsigned long long) * MSV_MAX_AGENTS));
   CK(cudaMemset(h->d_stat_misc, 0, sizeof(unsigned long long) * 4));
-  CK(msv_launch_stats(h->C.N, h->AC, h->S.sreward, h->S.skills, h->S.smisc, h->d_stat_reward, h->d_stat_kills, h->d_stat_misc, 0));
+  CK(msv_launch_stats(h->C.n_real, h->C.N, h->AC, h->S.sreward, h->S.skills, h->S.smisc, h->d_stat_reward, h->d_stat_kills, h->d_stat_misc, 0));
   h->launches++;
   double r[MSV_MAX_AGENTS]; unsigned long long k[MSV_MAX_AGENTS], mm[4];
   CK(cudaMemcpy(r, h->d_stat_reward, sizeof r, cudaMemcpyDeviceToHost));

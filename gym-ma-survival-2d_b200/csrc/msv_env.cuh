@@ -1056,93 +1056,22 @@ struct Env {
   // ======================================================================
   //                 OBSERVATIONS / REWARDS / DONE / STATS
   // ======================================================================
-  // fetch_observations (env:510-657); layout notes in msv_types.cuh
-  __device__ __noinline__ void observe(DevOut& O) {
-    const int A = C.A, B = C.B0, H = C.H0, Sw = C.S;
-    float rows[AC][9];
-    int rank[AC]; int r = 0;
-    for (int i = 0; i < A; ++i) {
-      int s = 0;
-      rows[i][s++] = (float)i;
-      if (C.teams) rows[i][s++] = (float)team_of(i);
-      if (alive(i)) {
-        rows[i][s++] = (float)health[i];
-        rows[i][s++] = AG(F_CX, i); rows[i][s++] = AG(F_CY, i); rows[i][s++] = AG(F_A, i);
-        rows[i][s++] = AG(F_VX, i); rows[i][s++] = AG(F_VY, i); rows[i][s++] = AG(F_W, i);
-        rank[i] = r++;
-      } else { for (int k = 0; k < 7; ++k) rows[i][s++] = 0.0f; rank[i] = -1; }
+  // others_mask (env:692-703) as bits: bit (i*AC + j) set <=> observer i sees
+  // agent j.  Q1: Cameras.seen is looked up by the POST-death list position.
+  // The observation tensors themselves are written by k_obs (msv_kernels.cu).
+  __device__ void store_obm() {
+    unsigned long long bits = 0ull;
+    int r = 0;
+    for (int i = 0; i < C.A; ++i) {
+      if (!alive(i)) continue;
+      unsigned sr = 0;
+#pragma unroll
+      for (int q = 0; q < AC; ++q) if (q == r) sr = seenA[q];
+      r++;
+      for (int j = 0; j < C.A; ++j)
+        if (j != i && alive(j) && ((sr >> j) & 1u)) bits |= 1ull << (i * AC + j);
     }
-    float* oa = O.agent + (size_t)e * A * Sw;
-    for (int i = 0; i < A; ++i) for (int s = 0; s < Sw; ++s) oa[i * Sw + s] = rows[i][s];
-    float* oo = O.others + (size_t)e * A * (A - 1) * Sw;
-    float* om = O.others_mask + (size_t)e * A * (A - 1);
-    for (int i = 0; i < A; ++i) {
-      int k = 0;
-      for (int j = 0; j < A; ++j) {
-        if (j == i) continue;
-        for (int s = 0; s < Sw; ++s) oo[(i * (A - 1) + k) * Sw + s] = rows[j][s];
-        // Q1: the seen-list is looked up by the POST-death list position
-        float m = 1.0f;
-        if (alive(i) && alive(j) && ((seenA[rank[i]] >> j) & 1u)) m = 0.0f;
-        om[i * (A - 1) + k] = m;
-        k++;
-      }
-    }
-    float* oz = O.zone + (size_t)e * 6;
-    oz[0] = zx; oz[1] = zy; oz[2] = zr;
-    if (zphase < C.zone_phases - 1) {
-      float2 nc = S.zonec[(zphase + 1) * N + e];
-      oz[3] = nc.x; oz[4] = nc.y; oz[5] = C.zone_r32[zphase + 1];
-    } else { oz[3] = 0.0f; oz[4] = 0.0f; oz[5] = 0.0f; }
-    if (H > 0) {
-      float* oh = O.heals + (size_t)e * H * 2;
-      for (int k = 0; k < H; ++k) {
-        float2 h = k < nh ? S.heal[k * N + e] : make_float2(0.0f, 0.0f);
-        oh[2 * k] = h.x; oh[2 * k + 1] = h.y;
-      }
-      float* ohm = O.heals_mask + (size_t)e * A * H;
-      for (int i = 0; i < A; ++i) for (int k = 0; k < H; ++k) ohm[i * H + k] = k < nh ? 0.0f : 1.0f;
-      float* hs = O.heal_slot + (size_t)e * A; float* hsm = O.heal_slot_mask + (size_t)e * A;
-      for (int i = 0; i < A; ++i) {
-        bool has = alive(i) && inv_n(i) > 0 && inv_kind(i, inv_n(i) - 1) == MSV_ITEM_HEAL;
-        hs[i] = has ? (float)C.healing : 0.0f; hsm[i] = has ? 0.0f : 1.0f;
-      }
-    }
-    if (B > 0) {
-      float* ob = O.boxes + (size_t)e * B * 11;
-      for (int k = 0; k < B; ++k) {
-        float* d = ob + k * 11;
-        if (k < nb) {
-          SBox bx = static_box(k);
-          for (int v = 0; v < 4; ++v) { f2 p = sb_vert(bx, v); d[2 * v] = p.x; d[2 * v + 1] = p.y; }
-          d[8] = bx.px; d[9] = bx.py; d[10] = 0.0f;
-        } else for (int v = 0; v < 11; ++v) d[v] = 0.0f;
-      }
-      float* obm = O.boxes_mask + (size_t)e * A * B;
-      for (int i = 0; i < A; ++i) for (int k = 0; k < B; ++k) obm[i * B + k] = k < nb ? 0.0f : 1.0f;
-      float* oi = O.box_items + (size_t)e * B * 10;
-      for (int k = 0; k < B; ++k) {
-        float* d = oi + k * 10;
-        if (k < ni) {
-          float4 it = S.item0[k * N + e];
-          SBox bx; sb_set_shape(bx, it.z, it.w, 1);
-          for (int v = 0; v < 4; ++v) { f2 p = sb_vert(bx, v); d[2 * v] = p.x; d[2 * v + 1] = p.y; }
-          d[8] = it.x; d[9] = it.y;
-        } else for (int v = 0; v < 10; ++v) d[v] = 0.0f;
-      }
-      float* oim = O.box_items_mask + (size_t)e * A * B;
-      for (int i = 0; i < A; ++i) for (int k = 0; k < B; ++k) oim[i * B + k] = k < ni ? 0.0f : 1.0f;
-      float* bs = O.box_slot + (size_t)e * A * 8; float* bsm = O.box_slot_mask + (size_t)e * A;
-      for (int i = 0; i < A; ++i) {
-        bool has = alive(i) && inv_n(i) > 0 && inv_kind(i, inv_n(i) - 1) == MSV_ITEM_BOX;
-        if (has) {
-          float4 pl = S.ainv[(i * 4 + inv_n(i) - 1) * N + e];
-          SBox bx; sb_set_shape(bx, pl.x, pl.y, __float_as_int(pl.w) & 1);
-          for (int v = 0; v < 4; ++v) { f2 p = sb_vert(bx, v); bs[i * 8 + 2 * v] = p.x; bs[i * 8 + 2 * v + 1] = p.y; }
-        } else for (int v = 0; v < 8; ++v) bs[i * 8 + v] = 0.0f;
-        bsm[i] = has ? 0.0f : 1.0f;
-      }
-    }
+    S.obm[e] = bits;
   }
 
   DEV bool team_alive(int t) {

@@ -20,7 +20,6 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
        const __grid_constant__ DevOut Oc, const uint8_t* __restrict__ actions) {
   extern __shared__ float sm[];
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= C.N) return;
   DevOut O = Oc;
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
   long long t_last = C.profile ? clock64() : 0;
@@ -28,7 +27,8 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   uint8_t act[AC * 6];
   {
     const uint8_t* src = actions + (size_t)e * C.A * 6;
-    for (int k = 0; k < AC * 6; ++k) act[k] = k < C.A * 6 ? src[k] : 0;
+    const bool real = e < C.n_real;   // padding envs (N rounded up to the block size) get the no-op action
+    for (int k = 0; k < AC * 6; ++k) act[k] = (real && k < C.A * 6) ? src[k] : (uint8_t)(k % 6 < 3 ? 1 : 0);
   }
   PROF(0);
   env.pre_step(act);                       // sim:234-235
@@ -51,16 +51,15 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   PROF(7);
   env.post_step_rest();                    // sim:241-242
   PROF(8);
-  env.observe(O);                          // env:84
-  PROF(9);
   bool done = env.rewards_done(O);         // env:85-89
-  if (done && C.auto_reset) {              // vector-env extension
+  if (done && C.auto_reset) {              // vector-env extension: the observation returned is the new episode's first
     env.st_episodes++;
     env.reset();
     env.cameras();
     if (C.lidar_n > 0) env.lidar(O);
-    env.observe(O);
   }
+  PROF(9);
+  env.store_obm();                         // env:84: the observation tensors are gathered by k_obs
   PROF(10);
   env.store();
   PROF(11);
@@ -72,14 +71,13 @@ k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
         const __grid_constant__ DevOut Oc) {
   extern __shared__ float sm[];
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= C.N) return;
   DevOut O = Oc;
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
   env.load();
   env.reset();
   env.cameras();
   if (C.lidar_n > 0) env.lidar(O);
-  env.observe(O);
+  env.store_obm();
   for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
   O.dones[e] = 0;
   env.store();
@@ -91,25 +89,88 @@ k_observe(const __grid_constant__ DevConst C, const __grid_constant__ DevState S
           const __grid_constant__ DevOut Oc) {
   extern __shared__ float sm[];
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= C.N) return;
   DevOut O = Oc;
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
   env.load();
   env.cameras();
   if (C.lidar_n > 0) env.lidar(O);
-  env.observe(O);
+  env.store_obm();
+}
+
+// fetch_observations (env:510-657): one thread per output float, gathered from
+// the SoA state after k_step / k_reset / k_observe stored it.  grid = (n_real,
+// ceil(n_elems/128)): blockIdx.x is the environment, consecutive threads
+// write consecutive floats of a key -> fully coalesced stores; the loads hit
+// the few sectors that hold this env's state (L1-resident within the block).
+__global__ void __launch_bounds__(128)
+k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC) {
+  const int el = blockIdx.y * 128 + threadIdx.x;
+  if (el >= Tb.n_elems) return;
+  const int e = blockIdx.x, N = C.N;
+  const ObsDesc d = Tb.desc[el];
+  float v = 0.0f;
+  auto alive = [&](int i) { return (__float_as_int(S.akin1[i * N + e].w) & 1) != 0; };
+  auto vert = [&](float hx, float hy, int rot, int comp) {   // b2PolygonShape vertex order (Q8)
+    int j = ((comp >> 1) + rot) & 3;
+    return (comp & 1) ? ((j >= 2) ? hy : -hy) : ((j == 1 || j == 2) ? hx : -hx);
+  };
+  switch (d.src) {
+    case OS_AGENT_ID: v = (float)d.slot; break;
+    case OS_AGENT_TEAM: v = (float)d.aux; break;
+    case OS_AGENT_HEALTH: if (alive(d.slot)) v = (float)S.aint[d.slot * N + e].x; break;
+    case OS_AKIN0: if (alive(d.slot)) { float4 k = S.akin0[d.slot * N + e]; v = d.comp == 0 ? k.x : d.comp == 1 ? k.y : d.comp == 2 ? k.z : k.w; } break;
+    case OS_AKIN1: if (alive(d.slot)) { float4 k = S.akin1[d.slot * N + e]; v = d.comp == 0 ? k.x : k.y; } break;
+    case OS_OTHERS_MASK: v = ((S.obm[e] >> (d.slot * AC + d.comp)) & 1ull) ? 0.0f : 1.0f; break;
+    case OS_ZONE_CUR: { float4 z = S.zonecur[e]; v = d.comp == 0 ? z.x : d.comp == 1 ? z.y : z.z; } break;
+    case OS_ZONE_NEXT: {
+      int ph = S.zoneint[e].x;
+      if (ph < C.zone_phases - 1) {
+        if (d.comp == 2) v = C.zone_r32[ph + 1];
+        else { float2 c = S.zonec[(ph + 1) * N + e]; v = d.comp == 0 ? c.x : c.y; }
+      }
+    } break;
+    case OS_HEAL: { int nh = (S.hdr0[e].x >> 16) & 255; if (d.slot < nh) { float2 h = S.heal[d.slot * N + e]; v = d.comp == 0 ? h.x : h.y; } } break;
+    case OS_LIST_MASK: { int cnt = (S.hdr0[e].x >> (d.aux * 8)) & 255; v = d.slot < cnt ? 0.0f : 1.0f; } break;
+    case OS_HEAL_SLOT: case OS_HEAL_SLOT_MASK: case OS_BOX_SLOT: case OS_BOX_SLOT_MASK: {
+      int want = (d.src == OS_HEAL_SLOT || d.src == OS_HEAL_SLOT_MASK) ? MSV_ITEM_HEAL : MSV_ITEM_BOX;
+      int inv = S.aint[d.slot * N + e].w, n = inv & 7;
+      bool has = alive(d.slot) && n > 0 && ((inv >> (4 + 2 * (n - 1))) & 3) == want;
+      if (d.src == OS_HEAL_SLOT) v = has ? (float)C.healing : 0.0f;
+      else if (d.src == OS_HEAL_SLOT_MASK || d.src == OS_BOX_SLOT_MASK) v = has ? 0.0f : 1.0f;
+      else if (has) { float4 pl = S.ainv[(d.slot * 4 + n - 1) * N + e]; v = vert(pl.x, pl.y, __float_as_int(pl.w) & 1, d.comp); }
+    } break;
+    case OS_BOX_VERT: case OS_BOX_POS: {
+      int nb = S.hdr0[e].x & 255;
+      if (d.slot < nb) {
+        float4 b0 = S.box0[d.slot * N + e];
+        if (d.src == OS_BOX_POS) v = d.comp == 0 ? b0.x : d.comp == 1 ? b0.y : 0.0f;
+        else v = vert(b0.z, b0.w, (S.box1[d.slot * N + e].y >> 1) & 1, d.comp);
+      }
+    } break;
+    case OS_ITEM_VERT: case OS_ITEM_POS: {
+      int ni = (S.hdr0[e].x >> 8) & 255;
+      if (d.slot < ni) {
+        float4 it = S.item0[d.slot * N + e];
+        if (d.src == OS_ITEM_POS) v = d.comp == 0 ? it.x : it.y;
+        else v = vert(it.z, it.w, 1, d.comp);
+      }
+    } break;
+    default: break;
+  }
+  const ObsKey k = Tb.keys[d.key];
+  k.base[(size_t)e * k.chunk + d.off] = v;
 }
 
 // flush_stats (env:471-480): sum the per-env accumulators, then zero them
-__global__ void k_stats(int N, int AC, float* sreward, int* skills, int4* smisc,
+__global__ void k_stats(int N, int stride, int AC, float* sreward, int* skills, int4* smisc,
                         double* out_reward, unsigned long long* out_kills, unsigned long long* out_misc) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   double r[MSV_MAX_AGENTS]; long long k[MSV_MAX_AGENTS]; long long m[4] = {0, 0, 0, 0};
   for (int i = 0; i < MSV_MAX_AGENTS; ++i) { r[i] = 0.0; k[i] = 0; }
   if (e < N) {
     for (int i = 0; i < AC; ++i) {
-      r[i] = sreward[i * N + e]; k[i] = skills[i * N + e];
-      sreward[i * N + e] = 0.0f; skills[i * N + e] = 0;
+      r[i] = sreward[i * stride + e]; k[i] = skills[i * stride + e];
+      sreward[i * stride + e] = 0.0f; skills[i * stride + e] = 0;
     }
     int4 s = smisc[e]; m[0] = s.x; m[1] = s.y; m[2] = s.z; m[3] = s.w;
     smisc[e] = make_int4(0, 0, 0, 0);
@@ -130,16 +191,15 @@ static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, con
                             const uint8_t* actions, cudaStream_t st) {
   int blocks = (C.N + MSV_TPB - 1) / MSV_TPB;
   size_t smem = (size_t)Env<AC, BC, HC>::SM_WORDS * MSV_TPB * sizeof(float);
-  if (which == 0) {
-    cudaFuncSetAttribute(k_step<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_step<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, actions);
-  } else if (which == 1) {
-    cudaFuncSetAttribute(k_reset<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_reset<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
-  } else {
-    cudaFuncSetAttribute(k_observe<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_observe<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
+  if (which == 3) {  // one-time: allow the dynamic shared memory the kernels need
+    cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_observe<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e;
   }
+  if (which == 0) k_step<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, actions);
+  else if (which == 1) k_reset<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
+  else k_observe<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
   return cudaPeekAtLastError();
 }
 
@@ -152,6 +212,12 @@ cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S,
   }
 }
 
+cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, cudaStream_t st) {
+  dim3 grid(C.n_real, (T.n_elems + 127) / 128);
+  k_obs<<<grid, 128, 0, st>>>(C, S, T, AC);
+  return cudaPeekAtLastError();
+}
+
 void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW) {
   switch (cap) {
     case 0: *AC = 2; *BC = 4; *HC = 4; *P = PairLayout<2, 4>::P; *PW = PairLayout<2, 4>::PW; break;
@@ -160,9 +226,9 @@ void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW) {
   }
 }
 
-cudaError_t msv_launch_stats(int N, int AC, float* sreward, int* skills, int4* smisc, double* out_reward,
+cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* skills, int4* smisc, double* out_reward,
                              unsigned long long* out_kills, unsigned long long* out_misc, cudaStream_t st) {
-  k_stats<<<(N + 127) / 128, 128, 0, st>>>(N, AC, sreward, skills, smisc, out_reward, out_kills, out_misc);
+  k_stats<<<(N + 127) / 128, 128, 0, st>>>(N, stride, AC, sreward, skills, smisc, out_reward, out_kills, out_misc);
   return cudaPeekAtLastError();
 }
 

@@ -10,7 +10,8 @@
 struct WallC { float px, py, qs, qc, ang; float fat[4]; };
 
 struct DevConst {
-  int N;                 // environments on this device
+  int N;                 // environments on this device, padded to a multiple of the block size (SoA stride)
+  int n_real;            // environments the caller asked for
   int A, B0, H0;         // n_agents, n_boxes, n_heals at reset
   int S;                 // agent row width: 8 (+1 with teams)
   int teams, omniscient, gameover_mode, health, melee_damage, melee_cooldown;
@@ -68,6 +69,7 @@ struct DevState {
   float* sreward;  // [AC][N]
   int* skills;     // [AC][N]
   int4* smisc;     // [N] steps, heals_used, boxes_placed, episodes
+  unsigned long long* obm;  // [N] others_mask bits (observer i sees agent j: bit i*AC+j)
 };
 
 struct DevOut {
@@ -90,3 +92,18 @@ struct DevOut {
   float* rewards;        // [N][A]
   uint8_t* dones;        // [N]
 };
+
+// ---- observation writer (k_obs) ------------------------------------------
+// One thread per output float.  The host flattens every observation key of
+// the config into a table of element descriptors (what to read, from which
+// slot/component, under which validity condition) so the kernel is a pure
+// gather from the SoA state with fully coalesced stores.
+enum ObsSrc : uint8_t {
+  OS_ZERO = 0, OS_AGENT_ID, OS_AGENT_TEAM, OS_AGENT_HEALTH, OS_AKIN0, OS_AKIN1, OS_OTHERS_MASK,
+  OS_ZONE_CUR, OS_ZONE_NEXT, OS_HEAL, OS_LIST_MASK, OS_HEAL_SLOT, OS_HEAL_SLOT_MASK,
+  OS_BOX_VERT, OS_BOX_POS, OS_ITEM_VERT, OS_ITEM_POS, OS_BOX_SLOT, OS_BOX_SLOT_MASK
+};
+struct ObsDesc { uint8_t src, slot, comp, aux; uint16_t key; uint16_t off; };
+struct ObsKey { float* base; int chunk; };
+#define MSV_OBS_KEYS 14
+struct ObsTable { const ObsDesc* desc; int n_elems; ObsKey keys[MSV_OBS_KEYS]; };

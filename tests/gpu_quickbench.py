@@ -33,7 +33,7 @@ def run(variant, N, steps=200, warm=50, prof=True):
         L.msv_debug_profile(h.h, 1, buf)
         for t in range(20): h.step(acts[t % 8].data_ptr())
         L.msv_debug_profile(h.h, 0, buf)
-        names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'observe', 'rewards+reset', 'store']
+        names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'observe', 'store']
         tot = sum(buf[:12])
         print('   phase cycles/thread/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(names)))
     h.close()
