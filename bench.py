@@ -120,8 +120,15 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     n_gpus = world
     N, A = args.envs, 4
-    env = MaSurvivalVec(variant(WORKLOAD), num_envs=N, device=local, seed=args.seed, env_offset=rank * N, auto_reset=True)
-    env.reset()
+    # ROT independent batches of N envs are stepped round-robin: their combined state +
+    # outputs (ROT x ~48 MB) exceed the 126 MB L2, so every step finds its data in HBM
+    # (timing rule: "inputs larger than L2") and no flush kernel perturbs the timed region.
+    ROT = args.rotate
+    envs = [MaSurvivalVec(variant(WORKLOAD), num_envs=N, device=local, seed=args.seed + r,
+                          env_offset=(rank * ROT + r) * N, auto_reset=True) for r in range(ROT)]
+    for e_ in envs:
+        e_.reset()
+    env = envs[0]
     dev = f'cuda:{local}'
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     NB = 8  # rotating pre-generated action batches
@@ -135,7 +142,7 @@ def run_ours(args):
     acts_host = acts_dev.cpu().pin_memory()
     rew_host = torch.empty((N, A), dtype=torch.float32).pin_memory()
     done_host = torch.empty((N,), dtype=torch.uint8).pin_memory()
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -145,42 +152,47 @@ def run_ours(args):
 
     # ---- device-resident arm ------------------------------------------------
     for t in range(args.warmup):
-        env.step(acts_dev[t % NB])
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        envs[t % ROT]._h.step(acts_dev[t % NB].data_ptr(), stream)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local); clk.start()
     barrier()
-    l0 = env.kernel_launches()
+    l0 = sum(e_.kernel_launches() for e_ in envs)
+    t0.record()
     for t in range(args.steps):
-        flush_buf.fill_(t & 255)          # evict state/obs from L2 (outside the event pair)
-        starts[t].record()
-        env._h.step(acts_dev[t % NB].data_ptr(), torch.cuda.current_stream().cuda_stream)
-        ends[t].record()
+        envs[t % ROT]._h.step(acts_dev[t % NB].data_ptr(), stream)
+    t1.record()
     barrier()
-    launches = env.kernel_launches() - l0
+    launches = sum(e_.kernel_launches() for e_ in envs) - l0
     clocks = clk.stop()
-    kernel_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = float(sum(kernel_ms))
+    total_ms = float(t0.elapsed_time(t1))
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX); total_ms = float(tt.item())
     ms_per_step = total_ms / args.steps
     value = n_gpus * N * A / (ms_per_step * 1e-3)
 
+    # ---- duration of the dominant kernel (k_step), CUDA events on the launch stream ----
+    ks = [torch.cuda.Event(enable_timing=True) for _ in range(64)]
+    ke = [torch.cuda.Event(enable_timing=True) for _ in range(64)]
+    for t in range(64):
+        ks[t].record()
+        envs[t % ROT]._h.step_kernel_only(acts_dev[t % NB].data_ptr(), stream)
+        ke[t].record()
+        envs[t % ROT]._h.observe_only(stream)
+    torch.cuda.synchronize()
+    kernel_ms = [s_.elapsed_time(e_) for s_, e_ in zip(ks, ke)]
+
     # ---- end-to-end arm: host buffers through msv_step_host ------------------
     for t in range(max(3, args.warmup // 4)):
-        env.step_host(acts_host[t % NB], rew_host, done_host)
+        envs[t % ROT].step_host(acts_host[t % NB], rew_host, done_host)
     barrier()
-    e2e_ms = 0.0
+    w0 = time.perf_counter()
+    t0.record()
     for t in range(args.steps):
-        flush_buf.fill_(t & 255)
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        env.step_host(acts_host[t % NB], rew_host, done_host)   # H2D + kernel + D2H + stream sync
-        e.record(); e.synchronize()
-        e2e_ms += s.elapsed_time(e)
+        envs[t % ROT].step_host(acts_host[t % NB], rew_host, done_host)   # H2D + kernels + D2H + stream sync
+    t1.record()
     barrier()
+    e2e_ms = float(t0.elapsed_time(t1))
     if world > 1:
         tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_ms = float(tt.item())
@@ -189,13 +201,13 @@ def run_ours(args):
 
     bytes_env = env.bytes_per_env_step()
     peak, peak_src = measured_peak()
-    kavg_ms = float(np.mean(kernel_ms))
+    kavg_ms = float(np.mean(kernel_ms[8:]))
     achieved = bytes_env * N / (kavg_ms * 1e-3) / 1e9
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': config_block(n_gpus, N, 'flushed between steps (256 MiB fill outside the per-step CUDA-event pairs; per-step times summed)'),
+        'config': config_block(n_gpus, N, f'{ROT} batches of {N} envs stepped round-robin (state+outputs {ROT}x~48 MB > 126 MB L2): inputs larger than L2, no flush'),
         'env_steps_per_sec': value / A,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': N * A * 6, 'd2h_bytes_per_step': N * A * 4 + N,
                 'api': 'MaSurvivalVec.step_host -> msv_step_host (pinned host buffers)', 'reward_checksum': checksum},
@@ -209,7 +221,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline(sample_envs=2048, steps=20)
         print(json.dumps(line))
-    env.close()
+    for e_ in envs:
+        e_.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -288,6 +301,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='environments per GPU')
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--rotate', type=int, default=4, help='independent env batches stepped round-robin (working set > L2)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -184,6 +185,8 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
     D->lidar_ang[r] = c->lidar_n > 1 ? r * (c->lidar_fov / (c->lidar_n - 1)) - c->lidar_fov / 2. : 0.0;
   D->seed_lo = (uint32_t)seed; D->seed_hi = (uint32_t)(seed >> 32);
   D->env_offset = (uint32_t)env_offset;
+  D->epw = 32;
+  if (const char* ev = getenv("MSV_EPW")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) D->epw = v; }
   return 0;
 }
 
@@ -429,6 +432,21 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
   return MSV_OK;
 }
 
+/* debug/bench: the two halves of msv_step separately, so that bench.py can put
+ * CUDA events around the dominant kernel alone */
+int msv_debug_step_kernel(msv_handle* h, const uint8_t* actions_dev, void* stream) {
+  if (!h || !actions_dev) return MSV_ERR_INVALID;
+  CK(msv_launch(h->cap, 0, h->C, h->S, h->O, actions_dev, (cudaStream_t)stream));
+  h->launches++;
+  return MSV_OK;
+}
+int msv_debug_obs_kernel(msv_handle* h, void* stream) {
+  if (!h) return MSV_ERR_INVALID;
+  CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, (cudaStream_t)stream));
+  h->launches++;
+  return MSV_OK;
+}
+
 int msv_reset(msv_handle* h, void* stream) { return h ? launch(h, 1, nullptr, stream) : MSV_ERR_INVALID; }
 int msv_observe(msv_handle* h, void* stream) { return h ? launch(h, 2, nullptr, stream) : MSV_ERR_INVALID; }
 int msv_step(msv_handle* h, const uint8_t* actions_dev, void* stream) {
@@ -660,7 +678,7 @@ int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }
 
 /* debug: enable / read the per-phase cycle profile of k_step (not part of
  * the stable ABI; used by tests/gpu_quickbench.py) */
-int msv_debug_profile(msv_handle* h, int enable, unsigned long long out[16]) {
+int msv_debug_profile(msv_handle* h, int enable, unsigned long long out[32]) {
   if (!h) return MSV_ERR_INVALID;
   CK(cudaSetDevice(h->device)); CK(cudaDeviceSynchronize());
   if (out) CK(msv_read_profile(out, 1));

@@ -348,10 +348,16 @@ DEV f2 point_at(f2 c0, f2 c, float beta) { return vadd(vmul(1.0f - beta, c0), vm
 #define TOI_TOUCHING 3
 #define TOI_SEPARATED 4
 
+#ifdef MSV_PROFILE
+__device__ unsigned long long g_dbg[8];
+#endif
 // b2TimeOfImpact(proxyA = box, proxyB = circle centre), tMax = 1
 __device__ __noinline__ int time_of_impact(const SBox& A, f2 c0, f2 c, float rB, float& tOut) {
   int state = 0; tOut = 1.0f;
   const float tMax = 1.0f;
+#ifdef MSV_PROFILE
+  long long dbg_t0 = clock64(); int dbg_roots = 0, dbg_push = 0;
+#endif
   float totalRadius = B2_POLY_RADIUS + rB;
   float target = fmax_(B2_LINEAR_SLOP, totalRadius - 3.0f * B2_LINEAR_SLOP);
   float tolerance = 0.25f * B2_LINEAR_SLOP;
@@ -359,6 +365,12 @@ __device__ __noinline__ int time_of_impact(const SBox& A, f2 c0, f2 c, float rB,
   int iter = 0;
   SimplexCache cache; cache.count = 0;
   for (;;) {
+    // One outer iteration is a pure function of (t1, simplex cache).  When it
+    // returns to the same (t1, cache) without finishing -- t1 already at tMax and
+    // the separating axis within tolerance of target while the true distance is
+    // not -- b2TimeOfImpact repeats it verbatim until iter == 20 and reports
+    // e_failed at t1; that fixed point is detected and cut short (same result).
+    const float t1_in = t1; const SimplexCache cache_in = cache;
     SBox xfA = box_at(A, t1); f2 pB = point_at(c0, c, t1);
     float distance = gjk_distance(cache, xfA, pB);
     if (distance <= 0.0f) { state = TOI_OVERLAPPED; tOut = 0.0f; break; }
@@ -421,18 +433,34 @@ __device__ __noinline__ int time_of_impact(const SBox& A, f2 c0, f2 c, float rB,
         if (rootIterCount & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
         else t = 0.5f * (a1 + a2);
         ++rootIterCount;
+#ifdef MSV_PROFILE
+        ++dbg_roots;
+#endif
         float s = evaluate(t);
         if (fabsf(s - target) < tolerance) { t2 = t; break; }
         if (s > target) { a1 = t; s1 = s; } else { a2 = t; s2 = s; }
         if (rootIterCount == 50) break;
       }
       ++pushBackIter;
+#ifdef MSV_PROFILE
+      ++dbg_push;
+#endif
       if (pushBackIter == 8) break;
     }
     ++iter;
     if (done) break;
     if (iter == 20) { state = TOI_FAILED; tOut = t1; break; }
+    if (t1 == t1_in && cache.count == cache_in.count && cache.metric == cache_in.metric &&
+        cache.indexA[0] == cache_in.indexA[0] && (cache.count < 2 || cache.indexA[1] == cache_in.indexA[1]) &&
+        (cache.count < 3 || cache.indexA[2] == cache_in.indexA[2])) {
+      state = TOI_FAILED; tOut = t1; break;
+    }
   }
+#ifdef MSV_PROFILE
+  atomicAdd(&g_dbg[0], 1ull); atomicMax(&g_dbg[1], (unsigned long long)iter); atomicMax(&g_dbg[2], (unsigned long long)dbg_roots);
+  atomicMax(&g_dbg[3], (unsigned long long)dbg_push); atomicMax(&g_dbg[4], (unsigned long long)(clock64() - dbg_t0));
+  atomicAdd(&g_dbg[5], (unsigned long long)(clock64() - dbg_t0));
+#endif
   return state;
 }
 

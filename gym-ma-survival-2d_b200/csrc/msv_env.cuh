@@ -79,6 +79,7 @@ struct Env {
   int use_heal, use_box;
   int new_box;
   TCon tcs[MAXC]; int ntc;
+  int dbg_toi_calls = 0, dbg_toi_guard = 0;
   // sensors
   unsigned seenA[AC];  // by PRE-death rank: bit j = agent j seen
   unsigned pre_alive;
@@ -336,7 +337,7 @@ struct Env {
   // b2ContactManager::FindNewContacts + AddPair over every body pair whose
   // fat AABBs overlap and that has no contact yet; new contacts are numbered
   // in ascending (proxyIdA, proxyIdB) order (creation sequence surrogate).
-  __device__ __noinline__ void find_new_contacts() {
+  __device__ __forceinline__ void find_new_contacts() {
     unsigned long long cand[PW];
 #pragma unroll
     for (int w = 0; w < PW; ++w) cand[w] = 0ull;
@@ -407,7 +408,7 @@ struct Env {
   }
 
   // b2ContactManager::Collide
-  __device__ __noinline__ void collide() {
+  __device__ __forceinline__ void collide() {
     ntc = 0;
     for (int w = 0; w < PW; ++w) {
       unsigned long long mbits = ex[w];
@@ -585,7 +586,7 @@ struct Env {
   // disjoint bodies, so all islands are built first and then advanced
   // together (per-island contact order, position-iteration early-out and sleep
   // decision are kept): a thread loops over ITS contacts once, not per seed.
-  __device__ __noinline__ void solve(float h, float dtRatio) {
+  __device__ __forceinline__ void solve(float h, float dtRatio) {
     for (int i = 0; i < C.A; ++i) AGF(i) &= ~(FL_ISLAND | FL_MOVED);
     for (int k = 0; k < ntc; ++k) tcs[k].flags = 0;
     int stack[AC], isl_of[AC];
@@ -691,6 +692,7 @@ struct Env {
     // per-contact toiCount: only contacts that produced events carry one
     int evP[8], evN[8], nev = 0;
     for (int guard = 0; guard < 64; ++guard) {
+      dbg_toi_guard++;
       int minP = -1, minSeq = -1; float minAlpha = 1.0f;
       for (int w = 0; w < PW; ++w) {
         // existing, enabled agent-vs-static contacts (pair index >= NAA), ascending
@@ -703,6 +705,7 @@ struct Env {
           int cnt = 0; for (int q = 0; q < nev; ++q) if (evP[q] == p) cnt = evN[q];
           if (cnt > B2_MAX_SUBSTEPS) continue;
           float beta;
+          dbg_toi_calls++;
           int state = time_of_impact(static_box(k), mk2(AG(F_C0X, i), AG(F_C0Y, i)), apos(i), C.agent_r, beta);
           float alpha0 = AG(F_ALPHA0, i);
           float alpha = 1.0f;
@@ -786,7 +789,7 @@ struct Env {
   // ======================================================================
   //                      SEMANTICS (pre_step / post_step)
   // ======================================================================
-  __device__ __noinline__ void pre_step(const uint8_t* act) {
+  __device__ __forceinline__ void pre_step(const uint8_t* act) {
     use_heal = 0; use_box = 0; new_box = 0;
     // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
     for (int q = 0; q < np; ++q) {
@@ -887,7 +890,7 @@ struct Env {
 
   // Cameras._update_seen (sim:336-354), agent targets (the only ones the
   // omniscient observation reads, env:692-703)
-  __device__ __noinline__ void cameras() {
+  __device__ __forceinline__ void cameras() {
     pre_alive = 0; int row = 0;
     int rowof[AC];
     for (int i = 0; i < AC; ++i) seenA[i] = 0;
@@ -948,7 +951,7 @@ struct Env {
 
   int n_deaths, deaths[AC], n_kills, kill_cause[AC];
 
-  __device__ __noinline__ void post_step_boxes() {
+  __device__ __forceinline__ void post_step_boxes() {
     // boxes/Health.post_step (sem:429-435) + Object.pre_despawn (sem:858-861, 911-912)
     for (int k = 0; k < nb;) {
       int4 b1 = S.box1[k * N + e];
@@ -964,7 +967,7 @@ struct Env {
     }
   }
   // agents/Cameras.post_step (sim:333-334) runs between the two halves
-  __device__ __noinline__ void post_step_rest() {
+  __device__ __forceinline__ void post_step_rest() {
     // agents/Health.post_step -> despawn(dead) (sem:429-448)
     n_deaths = 0; n_kills = 0;
     {
@@ -1081,7 +1084,7 @@ struct Env {
   }
 
   // compute_rewards (env:757-803), is_done (env:810-831), _update_stats (env:483-508)
-  __device__ __noinline__ bool rewards_done(DevOut& O) {
+  __device__ __forceinline__ bool rewards_done(DevOut& O) {
     const int A = C.A;
     float rew[AC]; int lk[AC];
     for (int i = 0; i < AC; ++i) { rew[i] = 0.0f; lk[i] = 0; }
@@ -1131,7 +1134,7 @@ struct Env {
   // RandomizeBoxShapes (sem:97-120), ThickRoomWalls, SafeZone.post_reset
   // (sem:739-756).  The numpy Generator is replaced by counter-based
   // Philox4x32-10 keyed by (seed, global env id, episode).
-  __device__ __noinline__ void reset() {
+  __device__ __forceinline__ void reset() {
     episode += 1; steps = 0;
     int n = C.grid_n;
     unsigned char perm[64];

@@ -11,18 +11,28 @@
 
 // debug phase profile (enabled by msv_debug_profile): sum over threads of the
 // clock64() cycles spent in each phase of k_step
-__device__ unsigned long long g_prof[16];
-#define PROF(k) do { if (C.profile) { long long _t = clock64(); atomicAdd(&g_prof[k], (unsigned long long)(_t - t_last)); t_last = _t; } } while (0)
+__device__ unsigned long long g_prof[32];   // [0..11] per-phase sums, [16+k] per-phase max over threads of one launch, [12] max total
+#ifdef MSV_PROFILE
+#define PROF(k) do { if (C.profile) { long long _t = clock64(); ph[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
+#else
+#define PROF(k) do { } while (0)
+#endif
 
 template <int AC, int BC, int HC>
 __global__ void __launch_bounds__(MSV_TPB)
 k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
        const __grid_constant__ DevOut Oc, const uint8_t* __restrict__ actions) {
   extern __shared__ float sm[];
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane_ = threadIdx.x & 31;
+  const int e = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * C.epw + lane_;
+  if (lane_ >= C.epw || e >= C.N) return;
   DevOut O = Oc;
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
+#ifdef MSV_PROFILE
   long long t_last = C.profile ? clock64() : 0;
+  const long long t_begin = t_last;
+  unsigned long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   env.load();
   uint8_t act[AC * 6];
   {
@@ -63,6 +73,17 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   PROF(10);
   env.store();
   PROF(11);
+#ifdef MSV_PROFILE
+  if (C.profile) {
+    for (int k = 0; k < 12; ++k) atomicAdd(&g_prof[k], ph[k]);
+    unsigned long long tot = (unsigned long long)(clock64() - t_begin);
+    unsigned long long prev = atomicMax(&g_prof[12], tot);
+    if (tot > prev) {   // (racy, indicative) phase breakdown + identity of the slowest thread so far
+      for (int k = 0; k < 12; ++k) g_prof[16 + k] = ph[k];
+      g_prof[13] = (unsigned long long)e; g_prof[14] = (unsigned long long)env.dbg_toi_calls; g_prof[15] = (unsigned long long)env.dbg_toi_guard;
+    }
+  }
+#endif
 }
 
 template <int AC, int BC, int HC>
@@ -70,7 +91,9 @@ __global__ void __launch_bounds__(MSV_TPB)
 k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
         const __grid_constant__ DevOut Oc) {
   extern __shared__ float sm[];
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane_ = threadIdx.x & 31;
+  const int e = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * C.epw + lane_;
+  if (lane_ >= C.epw || e >= C.N) return;
   DevOut O = Oc;
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
   env.load();
@@ -88,7 +111,9 @@ __global__ void __launch_bounds__(MSV_TPB)
 k_observe(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
           const __grid_constant__ DevOut Oc) {
   extern __shared__ float sm[];
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane_ = threadIdx.x & 31;
+  const int e = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * C.epw + lane_;
+  if (lane_ >= C.epw || e >= C.N) return;
   DevOut O = Oc;
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
   env.load();
@@ -189,7 +214,8 @@ __global__ void k_stats(int N, int stride, int AC, float* sreward, int* skills, 
 template <int AC, int BC, int HC>
 static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, const DevOut& O,
                             const uint8_t* actions, cudaStream_t st) {
-  int blocks = (C.N + MSV_TPB - 1) / MSV_TPB;
+  const int warps = (C.N + C.epw - 1) / C.epw;
+  int blocks = (warps + (MSV_TPB / 32) - 1) / (MSV_TPB / 32);
   size_t smem = (size_t)Env<AC, BC, HC>::SM_WORDS * MSV_TPB * sizeof(float);
   if (which == 3) {  // one-time: allow the dynamic shared memory the kernels need
     cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -232,9 +258,12 @@ cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* ski
   return cudaPeekAtLastError();
 }
 
-cudaError_t msv_read_profile(unsigned long long out[16], int reset) {
-  cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 16);
+cudaError_t msv_read_profile(unsigned long long out[32], int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 32);
   if (e != cudaSuccess) return e;
-  if (reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof z); }
+#ifdef MSV_PROFILE
+  { unsigned long long d[8]; cudaMemcpyFromSymbol(d, g_dbg, sizeof d); out[28] = d[0]; out[29] = d[1]; out[30] = d[2]; out[31] = d[4]; unsigned long long z8[8] = {0}; if (reset) cudaMemcpyToSymbol(g_dbg, z8, sizeof z8); }
+#endif
+  if (reset) { unsigned long long z[32] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof z); }
   return e;
 }

@@ -9,5 +9,5 @@ cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S,
 void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW);
 cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* skills, int4* smisc, double* out_reward,
                              unsigned long long* out_kills, unsigned long long* out_misc, cudaStream_t st);
-cudaError_t msv_read_profile(unsigned long long out[16], int reset);
+cudaError_t msv_read_profile(unsigned long long out[32], int reset);
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, cudaStream_t st);

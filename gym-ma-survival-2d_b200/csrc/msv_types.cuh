@@ -35,6 +35,7 @@ struct DevConst {
   double lidar_ang[MSV_MAX_LASERS];       // i*(fov/(n-1)) - fov/2, as Python doubles
   uint32_t seed_lo, seed_hi;
   uint32_t env_offset;
+  int epw;               // environments per warp (<= 32): fewer envs per warp = smaller union of divergent paths, more warps in flight
   int profile;           // debug: accumulate per-phase clock64() deltas into g_prof
 };
 

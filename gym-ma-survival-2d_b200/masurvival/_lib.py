@@ -67,6 +67,8 @@ def load():
     L.msv_last_error.argtypes = [vp]
     L.msv_last_error.restype = ctypes.c_char_p
     L.msv_philox4x32.argtypes = [vp, vp, vp]
+    L.msv_debug_step_kernel.argtypes = [vp, vp, vp]
+    L.msv_debug_obs_kernel.argtypes = [vp, vp]
     if L.msv_abi_version() != 1:
         raise MasurvError('libmasurv.so ABI version mismatch')
     for name, dt in (('msv_sizeof_config', CONFIG_DT), ('msv_sizeof_env_state', STATE_DT),
@@ -136,6 +138,12 @@ class Handle:
 
     def step(self, actions_dev_ptr, stream=0):
         check(load().msv_step(self.h, actions_dev_ptr, stream), self.h)
+
+    def step_kernel_only(self, actions_dev_ptr, stream=0):
+        check(load().msv_debug_step_kernel(self.h, actions_dev_ptr, stream), self.h)
+
+    def observe_only(self, stream=0):
+        check(load().msv_debug_obs_kernel(self.h, stream), self.h)
 
     def step_host(self, actions, rewards, dones, stream=0):
         check(load().msv_step_host(self.h, actions, rewards, dones, stream), self.h)

@@ -29,10 +29,11 @@ def run(variant, N, steps=200, warm=50, prof=True):
         import ctypes
         L = _lib.load()
         L.msv_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
-        buf = (ctypes.c_ulonglong * 16)()
+        buf = (ctypes.c_ulonglong * 32)()
         L.msv_debug_profile(h.h, 1, buf)
         for t in range(20): h.step(acts[t % 8].data_ptr())
         L.msv_debug_profile(h.h, 0, buf)
+        print('   max over threads (any of 20 launches): total=%d; ' % buf[12] + ', '.join(f'{n}={buf[16+i]}' for i, n in enumerate(['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'observe', 'store'])))
         names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'observe', 'store']
         tot = sum(buf[:12])
         print('   phase cycles/thread/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(names)))
