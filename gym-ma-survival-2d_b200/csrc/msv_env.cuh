@@ -79,7 +79,9 @@ struct Env {
   int use_heal, use_box;
   int new_box;
   TCon tcs[MAXC]; int ntc;
-  int dbg_toi_calls = 0, dbg_toi_guard = 0;
+#ifdef MSV_PROFILE
+  int dbg_toi_calls = 0, dbg_toi_guard = 0; long long dbg_scan = 0, dbg_event = 0;
+#endif
   // sensors
   unsigned seenA[AC];  // by PRE-death rank: bit j = agent j seen
   unsigned pre_alive;
@@ -394,8 +396,9 @@ struct Env {
   }
 
   // b2Contact::Update for one pair; returns touching.  Appends to tcs.
-  DEV bool contact_update(int p, int a, int sid, int b, bool list) {
+  DEV bool contact_update(int p, int a, int sid, int b, bool list, Manifold* mout = nullptr) {
     Manifold m; bool touching = evaluate(a, sid, b, m);
+    if (mout) *mout = m;
     bool was = bit(tc, p);
     setb(en, p);
     float2 imp = make_float2(0.0f, 0.0f);
@@ -547,6 +550,55 @@ struct Env {
     put_pos(t.a, A); put_pos(t.b, B);
     return separation;
   }
+  // ---- contacts whose body A is static (walls, boxes): the A side of every
+  // solver update is multiplied by invMass = invI = 0, and in the position
+  // solver rB == 0 (the manifold point is the circle centre).  Dropping those
+  // exact no-ops lets the agent's state stay in registers across iterations;
+  // the arithmetic that remains is bit-identical to the generic routines.
+  DEV void warm_start_static(const TCon& t, f2& vB, float& wB) {
+    f2 tangent = cross_vs(t.normal, 1.0f);
+    f2 Pv = vadd(vmul(t.ni, t.normal), vmul(t.ti, tangent));
+    wB += C.inv_I * vcross(t.rB, Pv);
+    vB = vadd(vB, vmul(C.inv_mass, Pv));
+  }
+  DEV void solve_velocity_static(TCon& t, f2& vB, float& wB) {
+    const f2 normal = t.normal, tangent = cross_vs(normal, 1.0f);
+    {
+      f2 dv = vadd(vB, cross_sv(wB, t.rB));
+      float vt = vdot(dv, tangent) - 0.0f;
+      float lambda = t.tangentMass * (-vt);
+      float maxFriction = C.friction * t.ni;
+      float newImpulse = fclamp_(t.ti + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - t.ti; t.ti = newImpulse;
+      f2 Pv = vmul(lambda, tangent);
+      vB = vadd(vB, vmul(C.inv_mass, Pv)); wB += C.inv_I * vcross(t.rB, Pv);
+    }
+    {
+      f2 dv = vadd(vB, cross_sv(wB, t.rB));
+      float vn = vdot(dv, normal);
+      float lambda = -t.normalMass * (vn - 0.0f);
+      float newImpulse = fmax_(t.ni + lambda, 0.0f);
+      lambda = newImpulse - t.ni; t.ni = newImpulse;
+      f2 Pv = vmul(lambda, normal);
+      vB = vadd(vB, vmul(C.inv_mass, Pv)); wB += C.inv_I * vcross(t.rB, Pv);
+    }
+  }
+  // world normal and plane point of a static face contact (constant while solving)
+  DEV void static_plane(const TCon& t, f2& normal, f2& planePoint) {
+    SBox bx = static_box(t.sid);
+    normal = qmul(bx.qs, bx.qc, t.m.localNormal);
+    planePoint = sb_mul(bx, t.m.localPoint);
+  }
+  DEV float solve_position_static(f2 normal, f2 planePoint, f2& cB, bool toi) {
+    float separation = vdot(vsub(cB, planePoint), normal) - B2_POLY_RADIUS - C.agent_r;
+    float Cc = fclamp_((toi ? B2_TOI_BAUMGARTE : B2_BAUMGARTE) * (separation + B2_LINEAR_SLOP), -B2_MAX_LIN_CORR, 0.0f);
+    float K = C.inv_mass;                       // mA + mB + iA*rnA^2 + iB*rnB^2 with mA = iA = 0, rnB = 0
+    float impulse = K > 0.0f ? -Cc / K : 0.0f;
+    f2 Pv = vmul(impulse, normal);
+    cB = vadd(cB, vmul(C.inv_mass, Pv));        // aB += iB * cross(0, P) == aB
+    return separation;
+  }
+
   DEV void integrate_position(int i, float h) {  // b2Island::Solve "Integrate positions"
     f2 v = mk2(AG(F_VX, i), AG(F_VY, i)); float w = AG(F_W, i);
     f2 translation = vmul(h, v);
@@ -592,6 +644,7 @@ struct Env {
     int stack[AC], isl_of[AC];
     unsigned char order[MAXC], cisl[MAXC];
     int nisl = 0, nc = 0;
+    unsigned multi = 0;                        // islands that contain an agent-agent contact
     for (int seed = C.A - 1; seed >= 0; --seed) {
       int fs = AGF(seed);
       if (!(fs & FL_ALIVE) || (fs & FL_ISLAND) || !(fs & FL_AWAKE)) continue;
@@ -616,6 +669,7 @@ struct Env {
           order[nc] = (unsigned char)best; cisl[nc] = (unsigned char)nisl; nc++;
           const TCon& t = tcs[best];
           if (t.a >= 0) {
+            multi |= 1u << nisl;
             int other = t.a == bI ? t.b : t.a;
             if (!(AGF(other) & FL_ISLAND)) { stack[sc++] = other; AGF(other) |= FL_ISLAND; }
           }
@@ -635,24 +689,51 @@ struct Env {
     if (nc > 0) {
       for (int k = 0; k < nc; ++k) { TCon& t = tcs[order[k]]; t.ni = dtRatio * t.ni; t.ti = dtRatio * t.ti; }
       for (int k = 0; k < nc; ++k) init_velocity(tcs[order[k]]);
-      for (int k = 0; k < nc; ++k) warm_start(tcs[order[k]]);
-      for (int it = 0; it < 10; ++it)
-        for (int k = 0; k < nc; ++k) solve_velocity(tcs[order[k]]);
+      for (int k0 = 0; k0 < nc;) {             // one island = one contiguous run of `order`
+        const int j = cisl[k0]; int k1 = k0;
+        while (k1 < nc && cisl[k1] == j) ++k1;
+        if ((multi >> j) & 1u) {               // agents touching agents: generic two-body updates
+          for (int k = k0; k < k1; ++k) warm_start(tcs[order[k]]);
+          for (int it = 0; it < 10; ++it)
+            for (int k = k0; k < k1; ++k) solve_velocity(tcs[order[k]]);
+        } else {                               // one agent against static bodies: state in registers
+          const int i = tcs[order[k0]].b;
+          f2 vB = mk2(AG(F_VX, i), AG(F_VY, i)); float wB = AG(F_W, i);
+          for (int k = k0; k < k1; ++k) warm_start_static(tcs[order[k]], vB, wB);
+          for (int it = 0; it < 10; ++it)
+            for (int k = k0; k < k1; ++k) solve_velocity_static(tcs[order[k]], vB, wB);
+          AG(F_VX, i) = vB.x; AG(F_VY, i) = vB.y; AG(F_W, i) = wB;
+        }
+        k0 = k1;
+      }
       for (int k = 0; k < nc; ++k) { const TCon& t = tcs[order[k]]; S.pimp[t.p * N + e] = make_float2(t.ni, t.ti); }
     }
     for (int i = 0; i < C.A; ++i) if (AGF(i) & FL_ISLAND) integrate_position(i, h);
-    if (nc > 0) {
-      for (int it = 0; it < 10 && solved != all_isl; ++it) {
-        unsigned bad = 0;                      // islands whose minSeparation < -3 slop this pass
-        for (int k = 0; k < nc; ++k) {
-          unsigned ib = 1u << cisl[k];
-          if (solved & ib) continue;
-          float sep = solve_position(tcs[order[k]], false, -1);
-          if (!(fmin_(0.0f, sep) >= -3.0f * B2_LINEAR_SLOP)) bad |= ib;
+    solved = all_isl;
+    for (int k0 = 0; k0 < nc;) {
+      const int j = cisl[k0]; int k1 = k0;
+      while (k1 < nc && cisl[k1] == j) ++k1;
+      bool ok = false;
+      if ((multi >> j) & 1u) {
+        for (int it = 0; it < 10 && !ok; ++it) {
+          float minSep = 0.0f;
+          for (int k = k0; k < k1; ++k) minSep = fmin_(minSep, solve_position(tcs[order[k]], false, -1));
+          ok = minSep >= -3.0f * B2_LINEAR_SLOP;
         }
-        solved |= all_isl & ~bad;
+      } else {
+        const int i = tcs[order[k0]].b;
+        f2 cB = apos(i);
+        for (int k = k0; k < k1; ++k) { TCon& t = tcs[order[k]]; static_plane(t, t.normal, t.rA); }  // rA := plane point
+        for (int it = 0; it < 10 && !ok; ++it) {
+          float minSep = 0.0f;
+          for (int k = k0; k < k1; ++k) { const TCon& t = tcs[order[k]]; minSep = fmin_(minSep, solve_position_static(t.normal, t.rA, cB, false)); }
+          ok = minSep >= -3.0f * B2_LINEAR_SLOP;
+        }
+        AG(F_CX, i) = cB.x; AG(F_CY, i) = cB.y;
       }
-    } else solved = all_isl;
+      if (!ok) solved &= ~(1u << j);
+      k0 = k1;
+    }
     {
       const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
       unsigned can_sleep = solved;             // islands with minSleepTime >= timeToSleep && positionSolved
@@ -691,9 +772,15 @@ struct Env {
     for (int i = 0; i < C.A; ++i) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
     // per-contact toiCount: only contacts that produced events carry one
     int evP[8], evN[8], nev = 0;
+    // cached TOIs (b2Contact::e_toiFlag / m_toi): valid until the contact's agent is displaced
+    constexpr int MAXT = 12;
+    int cP[MAXT]; float cAlpha[MAXT]; int ncache = 0;
     for (int guard = 0; guard < 64; ++guard) {
+#ifdef MSV_PROFILE
       dbg_toi_guard++;
-      int minP = -1, minSeq = -1; float minAlpha = 1.0f;
+      long long dbg_t0 = clock64();
+#endif
+      int minP = -1; float minAlpha = 1.0f;
       for (int w = 0; w < PW; ++w) {
         // existing, enabled agent-vs-static contacts (pair index >= NAA), ascending
         unsigned long long mbits = ex[w] & en[w];
@@ -704,24 +791,38 @@ struct Env {
           if (!alive(i) || !awake(i)) continue;
           int cnt = 0; for (int q = 0; q < nev; ++q) if (evP[q] == p) cnt = evN[q];
           if (cnt > B2_MAX_SUBSTEPS) continue;
-          float beta;
-          dbg_toi_calls++;
-          int state = time_of_impact(static_box(k), mk2(AG(F_C0X, i), AG(F_C0Y, i)), apos(i), C.agent_r, beta);
-          float alpha0 = AG(F_ALPHA0, i);
-          float alpha = 1.0f;
-          if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
-          if (alpha < minAlpha || (alpha == minAlpha && minP >= 0 && alpha < 1.0f && (int)S.pseq[p * N + e] > minSeq)) {
-            minAlpha = alpha; minP = p; minSeq = (int)S.pseq[p * N + e];
+          float alpha = 1.0f; bool have = false;
+          for (int q = 0; q < ncache; ++q) if (cP[q] == p) { alpha = cAlpha[q]; have = true; }
+          if (!have) {
+            float beta;
+#ifdef MSV_PROFILE
+            dbg_toi_calls++;
+#endif
+            int state = time_of_impact(static_box(k), mk2(AG(F_C0X, i), AG(F_C0Y, i)), apos(i), C.agent_r, beta);
+            float alpha0 = AG(F_ALPHA0, i);
+            if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+            if (ncache < MAXT) { cP[ncache] = p; cAlpha[ncache] = alpha; ncache++; }
+          }
+          // the world contact list is newest first and the scan keeps the FIRST minimum:
+          // on equal alpha the contact with the larger creation sequence wins
+          if (alpha < minAlpha || (alpha == minAlpha && minP >= 0 && alpha < 1.0f &&
+                                   S.pseq[p * N + e] > S.pseq[minP * N + e])) {
+            minAlpha = alpha; minP = p;
           }
         }
       }
+#ifdef MSV_PROFILE
+      long long dbg_t1 = clock64(); dbg_scan += dbg_t1 - dbg_t0;
+#endif
       if (minP < 0 || 1.0f - 10.0f * B2_EPS < minAlpha) break;
       int a, sid, b; decode(minP, a, sid, b);
+      { int q = 0; while (q < ncache) { if (cP[q] == minP) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q; } }
       // backup the agent's sweep, advance to the TOI, re-evaluate the contact
       float bk[7] = {AG(F_C0X, b), AG(F_C0Y, b), AG(F_CX, b), AG(F_CY, b), AG(F_A0, b), AG(F_A, b), AG(F_ALPHA0, b)};
       advance(b, minAlpha);
       int save_ntc = ntc;
-      bool touching = contact_update(minP, a, sid, b, false);
+      Manifold m_min;
+      bool touching = contact_update(minP, a, sid, b, false, &m_min);
       {
         int q = 0; for (; q < nev; ++q) if (evP[q] == minP) break;
         if (q == nev && nev < 8) { evP[nev] = minP; evN[nev] = 0; nev++; }
@@ -738,9 +839,8 @@ struct Env {
       // contacts against statics, newest first
       TCon isl[8]; int nisl = 0;
       {
-        Manifold m; evaluate(a, sid, b, m);
         TCon& t = isl[nisl++];
-        t.p = minP; t.seq = 0; t.a = -1; t.sid = sid; t.b = b; t.flags = 0; t.m = m; t.ni = 0.0f; t.ti = 0.0f;
+        t.p = minP; t.seq = 0; t.a = -1; t.sid = sid; t.b = b; t.flags = 0; t.m = m_min; t.ni = 0.0f; t.ti = 0.0f;
       }
       {
         unsigned long long done[PW];
@@ -760,29 +860,48 @@ struct Env {
           setb(done, best);
           if (nisl >= 8) { overflow++; break; }
           int a2, sid2, b2; decode(best, a2, sid2, b2);
-          bool t2 = contact_update(best, a2, sid2, b2, false);
+          Manifold m;
+          bool t2 = contact_update(best, a2, sid2, b2, false, &m);
           if (!t2) continue;
-          Manifold m; evaluate(a2, sid2, b2, m);
           TCon& t = isl[nisl++];
           t.p = best; t.seq = 0; t.a = -1; t.sid = sid2; t.b = b; t.flags = 0; t.m = m; t.ni = 0.0f; t.ti = 0.0f;
         }
       }
       ntc = save_ntc;
       float subdt = (1.0f - minAlpha) * dt;
-      // b2Island::SolveTOI
-      for (int it = 0; it < 20; ++it) {
-        float minSep = 0.0f;
-        for (int k = 0; k < nisl; ++k) minSep = fmin_(minSep, solve_position(isl[k], true, b));
-        if (minSep >= -1.5f * B2_LINEAR_SLOP) break;
+      // b2Island::SolveTOI -- every contact of the mini island has a static body A
+      {
+        f2 cB = apos(b);
+        for (int k = 0; k < nisl; ++k) static_plane(isl[k], isl[k].normal, isl[k].rA);  // rA := plane point
+        for (int it = 0; it < 20; ++it) {
+          float minSep = 0.0f;
+          for (int k = 0; k < nisl; ++k) minSep = fmin_(minSep, solve_position_static(isl[k].normal, isl[k].rA, cB, true));
+          if (minSep >= -1.5f * B2_LINEAR_SLOP) break;
+        }
+        AG(F_CX, b) = cB.x; AG(F_CY, b) = cB.y;
       }
       AG(F_C0X, b) = AG(F_CX, b); AG(F_C0Y, b) = AG(F_CY, b); AG(F_A0, b) = AG(F_A, b);
       for (int k = 0; k < nisl; ++k) init_velocity(isl[k]);
-      for (int it = 0; it < 10; ++it)
-        for (int k = 0; k < nisl; ++k) solve_velocity(isl[k]);
+      {
+        f2 vB = mk2(AG(F_VX, b), AG(F_VY, b)); float wB = AG(F_W, b);
+        for (int it = 0; it < 10; ++it)
+          for (int k = 0; k < nisl; ++k) solve_velocity_static(isl[k], vB, wB);
+        AG(F_VX, b) = vB.x; AG(F_VY, b) = vB.y; AG(F_W, b) = wB;
+      }
       integrate_position(b, subdt);
       AGF(b) &= ~FL_MOVED;
       synchronize_fixtures(b);
       if (AGF(b) & FL_MOVED) find_new_contacts();
+      {  // "Invalidate all contact TOIs on this displaced body"
+        int q = 0;
+        while (q < ncache) {
+          int a3, s3, b3; decode(cP[q], a3, s3, b3);
+          if (b3 == b) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q;
+        }
+      }
+#ifdef MSV_PROFILE
+      dbg_event += clock64() - dbg_t1;
+#endif
     }
   }
 

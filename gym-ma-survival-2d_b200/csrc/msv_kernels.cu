@@ -80,7 +80,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     unsigned long long prev = atomicMax(&g_prof[12], tot);
     if (tot > prev) {   // (racy, indicative) phase breakdown + identity of the slowest thread so far
       for (int k = 0; k < 12; ++k) g_prof[16 + k] = ph[k];
-      g_prof[13] = (unsigned long long)e; g_prof[14] = (unsigned long long)env.dbg_toi_calls; g_prof[15] = (unsigned long long)env.dbg_toi_guard;
+      g_prof[13] = (unsigned long long)e; g_prof[14] = (unsigned long long)env.dbg_toi_calls; g_prof[15] = (unsigned long long)env.dbg_toi_guard; g_prof[16 + 10] = (unsigned long long)env.dbg_scan; g_prof[16 + 11] = (unsigned long long)env.dbg_event;
     }
   }
 #endif

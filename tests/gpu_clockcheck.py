@@ -32,7 +32,7 @@ def run(mode, steps=40, rot=4):
     ms = np.array([a.elapsed_time(b) for a, b in ev])
     L.msv_debug_profile(hs[0].h, 0, buf)
     tot = sum(buf[:12]) / N / steps
-    names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'obm', 'store']
+    names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'TOI_SCAN', 'TOI_EVENT']
     print('   slowest thread: env', buf[13], 'toi_calls', buf[14], 'toi_guard_iters', buf[15], {n: buf[16 + i] for i, n in enumerate(names)})
     print('   TOI calls', buf[28], 'max outer iters', buf[29], 'max root iters/call', buf[30], 'max cycles/call', buf[31])
     print(f'{mode:14s} rot={rot}: k_step ms mean={ms.mean():.3f} min={ms.min():.3f} max={ms.max():.3f}; avg thread cycles={tot:.0f}, max thread cycles={buf[12]}, '
