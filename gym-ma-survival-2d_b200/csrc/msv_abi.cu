@@ -296,7 +296,6 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
       cfg->inv_slots < 1 || cfg->inv_slots > MSV_MAX_SLOTS || cfg->zone_n_radiuses + 1 > MSV_MAX_ZONES ||
       cfg->zone_phases > cfg->zone_n_radiuses + 1 || cfg->lidar_n < 0 || cfg->lidar_n > MSV_MAX_LASERS)
     return MSV_ERR_INVALID;
-  if (!cfg->omniscient) return MSV_ERR_INVALID;  // not built yet
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
     g_err = "no CUDA device: libmasurv has no CPU fallback";
@@ -336,7 +335,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   rc |= dalloc(h, &O.box_slot, N * A * 8); rc |= dalloc(h, &O.box_slot_mask, N * A);
   rc |= dalloc(h, &O.lidar_frac, N * A * L); rc |= dalloc(h, &O.lidar_hit, N * A * L);
   rc |= dalloc(h, &O.rewards, N * A); rc |= dalloc(h, &O.dones, N);
-  rc |= dalloc(h, &S.obm, N);
+  rc |= dalloc(h, &S.obm, N); rc |= dalloc(h, &S.omask, AC * N);
   rc |= dalloc(h, &h->d_actions, N * A * 6);
   rc |= dalloc(h, &h->d_stat_reward, (size_t)MSV_MAX_AGENTS); rc |= dalloc(h, &h->d_stat_kills, (size_t)MSV_MAX_AGENTS);
   rc |= dalloc(h, &h->d_stat_misc, (size_t)4);
@@ -370,7 +369,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
     for (int c2 = 0; c2 < 3; ++c2) { add(3, c2, OS_ZONE_CUR, 0, c2, 0); add(3, 3 + c2, OS_ZONE_NEXT, 0, c2, 0); }
     if (Hi > 0) {
       for (int k = 0; k < Hi; ++k) { add(4, 2 * k, OS_HEAL, k, 0, 0); add(4, 2 * k + 1, OS_HEAL, k, 1, 0); }
-      for (int i = 0; i < Ai; ++i) { for (int k = 0; k < Hi; ++k) add(5, i * Hi + k, OS_LIST_MASK, k, 0, 2); add(6, i, OS_HEAL_SLOT, i, 0, 0); add(7, i, OS_HEAL_SLOT_MASK, i, 0, 0); }
+      for (int i = 0; i < Ai; ++i) { for (int k = 0; k < Hi; ++k) add(5, i * Hi + k, OS_LIST_MASK, k, i, 2); add(6, i, OS_HEAL_SLOT, i, 0, 0); add(7, i, OS_HEAL_SLOT_MASK, i, 0, 0); }
     }
     if (Bi > 0) {
       for (int k = 0; k < Bi; ++k) {
@@ -379,7 +378,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
         for (int c2 = 0; c2 < 2; ++c2) add(10, k * 10 + 8 + c2, OS_ITEM_POS, k, c2, 0);
       }
       for (int i = 0; i < Ai; ++i) {
-        for (int k = 0; k < Bi; ++k) { add(9, i * Bi + k, OS_LIST_MASK, k, 0, 0); add(11, i * Bi + k, OS_LIST_MASK, k, 0, 1); }
+        for (int k = 0; k < Bi; ++k) { add(9, i * Bi + k, OS_LIST_MASK, k, i, 0); add(11, i * Bi + k, OS_LIST_MASK, k, i, 1); }
         for (int c2 = 0; c2 < 8; ++c2) add(12, i * 8 + c2, OS_BOX_SLOT, i, c2, 0);
         add(13, i, OS_BOX_SLOT_MASK, i, 0, 0);
       }
@@ -674,6 +673,7 @@ int64_t msv_bytes_per_env_step(msv_handle* h) {
   if (L > 0) obs += 8 * A * L;
   return state_r + state_w + A * 6 + obs + 4 * A + 1;
 }
+int64_t msv_obs_bytes_per_env(msv_handle* h) { return h ? (int64_t)h->obs.n_elems * 4 : 0; }
 int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }
 
 /* debug: enable / read the per-phase cycle profile of k_step (not part of

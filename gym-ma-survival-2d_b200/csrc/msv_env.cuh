@@ -84,6 +84,7 @@ struct Env {
 #endif
   // sensors
   unsigned seenA[AC];  // by PRE-death rank: bit j = agent j seen
+  unsigned seenX[AC];  // non-omniscient only: bits 0-15 heals, 16-23 boxes, 24-31 box items (list positions)
   unsigned pre_alive;
 
   __device__ Env(const DevConst& c, const DevState& s, float* smem, int T_, int tid_, int e_)
@@ -1009,42 +1010,78 @@ struct Env {
 
   // Cameras._update_seen (sim:336-354), agent targets (the only ones the
   // omniscient observation reads, env:692-703)
+  DEV bool in_cone(f2 pl) {                          // b2PolygonShape::TestPoint(vision cone)
+    bool inside = true;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      float d = vdot(mk2(C.cone_n[v][0], C.cone_n[v][1]), vsub(pl, mk2(C.cone_v[v][0], C.cone_v[v][1])));
+      if (d > 0.0f) inside = false;
+    }
+    return inside;
+  }
+  // position of camera target t: [0,AC) agents, then BC boxes, BC box items, HC heals
+  DEV f2 target_pos(int t) {
+    if (t < AC) return apos(t);
+    t -= AC;
+    if (t < BC) return mk2(BX(G_X, t), BX(G_Y, t));
+    t -= BC;
+    if (t < BC) { float4 it = S.item0[t * N + e]; return mk2(it.x, it.y); }
+    t -= BC;
+    float2 h = S.heal[t * N + e]; return mk2(h.x, h.y);
+  }
   __device__ __forceinline__ void cameras() {
     pre_alive = 0; int row = 0;
     int rowof[AC];
-    for (int i = 0; i < AC; ++i) seenA[i] = 0;
-    // pass 1: which (observer i, target j) pairs have the target inside the cone
-    unsigned long long incone = 0ull;                 // bit i*AC + j
+    for (int i = 0; i < AC; ++i) { seenA[i] = 0; seenX[i] = 0; }
+    const bool all_bodies = !C.omniscient;            // env:706-739 read the full seen-lists
+    // pass 1: which (observer i, target t) pairs have the target's centre inside the cone
+    unsigned long long incone[AC];
+    for (int i = 0; i < AC; ++i) incone[i] = 0ull;
     for (int i = 0; i < C.A; ++i) {
       rowof[i] = -1;
       if (!alive(i)) continue;
       pre_alive |= 1u << i; rowof[i] = row++;
       f2 me = apos(i); float s, c; rot_set(AG(F_A, i), s, c);
-      for (int j = 0; j < C.A; ++j) {
-        if (j == i || !alive(j)) continue;
-        f2 pl = qmulT(s, c, vsub(apos(j), me));      // b2PolygonShape::TestPoint(cone)
-        bool inside = true;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          float d = vdot(mk2(C.cone_n[v][0], C.cone_n[v][1]), vsub(pl, mk2(C.cone_v[v][0], C.cone_v[v][1])));
-          if (d > 0.0f) inside = false;
-        }
-        if (inside) incone |= 1ull << (i * AC + j);
+      unsigned long long m = 0ull;
+      for (int j = 0; j < C.A; ++j)
+        if (j != i && alive(j) && in_cone(qmulT(s, c, vsub(apos(j), me)))) m |= 1ull << j;
+      if (all_bodies) {
+        for (int k = 0; k < nb; ++k) if (in_cone(qmulT(s, c, vsub(target_pos(AC + k), me)))) m |= 1ull << (AC + k);
+        for (int k = 0; k < ni; ++k) if (in_cone(qmulT(s, c, vsub(target_pos(AC + BC + k), me)))) m |= 1ull << (AC + BC + k);
+        for (int k = 0; k < nh; ++k) if (in_cone(qmulT(s, c, vsub(target_pos(AC + 2 * BC + k), me)))) m |= 1ull << (AC + 2 * BC + k);
       }
+      incone[i] = m;
     }
     // pass 2: one line-of-sight ray per in-cone pair (a thread walks ITS list)
-    while (incone) {
-      int q = __ffsll((long long)incone) - 1; incone &= incone - 1;
-      int i = q / AC, j = q % AC;
-      f2 me = apos(i), o = apos(j);
-      f2 d = vsub(o, me);
-      f2 end = mk2(me.x + C.cam_k1 * d.x, me.y + C.cam_k1 * d.y);
-      int idx; float fr;
-      int kind = raycast(me, end, i, idx, fr);
-      if (kind == KIND_AGENT && idx == j) {
-#pragma unroll
-        for (int r = 0; r < AC; ++r) if (r == rowof[i]) seenA[r] |= 1u << j;
+    for (int i = 0; i < C.A; ++i) {
+      unsigned long long m = incone[i];
+      unsigned sa = 0, sx = 0;
+      while (m) {
+        int t = __ffsll((long long)m) - 1; m &= m - 1;
+        f2 me = apos(i), o = target_pos(t);
+        f2 d = vsub(o, me);
+        f2 end = mk2(me.x + C.cam_k1 * d.x, me.y + C.cam_k1 * d.y);
+        int idx; float fr;
+        int kind = raycast(me, end, i, idx, fr);
+        if (t < AC) { if (kind == KIND_AGENT && idx == t) sa |= 1u << t; }
+        else if (t < AC + BC) { if (kind == KIND_BOX && idx == t - AC) sx |= 1u << (16 + t - AC); }
+        else if (t < AC + 2 * BC) { if (kind == KIND_ITEM && idx == t - AC - BC) sx |= 1u << (24 + t - AC - BC); }
+        else { if (kind == KIND_HEAL && idx == t - AC - 2 * BC) sx |= 1u << (t - AC - 2 * BC); }
       }
+      if (rowof[i] >= 0) {
+#pragma unroll
+        for (int r = 0; r < AC; ++r) if (r == rowof[i]) { seenA[r] = sa; seenX[r] = sx; }
+      }
+    }
+  }
+  // a floor item / heal left its list after the cameras ran: compact the seen bits
+  DEV void seen_remove(int first_bit, int width, int k) {
+#pragma unroll
+    for (int r = 0; r < AC; ++r) {
+      unsigned field = (seenX[r] >> first_bit) & ((1u << width) - 1u);
+      unsigned lowm = (1u << k) - 1u;
+      field = (field & lowm) | ((field >> (k + 1)) << k);
+      seenX[r] = (seenX[r] & ~(((1u << width) - 1u) << first_bit)) | (field << first_bit);
     }
   }
 
@@ -1136,11 +1173,11 @@ struct Env {
           if (bkind == KIND_NONE) break;
           lastSeq = bestSeq;
           if (inv_n(i) + 1 > C.inv_slots) continue;  // sem:184-185
-          if (bkind == KIND_HEAL) { inv_push(i, MSV_ITEM_HEAL, make_float4(0.f, 0.f, 0.f, 0.f)); remove_heal(bidx); }
+          if (bkind == KIND_HEAL) { inv_push(i, MSV_ITEM_HEAL, make_float4(0.f, 0.f, 0.f, 0.f)); remove_heal(bidx); seen_remove(0, 16, bidx); }
           else {
             float4 it = S.item0[bidx * N + e]; int2 i1 = S.item1[bidx * N + e];
             inv_push(i, MSV_ITEM_BOX, make_float4(it.z, it.w, __int_as_float(i1.x), __int_as_float(1)));
-            remove_item(bidx);
+            remove_item(bidx); seen_remove(24, 8, bidx);
           }
         }
       }
@@ -1194,6 +1231,18 @@ struct Env {
         if (j != i && alive(j) && ((sr >> j) & 1u)) bits |= 1ull << (i * AC + j);
     }
     S.obm[e] = bits;
+    if (!C.omniscient) {   // env:706-739: zip(agents.bodies, cameras.seen) -> same Q1 row remap
+      int r2 = 0;
+      for (int i = 0; i < C.A; ++i) {
+        unsigned sx = 0;
+        if (alive(i)) {
+#pragma unroll
+          for (int q = 0; q < AC; ++q) if (q == r2) sx = seenX[q];
+          r2++;
+        }
+        S.omask[i * N + e] = sx;
+      }
+    }
   }
 
   DEV bool team_alive(int t) {

@@ -155,7 +155,15 @@ k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, co
       }
     } break;
     case OS_HEAL: { int nh = (S.hdr0[e].x >> 16) & 255; if (d.slot < nh) { float2 h = S.heal[d.slot * N + e]; v = d.comp == 0 ? h.x : h.y; } } break;
-    case OS_LIST_MASK: { int cnt = (S.hdr0[e].x >> (d.aux * 8)) & 255; v = d.slot < cnt ? 0.0f : 1.0f; } break;
+    case OS_LIST_MASK: {   // aux: 0 boxes, 1 box items, 2 heals; comp = observer
+      int cnt = (S.hdr0[e].x >> (d.aux * 8)) & 255;
+      if (C.omniscient) v = d.slot < cnt ? 0.0f : 1.0f;                      // env:564-568
+      else {                                                                  // env:706-739
+        int bitpos = d.aux == 2 ? d.slot : (d.aux == 0 ? 16 + d.slot : 24 + d.slot);
+        bool seen = d.slot < cnt && alive(d.comp) && ((S.omask[d.comp * N + e] >> bitpos) & 1u);
+        v = seen ? 0.0f : 1.0f;
+      }
+    } break;
     case OS_HEAL_SLOT: case OS_HEAL_SLOT_MASK: case OS_BOX_SLOT: case OS_BOX_SLOT_MASK: {
       int want = (d.src == OS_HEAL_SLOT || d.src == OS_HEAL_SLOT_MASK) ? MSV_ITEM_HEAL : MSV_ITEM_BOX;
       int inv = S.aint[d.slot * N + e].w, n = inv & 7;

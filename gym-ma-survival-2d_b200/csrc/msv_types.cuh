@@ -71,6 +71,7 @@ struct DevState {
   int* skills;     // [AC][N]
   int4* smisc;     // [N] steps, heals_used, boxes_placed, episodes
   unsigned long long* obm;  // [N] others_mask bits (observer i sees agent j: bit i*AC+j)
+  unsigned* omask;          // [AC][N] non-omniscient: per observer, seen heals (bits 0-15), boxes (16-23), box items (24-31)
 };
 
 struct DevOut {

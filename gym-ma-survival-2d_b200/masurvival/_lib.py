@@ -20,7 +20,7 @@ EXPORTS = [
     'msv_abi_version', 'msv_sizeof_config', 'msv_sizeof_env_state', 'msv_sizeof_stats',
     'msv_default_config', 'msv_create', 'msv_destroy', 'msv_reset', 'msv_step',
     'msv_step_host', 'msv_tensor', 'msv_tensor_info', 'msv_get_state', 'msv_set_state',
-    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_kernel_launches',
+    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_obs_bytes_per_env', 'msv_kernel_launches',
     'msv_last_error', 'msv_philox4x32',
 ]
 
@@ -62,6 +62,8 @@ def load():
     L.msv_flush_stats.argtypes = [vp, vp]
     L.msv_bytes_per_env_step.argtypes = [vp]
     L.msv_bytes_per_env_step.restype = i64
+    L.msv_obs_bytes_per_env.argtypes = [vp]
+    L.msv_obs_bytes_per_env.restype = i64
     L.msv_kernel_launches.argtypes = [vp]
     L.msv_kernel_launches.restype = i64
     L.msv_last_error.argtypes = [vp]
@@ -165,6 +167,9 @@ class Handle:
 
     def bytes_per_env_step(self):
         return int(load().msv_bytes_per_env_step(self.h))
+
+    def obs_bytes_per_env(self):
+        return int(load().msv_obs_bytes_per_env(self.h))
 
     def kernel_launches(self):
         return int(load().msv_kernel_launches(self.h))

@@ -188,6 +188,9 @@ class MaSurvivalVec:
     def bytes_per_env_step(self):
         return self._h.bytes_per_env_step()
 
+    def obs_bytes_per_env(self):
+        return self._h.obs_bytes_per_env()
+
     def kernel_launches(self):
         return self._h.kernel_launches()
 

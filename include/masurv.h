@@ -263,6 +263,8 @@ int msv_flush_stats(msv_handle* h, msv_stats* out);
 /* Algorithmic HBM bytes one msv_step moves per env (state read+write,
  * actions, observations, rewards, dones) -- the roofline numerator. */
 int64_t msv_bytes_per_env_step(msv_handle* h);
+/* The part of it written by the observation gather kernel (k_obs). */
+int64_t msv_obs_bytes_per_env(msv_handle* h);
 int64_t msv_kernel_launches(msv_handle* h); /* launches since create */
 
 const char* msv_last_error(msv_handle* h);

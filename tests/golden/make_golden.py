@@ -215,6 +215,8 @@ CASES = [
                                       'melee': {'damage': 50}}, 16, 7, 1000, 'scripted'),
     ('g_ffa_randomized', 'ffa', {'health': {'health': 60}}, 17, 4, 500, 'scripted'),
     ('g_1v1_continuous_melee', '1v1', {'melee': {'cooldown': None}}, 18, 6, 600, 'scripted'),
+    ('g_2v2_partial_obs', '2v2', {'observation': {'omniscent': False}, 'safe_zone': {'cooldown': 40}}, 19, 8, 900, 'scripted'),
+    ('g_ffa_partial_obs', 'ffa', {'observation': {'omniscent': False}, 'health': {'health': 60}}, 20, 9, 300, 'scripted'),
 ]
 
 

@@ -36,6 +36,15 @@ def test_lockstep_fast_zone_and_resets():
     assert r['dones'] > 40
 
 
+def test_lockstep_partial_observability():
+    """non-omniscient masks (env:706-739): Cameras over every body, Q1 row remap"""
+    import gpu_lockstep
+    r = gpu_lockstep.run('2v2', 48, 200, verbose=False, observation={'omniscent': False}, safe_zone={'cooldown': 20}, health={'health': 30})
+    _assert_clean(r)
+    r = gpu_lockstep.run('ffa', 12, 60, verbose=False, observation={'omniscent': False})
+    _assert_clean(r)
+
+
 def test_lockstep_ownership():
     import gpu_lockstep
     r = gpu_lockstep.run('2v2', 32, 120, verbose=False, boxes={'ownership': True}, p_attack=0.9)
@@ -90,6 +99,7 @@ def _scenario(variant, n, steps, seed, **over):
 @pytest.mark.parametrize('variant,n,steps,over', [
     ('2v2', 96, 40, {}), ('1v1', 96, 40, {}), ('ffa', 24, 30, {}),
     ('2v2', 64, 40, {'boxes': {'ownership': True}}),
+    ('2v2', 64, 40, {'observation': {'omniscent': False}}),
 ])
 def test_scrambled_scenarios(variant, n, steps, over):
     bad, events = _scenario(variant, n, steps, seed=11, **over)
