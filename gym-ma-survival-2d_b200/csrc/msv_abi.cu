@@ -428,6 +428,7 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
   CK(msv_launch(h->cap, which, h->C, h->S, h->O, actions, (cudaStream_t)stream));
   CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, (cudaStream_t)stream));   // fetch_observations
   h->launches += 2;
+  if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, (cudaStream_t)stream)); h->launches++; }
   return MSV_OK;
 }
 

@@ -1085,26 +1085,6 @@ struct Env {
     }
   }
 
-  // Lidars._update (sim:377-392): extension block, see DESIGN.md
-  __device__ __noinline__ void lidar(DevOut& O) {
-    int L = C.lidar_n;
-    for (int i = 0; i < C.A; ++i) {
-      for (int r = 0; r < L; ++r) {
-        float fr = 1.0f; int hit = 0;
-        if (alive(i)) {
-          f2 me = apos(i);
-          double ang = C.lidar_ang[r] + (double)AG(F_A, i);
-          f2 off = from_polar(C.lidar_depth, (float)ang);
-          int idx; float f;
-          int kind = raycast(me, vadd(me, off), i, idx, f);
-          if (kind != KIND_NONE) { fr = f; hit = (kind << 8) | idx; }
-        }
-        O.lidar_frac[((size_t)e * C.A + i) * L + r] = fr;
-        O.lidar_hit[((size_t)e * C.A + i) * L + r] = hit;
-      }
-    }
-  }
-
   int n_deaths, deaths[AC], n_kills, kill_cause[AC];
 
   __device__ __forceinline__ void post_step_boxes() {

@@ -57,7 +57,6 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   env.post_step_boxes();
   PROF(6);
   env.cameras();
-  if (C.lidar_n > 0) env.lidar(O);
   PROF(7);
   env.post_step_rest();                    // sim:241-242
   PROF(8);
@@ -66,7 +65,6 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     env.st_episodes++;
     env.reset();
     env.cameras();
-    if (C.lidar_n > 0) env.lidar(O);
   }
   PROF(9);
   env.store_obm();                         // env:84: the observation tensors are gathered by k_obs
@@ -99,7 +97,6 @@ k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   env.load();
   env.reset();
   env.cameras();
-  if (C.lidar_n > 0) env.lidar(O);
   env.store_obm();
   for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
   O.dones[e] = 0;
@@ -118,7 +115,6 @@ k_observe(const __grid_constant__ DevConst C, const __grid_constant__ DevState S
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
   env.load();
   env.cameras();
-  if (C.lidar_n > 0) env.lidar(O);
   env.store_obm();
 }
 
@@ -194,6 +190,91 @@ k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, co
   k.base[(size_t)e * k.chunk + d.off] = v;
 }
 
+// Lidars._update (simulation.py:377-392) as an extension observation block,
+// scanned on the state the observation describes.  ONE WARP PER AGENT: the
+// rays go across the lanes; when there are fewer than 32 rays each ray is
+// shared by 32/R' lanes (R' = rays rounded up to a power of two) that split
+// the body list, and the nearest hit is reduced with warp shuffles on a packed
+// (fraction bits << 32 | body order) key -- the minimum fraction wins, ties go
+// to the first body in scan order, exactly like the sequential scan.
+__global__ void __launch_bounds__(128)
+k_lidar(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ DevOut O, int BC) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int A = C.A, L = C.lidar_n, N = C.N;
+  if (warp >= C.n_real * A) return;
+  const int e = warp / A, i = warp - e * A;
+  int RP = 1; while (RP < L) RP <<= 1;              // rays rounded up to a power of two (<= 32)
+  const int LPR = 32 / RP;                           // lanes per ray
+  const int r = lane & (RP - 1), part = lane / RP;
+  const float4 k0 = S.akin0[i * N + e];
+  const bool alive_i = (__float_as_int(S.akin1[i * N + e].w) & 1) != 0;
+  unsigned long long best = ~0ull;                   // no hit
+  if (alive_i && r < L) {
+    const int4 h0 = S.hdr0[e];
+    const int nb = h0.x & 255, ni = (h0.x >> 8) & 255, nh = (h0.x >> 16) & 255;
+    const f2 me = mk2(k0.x, k0.y);
+    const double ang = C.lidar_ang[r] + (double)k0.z;
+    const f2 off = from_polar(C.lidar_depth, (float)ang);
+    const f2 p2 = vadd(me, off);
+    const int T = nb + ni + nh + 4 + A;              // scan order: boxes, box items, heals, walls, agents
+    // conservative reject before every exact test: the ray's AABB against a bound of the shape
+    const float lx = fmin_(me.x, p2.x), ly = fmin_(me.y, p2.y), ux = fmax_(me.x, p2.x), uy = fmax_(me.y, p2.y);
+    auto far_from = [&](float cx, float cy, float rad) { return cx + rad < lx || cx - rad > ux || cy + rad < ly || cy - rad > uy; };
+    for (int b = part; b < T; b += LPR) {
+      float f; bool hit = false; int q = b;
+      if (q < nb) {
+        float4 b0 = S.box0[q * N + e];
+        if (!far_from(b0.x, b0.y, b0.z + b0.w + 0.01f)) {
+          int reh = (S.box1[q * N + e].y >> 1) & 1;
+          SBox bx; bx.px = b0.x; bx.py = b0.y; bx.qs = 0.0f; bx.qc = 1.0f; bx.ang = 0.0f; sb_set_shape(bx, b0.z, b0.w, reh);
+          hit = ray_box(bx, me, p2, f);
+        }
+      } else if ((q -= nb) < ni) { float4 it = S.item0[q * N + e]; if (!far_from(it.x, it.y, C.item_r + 0.01f)) hit = ray_circle(mk2(it.x, it.y), C.item_r, me, p2, f); }
+      else if ((q -= ni) < nh) { float2 hh = S.heal[q * N + e]; if (!far_from(hh.x, hh.y, C.heal_r + 0.01f)) hit = ray_circle(mk2(hh.x, hh.y), C.heal_r, me, p2, f); }
+      else if ((q -= nh) < 4) {
+        const WallC& w = C.walls[q];
+        if (!(w.fat[2] < lx || w.fat[0] > ux || w.fat[3] < ly || w.fat[1] > uy)) {
+          SBox bx; bx.px = w.px; bx.py = w.py; bx.qs = w.qs; bx.qc = w.qc; bx.ang = w.ang; bx.hx = C.wall_hx; bx.hy = C.wall_hy; bx.ax = 1.0f; bx.ay = 1.0f; bx.rot = 0;
+          hit = ray_box(bx, me, p2, f);
+        }
+      } else {
+        q -= 4;
+        if (q != i) {
+          float4 o = S.akin0[q * N + e];
+          if (!far_from(o.x, o.y, C.agent_r + 0.01f) && (__float_as_int(S.akin1[q * N + e].w) & 1)) hit = ray_circle(mk2(o.x, o.y), C.agent_r, me, p2, f);
+        }
+      }
+      if (hit) {
+        unsigned long long key = ((unsigned long long)__float_as_uint(f) << 32) | (unsigned)b;
+        if (key < best) best = key;
+      }
+    }
+  }
+  for (int o = RP; o < 32; o <<= 1) {                // combine the lanes that share a ray
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    if (other < best) best = other;
+  }
+  if (part == 0 && r < L) {
+    float fr = 1.0f; int hitcode = 0;
+    if (best != ~0ull) {
+      const int4 h0 = S.hdr0[e];
+      const int nb = h0.x & 255, ni = (h0.x >> 8) & 255, nh = (h0.x >> 16) & 255;
+      int b = (int)(best & 0xffffffffu);
+      fr = __uint_as_float((unsigned)(best >> 32));
+      int kind, idx;
+      if (b < nb) { kind = KIND_BOX; idx = b; }
+      else if (b < nb + ni) { kind = KIND_ITEM; idx = b - nb; }
+      else if (b < nb + ni + nh) { kind = KIND_HEAL; idx = b - nb - ni; }
+      else if (b < nb + ni + nh + 4) { kind = KIND_WALL; idx = b - nb - ni - nh; }
+      else { kind = KIND_AGENT; idx = b - nb - ni - nh - 4; }
+      hitcode = (kind << 8) | idx;
+    }
+    O.lidar_frac[((size_t)e * A + i) * L + r] = fr;
+    O.lidar_hit[((size_t)e * A + i) * L + r] = hitcode;
+  }
+  (void)BC;
+}
+
 // flush_stats (env:471-480): sum the per-env accumulators, then zero them
 __global__ void k_stats(int N, int stride, int AC, float* sreward, int* skills, int4* smisc,
                         double* out_reward, unsigned long long* out_kills, unsigned long long* out_misc) {
@@ -249,6 +330,12 @@ cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S,
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, cudaStream_t st) {
   dim3 grid(C.n_real, (T.n_elems + 127) / 128);
   k_obs<<<grid, 128, 0, st>>>(C, S, T, AC);
+  return cudaPeekAtLastError();
+}
+
+cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut& O, int BC, cudaStream_t st) {
+  long long warps = (long long)C.n_real * C.A;
+  k_lidar<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(C, S, O, BC);
   return cudaPeekAtLastError();
 }
 

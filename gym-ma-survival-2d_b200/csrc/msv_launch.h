@@ -11,3 +11,4 @@ cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* ski
                              unsigned long long* out_kills, unsigned long long* out_misc, cudaStream_t st);
 cudaError_t msv_read_profile(unsigned long long out[32], int reset);
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, cudaStream_t st);
+cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut& O, int BC, cudaStream_t st);

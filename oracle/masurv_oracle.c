@@ -536,7 +536,6 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
   }
   /* agents/Cameras.post_step (sim:333-334) */
   cameras_update(e);
-  lidar_update(e);
   /* agents/Health.post_step -> despawn(dead) (sem:429-448) */
   {
     int dead[MA], nd = 0;
@@ -627,6 +626,7 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
   }
 
   /* ---- observations, rewards, done, stats (env:84-90) ---- */
+  lidar_update(e); /* Lidar extension block: scanned on the state the observation describes */
   if (out) orc_observe(e, out);
   float rewards[MA]; memset(rewards, 0, sizeof rewards);
   memset(e->last_kills, 0, sizeof e->last_kills);

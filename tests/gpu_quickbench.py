@@ -40,5 +40,5 @@ def run(variant, N, steps=200, warm=50, prof=True):
     h.close()
 
 if __name__ == '__main__':
-    for v, N in (('2v2', 4096), ('2v2', 16384), ('2v2', 65536), ('1v1_heal_only', 4096), ('ffa', 8192)):
+    for v, N in (('2v2', 16384), ('1v1_heal_only', 4096), ('ffa', 8192), ('ffa_lidar', 32768)):
         run(v, N)
