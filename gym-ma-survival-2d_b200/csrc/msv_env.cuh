@@ -776,6 +776,9 @@ struct Env {
     // cached TOIs (b2Contact::e_toiFlag / m_toi): valid until the contact's agent is displaced
     constexpr int MAXT = 12;
     int cP[MAXT]; float cAlpha[MAXT]; int ncache = 0;
+    constexpr int SNAPW = F_COUNT + 6 * PW + 1;
+    unsigned prev[SNAPW]; int prevP = -1;
+    for (int q = 0; q < SNAPW; ++q) prev[q] = 0xFFFFFFFFu;
     for (int guard = 0; guard < 64; ++guard) {
 #ifdef MSV_PROFILE
       dbg_toi_guard++;
@@ -799,7 +802,22 @@ struct Env {
 #ifdef MSV_PROFILE
             dbg_toi_calls++;
 #endif
-            int state = time_of_impact(static_box(k), mk2(AG(F_C0X, i), AG(F_C0Y, i)), apos(i), C.agent_r, beta);
+            const SBox sbx = static_box(k);
+            const f2 q0 = mk2(AG(F_C0X, i), AG(F_C0Y, i)), q1 = apos(i);
+            // b2TimeOfImpact can only report e_touching at a time where the true distance
+            // between the core shapes is below target + tolerance (0.49625).  The sweep is a
+            // straight segment against a static box, so if a lower bound of the segment-box
+            // distance (largest per-axis gap in the box frame) clears that with margin, the
+            // outcome is alpha = 1 whatever path the root finder takes: skip the call.
+            bool may_touch = true;
+            {
+              f2 l0 = sb_mulT(sbx, q0), l1 = sb_mulT(sbx, q1);
+              float gx = fmax_(fmin_(l0.x, l1.x) - sbx.hx, -sbx.hx - fmax_(l0.x, l1.x));
+              float gy = fmax_(fmin_(l0.y, l1.y) - sbx.hy, -sbx.hy - fmax_(l0.y, l1.y));
+              if (fmax_(gx, gy) > (B2_POLY_RADIUS + C.agent_r - 3.0f * B2_LINEAR_SLOP) + 0.25f * B2_LINEAR_SLOP + 0.004f) may_touch = false;
+            }
+            int state = 0; beta = 1.0f;
+            if (may_touch) state = time_of_impact(sbx, q0, q1, C.agent_r, beta);
             float alpha0 = AG(F_ALPHA0, i);
             if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
             if (ncache < MAXT) { cP[ncache] = p; cAlpha[ncache] = alpha; ncache++; }
@@ -899,6 +917,26 @@ struct Env {
           int a3, s3, b3; decode(cP[q], a3, s3, b3);
           if (b3 == b) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q;
         }
+      }
+      // A TOI event is a pure function of (agent b's sweep/velocity/AABB words, the pair
+      // bit-matrices, the contact counter).  If this event left all of them exactly as the
+      // previous event on the same contact did, every further event on it would repeat
+      // verbatim and only count up to b2_maxSubSteps (a body wedged between two static
+      // bodies does this): jump the contact's toiCount there instead of replaying them.
+      {
+        unsigned snap[SNAPW];
+        for (int f = 0; f < F_COUNT; ++f) snap[f] = __float_as_uint(AG(f, b));
+        for (int w = 0; w < PW; ++w) {
+          snap[F_COUNT + 6 * w + 0] = (unsigned)ex[w]; snap[F_COUNT + 6 * w + 1] = (unsigned)(ex[w] >> 32);
+          snap[F_COUNT + 6 * w + 2] = (unsigned)tc[w]; snap[F_COUNT + 6 * w + 3] = (unsigned)(tc[w] >> 32);
+          snap[F_COUNT + 6 * w + 4] = (unsigned)en[w]; snap[F_COUNT + 6 * w + 5] = (unsigned)(en[w] >> 32);
+        }
+        snap[SNAPW - 1] = (unsigned)contact_seq;
+        bool same = prevP == minP;
+        for (int q = 0; q < SNAPW; ++q) { if (prev[q] != snap[q]) same = false; prev[q] = snap[q]; }
+        prevP = minP;
+        if (same)
+          for (int q = 0; q < nev; ++q) if (evP[q] == minP && evN[q] <= B2_MAX_SUBSTEPS) evN[q] = B2_MAX_SUBSTEPS + 1;
       }
 #ifdef MSV_PROFILE
       dbg_event += clock64() - dbg_t1;
