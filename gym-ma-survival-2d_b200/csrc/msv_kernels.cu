@@ -119,16 +119,13 @@ k_observe(const __grid_constant__ DevConst C, const __grid_constant__ DevState S
 }
 
 // fetch_observations (env:510-657): one thread per output float, gathered from
-// the SoA state after k_step / k_reset / k_observe stored it.  grid = (n_real,
-// ceil(n_elems/128)): blockIdx.x is the environment, consecutive threads
-// write consecutive floats of a key -> fully coalesced stores; the loads hit
-// the few sectors that hold this env's state (L1-resident within the block).
-__global__ void __launch_bounds__(128)
-k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC) {
-  const int el = blockIdx.y * 128 + threadIdx.x;
-  if (el >= Tb.n_elems) return;
-  const int e = blockIdx.x, N = C.N;
-  const ObsDesc d = Tb.desc[el];
+// the SoA state after k_step / k_reset / k_observe stored it.  A block covers
+// OBS_EPB consecutive environments: a thread reads its element descriptor once
+// and emits that element for each of them (their SoA words share sectors);
+// consecutive threads write consecutive floats of a key -> coalesced stores.
+// value of one observation element of environment e (see ObsDesc)
+__device__ __forceinline__ float obs_value(const DevConst& C, const DevState& S, const ObsDesc d, int e, int AC) {
+  const int N = C.N;
   float v = 0.0f;
   auto alive = [&](int i) { return (__float_as_int(S.akin1[i * N + e].w) & 1) != 0; };
   auto vert = [&](float hx, float hy, int rot, int comp) {   // b2PolygonShape vertex order (Q8)
@@ -186,9 +183,24 @@ k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, co
     } break;
     default: break;
   }
-  const ObsKey k = Tb.keys[d.key];
-  k.base[(size_t)e * k.chunk + d.off] = v;
+  return v;
 }
+
+#define OBS_EPB 8   // environments per block
+__global__ void __launch_bounds__(256)
+k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC) {
+  const int e0 = blockIdx.x * OBS_EPB;
+  for (int el = threadIdx.x; el < Tb.n_elems; el += 256) {
+    const ObsDesc d = Tb.desc[el];           // read once, reused for the block's environments
+    const ObsKey k = Tb.keys[d.key];
+#pragma unroll
+    for (int j = 0; j < OBS_EPB; ++j) {
+      const int e = e0 + j;
+      if (e < C.n_real) k.base[(size_t)e * k.chunk + d.off] = obs_value(C, S, d, e, AC);
+    }
+  }
+}
+
 
 // Lidars._update (simulation.py:377-392) as an extension observation block,
 // scanned on the state the observation describes.  ONE WARP PER AGENT: the
@@ -328,8 +340,7 @@ cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S,
 }
 
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, cudaStream_t st) {
-  dim3 grid(C.n_real, (T.n_elems + 127) / 128);
-  k_obs<<<grid, 128, 0, st>>>(C, S, T, AC);
+  k_obs<<<(C.n_real + OBS_EPB - 1) / OBS_EPB, 256, 0, st>>>(C, S, T, AC);
   return cudaPeekAtLastError();
 }
 
