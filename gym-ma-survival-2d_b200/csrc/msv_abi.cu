@@ -432,6 +432,18 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
   return MSV_OK;
 }
 
+/* debug: number of capacity-overflow events (contact list, TOI island, item
+ * lists) any env has recorded since its last set_state -- must stay 0 */
+int64_t msv_debug_overflow(msv_handle* h) {
+  if (!h) return -1;
+  cudaSetDevice(h->device); cudaDeviceSynchronize();
+  std::vector<int4> v((size_t)h->C.N);
+  if (cudaMemcpy(v.data(), h->S.hdr1, v.size() * sizeof(int4), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  int64_t tot = 0;
+  for (int e = 0; e < h->C.n_real; ++e) tot += v[e].z;
+  return tot;
+}
+
 /* debug/bench: the two halves of msv_step separately, so that bench.py can put
  * CUDA events around the dominant kernel alone */
 int msv_debug_step_kernel(msv_handle* h, const uint8_t* actions_dev, void* stream) {

@@ -71,6 +71,8 @@ def load():
     L.msv_philox4x32.argtypes = [vp, vp, vp]
     L.msv_debug_step_kernel.argtypes = [vp, vp, vp]
     L.msv_debug_obs_kernel.argtypes = [vp, vp]
+    L.msv_debug_overflow.argtypes = [vp]
+    L.msv_debug_overflow.restype = i64
     if L.msv_abi_version() != 1:
         raise MasurvError('libmasurv.so ABI version mismatch')
     for name, dt in (('msv_sizeof_config', CONFIG_DT), ('msv_sizeof_env_state', STATE_DT),
@@ -164,6 +166,9 @@ class Handle:
         out = np.zeros(1, dtype=STATS_DT)
         check(load().msv_flush_stats(self.h, out.ctypes.data), self.h)
         return out[0]
+
+    def overflow_events(self):
+        return int(load().msv_debug_overflow(self.h))
 
     def bytes_per_env_step(self):
         return int(load().msv_bytes_per_env_step(self.h))

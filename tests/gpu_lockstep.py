@@ -86,6 +86,7 @@ def run(variant='2v2', n_envs=64, steps=300, seed=7, auto_reset=True, verbose=Tr
                               'boxes_placed': int(sum(s['boxes_placed'] for s in so)),
                               'episodes': int(sum(s['episodes'] for s in so)),
                               'kills': [int(sum(s['kills'][i] for s in so)) for i in range(A)]}
+    report['overflow_events'] = h.overflow_events()
     h.close()
     if verbose:
         print(json.dumps(report, default=str, indent=1))

@@ -92,6 +92,7 @@ def _scenario(variant, n, steps, seed, **over):
                 h.set_state(np.array([so]), first=e)
             events['deaths'] += int((so['alive'][:A] == 0).sum())
             events['pick'] += int(so['inv_n'][:A].sum())
+    assert h.overflow_events() == 0
     h.close()
     return bad, events
 
@@ -164,6 +165,7 @@ def test_full_size_properties():
     assert torch.all((r0 == 1) | (r0 == -1))
     st = envs[0].flush_stats()
     assert st['steps'] == N * 120 and st['episodes'] == tot_done
+    assert envs[0]._h.overflow_events() == 0      # no fixed-capacity list ever overflowed
     for e in envs:
         e.close()
 
