@@ -84,6 +84,10 @@ class PhiloxGenerator:
 def ref_config(name, over):
     user = parity.apply_overrides(parity.variant(name), over)
     user.pop('lidars', None)
+    import masurvival.simulation as rsim          # the reference wants b2CircleShape objects (env:222-227)
+    for k in ('auto_pickup', 'give'):
+        if k in user and not hasattr(user[k].get('shape'), 'radius'):
+            user[k] = dict(user[k]); user[k]['shape'] = rsim.circle_shape(user[k]['shape'])
     return user
 
 
@@ -215,6 +219,8 @@ CASES = [
                                       'melee': {'damage': 50}}, 16, 7, 1000, 'scripted'),
     ('g_ffa_randomized', 'ffa', {'health': {'health': 60}}, 17, 4, 500, 'scripted'),
     ('g_1v1_continuous_melee', '1v1', {'melee': {'cooldown': None}}, 18, 6, 600, 'scripted'),
+    ('g_exotic_3agents', '1v1', parity.EXOTIC_A, 21, 10, 700, 'scripted'),
+    ('g_exotic_noheals', '1v1', parity.EXOTIC_B, 22, 11, 500, 'scripted'),
     ('g_2v2_partial_obs', '2v2', {'observation': {'omniscent': False}, 'safe_zone': {'cooldown': 40}}, 19, 8, 900, 'scripted'),
     ('g_ffa_partial_obs', 'ffa', {'observation': {'omniscent': False}, 'health': {'health': 60}}, 20, 9, 300, 'scripted'),
 ]

@@ -14,11 +14,30 @@ from masurvival.config import merge_config, pack_config, variant  # noqa: E402
 REL_TOL = 1e-4  # BASELINE.json north_star: continuous outputs within 1e-4 relative
 
 
+# configs far from the defaults: every config-derived device constant is exercised
+EXOTIC_A = {
+    'agents': {'n_agents': 3, 'agent_size': 0.8}, 'spawn_grid': {'grid_size': 4, 'floor_size': 16},
+    'melee': {'range': 1.5, 'damage': 34, 'cooldown': 5}, 'inventory': {'slots': 2},
+    'auto_pickup': {'shape': 0.6}, 'give': {'shape': 3.0}, 'death_drop': {'radius': 0.7},
+    'heals': {'reset_spawns': {'n_items': 5, 'item_size': 0.4}, 'heal': {'healing': 30}},
+    'boxes': {'reset_spawns': {'n_boxes': 3, 'box_size': 1.4}, 'item': {'item_size': 0.6, 'offset': 1.1}, 'health': 40},
+    'safe_zone': {'phases': 4, 'cooldown': 30, 'damage': 2, 'radiuses': [8, 4, 2], 'centers': [[0, 0], [1, 1], [2, -1]]},
+    'reward_scheme': {'r_alive': 0.5, 'r_dead': -0.25, 'r_kill': 3, 'r_death': -1}, 'gameover': {'mode': 'lastalive'},
+    'health': {'health': 80}, 'motors': {'impulse': (0.3, 0.2, 0.02)}, 'cameras': {'fov': 1.0, 'depth': 6},
+}
+EXOTIC_B = {
+    'heals': {'reset_spawns': {'n_items': 0, 'item_size': 0.5}}, 'boxes': {'reset_spawns': {'n_boxes': 2, 'box_size': 2.0}, 'ownership': True},
+    'observation': {'omniscent': False}, 'safe_zone': {'cooldown': 25, 'damage': 3}, 'health': {'health': 50},
+}
+
+
 def apply_overrides(user, over):
     """user-config dict + overrides; a value of None deletes the key (e.g.
     {'melee': {'cooldown': None}} selects ContinuousMelee, env:309-312)."""
     for k, v in over.items():
         sub = user.setdefault(k, {})
+        if isinstance(v.get('reset_spawns'), dict):      # shallow |= of the reference (env:53-54): whole sub-dict
+            pass
         for kk, vv in v.items():
             if vv is None:
                 sub.pop(kk, None)

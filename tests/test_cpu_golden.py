@@ -22,6 +22,8 @@ CASE_CFG = {
                                       'melee': {'damage': 50}}),
     'g_ffa_randomized': ('ffa', {'health': {'health': 60}}),
     'g_1v1_continuous_melee': ('1v1', {'melee': {'cooldown': None}}),
+    'g_exotic_3agents': ('1v1', parity.EXOTIC_A),
+    'g_exotic_noheals': ('1v1', parity.EXOTIC_B),
     'g_2v2_partial_obs': ('2v2', {'observation': {'omniscent': False}, 'safe_zone': {'cooldown': 40}}),
     'g_ffa_partial_obs': ('ffa', {'observation': {'omniscent': False}, 'health': {'health': 60}}),
 }

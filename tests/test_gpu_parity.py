@@ -45,6 +45,17 @@ def test_lockstep_partial_observability():
     _assert_clean(r)
 
 
+def test_lockstep_exotic_configs():
+    """configs far from the defaults (agent size, room size, fixed zone centres, 3 agents,
+    2 inventory slots, lastalive, kill rewards, no heals, ownership without teams)"""
+    import gpu_lockstep
+    r = gpu_lockstep.run('1v1', 48, 200, verbose=False, **{k: dict(v) for k, v in parity.EXOTIC_A.items()})
+    _assert_clean(r)
+    assert r['dones'] > 10
+    r = gpu_lockstep.run('1v1', 48, 150, verbose=False, **{k: dict(v) for k, v in parity.EXOTIC_B.items()})
+    _assert_clean(r)
+
+
 def test_lockstep_ownership():
     import gpu_lockstep
     r = gpu_lockstep.run('2v2', 32, 120, verbose=False, boxes={'ownership': True}, p_attack=0.9)
