@@ -43,6 +43,7 @@ struct msv_handle {
   double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
   int64_t launches;
   ObsTable obs;
+  ObsTable obs_term;         // auto_reset == 2: same table, writing the "terminal_<key>" tensors
   int64_t exported;          // live DLPack exports
   std::string err;
 };
@@ -389,6 +390,14 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
     if (dalloc(h, &dd, D.size())) { g_err = h->err; msv_destroy(h); return MSV_ERR_ALLOC; }
     cudaMemcpy(dd, D.data(), D.size() * sizeof(ObsDesc), cudaMemcpyHostToDevice);
     h->obs.desc = dd; h->obs.n_elems = (int)D.size();
+    h->obs_term = h->obs;
+    if (cfg->auto_reset == 2) {
+      for (int k = 0; k < MSV_OBS_KEYS; ++k) {
+        float* buf = nullptr;
+        if (dalloc(h, &buf, N * (size_t)(K[k].chunk > 0 ? K[k].chunk : 1))) { g_err = h->err; msv_destroy(h); return MSV_ERR_ALLOC; }
+        h->obs_term.keys[k].base = buf;
+      }
+    }
   }
   const int64_t n = num_envs, a = A, b = B, hh = H, s = Sw, l = L;
   reg(h, "agent", O.agent, 0, {n, a, s});
@@ -407,6 +416,18 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   if (L > 0) { reg(h, "lidar_frac", O.lidar_frac, 0, {n, a, l}); reg(h, "lidar_hit", O.lidar_hit, 2, {n, a, l}); }
   reg(h, "rewards", O.rewards, 0, {n, a});
   reg(h, "dones", O.dones, 1, {n});
+  if (cfg->auto_reset == 2) {   // same shapes, "terminal_" prefix
+    std::map<std::string, TensorInfo> extra;
+    static const char* names[MSV_OBS_KEYS] = {"agent", "others", "others_mask", "zone", "heals", "heals_mask", "heal_slot",
+                                              "heal_slot_mask", "boxes", "boxes_mask", "box_items", "box_items_mask", "box_slot", "box_slot_mask"};
+    for (int k = 0; k < MSV_OBS_KEYS; ++k) {
+      auto it = h->tensors.find(names[k]);
+      if (it == h->tensors.end()) continue;
+      TensorInfo t = it->second; t.ptr = h->obs_term.keys[k].base;
+      extra[std::string("terminal_") + names[k]] = t;
+    }
+    for (auto& kv : extra) h->tensors[kv.first] = kv.second;
+  }
   *out = h;
   return MSV_OK;
 }
@@ -425,9 +446,21 @@ const char* msv_last_error(msv_handle* h) { return h ? h->err.c_str() : g_err.c_
 static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream) {
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) CK(cudaSetDevice(h->device));
-  CK(msv_launch(h->cap, which, h->C, h->S, h->O, actions, (cudaStream_t)stream));
-  CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, (cudaStream_t)stream));   // fetch_observations
-  h->launches += 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (which == 0 && h->cfg.auto_reset == 2) {
+    // step without the in-kernel reset, keep the finished episodes' last observation, then
+    // reset exactly the envs that finished (same Philox streams as the in-kernel reset)
+    DevConst C0 = h->C; C0.auto_reset = 0;
+    CK(msv_launch(h->cap, 0, C0, h->S, h->O, actions, st));
+    CK(msv_launch_obs(h->C, h->S, h->obs_term, h->AC, h->O.dones, st));
+    CK(msv_launch(h->cap, 4, h->C, h->S, h->O, nullptr, st));
+    h->launches += 3;
+  } else {
+    CK(msv_launch(h->cap, which, h->C, h->S, h->O, actions, st));
+    h->launches += 1;
+  }
+  CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, nullptr, st));   // fetch_observations
+  h->launches += 1;
   if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, (cudaStream_t)stream)); h->launches++; }
   return MSV_OK;
 }
@@ -454,7 +487,7 @@ int msv_debug_step_kernel(msv_handle* h, const uint8_t* actions_dev, void* strea
 }
 int msv_debug_obs_kernel(msv_handle* h, void* stream) {
   if (!h) return MSV_ERR_INVALID;
-  CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, (cudaStream_t)stream));
+  CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, nullptr, (cudaStream_t)stream));
   h->launches++;
   return MSV_OK;
 }

@@ -87,19 +87,23 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
 template <int AC, int BC, int HC>
 __global__ void __launch_bounds__(MSV_TPB)
 k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
-        const __grid_constant__ DevOut Oc) {
+        const __grid_constant__ DevOut Oc, int only_done) {
   extern __shared__ float sm[];
   const int lane_ = threadIdx.x & 31;
   const int e = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * C.epw + lane_;
   if (lane_ >= C.epw || e >= C.N) return;
   DevOut O = Oc;
+  if (only_done && !O.dones[e]) return;    // auto_reset = 2: only the envs that just finished
   Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
   env.load();
+  if (only_done) env.st_episodes++;
   env.reset();
   env.cameras();
   env.store_obm();
-  for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
-  O.dones[e] = 0;
+  if (!only_done) {
+    for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
+    O.dones[e] = 0;
+  }
   env.store();
 }
 
@@ -188,7 +192,8 @@ __device__ __forceinline__ float obs_value(const DevConst& C, const DevState& S,
 
 #define OBS_EPB 8   // environments per block
 __global__ void __launch_bounds__(256)
-k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC) {
+k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC,
+      const uint8_t* __restrict__ only_if) {
   const int e0 = blockIdx.x * OBS_EPB;
   for (int el = threadIdx.x; el < Tb.n_elems; el += 256) {
     const ObsDesc d = Tb.desc[el];           // read once, reused for the block's environments
@@ -196,7 +201,7 @@ k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, co
 #pragma unroll
     for (int j = 0; j < OBS_EPB; ++j) {
       const int e = e0 + j;
-      if (e < C.n_real) k.base[(size_t)e * k.chunk + d.off] = obs_value(C, S, d, e, AC);
+      if (e < C.n_real && (!only_if || only_if[e])) k.base[(size_t)e * k.chunk + d.off] = obs_value(C, S, d, e, AC);
     }
   }
 }
@@ -325,7 +330,8 @@ static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, con
     return e;
   }
   if (which == 0) k_step<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, actions);
-  else if (which == 1) k_reset<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
+  else if (which == 1) k_reset<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 0);
+  else if (which == 4) k_reset<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 1);
   else k_observe<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
   return cudaPeekAtLastError();
 }
@@ -339,8 +345,8 @@ cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S,
   }
 }
 
-cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, cudaStream_t st) {
-  k_obs<<<(C.n_real + OBS_EPB - 1) / OBS_EPB, 256, 0, st>>>(C, S, T, AC);
+cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, const uint8_t* only_if, cudaStream_t st) {
+  k_obs<<<(C.n_real + OBS_EPB - 1) / OBS_EPB, 256, 0, st>>>(C, S, T, AC, only_if);
   return cudaPeekAtLastError();
 }
 

@@ -169,7 +169,8 @@ def pack_config(cfg, continuous_melee=False, auto_reset=False):
     rec['lidar_n'] = lid.get('n_lasers', 0)
     rec['lidar_fov'] = lid.get('fov', 0.8 * math.pi)
     rec['lidar_depth'] = lid.get('depth', 10)
-    rec['auto_reset'] = int(bool(auto_reset))
+    # False/0 off, True/1 in-kernel reset, 'terminal'/2 reset + terminal observation capture
+    rec['auto_reset'] = 2 if auto_reset in ('terminal', 2) else int(bool(auto_reset))
     validate(rec)
     return rec
 

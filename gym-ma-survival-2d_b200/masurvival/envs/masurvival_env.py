@@ -28,9 +28,11 @@ class MaSurvivalVec:
     seed : int              Philox key (the reference's unseeded numpy RNG,
                             env:50, is replaced by counter-based Philox4x32-10)
     env_offset : int        global index of env 0 (multi-GPU sharding)
-    auto_reset : bool       reset finished envs inside step(); the returned
+    auto_reset : bool|str   True: reset finished envs inside step(); the returned
                             observation is then the first one of the new
-                            episode (rewards/dones still describe the old)
+                            episode (rewards/dones still describe the old).
+                            'terminal': same, and step()'s info dict carries
+                            info['terminal_observation'] (rows valid where done)
     """
 
     metadata = {'render_modes': [], 'render_fps': 30}
@@ -41,6 +43,7 @@ class MaSurvivalVec:
         self.num_envs = int(num_envs)
         self.device = int(device)
         self.auto_reset = bool(auto_reset)
+        self._terminal = int(self._rec['auto_reset']) == 2
         self._h = _lib.Handle(self._rec, self.num_envs, device, seed, env_offset)
         self.observation_space = self.compute_obs_space()
         self.action_space = self.compute_action_space()
@@ -99,7 +102,7 @@ class MaSurvivalVec:
         return spaces.Tuple((spaces.MultiDiscrete([3, 3, 3, 2, 2, 2]),) * self.n_agents)
 
     # ---- tensors -----------------------------------------------------------
-    def _obs(self):
+    def _obs(self, prefix=''):
         """Observation dict with the reference's per-env shapes and a leading
         N.  `zone`, `heals`, `boxes`, `box_items` are identical for every
         observer (env:550,559,582,610 tile them): they are stored once per env
@@ -107,7 +110,9 @@ class MaSurvivalVec:
         h, A = self._h, self.n_agents
         x = {}
         for k in self.obs_shapes():
-            t = h.tensor(k)
+            if prefix and k.startswith('lidar'):
+                continue
+            t = h.tensor(prefix + k)
             if k in ('zone', 'heals', 'boxes', 'box_items'):
                 t = t.unsqueeze(1).expand(t.shape[0], A, *t.shape[1:])
             x[k] = t
@@ -144,7 +149,8 @@ class MaSurvivalVec:
         self._act_buf = a  # keep alive until the stream has consumed it
         self._h.step(a.data_ptr(), self._stream())
         self.steps += 1
-        return self._obs(), self._h.tensor('rewards'), self._h.tensor('dones').bool(), {}
+        info = {'terminal_observation': self._obs('terminal_')} if self._terminal else {}
+        return self._obs(), self._h.tensor('rewards'), self._h.tensor('dones').bool(), info
 
     def step_host(self, actions, rewards_out=None, dones_out=None):
         """End-to-end step from HOST buffers: actions uint8[N,A,6] (numpy or

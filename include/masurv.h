@@ -88,7 +88,9 @@ typedef struct msv_config {
   int32_t zone_n_radiuses; /* len(radiuses) (without the appended 0) */
   int32_t zone_centers_random; /* centers == 'random' */
   int32_t lidar_n;         /* Lidars extension (simulation.py:357-392); 0 = off */
-  int32_t auto_reset;      /* vector-env extension: reset env in-kernel on done */
+  int32_t auto_reset;      /* vector-env extension: 0 off; 1 reset finished envs inside step();
+                              2 same + keep the finished episode's last observation in the
+                              "terminal_<key>" tensors (valid for envs whose done flag is set) */
   float r_alive, r_dead, r_kill, r_death; /* reward_scheme env:144-153 */
   double floor_size;       /* spawn_grid.floor_size */
   double agent_size;       /* agents.agent_size (diameter) */

@@ -211,3 +211,39 @@ def test_golden_fixtures_on_gpu():
                 assert np.array_equal(h.tensor('rewards').cpu().numpy()[0], g['rewards'][r]), (path, r)
                 assert bool(h.tensor('dones').cpu().numpy()[0]) == bool(g['done'][r]), (path, r)
         h.close()
+
+
+def test_terminal_observation_capture():
+    """auto_reset='terminal': same trajectory as the in-kernel reset, and the finished
+    episode's last observation equals what an env without auto-reset returns"""
+    import torch
+    from masurvival.envs import MaSurvivalVec
+    from masurvival.config import variant
+    N = 512
+    cfg = parity.apply_overrides(variant('2v2'), {'safe_zone': {'cooldown': 6}, 'health': {'health': 10}})
+    et = MaSurvivalVec(cfg, N, seed=9, auto_reset='terminal')
+    e1 = MaSurvivalVec(cfg, N, seed=9, auto_reset=True)
+    e0 = MaSurvivalVec(cfg, N, seed=9, auto_reset=False)
+    for e in (et, e1, e0):
+        e.reset()
+    rng = np.random.default_rng(1)
+    fresh = torch.ones(N, dtype=torch.bool, device='cuda')     # e0 envs still in their first episode
+    checked = 0
+    for t in range(90):
+        a = torch.as_tensor(random_actions(rng, N, 4)).cuda()
+        ot, rt, dt, info = et.step(a)
+        o1, r1, d1, _ = e1.step(a)
+        o0, r0, d0, _ = e0.step(a)
+        for k in o1:
+            assert torch.equal(ot[k], o1[k]), k
+        assert torch.equal(rt, r1) and torch.equal(dt, d1)
+        sel = dt & fresh
+        if sel.any():
+            for k, v in info['terminal_observation'].items():
+                assert torch.equal(v[sel], o0[k][sel]), k
+            checked += int(sel.sum())
+        fresh &= ~d0
+    assert et.get_state().tobytes() == e1.get_state().tobytes()
+    assert checked > 100
+    for e in (et, e1, e0):
+        e.close()
