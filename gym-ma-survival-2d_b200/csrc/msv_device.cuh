@@ -363,6 +363,18 @@ __device__ __noinline__ int time_of_impact(const SBox& A, f2 c0, f2 c, float rB,
   float tolerance = 0.25f * B2_LINEAR_SLOP;
   float t1 = 0.0f;
   int iter = 0;
+  {
+    // First outer iteration, t1 = 0: the sweep positions are exactly (A, c0) and the
+    // function returns e_touching at t = 0 iff the GJK distance is in (0, target + tol).
+    // GJK on a 4-vertex polygon against a point is exact to ~1e-6, so when the plain
+    // point-to-box distance is inside that interval by a 1e-3 margin the outcome is
+    // certain and the simplex iteration can be skipped (a body resting in, or wedged
+    // into, contact lands here every substep).
+    f2 l = sb_mulT(A, c0);
+    float dx = fmax_(fabsf(l.x) - A.hx, 0.0f), dy = fmax_(fabsf(l.y) - A.hy, 0.0f);
+    float d = sqrtf(dx * dx + dy * dy);
+    if (d > 1e-3f && d < (target + tolerance) - 1e-3f) { tOut = 0.0f; return TOI_TOUCHING; }
+  }
   SimplexCache cache; cache.count = 0;
   for (;;) {
     // One outer iteration is a pure function of (t1, simplex cache).  When it
