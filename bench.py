@@ -223,7 +223,7 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu:
-            line['cpu_baseline'] = cpu_baseline(sample_envs=2048, steps=20)
+            line['cpu_baseline'] = cpu_baseline(sample_envs=8192, steps=600)   # ~10-20 s of host work
         print(json.dumps(line))
     for e_ in envs:
         e_.close()
@@ -245,7 +245,7 @@ def cpu_baseline(sample_envs, steps, threads=None):
     acts = np.zeros((4, sample_envs, A, 6), dtype=np.uint8)
     acts[..., 0:3] = rng.integers(0, 3, size=(4, sample_envs, A, 3))
     acts[..., 3:6] = rng.integers(0, 2, size=(4, sample_envs, A, 3))
-    for t in range(3):
+    for t in range(10):
         b.step(acts[t % 4])
     t0 = time.perf_counter()
     for t in range(steps):
@@ -300,8 +300,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='environments per GPU')
     ap.add_argument('--seed', type=int, default=0)
