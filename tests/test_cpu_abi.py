@@ -105,3 +105,24 @@ def test_wrapper_shapes_without_gpu():
     assert f.entity_keys() == {'others', 'heals', 'heal_slot', 'boxes', 'box_items', 'box_slot'}
     sp = f.compute_action_space()
     assert len(sp) == 4 and sp.contains(tuple([1, 1, 1, 0, 0, 0] for _ in range(4))) and not sp.contains(tuple([3, 0, 0, 0, 0, 0] for _ in range(4)))
+
+
+def test_create_rejects_bad_arguments_before_touching_the_device():
+    """error behaviour of the C ABI: negative codes, no exception, no crash"""
+    L = _lib.load()
+    good = np.array(parity.make_config('2v2'), dtype=CONFIG_DT).reshape(1)
+    h = ctypes.c_void_p()
+    def create(rec, n=4):
+        return L.msv_create(rec.ctypes.data, n, 0, 0, 0, ctypes.byref(h))
+    assert create(good, 0) == -1                                   # MSV_ERR_INVALID: num_envs <= 0
+    for field, val in (('n_agents', 0), ('n_agents', 9), ('n_boxes', 9), ('n_heals', 17), ('grid_size', 9),
+                       ('inv_slots', 5), ('lidar_n', 33), ('zone_n_radiuses', 8)):
+        bad = good.copy(); bad[0][field] = val
+        assert create(bad) == -1, field
+    bad = good.copy(); bad[0]['grid_size'] = 2                        # 4+4+4 spawns > 4 cells
+    assert create(bad) == -1
+    assert L.msv_create(None, 4, 0, 0, 0, ctypes.byref(h)) == -1
+    for fn in (L.msv_reset, L.msv_observe):
+        assert fn(None, None) == -1
+    assert L.msv_step(None, None, None) == -1 and L.msv_destroy(None) == -1
+    assert L.msv_bytes_per_env_step(None) == 0 and L.msv_kernel_launches(None) == 0

@@ -247,3 +247,45 @@ def test_terminal_observation_capture():
     assert checked > 100
     for e in (et, e1, e0):
         e.close()
+
+
+def test_abi_tensor_info_errors_and_lifetime():
+    """msv_tensor_info shapes/strides/dtypes, unknown names, byte accounting, state round trip"""
+    import ctypes
+    import torch
+    from masurvival import _lib
+    rec = make_config('ffa_lidar', auto_reset=True)
+    h = _lib.Handle(rec, 100, 0, 1, 0)                 # 100 is not a multiple of the 64-env block
+    L = _lib.load()
+    h.reset()
+    ptr, nd, dt = ctypes.c_void_p(), ctypes.c_int32(), ctypes.c_int32()
+    shape, strides = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+    rc = L.msv_tensor_info(h.h, b'others', ctypes.byref(ptr), ctypes.byref(nd), shape, strides, ctypes.byref(dt))
+    assert rc == 0 and nd.value == 4 and list(shape) == [100, 8, 7, 8] and list(strides) == [448, 56, 8, 1] and dt.value == 0
+    assert L.msv_tensor_info(h.h, b'lidar_hit', ctypes.byref(ptr), ctypes.byref(nd), shape, strides, ctypes.byref(dt)) == 0 and dt.value == 2
+    assert L.msv_tensor_info(h.h, b'dones', ctypes.byref(ptr), ctypes.byref(nd), shape, strides, ctypes.byref(dt)) == 0 and dt.value == 1 and list(shape)[:1] == [100]
+    assert L.msv_tensor_info(h.h, b'nope', None, None, None, None, None) == -4      # MSV_ERR_NAME
+    assert b'nope' in L.msv_last_error(h.h)
+    t = h.tensor('agent')
+    assert t.shape == (100, 8, 8) and t.is_cuda and t.data_ptr() == h.tensor('agent').data_ptr()
+    assert h.tensor('lidar_hit').dtype == torch.int32 and h.tensor('dones').dtype == torch.uint8
+    assert h.bytes_per_env_step() > h.obs_bytes_per_env() > 0
+    # checkpoint / resume: get_state -> set_state is the identity, and a restored env continues identically
+    a = torch.zeros((100, 8, 6), dtype=torch.uint8, device='cuda'); a[..., :3] = 2; a[..., 3] = 1
+    for _ in range(25):
+        h.step(a.data_ptr())
+    snap = h.get_state()
+    for _ in range(10):
+        h.step(a.data_ptr())
+    torch.cuda.synchronize()
+    ref_obs = h.tensor('agent').clone(); ref_state = h.get_state()
+    h.set_state(snap)
+    assert h.get_state().tobytes() == snap.tobytes()
+    for _ in range(10):
+        h.step(a.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(h.tensor('agent'), ref_obs) and h.get_state().tobytes() == ref_state.tobytes()
+    assert h.get_state(first=99, count=1).shape == (1,)
+    with pytest.raises(_lib.MasurvError):
+        h.get_state(first=100, count=1)
+    h.close()
