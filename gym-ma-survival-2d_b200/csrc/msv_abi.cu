@@ -646,7 +646,7 @@ int msv_set_state(msv_handle* h, int32_t first, int32_t count, const msv_env_sta
       m.aint[i * N + e] = make_int4(s.health[i], s.cause[i], s.cooldown[i], inv);
     }
     m.hdr0[e] = make_int4(s.n_boxes | (s.n_items << 8) | (s.n_heals << 16) | (s.n_pending << 24), s.steps, s.episode, s.body_seq);
-    m.hdr1[e] = make_int4(s.contact_seq, s.first_step, 0, 0);
+    m.hdr1[e] = make_int4(s.contact_seq, s.first_step, 0, 1);   // .w: new fixtures -> the next Step searches for contacts first
     for (int k = 0; k < s.n_boxes; ++k) {
       m.box0[k * N + e] = make_float4(s.box_x[k], s.box_y[k], s.box_shape[k].hx, s.box_shape[k].hy);
       m.box1[k * N + e] = make_int4(s.box_health[k], (s.box_has_health[k] ? 1 : 0) | (s.box_shape[k].rehulled ? 2 : 0), s.box_cause[k], s.box_owner[k]);

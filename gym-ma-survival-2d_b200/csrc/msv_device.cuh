@@ -58,7 +58,7 @@ DEV float fclamp_(float a, float lo, float hi) { return fmax_(lo, fmin_(a, hi));
 
 // b2Rot::Set: sinf/cosf evaluated in double and rounded (correctly rounded
 // float on every platform the oracle runs on).
-DEV void rot_set(float angle, float& s, float& c) {
+__device__ __noinline__ void rot_set(float angle, float& s, float& c) {
   double ds, dc;
   sincos((double)angle, &ds, &dc);
   s = (float)ds; c = (float)dc;
@@ -140,7 +140,7 @@ DEV bool ray_circle(f2 center, float radius, f2 p1, f2 p2, float& fraction) {
   return false;
 }
 // b2PolygonShape::RayCast with maxFraction = 1
-DEV bool ray_box(const SBox& bx, f2 p1w, f2 p2w, float& fraction) {
+__device__ __noinline__ bool ray_box(const SBox& bx, f2 p1w, f2 p2w, float& fraction) {
   f2 p1 = sb_mulT(bx, p1w), p2 = sb_mulT(bx, p2w);
   f2 d = vsub(p2, p1);
   float lower = 0.0f, upper = 1.0f;

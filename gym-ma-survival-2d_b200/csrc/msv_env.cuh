@@ -1,8 +1,15 @@
-// msv_env.cuh -- one environment's step, executed by ONE thread of a block
-// whose threads hold consecutive environments (coalesced SoA traffic).  The
-// dynamically-indexed hot state (agent sweeps/velocities/fat AABBs, boxes)
-// lives in a bank-conflict-free shared-memory column per thread
-// (word w of thread t at sm[w * blockDim + t]).
+// msv_env.cuh -- one environment's step, executed by a GROUP of G adjacent
+// lanes of a warp (G = agent capacity of the kernel instance): lane g owns
+// agent g.  The per-agent phases -- motors, melee rays, broad phase, narrow
+// phase, the island of an agent that only touches static bodies, the TOI
+// scan, the camera rays -- run on all lanes at once, each on its own agent;
+// the cross-agent sequential rules (inventories, deaths, pickups, rewards,
+// agent-agent islands, TOI events, contact numbering) run on the group's
+// leader lane while the others wait at a group barrier.  The environment's hot
+// state (agent sweeps/velocities/fat AABBs, boxes, the touching-contact list)
+// lives in one shared-memory column per environment (word w of environment
+// slot s at sm[w * T + s]); lanes exchange the pair bit-matrices and small
+// results with warp shuffles of width G.
 //
 // Reference behaviour being reproduced (citations into /root/reference):
 //   env  = masurvival/envs/masurvival_env.py   sim = masurvival/simulation.py
@@ -11,12 +18,15 @@
 #pragma once
 #include "msv_device.cuh"
 #include "msv_types.cuh"
+#include "msv_launch.h"
 
 // shared-memory agent fields
 enum { F_CX, F_CY, F_A, F_VX, F_VY, F_W, F_C0X, F_C0Y, F_A0, F_ALPHA0, F_SLEEP,
-       F_FAT0, F_FAT1, F_FAT2, F_FAT3, F_FLAGS, F_COUNT };
+       F_FAT0, F_FAT1, F_FAT2, F_FAT3, F_FLAGS, F_QS, F_QC, F_COUNT };
 // shared-memory box fields
 enum { G_X, G_Y, G_HX, G_HY, G_AX, G_AY, G_ROT, G_COUNT };
+// shared-memory touching-contact fields (a b2Contact with a one-point manifold)
+enum { K_META, K_SEQ, K_MTYPE, K_LNX, K_LNY, K_LPX, K_LPY, K_NI, K_TI, K_COUNT };
 
 #define FL_ALIVE 1
 #define FL_AWAKE 2
@@ -58,46 +68,93 @@ struct TCon {
 
 struct BodyS { f2 c; float a; f2 v; float w; float invM, invI; };
 
-template <int AC, int BC, int HC>
+template <int AC, int BC, int HC, int G>
 struct Env {
   using PL = PairLayout<AC, BC>;
   static constexpr int P = PL::P, PW = PL::PW, NAA = PL::NAA;
   static constexpr int MAXC = AC <= 4 ? 16 : 24;
-  static constexpr int SM_WORDS = F_COUNT * AC + G_COUNT * BC;
+  static constexpr int SLOTS = AC / G;               // agents per lane
+  static constexpr int W_BOX = F_COUNT * AC, W_TC = W_BOX + G_COUNT * BC, W_MISC = W_TC + K_COUNT * MAXC;
+  static constexpr int SM_WORDS = W_MISC + 2;        // + contact counter, overflow counter
+  static constexpr int NR = 3;                       // contacts of a one-agent island kept in registers
+  static_assert(AC % G == 0 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two dividing AC");
 
   const DevConst& C;
   const DevState& S;
   float* sm;
-  int T, tid, e, N;
+  static constexpr int T = MSV_TPB / G;   // environment slots per block (shared-memory stride)
+  int es, g, e, N;        // es: my slot; g: my lane in the group
+  unsigned gmask;         // the group's lanes within the warp
+  bool lead;              // g == 0
 
+  // ---- registers that are only meaningful on the leader lane
   int health[AC], cause[AC], cooldown[AC], inv[AC];
-  int nb, ni, nh, np, steps, episode, body_seq, contact_seq, first_step, overflow;
-  unsigned long long ex[PW], tc[PW], en[PW];
+  int np, steps, episode, body_seq, contact_seq, first_step, overflow;
+  int newfix;             // b2World::e_newFixture: bodies were created since the last Step (reset, placed box, injected state)
   float zx, zy, zr; int zphase, ztcool, ztshrink, zend;
   float st_reward[AC]; int st_kills[AC]; int st_steps, st_heals, st_boxes, st_episodes;
-  // per-step trackers
   int use_heal, use_box;
   int new_box;
-  TCon tcs[MAXC]; int ntc;
-#ifdef MSV_PROFILE
-  int dbg_toi_calls = 0, dbg_toi_guard = 0; long long dbg_scan = 0, dbg_event = 0;
-#endif
-  // sensors
   unsigned seenA[AC];  // by PRE-death rank: bit j = agent j seen
   unsigned seenX[AC];  // non-omniscient only: bits 0-15 heals, 16-23 boxes, 24-31 box items (list positions)
   unsigned pre_alive;
+  // ---- replicated on every lane of the group (kept equal by share_*())
+  int nb, ni, nh;
+  unsigned long long ex[PW], tc[PW], en[PW];
+  unsigned long long own[PW];   // pairs whose body B is one of this lane's agents
+  int ntc;
 
-  __device__ Env(const DevConst& c, const DevState& s, float* smem, int T_, int tid_, int e_)
-      : C(c), S(s), sm(smem), T(T_), tid(tid_), e(e_), N(c.N) {}
+  __device__ Env(const DevConst& c, const DevState& s, float* smem, int es_, int g_, unsigned gmask_, int e_)
+      : C(c), S(s), sm(smem), es(es_), g(g_), e(e_), N(c.N), gmask(gmask_), lead(g_ == 0) {
+#pragma unroll
+    for (int w = 0; w < PW; ++w) own[w] = 0ull;
+    for (int i = g; i < AC; i += G) {
+      for (int a = 0; a < i; ++a) setb(own, p_aa(a, i));
+      for (int k = 0; k < BC; ++k) setb(own, p_ab(i, k));
+      for (int k = 0; k < 4; ++k) setb(own, p_aw(i, k));
+    }
+  }
+
+  // ---- group collectives (width-G shuffles; every lane of the group must call them together)
+  DEV void gsync() const { __syncwarp(gmask); }
+  template <class V> DEV V bc(V v) const { return __shfl_sync(gmask, v, 0, G); }
+  template <class V> DEV V from(V v, int j) const { return __shfl_sync(gmask, v, j, G); }
+  DEV unsigned or32(unsigned v) const {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) v |= __shfl_xor_sync(gmask, v, o, G);
+    return v;
+  }
+  DEV unsigned long long or64(unsigned long long v) const {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) v |= __shfl_xor_sync(gmask, v, o, G);
+    return v;
+  }
+  DEV void share_counts() { int c = bc(nb | (ni << 8) | (nh << 16)); nb = c & 255; ni = (c >> 8) & 255; nh = (c >> 16) & 255; }
+  DEV void share_bits() {
+#pragma unroll
+    for (int w = 0; w < PW; ++w) { ex[w] = bc(ex[w]); tc[w] = bc(tc[w]); en[w] = bc(en[w]); }
+  }
+  // every lane changed only the bits of its own pairs: reassemble the matrices
+  DEV void merge_bits() {
+#pragma unroll
+    for (int w = 0; w < PW; ++w) { ex[w] = or64(ex[w] & own[w]); tc[w] = or64(tc[w] & own[w]); en[w] = or64(en[w] & own[w]); }
+  }
 
   // ---- shared-memory accessors
-  DEV float& AG(int f, int i) { return sm[(f * AC + i) * T + tid]; }
-  DEV int& AGF(int i) { return reinterpret_cast<int*>(sm)[(F_FLAGS * AC + i) * T + tid]; }
-  DEV float& BX(int g, int k) { return sm[(F_COUNT * AC + g * BC + k) * T + tid]; }
-  DEV int& BXROT(int k) { return reinterpret_cast<int*>(sm)[(F_COUNT * AC + G_ROT * BC + k) * T + tid]; }
+  DEV float& AG(int f, int i) { return sm[(f * AC + i) * T + es]; }
+  DEV int& AGF(int i) { return reinterpret_cast<int*>(sm)[(F_FLAGS * AC + i) * T + es]; }
+  DEV float& BX(int f, int k) { return sm[(W_BOX + f * BC + k) * T + es]; }
+  DEV int& BXROT(int k) { return reinterpret_cast<int*>(sm)[(W_BOX + G_ROT * BC + k) * T + es]; }
+  DEV float& KF(int f, int k) { return sm[(W_TC + f * MAXC + k) * T + es]; }
+  DEV int& KI(int f, int k) { return reinterpret_cast<int*>(sm)[(W_TC + f * MAXC + k) * T + es]; }
+  DEV int& NTC() { return reinterpret_cast<int*>(sm)[(W_MISC + 0) * T + es]; }
+  DEV int& OVF() { return reinterpret_cast<int*>(sm)[(W_MISC + 1) * T + es]; }
   DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
   DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
   DEV f2 apos(int i) { return mk2(AG(F_CX, i), AG(F_CY, i)); }
+  // K_META: pair | (a + 1) << 8 | sid << 12 | b << 16
+  DEV static int meta_pack(int p, int a, int sid, int b) { return p | ((a + 1) << 8) | ((sid < 0 ? 0 : sid) << 12) | (b << 16); }
+  DEV static void meta_unpack(int m, int& p, int& a, int& sid, int& b) { p = m & 255; a = ((m >> 8) & 15) - 1; sid = (m >> 12) & 15; b = (m >> 16) & 15; }
 
   // ---- pair bit helpers
   DEV static bool bit(const unsigned long long* m, int p) { return (m[p >> 6] >> (p & 63)) & 1ull; }
@@ -120,33 +177,45 @@ struct Env {
 
   // ---- global state I/O -------------------------------------------------
   __device__ void load() {
-#pragma unroll
-    for (int i = 0; i < AC; ++i) {
+    for (int i = g; i < AC; i += G) {        // every lane: its agents' kinematics
       if (i < C.A) {
         float4 k0 = S.akin0[i * N + e], k1 = S.akin1[i * N + e], ft = S.afat[i * N + e];
-        int4 ai = S.aint[i * N + e];
         AG(F_CX, i) = k0.x; AG(F_CY, i) = k0.y; AG(F_A, i) = k0.z; AG(F_VX, i) = k0.w;
         AG(F_VY, i) = k1.x; AG(F_W, i) = k1.y; AG(F_SLEEP, i) = k1.z; AGF(i) = __float_as_int(k1.w) & 3;
         AG(F_FAT0, i) = ft.x; AG(F_FAT1, i) = ft.y; AG(F_FAT2, i) = ft.z; AG(F_FAT3, i) = ft.w;
         AG(F_C0X, i) = k0.x; AG(F_C0Y, i) = k0.y; AG(F_A0, i) = k0.z; AG(F_ALPHA0, i) = 0.0f;
-        health[i] = ai.x; cause[i] = ai.y; cooldown[i] = ai.z; inv[i] = ai.w;
-      } else { AGF(i) = 0; health[i] = 0; cause[i] = MSV_CAUSE_NONE; cooldown[i] = 0; inv[i] = 0; }
-      st_reward[i] = S.sreward[i * N + e]; st_kills[i] = S.skills[i * N + e];
+        AG(F_QS, i) = 0.0f; AG(F_QC, i) = 1.0f;
+      } else AGF(i) = 0;
     }
-    int4 h0 = S.hdr0[e], h1 = S.hdr1[e];
-    nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; np = (h0.x >> 24) & 255;
-    steps = h0.y; episode = h0.z; body_seq = h0.w;
-    contact_seq = h1.x; first_step = h1.y; overflow = h1.z;
+    nb = ni = nh = 0;
 #pragma unroll
-    for (int k = 0; k < BC; ++k) {
-      if (k < nb) load_box(k, k);
+    for (int w = 0; w < PW; ++w) { ex[w] = 0ull; tc[w] = 0ull; en[w] = 0ull; }
+    if (lead) {
+#pragma unroll
+      for (int i = 0; i < AC; ++i) {
+        if (i < C.A) { int4 ai = S.aint[i * N + e]; health[i] = ai.x; cause[i] = ai.y; cooldown[i] = ai.z; inv[i] = ai.w; }
+        else { health[i] = 0; cause[i] = MSV_CAUSE_NONE; cooldown[i] = 0; inv[i] = 0; }
+        st_reward[i] = S.sreward[i * N + e]; st_kills[i] = S.skills[i * N + e];
+      }
+      int4 h0 = S.hdr0[e], h1 = S.hdr1[e];
+      nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; np = (h0.x >> 24) & 255;
+      steps = h0.y; episode = h0.z; body_seq = h0.w;
+      contact_seq = h1.x; first_step = h1.y; overflow = h1.z; newfix = h1.w;
+#pragma unroll
+      for (int k = 0; k < BC; ++k) {
+        if (k < nb) load_box(k, k);
+      }
+#pragma unroll
+      for (int w = 0; w < PW; ++w) { ex[w] = S.pex[w * N + e]; tc[w] = S.ptc[w * N + e]; en[w] = S.pen[w * N + e]; }
+      float4 zc = S.zonecur[e]; int4 zi = S.zoneint[e];
+      zx = zc.x; zy = zc.y; zr = zc.z; zphase = zi.x; ztcool = zi.y; ztshrink = zi.z; zend = zi.w;
+      int4 sm_ = S.smisc[e];
+      st_steps = sm_.x; st_heals = sm_.y; st_boxes = sm_.z; st_episodes = sm_.w;
+      NTC() = 0; OVF() = 0;
     }
-#pragma unroll
-    for (int w = 0; w < PW; ++w) { ex[w] = S.pex[w * N + e]; tc[w] = S.ptc[w * N + e]; en[w] = S.pen[w * N + e]; }
-    float4 zc = S.zonecur[e]; int4 zi = S.zoneint[e];
-    zx = zc.x; zy = zc.y; zr = zc.z; zphase = zi.x; ztcool = zi.y; ztshrink = zi.z; zend = zi.w;
-    int4 sm_ = S.smisc[e];
-    st_steps = sm_.x; st_heals = sm_.y; st_boxes = sm_.z; st_episodes = sm_.w;
+    ntc = 0;
+    gsync();
+    share_counts(); share_bits();
   }
   // read box at global slot `src` into shared slot `dst`
   DEV void load_box(int dst, int src) {
@@ -156,24 +225,27 @@ struct Env {
     BX(G_HX, dst) = t.hx; BX(G_HY, dst) = t.hy; BX(G_AX, dst) = t.ax; BX(G_AY, dst) = t.ay; BXROT(dst) = t.rot;
   }
   __device__ void store() {
-#pragma unroll
-    for (int i = 0; i < AC; ++i) {
-      if (i < C.A) {
-        S.akin0[i * N + e] = make_float4(AG(F_CX, i), AG(F_CY, i), AG(F_A, i), AG(F_VX, i));
-        S.akin1[i * N + e] = make_float4(AG(F_VY, i), AG(F_W, i), AG(F_SLEEP, i), __int_as_float(AGF(i) & 3));
-        S.afat[i * N + e] = make_float4(AG(F_FAT0, i), AG(F_FAT1, i), AG(F_FAT2, i), AG(F_FAT3, i));
-        S.aint[i * N + e] = make_int4(health[i], cause[i], cooldown[i], inv[i]);
-      }
-      S.sreward[i * N + e] = st_reward[i]; S.skills[i * N + e] = st_kills[i];
+    gsync();
+    for (int i = g; i < C.A; i += G) {
+      S.akin0[i * N + e] = make_float4(AG(F_CX, i), AG(F_CY, i), AG(F_A, i), AG(F_VX, i));
+      S.akin1[i * N + e] = make_float4(AG(F_VY, i), AG(F_W, i), AG(F_SLEEP, i), __int_as_float(AGF(i) & 3));
+      S.afat[i * N + e] = make_float4(AG(F_FAT0, i), AG(F_FAT1, i), AG(F_FAT2, i), AG(F_FAT3, i));
     }
-    S.hdr0[e] = make_int4(nb | (ni << 8) | (nh << 16) | (np << 24), steps, episode, body_seq);
-    S.hdr1[e] = make_int4(contact_seq, first_step, overflow, 0);
-    // box positions/shapes only change on spawn/despawn, which write through
+    if (lead) {
 #pragma unroll
-    for (int w = 0; w < PW; ++w) { S.pex[w * N + e] = ex[w]; S.ptc[w * N + e] = tc[w]; S.pen[w * N + e] = en[w]; }
-    S.zonecur[e] = make_float4(zx, zy, zr, 0.0f);
-    S.zoneint[e] = make_int4(zphase, ztcool, ztshrink, zend);
-    S.smisc[e] = make_int4(st_steps, st_heals, st_boxes, st_episodes);
+      for (int i = 0; i < AC; ++i) {
+        if (i < C.A) S.aint[i * N + e] = make_int4(health[i], cause[i], cooldown[i], inv[i]);
+        S.sreward[i * N + e] = st_reward[i]; S.skills[i * N + e] = st_kills[i];
+      }
+      S.hdr0[e] = make_int4(nb | (ni << 8) | (nh << 16) | (np << 24), steps, episode, body_seq);
+      S.hdr1[e] = make_int4(contact_seq, first_step, overflow + OVF(), newfix);
+      // box positions/shapes only change on spawn/despawn, which write through
+#pragma unroll
+      for (int w = 0; w < PW; ++w) { S.pex[w * N + e] = ex[w]; S.ptc[w * N + e] = tc[w]; S.pen[w * N + e] = en[w]; }
+      S.zonecur[e] = make_float4(zx, zy, zr, 0.0f);
+      S.zoneint[e] = make_int4(zphase, ztcool, ztshrink, zend);
+      S.smisc[e] = make_int4(st_steps, st_heals, st_boxes, st_episodes);
+    }
   }
 
   // ---- geometry helpers ---------------------------------------------------
@@ -202,6 +274,7 @@ struct Env {
     int f = AGF(i);
     if (!(f & FL_AWAKE)) { AGF(i) = f | FL_AWAKE; AG(F_SLEEP, i) = 0.0f; }
   }
+  DEV void wake_all(unsigned m) { for (int i = 0; i < C.A; ++i) if ((m >> i) & 1u) wake(i); }
   DEV void sleep_body(int i) {  // b2Body::SetAwake(false)
     AGF(i) &= ~FL_AWAKE; AG(F_SLEEP, i) = 0.0f; AG(F_VX, i) = 0.0f; AG(F_VY, i) = 0.0f; AG(F_W, i) = 0.0f;
   }
@@ -246,7 +319,7 @@ struct Env {
     return kind;
   }
 
-  // Health._change_health (sem:490-500)
+  // Health._change_health (sem:490-500)                                [leader]
   DEV void agent_change_health(int i, int delta, int cz) {
     if (!alive(i)) return;
     if (C.teams && cz == MSV_CAUSE_TEAM0 + team_of(i)) return;  // immunities sem:942-946
@@ -275,9 +348,9 @@ struct Env {
     return kind;
   }
 
-  // ---- list maintenance (stable compaction, sim:185-189) -----------------
+  // ---- list maintenance (stable compaction, sim:185-189)            [leader]
   // shift the AB pair column k+1.. down by one for every agent
-  __device__ void remove_box(int k) {
+  __device__ __noinline__ void remove_box(int k) {
     for (int i = 0; i < C.A; ++i) {   // b2World::DestroyBody -> contacts die, touching ones wake
       int p = p_ab(i, k);
       if (bit(ex, p) && bit(tc, p)) wake(i);
@@ -340,30 +413,28 @@ struct Env {
   // b2ContactManager::FindNewContacts + AddPair over every body pair whose
   // fat AABBs overlap and that has no contact yet; new contacts are numbered
   // in ascending (proxyIdA, proxyIdB) order (creation sequence surrogate).
-  __device__ __forceinline__ void find_new_contacts() {
-    unsigned long long cand[PW];
-#pragma unroll
-    for (int w = 0; w < PW; ++w) cand[w] = 0ull;
-    bool any = false;
-    for (int i = 0; i < C.A; ++i) {
+  // candidate pairs whose body B is agent j
+  __device__ __noinline__ void candidates_of(int j, unsigned long long* cand) {
+    if (!alive(j)) return;
+    float fj[4]; agent_fat(j, fj);
+    for (int i = 0; i < j; ++i) {
       if (!alive(i)) continue;
+      int p = p_aa(i, j);
+      if (bit(ex, p)) continue;
       float fi[4]; agent_fat(i, fi);
-      for (int j = i + 1; j < C.A; ++j) {
-        if (!alive(j)) continue;
-        int p = p_aa(i, j);
-        if (bit(ex, p)) continue;
-        float fj[4]; agent_fat(j, fj);
-        if (aabb_overlap(fi, fj)) { setb(cand, p); any = true; }
-      }
-      for (int k = 0; k < BC + 4; ++k) {
-        if (k < BC && k >= nb) continue;
-        int p = k < BC ? p_ab(i, k) : p_aw(i, k - BC);
-        if (bit(ex, p)) continue;
-        float fs[4]; static_fat(k, fs);
-        if (aabb_overlap(fi, fs)) { setb(cand, p); any = true; }
-      }
+      if (aabb_overlap(fi, fj)) setb(cand, p);
     }
-    while (any) {
+    for (int k = 0; k < BC + 4; ++k) {
+      if (k < BC && k >= nb) continue;
+      int p = k < BC ? p_ab(j, k) : p_aw(j, k - BC);
+      if (bit(ex, p)) continue;
+      float fs[4]; static_fat(k, fs);
+      if (aabb_overlap(fj, fs)) setb(cand, p);
+    }
+  }
+  // [leader] create the candidate contacts in proxy-pair order
+  __device__ __noinline__ void number_candidates(unsigned long long* cand) {
+    for (;;) {
       int best = -1; unsigned bestKey = 0xFFFFFFFFu;
       for (int w = 0; w < PW; ++w) {
         unsigned long long m = cand[w];
@@ -383,21 +454,47 @@ struct Env {
       S.pimp[best * N + e] = make_float2(0.0f, 0.0f);
     }
   }
+  // [all lanes] every lane tests the pairs of its own agents; the leader numbers the new contacts
+  __device__ __noinline__ void find_new_contacts() {
+    unsigned long long cand[PW];
+#pragma unroll
+    for (int w = 0; w < PW; ++w) cand[w] = 0ull;
+    for (int j = g; j < C.A; j += G) candidates_of(j, cand);
+    bool any = false;
+#pragma unroll
+    for (int w = 0; w < PW; ++w) { cand[w] = or64(cand[w]); any |= cand[w] != 0ull; }
+    if (any) {                               // group-uniform
+      if (lead) number_candidates(cand);
+      share_bits();
+    }
+  }
+  // [leader] the same, sequentially (inside TOI events)
+  __device__ __noinline__ void find_new_contacts_seq() {
+    unsigned long long cand[PW];
+#pragma unroll
+    for (int w = 0; w < PW; ++w) cand[w] = 0ull;
+    for (int j = 0; j < C.A; ++j) candidates_of(j, cand);
+    number_candidates(cand);
+  }
 
   // evaluate the manifold of pair (a|sid, b) at the bodies' current transforms
-  DEV bool evaluate(int a, int sid, int b, Manifold& m) {
+  __device__ __noinline__ bool evaluate(int a, int sid, int b, Manifold& m) {
     if (a >= 0) return collide_circles(apos(a), apos(b), C.agent_r, C.agent_r, m);
     return collide_box_circle(static_box(sid), apos(b), C.agent_r, m);
   }
 
+  // append a touching contact to the environment's shared list (any lane)
   DEV void tcon_add(int p, int a, int sid, int b, const Manifold& m, float nimp, float timp) {
-    if (ntc >= MAXC) { overflow++; return; }
-    TCon& t = tcs[ntc++];
-    t.p = p; t.seq = (int)S.pseq[p * N + e]; t.a = a; t.sid = sid; t.b = b; t.flags = 0; t.m = m; t.ni = nimp; t.ti = timp;
+    int k = atomicAdd(&NTC(), 1);
+    if (k >= MAXC) { atomicAdd(&OVF(), 1); return; }
+    KI(K_META, k) = meta_pack(p, a, sid, b); KI(K_SEQ, k) = (int)S.pseq[p * N + e];
+    KI(K_MTYPE, k) = m.type; KF(K_LNX, k) = m.localNormal.x; KF(K_LNY, k) = m.localNormal.y;
+    KF(K_LPX, k) = m.localPoint.x; KF(K_LPY, k) = m.localPoint.y; KF(K_NI, k) = nimp; KF(K_TI, k) = timp;
   }
 
-  // b2Contact::Update for one pair; returns touching.  Appends to tcs.
-  DEV bool contact_update(int p, int a, int sid, int b, bool list, Manifold* mout = nullptr) {
+  // b2Contact::Update for one pair; returns touching.  Bodies to wake are
+  // collected in `wakem` (the caller applies them); appends to the list.
+  DEV bool contact_update(int p, int a, int sid, int b, bool list, unsigned& wakem, Manifold* mout = nullptr) {
     Manifold m; bool touching = evaluate(a, sid, b, m);
     if (mout) *mout = m;
     bool was = bit(tc, p);
@@ -405,17 +502,22 @@ struct Env {
     float2 imp = make_float2(0.0f, 0.0f);
     if (touching && was) imp = S.pimp[p * N + e];
     else if (was || touching) S.pimp[p * N + e] = imp;
-    if (touching != was) { if (a >= 0) wake(a); wake(b); }
+    if (touching != was) { if (a >= 0) wakem |= 1u << a; wakem |= 1u << b; }
     if (touching) setb(tc, p); else clrb(tc, p);
     if (touching && list) tcon_add(p, a, sid, b, m, imp.x, imp.y);
     return touching;
   }
 
-  // b2ContactManager::Collide
+  // b2ContactManager::Collide.  Every lane updates the contacts whose body B
+  // is one of its agents.  SetAwake calls are applied after the pass: a contact
+  // between two sleeping bodies is skipped by Box2D, and re-evaluating it for
+  // unmoved bodies returns the state it already has.
   __device__ __forceinline__ void collide() {
-    ntc = 0;
+    if (lead) NTC() = 0;
+    gsync();
+    unsigned wakem = 0;
     for (int w = 0; w < PW; ++w) {
-      unsigned long long mbits = ex[w];
+      unsigned long long mbits = ex[w] & own[w];
       while (mbits) {
         int p = w * 64 + __ffsll((long long)mbits) - 1; mbits &= mbits - 1;
         int a, sid, b; decode(p, a, sid, b);
@@ -430,13 +532,19 @@ struct Env {
         if (a >= 0) agent_fat(a, fa); else static_fat(sid, fa);
         agent_fat(b, fb);
         if (!aabb_overlap(fa, fb)) {  // b2ContactManager::Destroy
-          if (bit(tc, p)) { if (a >= 0) wake(a); wake(b); }
+          if (bit(tc, p)) { if (a >= 0) wakem |= 1u << a; wakem |= 1u << b; }
           clrb(ex, p); clrb(tc, p); clrb(en, p);
           continue;
         }
-        contact_update(p, a, sid, b, true);
+        contact_update(p, a, sid, b, true, wakem);
       }
     }
+    merge_bits();
+    wakem = or32(wakem);
+    gsync();                                 // every lane has read the awake flags
+    for (int i = g; i < C.A; i += G) if ((wakem >> i) & 1u) wake(i);
+    gsync();
+    ntc = NTC(); if (ntc > MAXC) ntc = MAXC;
   }
 
   // ---- contact solver (single manifold point) ----------------------------
@@ -556,33 +664,52 @@ struct Env {
   // solver rB == 0 (the manifold point is the circle centre).  Dropping those
   // exact no-ops lets the agent's state stay in registers across iterations;
   // the arithmetic that remains is bit-identical to the generic routines.
-  DEV void warm_start_static(const TCon& t, f2& vB, float& wB) {
-    f2 tangent = cross_vs(t.normal, 1.0f);
-    f2 Pv = vadd(vmul(t.ni, t.normal), vmul(t.ti, tangent));
-    wB += C.inv_I * vcross(t.rB, Pv);
+  DEV void warm_start_static(f2 normal, f2 rB, float ni_, float ti_, f2& vB, float& wB) {
+    f2 tangent = cross_vs(normal, 1.0f);
+    f2 Pv = vadd(vmul(ni_, normal), vmul(ti_, tangent));
+    wB += C.inv_I * vcross(rB, Pv);
     vB = vadd(vB, vmul(C.inv_mass, Pv));
   }
-  DEV void solve_velocity_static(TCon& t, f2& vB, float& wB) {
-    const f2 normal = t.normal, tangent = cross_vs(normal, 1.0f);
+  DEV void solve_velocity_static(f2 normal, f2 rB, float normalMass, float tangentMass, float& ni_, float& ti_, f2& vB, float& wB) {
+    const f2 tangent = cross_vs(normal, 1.0f);
     {
-      f2 dv = vadd(vB, cross_sv(wB, t.rB));
+      f2 dv = vadd(vB, cross_sv(wB, rB));
       float vt = vdot(dv, tangent) - 0.0f;
-      float lambda = t.tangentMass * (-vt);
-      float maxFriction = C.friction * t.ni;
-      float newImpulse = fclamp_(t.ti + lambda, -maxFriction, maxFriction);
-      lambda = newImpulse - t.ti; t.ti = newImpulse;
+      float lambda = tangentMass * (-vt);
+      float maxFriction = C.friction * ni_;
+      float newImpulse = fclamp_(ti_ + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - ti_; ti_ = newImpulse;
       f2 Pv = vmul(lambda, tangent);
-      vB = vadd(vB, vmul(C.inv_mass, Pv)); wB += C.inv_I * vcross(t.rB, Pv);
+      vB = vadd(vB, vmul(C.inv_mass, Pv)); wB += C.inv_I * vcross(rB, Pv);
     }
     {
-      f2 dv = vadd(vB, cross_sv(wB, t.rB));
+      f2 dv = vadd(vB, cross_sv(wB, rB));
       float vn = vdot(dv, normal);
-      float lambda = -t.normalMass * (vn - 0.0f);
-      float newImpulse = fmax_(t.ni + lambda, 0.0f);
-      lambda = newImpulse - t.ni; t.ni = newImpulse;
+      float lambda = -normalMass * (vn - 0.0f);
+      float newImpulse = fmax_(ni_ + lambda, 0.0f);
+      lambda = newImpulse - ni_; ni_ = newImpulse;
       f2 Pv = vmul(lambda, normal);
-      vB = vadd(vB, vmul(C.inv_mass, Pv)); wB += C.inv_I * vcross(t.rB, Pv);
+      vB = vadd(vB, vmul(C.inv_mass, Pv)); wB += C.inv_I * vcross(rB, Pv);
     }
+  }
+  // init_velocity for a static body A and agent B at cB: world normal, plane
+  // point, rB and the effective masses (mA = iA = 0 terms are exact zeros)
+  DEV void init_velocity_static(int sid, f2 localNormal, f2 localPoint, f2 cB, f2& normal, f2& planePoint, f2& rB,
+                                float& normalMass, float& tangentMass) {
+    SBox bx = static_box(sid);
+    normal = qmul(bx.qs, bx.qc, localNormal);
+    planePoint = sb_mul(bx, localPoint);
+    f2 pA = vadd(cB, vmul(B2_POLY_RADIUS - vdot(vsub(cB, planePoint), normal), normal));
+    f2 pB = vsub(cB, vmul(C.agent_r, normal));
+    f2 point = vmul(0.5f, vadd(pA, pB));
+    rB = vsub(point, cB);
+    float rnB = vcross(rB, normal);
+    float kNormal = C.inv_mass + C.inv_I * rnB * rnB;
+    normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+    f2 tangent = cross_vs(normal, 1.0f);
+    float rtB = vcross(rB, tangent);
+    float kTangent = C.inv_mass + C.inv_I * rtB * rtB;
+    tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
   }
   // world normal and plane point of a static face contact (constant while solving)
   DEV void static_plane(const TCon& t, f2& normal, f2& planePoint) {
@@ -633,15 +760,103 @@ struct Env {
     AGF(i) |= FL_MOVED;
   }
 
+  // b2Island::Solve for the island of ONE awake agent whose touching contacts
+  // are all against static bodies (the usual case).  `ord` lists the contacts
+  // (shared-list slots, 5 bits each) in island order = newest first.  With
+  // NRr <= NR the contact constants and impulses stay in registers.
+  template <int NRr>
+  __device__ __noinline__ void island_single(int i, int cnt, unsigned long long ord, float h, float dtRatio) {
+    f2 cB = apos(i);
+    AG(F_C0X, i) = cB.x; AG(F_C0Y, i) = cB.y; AG(F_A0, i) = AG(F_A, i);
+    f2 vB = mk2(C.damp * AG(F_VX, i), C.damp * AG(F_VY, i)); float wB = AG(F_W, i) * C.damp;  // v *= 1/(1+h*damping)
+    f2 nrm[NRr], pp[NRr];
+    bool ok = true;
+    if (cnt > 0) {
+      f2 rB[NRr]; float nm[NRr], tm[NRr], ni_[NRr], ti_[NRr]; int pr[NRr];
+#pragma unroll (NRr <= NR ? NRr : 1)
+      for (int k = 0; k < NRr; ++k) {
+        if (k < cnt) {
+          int s = (int)((ord >> (5 * k)) & 31ull);
+          int a_, sid, b_; meta_unpack(KI(K_META, s), pr[k], a_, sid, b_);
+          ni_[k] = dtRatio * KF(K_NI, s); ti_[k] = dtRatio * KF(K_TI, s);
+          init_velocity_static(sid, mk2(KF(K_LNX, s), KF(K_LNY, s)), mk2(KF(K_LPX, s), KF(K_LPY, s)), cB,
+                               nrm[k], pp[k], rB[k], nm[k], tm[k]);
+        }
+      }
+#pragma unroll (NRr <= NR ? NRr : 1)
+      for (int k = 0; k < NRr; ++k) if (k < cnt) warm_start_static(nrm[k], rB[k], ni_[k], ti_[k], vB, wB);
+      for (int it = 0; it < 10; ++it) {
+#pragma unroll (NRr <= NR ? NRr : 1)
+        for (int k = 0; k < NRr; ++k) if (k < cnt) solve_velocity_static(nrm[k], rB[k], nm[k], tm[k], ni_[k], ti_[k], vB, wB);
+      }
+#pragma unroll (NRr <= NR ? NRr : 1)
+      for (int k = 0; k < NRr; ++k) if (k < cnt) S.pimp[pr[k] * N + e] = make_float2(ni_[k], ti_[k]);
+    }
+    AG(F_VX, i) = vB.x; AG(F_VY, i) = vB.y; AG(F_W, i) = wB;
+    integrate_position(i, h);
+    if (cnt > 0) {
+      ok = false;
+      cB = apos(i);
+      for (int it = 0; it < 10 && !ok; ++it) {
+        float minSep = 0.0f;
+#pragma unroll (NRr <= NR ? NRr : 1)
+        for (int k = 0; k < NRr; ++k) if (k < cnt) minSep = fmin_(minSep, solve_position_static(nrm[k], pp[k], cB, false));
+        ok = minSep >= -3.0f * B2_LINEAR_SLOP;
+      }
+      AG(F_CX, i) = cB.x; AG(F_CY, i) = cB.y;
+    }
+    {
+      const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
+      float w = AG(F_W, i); f2 v = mk2(AG(F_VX, i), AG(F_VY, i));
+      float st;
+      if (w * w > angTol || vdot(v, v) > linTol) st = 0.0f; else st = AG(F_SLEEP, i) + h;
+      AG(F_SLEEP, i) = st;
+      if (ok && st >= B2_TIME_TO_SLEEP) sleep_body(i);
+    }
+    synchronize_fixtures(i);
+  }
+  // [lane] island of agent i when no agent touches another agent
+  DEV void solve_single(int i, float h, float dtRatio) {
+    int f = AGF(i);
+    if (!(f & FL_ALIVE) || !(f & FL_AWAKE)) return;
+    AGF(i) = f | FL_ISLAND;
+    // the agent's contact edges, newest (largest creation sequence) first
+    unsigned long long ord = 0ull; int cnt = 0; unsigned taken = 0;
+    for (;;) {
+      int best = -1, bestSeq = -1;
+      for (int k = 0; k < ntc; ++k) {
+        if ((taken >> k) & 1u) continue;
+        int p, a_, sid, b_; meta_unpack(KI(K_META, k), p, a_, sid, b_);
+        if (b_ != i || a_ >= 0) continue;
+        if (!bit(en, p) || !bit(tc, p)) continue;
+        int sq = KI(K_SEQ, k);
+        if (sq > bestSeq) { bestSeq = sq; best = k; }
+      }
+      if (best < 0) break;
+      taken |= 1u << best;
+      ord |= (unsigned long long)best << (5 * cnt); cnt++;
+    }
+    if (cnt <= NR) island_single<NR>(i, cnt, ord, h, dtRatio);
+    else island_single<BC + 4>(i, cnt, ord, h, dtRatio);
+  }
+
   // b2World::Solve: islands by DFS over touching contacts, seeds in body-list
   // order (newest body first = highest agent index first), contact edges
   // newest first; each island solved by b2Island::Solve.  Islands touch
   // disjoint bodies, so all islands are built first and then advanced
   // together (per-island contact order, position-iteration early-out and sleep
-  // decision are kept): a thread loops over ITS contacts once, not per seed.
-  __device__ __forceinline__ void solve(float h, float dtRatio) {
-    for (int i = 0; i < C.A; ++i) AGF(i) &= ~(FL_ISLAND | FL_MOVED);
-    for (int k = 0; k < ntc; ++k) tcs[k].flags = 0;
+  // decision are kept).  [leader] generic version, used when some agent touches
+  // another agent; works on a private copy of the shared contact list.
+  __device__ __noinline__ void solve_generic(float h, float dtRatio) {
+    TCon tcs[MAXC];
+    for (int k = 0; k < ntc; ++k) {
+      TCon& t = tcs[k];
+      meta_unpack(KI(K_META, k), t.p, t.a, t.sid, t.b);
+      if (t.a >= 0) t.sid = -1;
+      t.seq = KI(K_SEQ, k); t.flags = 0; t.m.type = KI(K_MTYPE, k);
+      t.m.localNormal = mk2(KF(K_LNX, k), KF(K_LNY, k)); t.m.localPoint = mk2(KF(K_LPX, k), KF(K_LPY, k));
+      t.ni = KF(K_NI, k); t.ti = KF(K_TI, k);
+    }
     int stack[AC], isl_of[AC];
     unsigned char order[MAXC], cisl[MAXC];
     int nisl = 0, nc = 0;
@@ -700,9 +915,9 @@ struct Env {
         } else {                               // one agent against static bodies: state in registers
           const int i = tcs[order[k0]].b;
           f2 vB = mk2(AG(F_VX, i), AG(F_VY, i)); float wB = AG(F_W, i);
-          for (int k = k0; k < k1; ++k) warm_start_static(tcs[order[k]], vB, wB);
+          for (int k = k0; k < k1; ++k) { TCon& t = tcs[order[k]]; warm_start_static(t.normal, t.rB, t.ni, t.ti, vB, wB); }
           for (int it = 0; it < 10; ++it)
-            for (int k = k0; k < k1; ++k) solve_velocity_static(tcs[order[k]], vB, wB);
+            for (int k = k0; k < k1; ++k) { TCon& t = tcs[order[k]]; solve_velocity_static(t.normal, t.rB, t.normalMass, t.tangentMass, t.ni, t.ti, vB, wB); }
           AG(F_VX, i) = vB.x; AG(F_VY, i) = vB.y; AG(F_W, i) = wB;
         }
         k0 = k1;
@@ -750,10 +965,22 @@ struct Env {
         for (int i = 0; i < C.A; ++i)
           if ((AGF(i) & FL_ISLAND) && ((can_sleep >> isl_of[i]) & 1u)) sleep_body(i);
     }
-    bool moved = false;
     for (int i = 0; i < C.A; ++i)
-      if (AGF(i) & FL_ISLAND) { synchronize_fixtures(i); moved |= (AGF(i) & FL_MOVED) != 0; }
-    if (moved) find_new_contacts();
+      if (AGF(i) & FL_ISLAND) synchronize_fixtures(i);
+  }
+
+  // b2World::Solve                                                   [all lanes]
+  __device__ __forceinline__ void solve(float h, float dtRatio) {
+    for (int i = g; i < C.A; i += G) AGF(i) &= ~(FL_ISLAND | FL_MOVED);
+    bool aa = false;                           // does any agent touch another agent? (group-uniform)
+    { unsigned long long m = tc[0] & en[0]; if (NAA < 64) m &= (1ull << NAA) - 1ull; aa = m != 0ull; }
+    gsync();
+    if (aa) { if (lead) solve_generic(h, dtRatio); }
+    else for (int i = g; i < C.A; i += G) solve_single(i, h, dtRatio);
+    gsync();
+    unsigned mv = 0;
+    for (int i = g; i < C.A; i += G) if (AGF(i) & FL_MOVED) mv = 1u;
+    if (or32(mv)) find_new_contacts();
   }
 
   // b2Body::Advance for agent i
@@ -767,27 +994,119 @@ struct Env {
     AG(F_CX, i) = AG(F_C0X, i); AG(F_CY, i) = AG(F_C0Y, i); AG(F_A, i) = AG(F_A0, i);
   }
 
+  // [leader] one TOI event of b2World::SolveTOI on contact minP at minAlpha.
+  // Returns bit 0: the contact was touching at the TOI (the sub-step ran);
+  // bit 1: the event left everything exactly as the previous one on minP did.
+  static constexpr int SNAPW = F_COUNT + 6 * PW + 1;
+  __device__ __noinline__ int toi_event(int minP, float minAlpha, float dt, unsigned* prev, int& prevP) {
+    int a, sid, b; decode(minP, a, sid, b);
+    // backup the agent's sweep, advance to the TOI, re-evaluate the contact
+    float bk[7] = {AG(F_C0X, b), AG(F_C0Y, b), AG(F_CX, b), AG(F_CY, b), AG(F_A0, b), AG(F_A, b), AG(F_ALPHA0, b)};
+    advance(b, minAlpha);
+    Manifold m_min; unsigned wk = 0;
+    bool touching = contact_update(minP, a, sid, b, false, wk, &m_min);
+    wake_all(wk);
+    if (!touching) {
+      clrb(en, minP);
+      AG(F_C0X, b) = bk[0]; AG(F_C0Y, b) = bk[1]; AG(F_CX, b) = bk[2]; AG(F_CY, b) = bk[3];
+      AG(F_A0, b) = bk[4]; AG(F_A, b) = bk[5]; AG(F_ALPHA0, b) = bk[6];
+      return 0;
+    }
+    wake(b);
+    // mini island: the TOI contact first, then the agent's other touching
+    // contacts against statics, newest first
+    TCon isl[8]; int nisl = 0;
+    {
+      TCon& t = isl[nisl++];
+      t.p = minP; t.seq = 0; t.a = -1; t.sid = sid; t.b = b; t.flags = 0; t.m = m_min; t.ni = 0.0f; t.ti = 0.0f;
+    }
+    {
+      unsigned long long done[PW];
+#pragma unroll
+      for (int w = 0; w < PW; ++w) done[w] = 0ull;
+      setb(done, minP);
+      for (;;) {
+        int best = -1, bestSeq = -1;
+        for (int k = 0; k < BC + 4; ++k) {
+          if (k < BC && k >= nb) continue;
+          int p = k < BC ? p_ab(b, k) : p_aw(b, k - BC);
+          if (!bit(ex, p) || bit(done, p)) continue;
+          int sq = (int)S.pseq[p * N + e];
+          if (sq > bestSeq) { bestSeq = sq; best = p; }
+        }
+        if (best < 0) break;
+        setb(done, best);
+        if (nisl >= 8) { overflow++; break; }
+        int a2, sid2, b2; decode(best, a2, sid2, b2);
+        Manifold m; unsigned wk2 = 0;
+        bool t2 = contact_update(best, a2, sid2, b2, false, wk2, &m);
+        wake_all(wk2);
+        if (!t2) continue;
+        TCon& t = isl[nisl++];
+        t.p = best; t.seq = 0; t.a = -1; t.sid = sid2; t.b = b; t.flags = 0; t.m = m; t.ni = 0.0f; t.ti = 0.0f;
+      }
+    }
+    float subdt = (1.0f - minAlpha) * dt;
+    // b2Island::SolveTOI -- every contact of the mini island has a static body A
+    {
+      f2 cB = apos(b);
+      for (int k = 0; k < nisl; ++k) static_plane(isl[k], isl[k].normal, isl[k].rA);  // rA := plane point
+      for (int it = 0; it < 20; ++it) {
+        float minSep = 0.0f;
+        for (int k = 0; k < nisl; ++k) minSep = fmin_(minSep, solve_position_static(isl[k].normal, isl[k].rA, cB, true));
+        if (minSep >= -1.5f * B2_LINEAR_SLOP) break;
+      }
+      AG(F_CX, b) = cB.x; AG(F_CY, b) = cB.y;
+    }
+    AG(F_C0X, b) = AG(F_CX, b); AG(F_C0Y, b) = AG(F_CY, b); AG(F_A0, b) = AG(F_A, b);
+    for (int k = 0; k < nisl; ++k) init_velocity(isl[k]);
+    {
+      f2 vB = mk2(AG(F_VX, b), AG(F_VY, b)); float wB = AG(F_W, b);
+      for (int it = 0; it < 10; ++it)
+        for (int k = 0; k < nisl; ++k) { TCon& t = isl[k]; solve_velocity_static(t.normal, t.rB, t.normalMass, t.tangentMass, t.ni, t.ti, vB, wB); }
+      AG(F_VX, b) = vB.x; AG(F_VY, b) = vB.y; AG(F_W, b) = wB;
+    }
+    integrate_position(b, subdt);
+    AGF(b) &= ~FL_MOVED;
+    synchronize_fixtures(b);
+    if (AGF(b) & FL_MOVED) find_new_contacts_seq();
+    // A TOI event is a pure function of (agent b's sweep/velocity/AABB words, the pair
+    // bit-matrices, the contact counter).  If this event left all of them exactly as the
+    // previous event on the same contact did, every further event on it would repeat
+    // verbatim and only count up to b2_maxSubSteps (a body wedged between two static
+    // bodies does this): the caller jumps the contact's toiCount there instead of replaying them.
+    unsigned snap[SNAPW];
+    for (int f = 0; f < F_COUNT; ++f) snap[f] = __float_as_uint(AG(f, b));
+    for (int w = 0; w < PW; ++w) {
+      snap[F_COUNT + 6 * w + 0] = (unsigned)ex[w]; snap[F_COUNT + 6 * w + 1] = (unsigned)(ex[w] >> 32);
+      snap[F_COUNT + 6 * w + 2] = (unsigned)tc[w]; snap[F_COUNT + 6 * w + 3] = (unsigned)(tc[w] >> 32);
+      snap[F_COUNT + 6 * w + 4] = (unsigned)en[w]; snap[F_COUNT + 6 * w + 5] = (unsigned)(en[w] >> 32);
+    }
+    snap[SNAPW - 1] = (unsigned)contact_seq;
+    bool same = prevP == minP;
+    for (int q = 0; q < SNAPW; ++q) { if (prev[q] != snap[q]) same = false; prev[q] = snap[q]; }
+    prevP = minP;
+    return 1 | (same ? 2 : 0);
+  }
+
   // b2World::SolveTOI: continuous collision of agents against static boxes
-  // and walls (agent-agent pairs are "two non-bullet dynamic bodies": skipped)
+  // and walls (agent-agent pairs are "two non-bullet dynamic bodies": skipped).
+  // Every lane evaluates b2TimeOfImpact for the contacts of its own agents;
+  // the group picks the minimum; the leader runs the event.
   __device__ __noinline__ void solve_toi(float dt) {
-    for (int i = 0; i < C.A; ++i) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
-    // per-contact toiCount: only contacts that produced events carry one
+    for (int i = g; i < C.A; i += G) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
+    // per-contact toiCount: only contacts that produced events carry one (replicated on every lane)
     int evP[8], evN[8], nev = 0;
-    // cached TOIs (b2Contact::e_toiFlag / m_toi): valid until the contact's agent is displaced
-    constexpr int MAXT = 12;
+    // cached TOIs (b2Contact::e_toiFlag / m_toi) of this lane's contacts: valid until the agent is displaced
+    constexpr int MAXT = SLOTS * (BC + 4) < 12 ? SLOTS * (BC + 4) : 12;
     int cP[MAXT]; float cAlpha[MAXT]; int ncache = 0;
-    constexpr int SNAPW = F_COUNT + 6 * PW + 1;
-    unsigned prev[SNAPW]; int prevP = -1;
+    unsigned prev[SNAPW]; int prevP = -1;      // leader: state after the previous event
     for (int q = 0; q < SNAPW; ++q) prev[q] = 0xFFFFFFFFu;
     for (int guard = 0; guard < 64; ++guard) {
-#ifdef MSV_PROFILE
-      dbg_toi_guard++;
-      long long dbg_t0 = clock64();
-#endif
-      int minP = -1; float minAlpha = 1.0f;
+      int minP = -1, minSeq = -1; float minAlpha = 1.0f;
       for (int w = 0; w < PW; ++w) {
-        // existing, enabled agent-vs-static contacts (pair index >= NAA), ascending
-        unsigned long long mbits = ex[w] & en[w];
+        // existing, enabled agent-vs-static contacts (pair index >= NAA) of my agents
+        unsigned long long mbits = ex[w] & en[w] & own[w];
         if (w == 0) mbits &= ~((1ull << NAA) - 1ull);
         while (mbits) {
           int p = w * 64 + __ffsll((long long)mbits) - 1; mbits &= mbits - 1;
@@ -799,9 +1118,6 @@ struct Env {
           for (int q = 0; q < ncache; ++q) if (cP[q] == p) { alpha = cAlpha[q]; have = true; }
           if (!have) {
             float beta;
-#ifdef MSV_PROFILE
-            dbg_toi_calls++;
-#endif
             const SBox sbx = static_box(k);
             const f2 q0 = mk2(AG(F_C0X, i), AG(F_C0Y, i)), q1 = apos(i);
             // b2TimeOfImpact can only report e_touching at a time where the true distance
@@ -824,151 +1140,79 @@ struct Env {
           }
           // the world contact list is newest first and the scan keeps the FIRST minimum:
           // on equal alpha the contact with the larger creation sequence wins
-          if (alpha < minAlpha || (alpha == minAlpha && minP >= 0 && alpha < 1.0f &&
-                                   S.pseq[p * N + e] > S.pseq[minP * N + e])) {
-            minAlpha = alpha; minP = p;
+          if (alpha < 1.0f) {
+            int sq = (int)S.pseq[p * N + e];
+            if (alpha < minAlpha || (alpha == minAlpha && sq > minSeq)) { minAlpha = alpha; minP = p; minSeq = sq; }
           }
         }
       }
-#ifdef MSV_PROFILE
-      long long dbg_t1 = clock64(); dbg_scan += dbg_t1 - dbg_t0;
-#endif
-      if (minP < 0 || 1.0f - 10.0f * B2_EPS < minAlpha) break;
-      int a, sid, b; decode(minP, a, sid, b);
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1) {        // group minimum (alpha ascending, creation sequence descending)
+        float oa = __shfl_xor_sync(gmask, minAlpha, o, G);
+        int op = __shfl_xor_sync(gmask, minP, o, G), os = __shfl_xor_sync(gmask, minSeq, o, G);
+        if (op >= 0 && (oa < minAlpha || (oa == minAlpha && os > minSeq))) { minAlpha = oa; minP = op; minSeq = os; }
+      }
+      if (minP < 0 || 1.0f - 10.0f * B2_EPS < minAlpha) break;   // group-uniform
       { int q = 0; while (q < ncache) { if (cP[q] == minP) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q; } }
-      // backup the agent's sweep, advance to the TOI, re-evaluate the contact
-      float bk[7] = {AG(F_C0X, b), AG(F_C0Y, b), AG(F_CX, b), AG(F_CY, b), AG(F_A0, b), AG(F_A, b), AG(F_ALPHA0, b)};
-      advance(b, minAlpha);
-      int save_ntc = ntc;
-      Manifold m_min;
-      bool touching = contact_update(minP, a, sid, b, false, &m_min);
+      gsync();
+      int r = 0;
+      if (lead) r = toi_event(minP, minAlpha, dt, prev, prevP);
+      gsync();
+      r = bc(r);
+      share_bits();
       {
         int q = 0; for (; q < nev; ++q) if (evP[q] == minP) break;
         if (q == nev && nev < 8) { evP[nev] = minP; evN[nev] = 0; nev++; }
         if (q < nev) evN[q]++;
       }
-      if (!touching) {
-        clrb(en, minP);
-        AG(F_C0X, b) = bk[0]; AG(F_C0Y, b) = bk[1]; AG(F_CX, b) = bk[2]; AG(F_CY, b) = bk[3];
-        AG(F_A0, b) = bk[4]; AG(F_A, b) = bk[5]; AG(F_ALPHA0, b) = bk[6];
-        continue;
-      }
-      wake(b);
-      // mini island: the TOI contact first, then the agent's other touching
-      // contacts against statics, newest first
-      TCon isl[8]; int nisl = 0;
-      {
-        TCon& t = isl[nisl++];
-        t.p = minP; t.seq = 0; t.a = -1; t.sid = sid; t.b = b; t.flags = 0; t.m = m_min; t.ni = 0.0f; t.ti = 0.0f;
-      }
-      {
-        unsigned long long done[PW];
-#pragma unroll
-        for (int w = 0; w < PW; ++w) done[w] = 0ull;
-        setb(done, minP);
-        for (;;) {
-          int best = -1, bestSeq = -1;
-          for (int k = 0; k < BC + 4; ++k) {
-            if (k < BC && k >= nb) continue;
-            int p = k < BC ? p_ab(b, k) : p_aw(b, k - BC);
-            if (!bit(ex, p) || bit(done, p)) continue;
-            int sq = (int)S.pseq[p * N + e];
-            if (sq > bestSeq) { bestSeq = sq; best = p; }
-          }
-          if (best < 0) break;
-          setb(done, best);
-          if (nisl >= 8) { overflow++; break; }
-          int a2, sid2, b2; decode(best, a2, sid2, b2);
-          Manifold m;
-          bool t2 = contact_update(best, a2, sid2, b2, false, &m);
-          if (!t2) continue;
-          TCon& t = isl[nisl++];
-          t.p = best; t.seq = 0; t.a = -1; t.sid = sid2; t.b = b; t.flags = 0; t.m = m; t.ni = 0.0f; t.ti = 0.0f;
-        }
-      }
-      ntc = save_ntc;
-      float subdt = (1.0f - minAlpha) * dt;
-      // b2Island::SolveTOI -- every contact of the mini island has a static body A
-      {
-        f2 cB = apos(b);
-        for (int k = 0; k < nisl; ++k) static_plane(isl[k], isl[k].normal, isl[k].rA);  // rA := plane point
-        for (int it = 0; it < 20; ++it) {
-          float minSep = 0.0f;
-          for (int k = 0; k < nisl; ++k) minSep = fmin_(minSep, solve_position_static(isl[k].normal, isl[k].rA, cB, true));
-          if (minSep >= -1.5f * B2_LINEAR_SLOP) break;
-        }
-        AG(F_CX, b) = cB.x; AG(F_CY, b) = cB.y;
-      }
-      AG(F_C0X, b) = AG(F_CX, b); AG(F_C0Y, b) = AG(F_CY, b); AG(F_A0, b) = AG(F_A, b);
-      for (int k = 0; k < nisl; ++k) init_velocity(isl[k]);
-      {
-        f2 vB = mk2(AG(F_VX, b), AG(F_VY, b)); float wB = AG(F_W, b);
-        for (int it = 0; it < 10; ++it)
-          for (int k = 0; k < nisl; ++k) solve_velocity_static(isl[k], vB, wB);
-        AG(F_VX, b) = vB.x; AG(F_VY, b) = vB.y; AG(F_W, b) = wB;
-      }
-      integrate_position(b, subdt);
-      AGF(b) &= ~FL_MOVED;
-      synchronize_fixtures(b);
-      if (AGF(b) & FL_MOVED) find_new_contacts();
+      if (!(r & 1)) continue;
       {  // "Invalidate all contact TOIs on this displaced body"
+        int a3, s3, b; decode(minP, a3, s3, b);
         int q = 0;
         while (q < ncache) {
-          int a3, s3, b3; decode(cP[q], a3, s3, b3);
-          if (b3 == b) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q;
+          int a4, s4, b4; decode(cP[q], a4, s4, b4);
+          if (b4 == b) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q;
         }
       }
-      // A TOI event is a pure function of (agent b's sweep/velocity/AABB words, the pair
-      // bit-matrices, the contact counter).  If this event left all of them exactly as the
-      // previous event on the same contact did, every further event on it would repeat
-      // verbatim and only count up to b2_maxSubSteps (a body wedged between two static
-      // bodies does this): jump the contact's toiCount there instead of replaying them.
-      {
-        unsigned snap[SNAPW];
-        for (int f = 0; f < F_COUNT; ++f) snap[f] = __float_as_uint(AG(f, b));
-        for (int w = 0; w < PW; ++w) {
-          snap[F_COUNT + 6 * w + 0] = (unsigned)ex[w]; snap[F_COUNT + 6 * w + 1] = (unsigned)(ex[w] >> 32);
-          snap[F_COUNT + 6 * w + 2] = (unsigned)tc[w]; snap[F_COUNT + 6 * w + 3] = (unsigned)(tc[w] >> 32);
-          snap[F_COUNT + 6 * w + 4] = (unsigned)en[w]; snap[F_COUNT + 6 * w + 5] = (unsigned)(en[w] >> 32);
-        }
-        snap[SNAPW - 1] = (unsigned)contact_seq;
-        bool same = prevP == minP;
-        for (int q = 0; q < SNAPW; ++q) { if (prev[q] != snap[q]) same = false; prev[q] = snap[q]; }
-        prevP = minP;
-        if (same)
-          for (int q = 0; q < nev; ++q) if (evP[q] == minP && evN[q] <= B2_MAX_SUBSTEPS) evN[q] = B2_MAX_SUBSTEPS + 1;
-      }
-#ifdef MSV_PROFILE
-      dbg_event += clock64() - dbg_t1;
-#endif
+      if (r & 2)
+        for (int q = 0; q < nev; ++q) if (evP[q] == minP && evN[q] <= B2_MAX_SUBSTEPS) evN[q] = B2_MAX_SUBSTEPS + 1;
     }
+    gsync();
   }
 
   // ======================================================================
   //                      SEMANTICS (pre_step / post_step)
   // ======================================================================
-  __device__ __forceinline__ void pre_step(const uint8_t* act) {
+  // agents/DynamicMotors.pre_step (sim:407-424)                      [all lanes]
+  __device__ __forceinline__ void pre_motors(const uint8_t* actions, bool real) {
+    for (int i = g; i < C.A; i += G) {
+      if (!alive(i)) continue;
+      int a0 = 1, a1 = 1, a2 = 1;            // padding envs (N rounded up to the block size) get the no-op action
+      if (real) { const uint8_t* a = actions + ((size_t)e * C.A + i) * 6; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
+      float s, c; rot_set(AG(F_A, i), s, c);
+      AG(F_QS, i) = s; AG(F_QC, i) = c;
+      float par = C.imp_par[a0], nor = C.imp_nor[a1];
+      float ix = c * par + (-s) * nor, iy = s * par + c * nor;
+      wake(i);
+      AG(F_VX, i) += C.inv_mass * ix; AG(F_VY, i) += C.inv_mass * iy;
+      AG(F_W, i) += C.inv_I * C.imp_ang[a2];
+    }
+  }
+  // [leader] pending drops, UseLast, GiveLast
+  DEV void pre_use_give(const uint8_t* act) {
     use_heal = 0; use_box = 0; new_box = 0;
+    bool any = np > 0;
+#pragma unroll
+    for (int i = 0; i < AC; ++i) if (i < C.A && (act[6 * i + 4] | act[6 * i + 5])) any = true;
+    if (any) pre_use_give_body(act);
+  }
+  __device__ __noinline__ void pre_use_give_body(const uint8_t* act) {
     // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
     for (int q = 0; q < np; ++q) {
       float4 p0 = S.pend0[q * N + e];
       add_item(p0.x, p0.y, p0.z, p0.w, S.pend1[q * N + e]);
     }
     np = 0;
-    float qs[AC], qc[AC];
-    // agents/DynamicMotors.pre_step (sim:407-424)
-#pragma unroll
-    for (int i = 0; i < AC; ++i) {
-      qs[i] = 0.0f; qc[i] = 1.0f;
-      if (i >= C.A || !alive(i)) continue;
-      rot_set(AG(F_A, i), qs[i], qc[i]);
-      const uint8_t* a = act + 6 * i;
-      float par = C.imp_par[a[0]], nor = C.imp_nor[a[1]];
-      float ix = qc[i] * par + (-qs[i]) * nor, iy = qs[i] * par + qc[i] * nor;
-      wake(i);
-      AG(F_VX, i) += C.inv_mass * ix; AG(F_VY, i) += C.inv_mass * iy;
-      AG(F_W, i) += C.inv_I * C.imp_ang[a[2]];
-    }
     // agents/UseLast.pre_step (sem:300-309) -> Inventory.use (sem:206-213)
 #pragma unroll
     for (int i = 0; i < AC; ++i) {
@@ -979,7 +1223,8 @@ struct Env {
         use_box++;
         if (nb >= BC) { overflow++; continue; }
         float L = C.box_item_offset;
-        f2 off = mk2(qc[i] * L + (-qs[i]) * 0.0f, qs[i] * L + qc[i] * 0.0f);
+        float qs = AG(F_QS, i), qc = AG(F_QC, i);
+        f2 off = mk2(qc * L + (-qs) * 0.0f, qs * L + qc * 0.0f);
         float x = AG(F_CX, i) + off.x, y = AG(F_CY, i) + off.y;
         int reh = __float_as_int(pl.w) & 1;
         S.box0[nb * N + e] = make_float4(x, y, pl.x, pl.y);
@@ -987,7 +1232,7 @@ struct Env {
         S.boxseq[nb * N + e] = body_seq++;
         load_box(nb, nb);
         for (int j = 0; j < C.A; ++j) { int p = p_ab(j, nb); clrb(ex, p); clrb(tc, p); clrb(en, p); }
-        nb++; new_box = 1;
+        nb++; new_box = 1; newfix = 1;
       }
     }
     // agents/GiveLast.pre_step (sem:335-370): taker = nearest body of any kind
@@ -1016,30 +1261,59 @@ struct Env {
         for (int j = 0; j < AC; ++j) if (j == tidx) inv_push(j, kind, pl);
       }                                                                // else lost (Q6)
     }
-    // agents/Melee.pre_step (sem:584-617) / ContinuousMelee (sem:531-554)
+  }
+  // agents/Melee.pre_step (sem:584-617) / ContinuousMelee (sem:531-554).  The
+  // rays only depend on geometry (boxes placed above included), which the
+  // health changes do not alter: every lane casts its agents' rays, then the
+  // leader applies the hits in agent order.                          [all lanes]
+  __device__ __forceinline__ void pre_melee(const uint8_t* act) {
+    unsigned raymask = 0;
+    if (lead) {
 #pragma unroll
-    for (int i = 0; i < AC; ++i) {
-      if (i >= C.A || !alive(i)) continue;
-      bool on_cd = C.melee_cooldown >= 0 && cooldown[i] > 0;
-      if (!act[6 * i + 3] || on_cd) continue;
-      f2 me = apos(i);
-      float L = C.melee_range;
-      f2 hand = mk2(qc[i] * L + (-qs[i]) * 0.0f, qs[i] * L + qc[i] * 0.0f);
-      int tidx; float frac;
-      int kind = raycast(me, vadd(me, hand), i, tidx, frac);
-      if (kind == KIND_NONE) continue;
-      int cz = C.teams ? MSV_CAUSE_TEAM0 + team_of(i) : i;
-      if (kind == KIND_AGENT) agent_change_health(tidx, -C.melee_damage, cz);
-      else if (kind == KIND_BOX) box_change_health(tidx, -C.melee_damage, cz);
-      if (C.melee_cooldown >= 0) cooldown[i] = C.melee_cooldown;
+      for (int i = 0; i < AC; ++i) {
+        if (i >= C.A || !alive(i)) continue;
+        bool on_cd = C.melee_cooldown >= 0 && cooldown[i] > 0;
+        if (act[6 * i + 3] && !on_cd) raymask |= 1u << i;
+      }
     }
-    if (C.melee_cooldown >= 0) {
+    raymask = bc(raymask);
+    if (raymask) {                             // group-uniform
+      int res[AC];
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        const int i = s * G + g;
+        int r = 0;
+        if ((raymask >> i) & 1u) {
+          f2 me = apos(i);
+          float L = C.melee_range, qs = AG(F_QS, i), qc = AG(F_QC, i);
+          f2 hand = mk2(qc * L + (-qs) * 0.0f, qs * L + qc * 0.0f);
+          int tidx; float frac;
+          int kind = raycast(me, vadd(me, hand), i, tidx, frac);
+          r = kind | ((tidx & 255) << 8);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) res[s * G + j] = from(r, j);
+      }
+      if (lead) {
+#pragma unroll
+        for (int i = 0; i < AC; ++i) {
+          if (!((raymask >> i) & 1u)) continue;
+          int kind = res[i] & 255, tidx = (res[i] >> 8) & 255;
+          if (kind == KIND_NONE) continue;
+          int cz = C.teams ? MSV_CAUSE_TEAM0 + team_of(i) : i;
+          if (kind == KIND_AGENT) agent_change_health(tidx, -C.melee_damage, cz);
+          else if (kind == KIND_BOX) box_change_health(tidx, -C.melee_damage, cz);
+          if (C.melee_cooldown >= 0) cooldown[i] = C.melee_cooldown;
+        }
+      }
+    }
+    if (lead && C.melee_cooldown >= 0) {
 #pragma unroll
       for (int i = 0; i < AC; ++i) if (cooldown[i] > 0) cooldown[i]--;
     }
   }
 
-  DEV double philox_uniform(uint32_t step, uint32_t stream, uint32_t k) {
+  __device__ __noinline__ double philox_uniform(uint32_t step, uint32_t stream, uint32_t k) {
     uint32_t o[4];
     philox4x32(C.env_offset + (uint32_t)e, (uint32_t)episode, step, (stream << 16) | (k >> 1), C.seed_lo, C.seed_hi, o);
     uint32_t a = o[(k & 1) * 2], b = o[(k & 1) * 2 + 1];
@@ -1067,48 +1341,60 @@ struct Env {
     t -= BC;
     float2 h = S.heal[t * N + e]; return mk2(h.x, h.y);
   }
-  __device__ __forceinline__ void cameras() {
-    pre_alive = 0; int row = 0;
-    int rowof[AC];
-    for (int i = 0; i < AC; ++i) { seenA[i] = 0; seenX[i] = 0; }
+  // every lane is the camera of its own agents                      [all lanes]
+  __device__ __noinline__ void cameras() {
+    gsync();
     const bool all_bodies = !C.omniscient;            // env:706-739 read the full seen-lists
-    // pass 1: which (observer i, target t) pairs have the target's centre inside the cone
-    unsigned long long incone[AC];
-    for (int i = 0; i < AC; ++i) incone[i] = 0ull;
-    for (int i = 0; i < C.A; ++i) {
-      rowof[i] = -1;
-      if (!alive(i)) continue;
-      pre_alive |= 1u << i; rowof[i] = row++;
-      f2 me = apos(i); float s, c; rot_set(AG(F_A, i), s, c);
-      unsigned long long m = 0ull;
-      for (int j = 0; j < C.A; ++j)
-        if (j != i && alive(j) && in_cone(qmulT(s, c, vsub(apos(j), me)))) m |= 1ull << j;
-      if (all_bodies) {
-        for (int k = 0; k < nb; ++k) if (in_cone(qmulT(s, c, vsub(target_pos(AC + k), me)))) m |= 1ull << (AC + k);
-        for (int k = 0; k < ni; ++k) if (in_cone(qmulT(s, c, vsub(target_pos(AC + BC + k), me)))) m |= 1ull << (AC + BC + k);
-        for (int k = 0; k < nh; ++k) if (in_cone(qmulT(s, c, vsub(target_pos(AC + 2 * BC + k), me)))) m |= 1ull << (AC + 2 * BC + k);
-      }
-      incone[i] = m;
-    }
-    // pass 2: one line-of-sight ray per in-cone pair (a thread walks ITS list)
-    for (int i = 0; i < C.A; ++i) {
-      unsigned long long m = incone[i];
-      unsigned sa = 0, sx = 0;
-      while (m) {
-        int t = __ffsll((long long)m) - 1; m &= m - 1;
-        f2 me = apos(i), o = target_pos(t);
-        f2 d = vsub(o, me);
-        f2 end = mk2(me.x + C.cam_k1 * d.x, me.y + C.cam_k1 * d.y);
-        int idx; float fr;
-        int kind = raycast(me, end, i, idx, fr);
-        if (t < AC) { if (kind == KIND_AGENT && idx == t) sa |= 1u << t; }
-        else if (t < AC + BC) { if (kind == KIND_BOX && idx == t - AC) sx |= 1u << (16 + t - AC); }
-        else if (t < AC + 2 * BC) { if (kind == KIND_ITEM && idx == t - AC - BC) sx |= 1u << (24 + t - AC - BC); }
-        else { if (kind == KIND_HEAL && idx == t - AC - 2 * BC) sx |= 1u << (t - AC - 2 * BC); }
-      }
-      if (rowof[i] >= 0) {
+    unsigned saL[SLOTS], sxL[SLOTS];
 #pragma unroll
-        for (int r = 0; r < AC; ++r) if (r == rowof[i]) { seenA[r] = sa; seenX[r] = sx; }
+    for (int s = 0; s < SLOTS; ++s) {
+      const int i = s * G + g;
+      unsigned sa = 0, sx = 0;
+      if (i < C.A && alive(i)) {
+        // pass 1: which targets have their centre inside the cone
+        f2 me = apos(i); float sn, cs; rot_set(AG(F_A, i), sn, cs);
+        unsigned long long m = 0ull;
+        for (int j = 0; j < C.A; ++j)
+          if (j != i && alive(j) && in_cone(qmulT(sn, cs, vsub(apos(j), me)))) m |= 1ull << j;
+        if (all_bodies) {
+          for (int k = 0; k < nb; ++k) if (in_cone(qmulT(sn, cs, vsub(target_pos(AC + k), me)))) m |= 1ull << (AC + k);
+          for (int k = 0; k < ni; ++k) if (in_cone(qmulT(sn, cs, vsub(target_pos(AC + BC + k), me)))) m |= 1ull << (AC + BC + k);
+          for (int k = 0; k < nh; ++k) if (in_cone(qmulT(sn, cs, vsub(target_pos(AC + 2 * BC + k), me)))) m |= 1ull << (AC + 2 * BC + k);
+        }
+        // pass 2: one line-of-sight ray per in-cone target
+        while (m) {
+          int t = __ffsll((long long)m) - 1; m &= m - 1;
+          f2 o = target_pos(t);
+          f2 d = vsub(o, me);
+          f2 end = mk2(me.x + C.cam_k1 * d.x, me.y + C.cam_k1 * d.y);
+          int idx; float fr;
+          int kind = raycast(me, end, i, idx, fr);
+          if (t < AC) { if (kind == KIND_AGENT && idx == t) sa |= 1u << t; }
+          else if (t < AC + BC) { if (kind == KIND_BOX && idx == t - AC) sx |= 1u << (16 + t - AC); }
+          else if (t < AC + 2 * BC) { if (kind == KIND_ITEM && idx == t - AC - BC) sx |= 1u << (24 + t - AC - BC); }
+          else { if (kind == KIND_HEAL && idx == t - AC - 2 * BC) sx |= 1u << (t - AC - 2 * BC); }
+        }
+      }
+      saL[s] = sa; sxL[s] = sx;
+    }
+    // rows of Cameras.seen are in the order of the bodies alive NOW (before this step's deaths)
+    unsigned saA[AC], sxA[AC];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) { saA[s * G + j] = from(saL[s], j); sxA[s * G + j] = from(sxL[s], j); }
+    }
+    if (lead) {
+      pre_alive = 0; int row = 0;
+#pragma unroll
+      for (int i = 0; i < AC; ++i) { seenA[i] = 0; seenX[i] = 0; }
+#pragma unroll
+      for (int i = 0; i < AC; ++i) {
+        if (i >= C.A || !alive(i)) continue;
+        pre_alive |= 1u << i;
+#pragma unroll
+        for (int r = 0; r < AC; ++r) if (r == row) { seenA[r] = saA[i]; seenX[r] = sxA[i]; }
+        row++;
       }
     }
   }
@@ -1125,6 +1411,7 @@ struct Env {
 
   int n_deaths, deaths[AC], n_kills, kill_cause[AC];
 
+  // [leader]
   __device__ __forceinline__ void post_step_boxes() {
     // boxes/Health.post_step (sem:429-435) + Object.pre_despawn (sem:858-861, 911-912)
     for (int k = 0; k < nb;) {
@@ -1141,65 +1428,92 @@ struct Env {
     }
   }
   // agents/Cameras.post_step (sim:333-334) runs between the two halves
+  // [leader] agents/Health.post_step -> despawn(dead) (sem:429-448)
+  __device__ __noinline__ void handle_deaths() {
+    int total = 0;
+    for (int d = 0; d < n_deaths; ++d) total += inv_n(deaths[d]);
+    int top = total;
+    for (int d = 0; d < n_deaths; ++d) {  // DeathDrop.pre_despawn (sem:387-396)
+      int i = deaths[d];
+      f2 me = apos(i);
+      int n = inv_n(i);
+      for (int j = 0; j < n; ++j) {
+        double ang = 2 * 3.141592653589793 * philox_uniform((uint32_t)steps, STREAM_DEATH, (uint32_t)(--top));
+        f2 off = from_polar(C.drop_radius, (float)ang);
+        float x = me.x + off.x, y = me.y + off.y;
+        int kind = inv_kind(i, j);
+        if (kind == MSV_ITEM_HEAL) add_heal(x, y);
+        else { float4 pl = S.ainv[(i * 4 + j) * N + e]; add_item(x, y, pl.x, pl.y, __float_as_int(pl.z)); }
+      }
+#pragma unroll
+      for (int q = 0; q < AC; ++q) if (q == i) inv[q] = 0;
+    }
+    for (int d = 0; d < n_deaths; ++d) {
+      int cz = MSV_CAUSE_NONE;
+#pragma unroll
+      for (int q = 0; q < AC; ++q) if (q == deaths[d]) cz = cause[q];
+      kill_cause[n_kills++] = cz;           // TrackKills sem:628-629
+    }
+    for (int d = 0; d < n_deaths; ++d) kill_agent(deaths[d]);
+  }
+  // [leader] agents/AutoPickup.post_step (sem:278-283) for agent i: bodies in creation order
+  __device__ __noinline__ void pickup_agent(int i) {
+    const float r2 = C.pickup_r * C.pickup_r;
+    f2 me = apos(i);
+    int lastSeq = -1;
+    for (;;) {
+      int bestSeq = 0x7FFFFFFF, bkind = KIND_NONE, bidx = -1;
+      for (int k = 0; k < ni; ++k) {
+        float4 it = S.item0[k * N + e]; f2 d = vsub(mk2(it.x, it.y), me);
+        if (!(vdot(d, d) <= r2)) continue;
+        int sq = S.item1[k * N + e].y;
+        if (sq > lastSeq && sq < bestSeq) { bestSeq = sq; bkind = KIND_ITEM; bidx = k; }
+      }
+      for (int k = 0; k < nh; ++k) {
+        float2 h = S.heal[k * N + e]; f2 d = vsub(mk2(h.x, h.y), me);
+        if (!(vdot(d, d) <= r2)) continue;
+        int sq = S.healseq[k * N + e];
+        if (sq > lastSeq && sq < bestSeq) { bestSeq = sq; bkind = KIND_HEAL; bidx = k; }
+      }
+      if (bkind == KIND_NONE) break;
+      lastSeq = bestSeq;
+      if (inv_n(i) + 1 > C.inv_slots) continue;  // sem:184-185
+      if (bkind == KIND_HEAL) { inv_push(i, MSV_ITEM_HEAL, make_float4(0.f, 0.f, 0.f, 0.f)); remove_heal(bidx); seen_remove(0, 16, bidx); }
+      else {
+        float4 it = S.item0[bidx * N + e]; int2 i1 = S.item1[bidx * N + e];
+        inv_push(i, MSV_ITEM_BOX, make_float4(it.z, it.w, __int_as_float(i1.x), __int_as_float(1)));
+        remove_item(bidx); seen_remove(24, 8, bidx);
+      }
+    }
+  }
+  // [all lanes] the post_step hooks after the cameras.  Every lane pre-checks
+  // whether anything lies within pickup range of its own agents (removals by
+  // earlier agents can only shrink that set), the leader runs the exact
+  // sequential pickups for those agents only.
   __device__ __forceinline__ void post_step_rest() {
-    // agents/Health.post_step -> despawn(dead) (sem:429-448)
-    n_deaths = 0; n_kills = 0;
-    {
-      int total = 0;
-      for (int i = 0; i < C.A; ++i) if (alive(i) && health[i] <= 0) { deaths[n_deaths++] = i; total += inv_n(i); }
-      if (n_deaths > 0) {
-        int top = total;
-        for (int d = 0; d < n_deaths; ++d) {  // DeathDrop.pre_despawn (sem:387-396)
-          int i = deaths[d];
-          f2 me = apos(i);
-          int n = inv_n(i);
-          for (int j = 0; j < n; ++j) {
-            double ang = 2 * 3.141592653589793 * philox_uniform((uint32_t)steps, STREAM_DEATH, (uint32_t)(--top));
-            f2 off = from_polar(C.drop_radius, (float)ang);
-            float x = me.x + off.x, y = me.y + off.y;
-            int kind = inv_kind(i, j);
-            if (kind == MSV_ITEM_HEAL) add_heal(x, y);
-            else { float4 pl = S.ainv[(i * 4 + j) * N + e]; add_item(x, y, pl.x, pl.y, __float_as_int(pl.z)); }
-          }
-          inv[i] = 0;
-        }
-        for (int d = 0; d < n_deaths; ++d) kill_cause[n_kills++] = cause[deaths[d]];  // TrackKills sem:628-629
-        for (int d = 0; d < n_deaths; ++d) kill_agent(deaths[d]);
-      }
+    int dflag = 0;
+    if (lead) {
+      n_deaths = 0; n_kills = 0;
+#pragma unroll
+      for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && health[i] <= 0) deaths[n_deaths++] = i;
+      if (n_deaths > 0) { handle_deaths(); dflag = 1; }
     }
-    // agents/AutoPickup.post_step (sem:278-283): bodies in creation order
+    dflag = bc(dflag);
+    if (dflag) { gsync(); share_counts(); }   // drops changed the lists, deaths the flags
+    unsigned near = 0;
     {
-      float r2 = C.pickup_r * C.pickup_r;
-      for (int i = 0; i < C.A; ++i) {
+      const float r2 = C.pickup_r * C.pickup_r;
+      for (int i = g; i < C.A; i += G) {
         if (!alive(i)) continue;
-        f2 me = apos(i);
-        int lastSeq = -1;
-        for (;;) {
-          int bestSeq = 0x7FFFFFFF, bkind = KIND_NONE, bidx = -1;
-          for (int k = 0; k < ni; ++k) {
-            float4 it = S.item0[k * N + e]; f2 d = vsub(mk2(it.x, it.y), me);
-            if (!(vdot(d, d) <= r2)) continue;
-            int sq = S.item1[k * N + e].y;
-            if (sq > lastSeq && sq < bestSeq) { bestSeq = sq; bkind = KIND_ITEM; bidx = k; }
-          }
-          for (int k = 0; k < nh; ++k) {
-            float2 h = S.heal[k * N + e]; f2 d = vsub(mk2(h.x, h.y), me);
-            if (!(vdot(d, d) <= r2)) continue;
-            int sq = S.healseq[k * N + e];
-            if (sq > lastSeq && sq < bestSeq) { bestSeq = sq; bkind = KIND_HEAL; bidx = k; }
-          }
-          if (bkind == KIND_NONE) break;
-          lastSeq = bestSeq;
-          if (inv_n(i) + 1 > C.inv_slots) continue;  // sem:184-185
-          if (bkind == KIND_HEAL) { inv_push(i, MSV_ITEM_HEAL, make_float4(0.f, 0.f, 0.f, 0.f)); remove_heal(bidx); seen_remove(0, 16, bidx); }
-          else {
-            float4 it = S.item0[bidx * N + e]; int2 i1 = S.item1[bidx * N + e];
-            inv_push(i, MSV_ITEM_BOX, make_float4(it.z, it.w, __int_as_float(i1.x), __int_as_float(1)));
-            remove_item(bidx); seen_remove(24, 8, bidx);
-          }
-        }
+        f2 me = apos(i); bool any = false;
+        for (int k = 0; k < ni; ++k) { float4 it = S.item0[k * N + e]; f2 d = vsub(mk2(it.x, it.y), me); if (vdot(d, d) <= r2) any = true; }
+        for (int k = 0; k < nh; ++k) { float2 h = S.heal[k * N + e]; f2 d = vsub(mk2(h.x, h.y), me); if (vdot(d, d) <= r2) any = true; }
+        if (any) near |= 1u << i;
       }
     }
+    near = or32(near);
+    if (!lead) return;
+    for (int i = 0; i < C.A; ++i) if ((near >> i) & 1u) pickup_agent(i);
     // agents/SafeZone.post_step (sem:758-768) + tick (sem:776-811)
     for (int i = 0; i < C.A; ++i) {
       if (!alive(i)) continue;
@@ -1236,7 +1550,8 @@ struct Env {
   // others_mask (env:692-703) as bits: bit (i*AC + j) set <=> observer i sees
   // agent j.  Q1: Cameras.seen is looked up by the POST-death list position.
   // The observation tensors themselves are written by k_obs (msv_kernels.cu).
-  __device__ void store_obm() {
+  // [leader]
+  __device__ __noinline__ void store_obm() {
     unsigned long long bits = 0ull;
     int r = 0;
     for (int i = 0; i < C.A; ++i) {
@@ -1269,8 +1584,8 @@ struct Env {
     return any;
   }
 
-  // compute_rewards (env:757-803), is_done (env:810-831), _update_stats (env:483-508)
-  __device__ __forceinline__ bool rewards_done(DevOut& O) {
+  // compute_rewards (env:757-803), is_done (env:810-831), _update_stats (env:483-508)   [leader]
+  __device__ __noinline__ bool rewards_done(DevOut& O) {
     const int A = C.A;
     float rew[AC]; int lk[AC];
     for (int i = 0; i < AC; ++i) { rew[i] = 0.0f; lk[i] = 0; }
@@ -1319,8 +1634,8 @@ struct Env {
   // BaseEnv.reset (env:59-74): SpawnGrid (sem:59-79), ResetSpawns (sem:82-94),
   // RandomizeBoxShapes (sem:97-120), ThickRoomWalls, SafeZone.post_reset
   // (sem:739-756).  The numpy Generator is replaced by counter-based
-  // Philox4x32-10 keyed by (seed, global env id, episode).
-  __device__ __forceinline__ void reset() {
+  // Philox4x32-10 keyed by (seed, global env id, episode).          [leader]
+  __device__ __noinline__ void reset() {
     episode += 1; steps = 0;
     int n = C.grid_n;
     unsigned char perm[64];
@@ -1331,7 +1646,7 @@ struct Env {
       unsigned char t = perm[i]; perm[i] = perm[j]; perm[j] = t;
     }
     int top = n;
-    body_seq = 0; contact_seq = 0; first_step = 1;
+    body_seq = 0; contact_seq = 0; first_step = 1; newfix = 1;
     nb = 0; ni = 0; nh = 0; np = 0;
 #pragma unroll
     for (int w = 0; w < PW; ++w) { ex[w] = 0ull; tc[w] = 0ull; en[w] = 0ull; }

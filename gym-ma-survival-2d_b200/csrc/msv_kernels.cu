@@ -1,6 +1,7 @@
 // msv_kernels.cu -- the sm_100a kernels of libmasurv.so and their launchers.
 //
-// k_step  : one full MaSurvival.step (env:76-90) for every environment:
+// k_step  : one full MaSurvival.step (env:76-90) for every environment, a group
+//           of G lanes per environment (lane g = agent g, see msv_env.cuh):
 //           queue_actions -> pre_step hooks -> b2World::Step x2 -> post_step
 //           hooks -> observations -> rewards -> done -> stats (-> auto-reset).
 // k_reset : BaseEnv.reset (env:59-74) for every environment.
@@ -9,117 +10,147 @@
 #include "msv_env.cuh"
 #include "msv_launch.h"
 
-// debug phase profile (enabled by msv_debug_profile): sum over threads of the
-// clock64() cycles spent in each phase of k_step
-__device__ unsigned long long g_prof[32];   // [0..11] per-phase sums, [16+k] per-phase max over threads of one launch, [12] max total
+// debug phase profile (make PROFILE=1 + msv_debug_profile): sum over the
+// leader lanes of the clock64() cycles spent in each phase of k_step
+__device__ unsigned long long g_prof[32];   // [0..11] per-phase sums, [12] max total, [16+k] phases of the slowest group
 #ifdef MSV_PROFILE
 #define PROF(k) do { if (C.profile) { long long _t = clock64(); ph[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
 #else
 #define PROF(k) do { } while (0)
 #endif
 
-template <int AC, int BC, int HC>
+// thread -> (environment slot of the block, lane of the group)
+// keep the warps of a block in the same phase: they then share instruction-cache lines
+#ifdef MSV_NO_PHASE_SYNC
+#define PHASE_SYNC() do { } while (0)
+#else
+#define PHASE_SYNC() __syncthreads()
+#endif
+#define MSV_GROUP_SETUP(G)                                                                       \
+  const int T = MSV_TPB / (G), es = threadIdx.x / (G), g = threadIdx.x % (G);                    \
+  const int e = blockIdx.x * T + es;  /* C.N is a multiple of MSV_TPB, hence of T */             \
+  const unsigned gmask = (((G) >= 32) ? 0xffffffffu : ((1u << (G)) - 1u)) << ((threadIdx.x & 31) & ~((G) - 1))
+
+template <int AC, int BC, int HC, int G>
 __global__ void __launch_bounds__(MSV_TPB)
 k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
        const __grid_constant__ DevOut Oc, const uint8_t* __restrict__ actions) {
   extern __shared__ float sm[];
-  const int lane_ = threadIdx.x & 31;
-  const int e = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * C.epw + lane_;
-  if (lane_ >= C.epw || e >= C.N) return;
+  MSV_GROUP_SETUP(G);
   DevOut O = Oc;
-  Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
+  Env<AC, BC, HC, G> env(C, S, sm, es, g, gmask, e);
 #ifdef MSV_PROFILE
   long long t_last = C.profile ? clock64() : 0;
   const long long t_begin = t_last;
   unsigned long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   env.load();
+  const bool real = e < C.n_real;   // padding envs (N rounded up to the block size) get the no-op action
   uint8_t act[AC * 6];
-  {
+  if (env.lead) {
     const uint8_t* src = actions + (size_t)e * C.A * 6;
-    const bool real = e < C.n_real;   // padding envs (N rounded up to the block size) get the no-op action
     for (int k = 0; k < AC * 6; ++k) act[k] = (real && k < C.A * 6) ? src[k] : (uint8_t)(k % 6 < 3 ? 1 : 0);
   }
   PROF(0);
-  env.pre_step(act);                       // sim:234-235
+  PHASE_SYNC();
+  env.pre_motors(actions, real);           // sim:234-235
+  env.gsync();
+  if (env.lead) env.pre_use_give(act);
+  env.gsync();
+  env.share_counts();
+  const int newfix = env.bc(env.newfix);
+  if (env.bc(env.new_box)) env.share_bits();
+  env.pre_melee(act);
   PROF(1);
+#pragma unroll 1
   for (int sub = 0; sub < 2; ++sub) {      // sim:236-239: b2World::Step x2
-    if (sub == 0) env.find_new_contacts(); // newFixture (boxes placed in pre_step)
+    if (sub == 0 && newfix) { env.find_new_contacts(); env.newfix = 0; }  // b2World::Step: e_newFixture
     PROF(2);
+    PHASE_SYNC();
     env.collide();
     PROF(3);
-    env.solve(C.dt, env.first_step ? 0.0f : C.dt_ratio1);
+    PHASE_SYNC();
+    const int first = env.bc(env.first_step);
+    env.solve(C.dt, first ? 0.0f : C.dt_ratio1);
     PROF(4);
+    PHASE_SYNC();
     env.solve_toi(C.dt);
     env.first_step = 0;
     PROF(5);
   }
-  env.post_step_boxes();
+  if (env.lead) env.post_step_boxes();
+  env.share_counts();
   PROF(6);
+  PHASE_SYNC();
   env.cameras();
   PROF(7);
+  PHASE_SYNC();
+  int again = 0;
   env.post_step_rest();                    // sim:241-242
   PROF(8);
-  bool done = env.rewards_done(O);         // env:85-89
-  if (done && C.auto_reset) {              // vector-env extension: the observation returned is the new episode's first
-    env.st_episodes++;
-    env.reset();
-    env.cameras();
+  if (env.lead) {
+    bool done = env.rewards_done(O);       // env:85-89
+    if (done && C.auto_reset) {            // vector-env extension: the observation returned is the new episode's first
+      env.st_episodes++;
+      env.reset();
+      again = 1;
+    }
   }
+  if (env.bc(again)) { env.share_counts(); env.cameras(); }
   PROF(9);
-  env.store_obm();                         // env:84: the observation tensors are gathered by k_obs
+  if (env.lead) env.store_obm();           // env:84: the observation tensors are gathered by k_obs
   PROF(10);
   env.store();
   PROF(11);
 #ifdef MSV_PROFILE
-  if (C.profile) {
+  if (C.profile && env.lead) {
     for (int k = 0; k < 12; ++k) atomicAdd(&g_prof[k], ph[k]);
     unsigned long long tot = (unsigned long long)(clock64() - t_begin);
     unsigned long long prev = atomicMax(&g_prof[12], tot);
-    if (tot > prev) {   // (racy, indicative) phase breakdown + identity of the slowest thread so far
+    if (tot > prev) {   // (racy, indicative) phase breakdown + identity of the slowest group so far
       for (int k = 0; k < 12; ++k) g_prof[16 + k] = ph[k];
-      g_prof[13] = (unsigned long long)e; g_prof[14] = (unsigned long long)env.dbg_toi_calls; g_prof[15] = (unsigned long long)env.dbg_toi_guard; g_prof[16 + 10] = (unsigned long long)env.dbg_scan; g_prof[16 + 11] = (unsigned long long)env.dbg_event;
+      g_prof[13] = (unsigned long long)e;
     }
   }
 #endif
 }
 
-template <int AC, int BC, int HC>
+template <int AC, int BC, int HC, int G>
 __global__ void __launch_bounds__(MSV_TPB)
 k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
         const __grid_constant__ DevOut Oc, int only_done) {
   extern __shared__ float sm[];
-  const int lane_ = threadIdx.x & 31;
-  const int e = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * C.epw + lane_;
-  if (lane_ >= C.epw || e >= C.N) return;
+  MSV_GROUP_SETUP(G);
   DevOut O = Oc;
-  if (only_done && !O.dones[e]) return;    // auto_reset = 2: only the envs that just finished
-  Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
+  if (only_done && !O.dones[e]) return;    // auto_reset = 2: only the envs that just finished (whole group leaves)
+  Env<AC, BC, HC, G> env(C, S, sm, es, g, gmask, e);
   env.load();
-  if (only_done) env.st_episodes++;
-  env.reset();
+  if (env.lead) {
+    if (only_done) env.st_episodes++;
+    env.reset();
+  }
+  env.share_counts();
   env.cameras();
-  env.store_obm();
-  if (!only_done) {
-    for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
-    O.dones[e] = 0;
+  if (env.lead) {
+    env.store_obm();
+    if (!only_done) {
+      for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
+      O.dones[e] = 0;
+    }
   }
   env.store();
 }
 
-template <int AC, int BC, int HC>
+template <int AC, int BC, int HC, int G>
 __global__ void __launch_bounds__(MSV_TPB)
 k_observe(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
           const __grid_constant__ DevOut Oc) {
   extern __shared__ float sm[];
-  const int lane_ = threadIdx.x & 31;
-  const int e = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * C.epw + lane_;
-  if (lane_ >= C.epw || e >= C.N) return;
-  DevOut O = Oc;
-  Env<AC, BC, HC> env(C, S, sm, blockDim.x, threadIdx.x, e);
+  MSV_GROUP_SETUP(G);
+  Env<AC, BC, HC, G> env(C, S, sm, es, g, gmask, e);
   env.load();
   env.cameras();
-  env.store_obm();
+  if (env.lead) env.store_obm();
 }
 
 // fetch_observations (env:510-657): one thread per output float, gathered from
@@ -317,31 +348,31 @@ __global__ void k_stats(int N, int stride, int AC, float* sreward, int* skills, 
 }
 
 // ------------------------------------------------------------- launchers ---
-template <int AC, int BC, int HC>
+template <int AC, int BC, int HC, int G>
 static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, const DevOut& O,
                             const uint8_t* actions, cudaStream_t st) {
-  const int warps = (C.N + C.epw - 1) / C.epw;
-  int blocks = (warps + (MSV_TPB / 32) - 1) / (MSV_TPB / 32);
-  size_t smem = (size_t)Env<AC, BC, HC>::SM_WORDS * MSV_TPB * sizeof(float);
+  const int epb = MSV_TPB / G;                       // environments per block
+  const int blocks = C.N / epb;
+  size_t smem = (size_t)Env<AC, BC, HC, G>::SM_WORDS * epb * sizeof(float);
   if (which == 3) {  // one-time: allow the dynamic shared memory the kernels need
-    cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_observe<AC, BC, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_observe<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
   }
-  if (which == 0) k_step<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, actions);
-  else if (which == 1) k_reset<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 0);
-  else if (which == 4) k_reset<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 1);
-  else k_observe<AC, BC, HC><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
+  if (which == 0) k_step<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O, actions);
+  else if (which == 1) k_reset<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 0);
+  else if (which == 4) k_reset<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 1);
+  else k_observe<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
   return cudaPeekAtLastError();
 }
 
 cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S, const DevOut& O,
                        const uint8_t* actions, cudaStream_t st) {
   switch (cap) {
-    case 0: return launch_t<2, 4, 4>(which, C, S, O, actions, st);
-    case 1: return launch_t<4, 4, 4>(which, C, S, O, actions, st);
-    default: return launch_t<8, 8, 16>(which, C, S, O, actions, st);
+    case 0: return launch_t<2, 4, 4, 2>(which, C, S, O, actions, st);
+    case 1: return launch_t<4, 4, 4, 4>(which, C, S, O, actions, st);
+    default: return launch_t<8, 8, 16, 8>(which, C, S, O, actions, st);
   }
 }
 

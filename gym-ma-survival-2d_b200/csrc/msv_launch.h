@@ -2,7 +2,9 @@
 // kernel launchers (msv_kernels.cu).
 #pragma once
 #include "msv_types.cuh"
-#define MSV_TPB 64
+#ifndef MSV_TPB
+#define MSV_TPB 256
+#endif
 // cap: capacity class 0 = <2,4,4>, 1 = <4,4,4>, 2 = <8,8,16>; which: 0 step, 1 reset, 2 observe, 3 one-time kernel attribute setup, 4 reset only the envs whose done flag is set
 cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S, const DevOut& O,
                        const uint8_t* actions, cudaStream_t st);

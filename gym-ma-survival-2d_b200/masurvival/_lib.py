@@ -10,7 +10,7 @@ import numpy as np
 from .config import CONFIG_DT, STATE_DT, STATS_DT
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmasurv.so')
+LIB_PATH = os.environ.get('MSV_LIB') or os.path.join(_HERE, 'libmasurv.so')   # MSV_LIB: development override
 
 MSV_OK = 0
 ERRORS = {-1: 'MSV_ERR_INVALID', -2: 'MSV_ERR_CUDA', -3: 'MSV_ERR_NO_DEVICE',

@@ -35,7 +35,7 @@ def run(variant, N, steps=200, warm=50, prof=True):
         L.msv_debug_profile(h.h, 0, buf)
         print('   max over threads (any of 20 launches): total=%d; ' % buf[12] + ', '.join(f'{n}={buf[16+i]}' for i, n in enumerate(['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'observe', 'store'])))
         names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'observe', 'store']
-        tot = sum(buf[:12])
+        tot = sum(buf[:12]) or 1
         print('   phase cycles/thread/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(names)))
     h.close()
 
