@@ -68,6 +68,9 @@ struct TCon {
 
 struct BodyS { f2 c; float a; f2 v; float w; float invM, invI; };
 
+// the block's dynamic shared memory (addressed as shared, not through a generic pointer)
+extern __shared__ float msv_sm[];
+
 template <int AC, int BC, int HC, int G>
 struct Env {
   using PL = PairLayout<AC, BC>;
@@ -81,7 +84,6 @@ struct Env {
 
   const DevConst& C;
   const DevState& S;
-  float* sm;
   static constexpr int T = MSV_TPB / G;   // environment slots per block (shared-memory stride)
   int es, g, e, N;        // es: my slot; g: my lane in the group
   unsigned gmask;         // the group's lanes within the warp
@@ -104,8 +106,8 @@ struct Env {
   unsigned long long own[PW];   // pairs whose body B is one of this lane's agents
   int ntc;
 
-  __device__ Env(const DevConst& c, const DevState& s, float* smem, int es_, int g_, unsigned gmask_, int e_)
-      : C(c), S(s), sm(smem), es(es_), g(g_), e(e_), N(c.N), gmask(gmask_), lead(g_ == 0) {
+  __device__ __forceinline__ Env(const DevConst& c, const DevState& s, int es_, int g_, unsigned gmask_, int e_)
+      : C(c), S(s), es(es_), g(g_), e(e_), N(c.N), gmask(gmask_), lead(g_ == 0) {
 #pragma unroll
     for (int w = 0; w < PW; ++w) own[w] = 0ull;
     for (int i = g; i < AC; i += G) {
@@ -140,15 +142,38 @@ struct Env {
     for (int w = 0; w < PW; ++w) { ex[w] = or64(ex[w] & own[w]); tc[w] = or64(tc[w] & own[w]); en[w] = or64(en[w] & own[w]); }
   }
 
+  // ---- cold paths.  The functions marked __noinline__ below (rare events and
+  // the leader's heavy sequential rules) are compiled once, out of line, and
+  // are only ever invoked on a COPY of the environment's registers: the object
+  // the hot code works on never has its address taken, so the compiler keeps
+  // it in registers instead of spilling every field around the calls.
+  DEV void take(const Env& o) {
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      health[i] = o.health[i]; cause[i] = o.cause[i]; cooldown[i] = o.cooldown[i]; inv[i] = o.inv[i];
+      st_reward[i] = o.st_reward[i]; st_kills[i] = o.st_kills[i]; seenA[i] = o.seenA[i]; seenX[i] = o.seenX[i];
+      kill_cause[i] = o.kill_cause[i];
+    }
+    np = o.np; steps = o.steps; episode = o.episode; body_seq = o.body_seq; contact_seq = o.contact_seq;
+    first_step = o.first_step; overflow = o.overflow; newfix = o.newfix;
+    zx = o.zx; zy = o.zy; zr = o.zr; zphase = o.zphase; ztcool = o.ztcool; ztshrink = o.ztshrink; zend = o.zend;
+    st_steps = o.st_steps; st_heals = o.st_heals; st_boxes = o.st_boxes; st_episodes = o.st_episodes;
+    use_heal = o.use_heal; use_box = o.use_box; new_box = o.new_box; pre_alive = o.pre_alive;
+    nb = o.nb; ni = o.ni; nh = o.nh; ntc = o.ntc; dmask = o.dmask; n_kills = o.n_kills;
+#pragma unroll
+    for (int w = 0; w < PW; ++w) { ex[w] = o.ex[w]; tc[w] = o.tc[w]; en[w] = o.en[w]; }
+  }
+#define MSV_COLD(call) do { Env c_(*this); c_.call; take(c_); } while (0)
+
   // ---- shared-memory accessors
-  DEV float& AG(int f, int i) { return sm[(f * AC + i) * T + es]; }
-  DEV int& AGF(int i) { return reinterpret_cast<int*>(sm)[(F_FLAGS * AC + i) * T + es]; }
-  DEV float& BX(int f, int k) { return sm[(W_BOX + f * BC + k) * T + es]; }
-  DEV int& BXROT(int k) { return reinterpret_cast<int*>(sm)[(W_BOX + G_ROT * BC + k) * T + es]; }
-  DEV float& KF(int f, int k) { return sm[(W_TC + f * MAXC + k) * T + es]; }
-  DEV int& KI(int f, int k) { return reinterpret_cast<int*>(sm)[(W_TC + f * MAXC + k) * T + es]; }
-  DEV int& NTC() { return reinterpret_cast<int*>(sm)[(W_MISC + 0) * T + es]; }
-  DEV int& OVF() { return reinterpret_cast<int*>(sm)[(W_MISC + 1) * T + es]; }
+  DEV float& AG(int f, int i) { return msv_sm[(f * AC + i) * T + es]; }
+  DEV int& AGF(int i) { return reinterpret_cast<int*>(msv_sm)[(F_FLAGS * AC + i) * T + es]; }
+  DEV float& BX(int f, int k) { return msv_sm[(W_BOX + f * BC + k) * T + es]; }
+  DEV int& BXROT(int k) { return reinterpret_cast<int*>(msv_sm)[(W_BOX + G_ROT * BC + k) * T + es]; }
+  DEV float& KF(int f, int k) { return msv_sm[(W_TC + f * MAXC + k) * T + es]; }
+  DEV int& KI(int f, int k) { return reinterpret_cast<int*>(msv_sm)[(W_TC + f * MAXC + k) * T + es]; }
+  DEV int& NTC() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 0) * T + es]; }
+  DEV int& OVF() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 1) * T + es]; }
   DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
   DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
   DEV f2 apos(int i) { return mk2(AG(F_CX, i), AG(F_CY, i)); }
@@ -176,7 +201,7 @@ struct Env {
   }
 
   // ---- global state I/O -------------------------------------------------
-  __device__ void load() {
+  DEV void load() {
     for (int i = g; i < AC; i += G) {        // every lane: its agents' kinematics
       if (i < C.A) {
         float4 k0 = S.akin0[i * N + e], k1 = S.akin1[i * N + e], ft = S.afat[i * N + e];
@@ -224,7 +249,7 @@ struct Env {
     SBox t; sb_set_shape(t, b0.z, b0.w, (b1.y >> 1) & 1);
     BX(G_HX, dst) = t.hx; BX(G_HY, dst) = t.hy; BX(G_AX, dst) = t.ax; BX(G_AY, dst) = t.ay; BXROT(dst) = t.rot;
   }
-  __device__ void store() {
+  DEV void store() {
     gsync();
     for (int i = g; i < C.A; i += G) {
       S.akin0[i * N + e] = make_float4(AG(F_CX, i), AG(F_CY, i), AG(F_A, i), AG(F_VX, i));
@@ -285,7 +310,7 @@ struct Env {
   // fraction over independent b2Shape::RayCast tests (sim:431-439, 471-484).
   // Every exact test is preceded by a conservative reject (segment AABB vs a
   // bound of the shape): it can only skip shapes the exact test would miss.
-  __device__ __noinline__ int raycast(f2 p1, f2 p2, int self, int& idx, float& frac) {
+  DEV int raycast(f2 p1, f2 p2, int self, int& idx, float& frac) {
     int kind = KIND_NONE; idx = -1; frac = 0.0f; float f;
     const float lx = fmin_(p1.x, p2.x), ly = fmin_(p1.y, p2.y), ux = fmax_(p1.x, p2.x), uy = fmax_(p1.y, p2.y);
     auto far_from = [&](float cx, float cy, float rad) {  // rad already includes slack
@@ -414,7 +439,7 @@ struct Env {
   // fat AABBs overlap and that has no contact yet; new contacts are numbered
   // in ascending (proxyIdA, proxyIdB) order (creation sequence surrogate).
   // candidate pairs whose body B is agent j
-  __device__ __noinline__ void candidates_of(int j, unsigned long long* cand) {
+  DEV void candidates_of(int j, unsigned long long* cand) {
     if (!alive(j)) return;
     float fj[4]; agent_fat(j, fj);
     for (int i = 0; i < j; ++i) {
@@ -455,7 +480,7 @@ struct Env {
     }
   }
   // [all lanes] every lane tests the pairs of its own agents; the leader numbers the new contacts
-  __device__ __noinline__ void find_new_contacts() {
+  DEV void find_new_contacts() {
     unsigned long long cand[PW];
 #pragma unroll
     for (int w = 0; w < PW; ++w) cand[w] = 0ull;
@@ -464,7 +489,7 @@ struct Env {
 #pragma unroll
     for (int w = 0; w < PW; ++w) { cand[w] = or64(cand[w]); any |= cand[w] != 0ull; }
     if (any) {                               // group-uniform
-      if (lead) number_candidates(cand);
+      if (lead) { unsigned long long cc[PW]; for (int w = 0; w < PW; ++w) cc[w] = cand[w]; MSV_COLD(number_candidates(cc)); }
       share_bits();
     }
   }
@@ -478,7 +503,7 @@ struct Env {
   }
 
   // evaluate the manifold of pair (a|sid, b) at the bodies' current transforms
-  __device__ __noinline__ bool evaluate(int a, int sid, int b, Manifold& m) {
+  DEV bool evaluate(int a, int sid, int b, Manifold& m) {
     if (a >= 0) return collide_circles(apos(a), apos(b), C.agent_r, C.agent_r, m);
     return collide_box_circle(static_box(sid), apos(b), C.agent_r, m);
   }
@@ -765,7 +790,7 @@ struct Env {
   // (shared-list slots, 5 bits each) in island order = newest first.  With
   // NRr <= NR the contact constants and impulses stay in registers.
   template <int NRr>
-  __device__ __noinline__ void island_single(int i, int cnt, unsigned long long ord, float h, float dtRatio) {
+  DEV void island_single(int i, int cnt, unsigned long long ord, float h, float dtRatio) {
     f2 cB = apos(i);
     AG(F_C0X, i) = cB.x; AG(F_C0Y, i) = cB.y; AG(F_A0, i) = AG(F_A, i);
     f2 vB = mk2(C.damp * AG(F_VX, i), C.damp * AG(F_VY, i)); float wB = AG(F_W, i) * C.damp;  // v *= 1/(1+h*damping)
@@ -975,7 +1000,7 @@ struct Env {
     bool aa = false;                           // does any agent touch another agent? (group-uniform)
     { unsigned long long m = tc[0] & en[0]; if (NAA < 64) m &= (1ull << NAA) - 1ull; aa = m != 0ull; }
     gsync();
-    if (aa) { if (lead) solve_generic(h, dtRatio); }
+    if (aa) { if (lead) MSV_COLD(solve_generic(h, dtRatio)); }
     else for (int i = g; i < C.A; i += G) solve_single(i, h, dtRatio);
     gsync();
     unsigned mv = 0;
@@ -1093,15 +1118,14 @@ struct Env {
   // and walls (agent-agent pairs are "two non-bullet dynamic bodies": skipped).
   // Every lane evaluates b2TimeOfImpact for the contacts of its own agents;
   // the group picks the minimum; the leader runs the event.
-  __device__ __noinline__ void solve_toi(float dt) {
+  DEV void solve_toi(float dt) {
     for (int i = g; i < C.A; i += G) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
     // per-contact toiCount: only contacts that produced events carry one (replicated on every lane)
     int evP[8], evN[8], nev = 0;
     // cached TOIs (b2Contact::e_toiFlag / m_toi) of this lane's contacts: valid until the agent is displaced
     constexpr int MAXT = SLOTS * (BC + 4) < 12 ? SLOTS * (BC + 4) : 12;
     int cP[MAXT]; float cAlpha[MAXT]; int ncache = 0;
-    unsigned prev[SNAPW]; int prevP = -1;      // leader: state after the previous event
-    for (int q = 0; q < SNAPW; ++q) prev[q] = 0xFFFFFFFFu;
+    unsigned prev[SNAPW]; int prevP = -1;      // leader: state after the previous event (compared only once prevP is set)
     for (int guard = 0; guard < 64; ++guard) {
       int minP = -1, minSeq = -1; float minAlpha = 1.0f;
       for (int w = 0; w < PW; ++w) {
@@ -1156,7 +1180,7 @@ struct Env {
       { int q = 0; while (q < ncache) { if (cP[q] == minP) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q; } }
       gsync();
       int r = 0;
-      if (lead) r = toi_event(minP, minAlpha, dt, prev, prevP);
+      if (lead) { Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prev, prevP); take(c_); }
       gsync();
       r = bc(r);
       share_bits();
@@ -1204,7 +1228,7 @@ struct Env {
     bool any = np > 0;
 #pragma unroll
     for (int i = 0; i < AC; ++i) if (i < C.A && (act[6 * i + 4] | act[6 * i + 5])) any = true;
-    if (any) pre_use_give_body(act);
+    if (any) MSV_COLD(pre_use_give_body(act));
   }
   __device__ __noinline__ void pre_use_give_body(const uint8_t* act) {
     // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
@@ -1342,7 +1366,7 @@ struct Env {
     float2 h = S.heal[t * N + e]; return mk2(h.x, h.y);
   }
   // every lane is the camera of its own agents                      [all lanes]
-  __device__ __noinline__ void cameras() {
+  DEV void cameras() {
     gsync();
     const bool all_bodies = !C.omniscient;            // env:706-739 read the full seen-lists
     unsigned saL[SLOTS], sxL[SLOTS];
@@ -1409,7 +1433,8 @@ struct Env {
     }
   }
 
-  int n_deaths, deaths[AC], n_kills, kill_cause[AC];
+  unsigned dmask;          // agents that died this step (bit i); Health.post_step visits them in index order
+  int n_kills, kill_cause[AC];
 
   // [leader]
   __device__ __forceinline__ void post_step_boxes() {
@@ -1423,7 +1448,7 @@ struct Env {
           S.pend1[np * N + e] = C.box_ownership ? b1.z : MSV_CAUSE_NONE;
           np++;
         } else overflow++;
-        remove_box(k);
+        MSV_COLD(remove_box(k));
       } else ++k;
     }
   }
@@ -1431,10 +1456,10 @@ struct Env {
   // [leader] agents/Health.post_step -> despawn(dead) (sem:429-448)
   __device__ __noinline__ void handle_deaths() {
     int total = 0;
-    for (int d = 0; d < n_deaths; ++d) total += inv_n(deaths[d]);
+    for (int i = 0; i < C.A; ++i) if ((dmask >> i) & 1u) total += inv_n(i);
     int top = total;
-    for (int d = 0; d < n_deaths; ++d) {  // DeathDrop.pre_despawn (sem:387-396)
-      int i = deaths[d];
+    for (int i = 0; i < C.A; ++i) {         // DeathDrop.pre_despawn (sem:387-396)
+      if (!((dmask >> i) & 1u)) continue;
       f2 me = apos(i);
       int n = inv_n(i);
       for (int j = 0; j < n; ++j) {
@@ -1445,16 +1470,10 @@ struct Env {
         if (kind == MSV_ITEM_HEAL) add_heal(x, y);
         else { float4 pl = S.ainv[(i * 4 + j) * N + e]; add_item(x, y, pl.x, pl.y, __float_as_int(pl.z)); }
       }
-#pragma unroll
-      for (int q = 0; q < AC; ++q) if (q == i) inv[q] = 0;
+      inv[i] = 0;
     }
-    for (int d = 0; d < n_deaths; ++d) {
-      int cz = MSV_CAUSE_NONE;
-#pragma unroll
-      for (int q = 0; q < AC; ++q) if (q == deaths[d]) cz = cause[q];
-      kill_cause[n_kills++] = cz;           // TrackKills sem:628-629
-    }
-    for (int d = 0; d < n_deaths; ++d) kill_agent(deaths[d]);
+    for (int i = 0; i < C.A; ++i) if ((dmask >> i) & 1u) kill_cause[n_kills++] = cause[i];  // TrackKills sem:628-629
+    for (int i = 0; i < C.A; ++i) if ((dmask >> i) & 1u) kill_agent(i);
   }
   // [leader] agents/AutoPickup.post_step (sem:278-283) for agent i: bodies in creation order
   __device__ __noinline__ void pickup_agent(int i) {
@@ -1493,10 +1512,10 @@ struct Env {
   __device__ __forceinline__ void post_step_rest() {
     int dflag = 0;
     if (lead) {
-      n_deaths = 0; n_kills = 0;
+      dmask = 0; n_kills = 0;
 #pragma unroll
-      for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && health[i] <= 0) deaths[n_deaths++] = i;
-      if (n_deaths > 0) { handle_deaths(); dflag = 1; }
+      for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && health[i] <= 0) dmask |= 1u << i;
+      if (dmask) { MSV_COLD(handle_deaths()); dflag = 1; }
     }
     dflag = bc(dflag);
     if (dflag) { gsync(); share_counts(); }   // drops changed the lists, deaths the flags
@@ -1513,7 +1532,7 @@ struct Env {
     }
     near = or32(near);
     if (!lead) return;
-    for (int i = 0; i < C.A; ++i) if ((near >> i) & 1u) pickup_agent(i);
+    for (int i = 0; i < C.A; ++i) if ((near >> i) & 1u) MSV_COLD(pickup_agent(i));
     // agents/SafeZone.post_step (sem:758-768) + tick (sem:776-811)
     for (int i = 0; i < C.A; ++i) {
       if (!alive(i)) continue;
@@ -1551,7 +1570,7 @@ struct Env {
   // agent j.  Q1: Cameras.seen is looked up by the POST-death list position.
   // The observation tensors themselves are written by k_obs (msv_kernels.cu).
   // [leader]
-  __device__ __noinline__ void store_obm() {
+  DEV void store_obm() {
     unsigned long long bits = 0ull;
     int r = 0;
     for (int i = 0; i < C.A; ++i) {
@@ -1585,45 +1604,68 @@ struct Env {
   }
 
   // compute_rewards (env:757-803), is_done (env:810-831), _update_stats (env:483-508)   [leader]
-  __device__ __noinline__ bool rewards_done(DevOut& O) {
-    const int A = C.A;
+  // (register arrays are only indexed by unrolled loop counters)
+  DEV bool rewards_done(DevOut& O) {
+    const int A = C.A, split = A / 2;
     float rew[AC]; int lk[AC];
+#pragma unroll
     for (int i = 0; i < AC; ++i) { rew[i] = 0.0f; lk[i] = 0; }
+    const bool ta0 = team_alive(0), ta1 = team_alive(1);
     if (!C.teams) {
-      for (int i = 0; i < A; ++i) rew[i] += alive(i) ? C.r_alive : C.r_dead;
+#pragma unroll
+      for (int i = 0; i < AC; ++i) if (i < A) rew[i] += alive(i) ? C.r_alive : C.r_dead;
       for (int k = 0; k < n_kills; ++k) {
         int killer = kill_cause[k];
-        if (killer >= 0 && killer < A && alive(killer)) { rew[killer] += C.r_kill; lk[killer]++; }
+        if (killer >= 0 && killer < A && alive(killer)) {
+#pragma unroll
+          for (int i = 0; i < AC; ++i) if (i == killer) { rew[i] += C.r_kill; lk[i]++; }
+        }
       }
-      for (int k = 0; k < n_deaths; ++k) rew[deaths[k]] += C.r_death;
+      if (dmask) {
+#pragma unroll
+        for (int i = 0; i < AC; ++i) if ((dmask >> i) & 1u) rew[i] += C.r_death;
+      }
     } else {
-      int split = A / 2;
-      for (int t = 0; t < 2; ++t) {
-        float rr = team_alive(t) ? C.r_alive : C.r_dead;
-        for (int i = (t ? split : 0); i < (t ? A : split); ++i) rew[i] += rr;
-      }
+#pragma unroll
+      for (int i = 0; i < AC; ++i) if (i < A) rew[i] += (i < split ? ta0 : ta1) ? C.r_alive : C.r_dead;
       for (int k = 0; k < n_kills; ++k) {
         int cz = kill_cause[k];
         if (cz != MSV_CAUSE_TEAM0 && cz != MSV_CAUSE_TEAM0 + 1) continue;
         int t = cz - MSV_CAUSE_TEAM0;
-        for (int i = (t ? split : 0); i < (t ? A : split); ++i) rew[i] += C.r_kill;
-        lk[t]++;
+#pragma unroll
+        for (int i = 0; i < AC; ++i) if (i < A && (i < split ? 0 : 1) == t) rew[i] += C.r_kill;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) if (i == t) lk[i]++;
       }
-      for (int k = 0; k < n_deaths; ++k) {
-        int t = team_of(deaths[k]);
-        for (int i = (t ? split : 0); i < (t ? A : split); ++i) rew[i] += C.r_death;
+      if (dmask) {
+        for (int d = 0; d < A; ++d) {         // deaths in index order
+          if (!((dmask >> d) & 1u)) continue;
+          int t = team_of(d);
+#pragma unroll
+          for (int i = 0; i < AC; ++i) if (i < A && (i < split ? 0 : 1) == t) rew[i] += C.r_death;
+        }
       }
     }
     int n_alive = 0;
-    if (C.teams) n_alive = (int)team_alive(0) + (int)team_alive(1);
+    if (C.teams) n_alive = (int)ta0 + (int)ta1;
     else for (int i = 0; i < A; ++i) n_alive += alive(i);
     bool done = C.gameover_mode == MSV_GAMEOVER_ALLDEAD ? n_alive == 0 : n_alive <= 1;
     steps += 1;
-    if (!C.teams) for (int i = 0; i < A; ++i) st_reward[i] += rew[i];
-    else { st_reward[0] += rew[0]; st_reward[1] += rew[A / 2]; }
-    for (int i = 0; i < (C.teams ? 2 : A); ++i) st_kills[i] += lk[i];
+    if (!C.teams) {
+#pragma unroll
+      for (int i = 0; i < AC; ++i) if (i < A) st_reward[i] += rew[i];
+    } else {
+      st_reward[0] += rew[0];
+      float rs = 0.0f;
+#pragma unroll
+      for (int i = 0; i < AC; ++i) if (i == split) rs = rew[i];
+      st_reward[1] += rs;
+    }
+#pragma unroll
+    for (int i = 0; i < AC; ++i) if (i < (C.teams ? 2 : A)) st_kills[i] += lk[i];
     st_steps += 1; st_heals += use_heal; st_boxes += use_box;
-    for (int i = 0; i < A; ++i) O.rewards[(size_t)e * A + i] = rew[i];
+#pragma unroll
+    for (int i = 0; i < AC; ++i) if (i < A) O.rewards[(size_t)e * A + i] = rew[i];
     O.dones[e] = done ? 1 : 0;
     return done;
   }
@@ -1705,6 +1747,6 @@ struct Env {
     ztcool = C.zone_cooldown; ztshrink = 0; zphase = 0; zend = 0;
     zr = C.zone_r32[0];
     float2 c0 = S.zonec[e]; zx = c0.x; zy = c0.y;
-    n_deaths = 0; n_kills = 0; use_heal = 0; use_box = 0;
+    dmask = 0; n_kills = 0; use_heal = 0; use_box = 0;
   }
 };

@@ -21,6 +21,7 @@ __device__ unsigned long long g_prof[32];   // [0..11] per-phase sums, [12] max 
 
 // thread -> (environment slot of the block, lane of the group)
 // keep the warps of a block in the same phase: they then share instruction-cache lines
+#define MSV_COLD_ON(env, call) do { auto c_ = env; c_.call; env.take(c_); } while (0)
 #ifdef MSV_NO_PHASE_SYNC
 #define PHASE_SYNC() do { } while (0)
 #else
@@ -35,10 +36,9 @@ template <int AC, int BC, int HC, int G>
 __global__ void __launch_bounds__(MSV_TPB)
 k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
        const __grid_constant__ DevOut Oc, const uint8_t* __restrict__ actions) {
-  extern __shared__ float sm[];
   MSV_GROUP_SETUP(G);
   DevOut O = Oc;
-  Env<AC, BC, HC, G> env(C, S, sm, es, g, gmask, e);
+  Env<AC, BC, HC, G> env(C, S, es, g, gmask, e);
 #ifdef MSV_PROFILE
   long long t_last = C.profile ? clock64() : 0;
   const long long t_begin = t_last;
@@ -92,7 +92,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     bool done = env.rewards_done(O);       // env:85-89
     if (done && C.auto_reset) {            // vector-env extension: the observation returned is the new episode's first
       env.st_episodes++;
-      env.reset();
+      MSV_COLD_ON(env, reset());
       again = 1;
     }
   }
@@ -119,15 +119,14 @@ template <int AC, int BC, int HC, int G>
 __global__ void __launch_bounds__(MSV_TPB)
 k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
         const __grid_constant__ DevOut Oc, int only_done) {
-  extern __shared__ float sm[];
   MSV_GROUP_SETUP(G);
   DevOut O = Oc;
   if (only_done && !O.dones[e]) return;    // auto_reset = 2: only the envs that just finished (whole group leaves)
-  Env<AC, BC, HC, G> env(C, S, sm, es, g, gmask, e);
+  Env<AC, BC, HC, G> env(C, S, es, g, gmask, e);
   env.load();
   if (env.lead) {
     if (only_done) env.st_episodes++;
-    env.reset();
+    MSV_COLD_ON(env, reset());
   }
   env.share_counts();
   env.cameras();
@@ -145,9 +144,8 @@ template <int AC, int BC, int HC, int G>
 __global__ void __launch_bounds__(MSV_TPB)
 k_observe(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
           const __grid_constant__ DevOut Oc) {
-  extern __shared__ float sm[];
   MSV_GROUP_SETUP(G);
-  Env<AC, BC, HC, G> env(C, S, sm, es, g, gmask, e);
+  Env<AC, BC, HC, G> env(C, S, es, g, gmask, e);
   env.load();
   env.cameras();
   if (env.lead) env.store_obm();
