@@ -182,9 +182,21 @@ struct Env {
   DEV static void meta_unpack(int m, int& p, int& a, int& sid, int& b) { p = m & 255; a = ((m >> 8) & 15) - 1; sid = (m >> 12) & 15; b = (m >> 16) & 15; }
 
   // ---- pair bit helpers
-  DEV static bool bit(const unsigned long long* m, int p) { return (m[p >> 6] >> (p & 63)) & 1ull; }
-  DEV static void setb(unsigned long long* m, int p) { m[p >> 6] |= 1ull << (p & 63); }
-  DEV static void clrb(unsigned long long* m, int p) { m[p >> 6] &= ~(1ull << (p & 63)); }
+  // (the word index is resolved with an unrolled select so that the matrices stay in registers)
+  DEV static bool bit(const unsigned long long* m, int p) {
+    unsigned long long w = m[0];
+#pragma unroll
+    for (int q = 1; q < PW; ++q) if ((p >> 6) == q) w = m[q];
+    return (w >> (p & 63)) & 1ull;
+  }
+  DEV static void setb(unsigned long long* m, int p) {
+#pragma unroll
+    for (int q = 0; q < PW; ++q) if (PW == 1 || (p >> 6) == q) m[q] |= 1ull << (p & 63);
+  }
+  DEV static void clrb(unsigned long long* m, int p) {
+#pragma unroll
+    for (int q = 0; q < PW; ++q) if (PW == 1 || (p >> 6) == q) m[q] &= ~(1ull << (p & 63));
+  }
   DEV static int p_aa(int i, int j) { return j * (j - 1) / 2 + i; }  // i < j
   DEV static int p_ab(int i, int k) { return NAA + i * BC + k; }
   DEV static int p_aw(int i, int k) { return NAA + AC * BC + i * 4 + k; }
@@ -541,6 +553,7 @@ struct Env {
     if (lead) NTC() = 0;
     gsync();
     unsigned wakem = 0;
+#pragma unroll
     for (int w = 0; w < PW; ++w) {
       unsigned long long mbits = ex[w] & own[w];
       while (mbits) {
@@ -1128,6 +1141,7 @@ struct Env {
     unsigned prev[SNAPW]; int prevP = -1;      // leader: state after the previous event (compared only once prevP is set)
     for (int guard = 0; guard < 64; ++guard) {
       int minP = -1, minSeq = -1; float minAlpha = 1.0f;
+#pragma unroll
       for (int w = 0; w < PW; ++w) {
         // existing, enabled agent-vs-static contacts (pair index >= NAA) of my agents
         unsigned long long mbits = ex[w] & en[w] & own[w];
@@ -1225,9 +1239,9 @@ struct Env {
   // [leader] pending drops, UseLast, GiveLast
   DEV void pre_use_give(const uint8_t* act) {
     use_heal = 0; use_box = 0; new_box = 0;
-    bool any = np > 0;
+    bool any = np > 0;                       // nothing to do unless a drop is pending or an agent with items uses/gives
 #pragma unroll
-    for (int i = 0; i < AC; ++i) if (i < C.A && (act[6 * i + 4] | act[6 * i + 5])) any = true;
+    for (int i = 0; i < AC; ++i) if (i < C.A && (act[6 * i + 4] | act[6 * i + 5]) && (inv[i] & 7) != 0 && alive(i)) any = true;
     if (any) MSV_COLD(pre_use_give_body(act));
   }
   __device__ __noinline__ void pre_use_give_body(const uint8_t* act) {
