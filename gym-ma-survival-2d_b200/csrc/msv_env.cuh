@@ -71,6 +71,10 @@ struct BodyS { f2 c; float a; f2 v; float w; float invM, invI; };
 // the block's dynamic shared memory (addressed as shared, not through a generic pointer)
 extern __shared__ float msv_sm[];
 
+#ifndef MSV_SOLVE_SYNC
+#define MSV_SOLVE_SYNC() do { } while (0)
+#endif
+
 template <int AC, int BC, int HC, int G>
 struct Env {
   using PL = PairLayout<AC, BC>;
@@ -78,13 +82,17 @@ struct Env {
   static constexpr int MAXC = AC <= 4 ? 16 : 24;
   static constexpr int SLOTS = AC / G;               // agents per lane
   static constexpr int W_BOX = F_COUNT * AC, W_TC = W_BOX + G_COUNT * BC, W_MISC = W_TC + K_COUNT * MAXC;
-  static constexpr int SM_WORDS = W_MISC + 2;        // + contact counter, overflow counter
+  static constexpr int W_ITEM = W_MISC + 2, W_HEAL = W_ITEM + 2 * BC;   // floor item / heal positions (x then y)
+  static constexpr int SM_WORDS = W_HEAL + 2 * HC;
   static constexpr int NR = 3;                       // contacts of a one-agent island kept in registers
   static_assert(AC % G == 0 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two dividing AC");
 
   const DevConst& C;
   const DevState& S;
-  static constexpr int T = MSV_TPB / G;   // environment slots per block (shared-memory stride)
+  static constexpr int EPB = MSV_TPB / G;  // environment slots per block
+  // shared-memory word stride: EPB + 32/G, so that the G lanes of a group (same slot, words of
+  // different agents) and the 32/G slots of a warp fall into 32 different banks
+  static constexpr int T = EPB + 32 / G;
   int es, g, e, N;        // es: my slot; g: my lane in the group
   unsigned gmask;         // the group's lanes within the warp
   bool lead;              // g == 0
@@ -173,6 +181,8 @@ struct Env {
   DEV float& KF(int f, int k) { return msv_sm[(W_TC + f * MAXC + k) * T + es]; }
   DEV int& KI(int f, int k) { return reinterpret_cast<int*>(msv_sm)[(W_TC + f * MAXC + k) * T + es]; }
   DEV int& NTC() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 0) * T + es]; }
+  DEV float& ITP(int c, int k) { return msv_sm[(W_ITEM + c * BC + k) * T + es]; }
+  DEV float& HLP(int c, int k) { return msv_sm[(W_HEAL + c * HC + k) * T + es]; }
   DEV int& OVF() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 1) * T + es]; }
   DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
   DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
@@ -224,6 +234,11 @@ struct Env {
         AG(F_QS, i) = 0.0f; AG(F_QC, i) = 1.0f;
       } else AGF(i) = 0;
     }
+    for (int k = g; k < BC; k += G) {          // slots past the list lengths hold stale data that is never read
+      load_box(k, k);
+      float4 it = S.item0[k * N + e]; ITP(0, k) = it.x; ITP(1, k) = it.y;
+    }
+    for (int k = g; k < HC; k += G) { float2 h = S.heal[k * N + e]; HLP(0, k) = h.x; HLP(1, k) = h.y; }
     nb = ni = nh = 0;
 #pragma unroll
     for (int w = 0; w < PW; ++w) { ex[w] = 0ull; tc[w] = 0ull; en[w] = 0ull; }
@@ -238,10 +253,6 @@ struct Env {
       nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; np = (h0.x >> 24) & 255;
       steps = h0.y; episode = h0.z; body_seq = h0.w;
       contact_seq = h1.x; first_step = h1.y; overflow = h1.z; newfix = h1.w;
-#pragma unroll
-      for (int k = 0; k < BC; ++k) {
-        if (k < nb) load_box(k, k);
-      }
 #pragma unroll
       for (int w = 0; w < PW; ++w) { ex[w] = S.pex[w * N + e]; tc[w] = S.ptc[w * N + e]; en[w] = S.pen[w * N + e]; }
       float4 zc = S.zonecur[e]; int4 zi = S.zoneint[e];
@@ -334,14 +345,14 @@ struct Env {
       if (ray_box(static_box(k), p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_BOX; idx = k; frac = f; }
     }
     for (int k = 0; k < ni; ++k) {
-      float4 it = S.item0[k * N + e];
-      if (far_from(it.x, it.y, C.item_r + 0.01f)) continue;
-      if (ray_circle(mk2(it.x, it.y), C.item_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_ITEM; idx = k; frac = f; }
+      const float itx = ITP(0, k), ity = ITP(1, k);
+      if (far_from(itx, ity, C.item_r + 0.01f)) continue;
+      if (ray_circle(mk2(itx, ity), C.item_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_ITEM; idx = k; frac = f; }
     }
     for (int k = 0; k < nh; ++k) {
-      float2 h = S.heal[k * N + e];
-      if (far_from(h.x, h.y, C.heal_r + 0.01f)) continue;
-      if (ray_circle(mk2(h.x, h.y), C.heal_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_HEAL; idx = k; frac = f; }
+      const float hx_ = HLP(0, k), hy_ = HLP(1, k);
+      if (far_from(hx_, hy_, C.heal_r + 0.01f)) continue;
+      if (ray_circle(mk2(hx_, hy_), C.heal_r, p1, p2, f) && (kind == KIND_NONE || f < frac)) { kind = KIND_HEAL; idx = k; frac = f; }
     }
     for (int k = 0; k < 4; ++k) {
       const WallC& w = C.walls[k];                        // fat AABB = tight AABB + 0.11
@@ -411,22 +422,22 @@ struct Env {
     nb--;
   }
   DEV void remove_item(int k) {
-    for (int q = k; q + 1 < ni; ++q) { S.item0[q * N + e] = S.item0[(q + 1) * N + e]; S.item1[q * N + e] = S.item1[(q + 1) * N + e]; }
+    for (int q = k; q + 1 < ni; ++q) { S.item0[q * N + e] = S.item0[(q + 1) * N + e]; S.item1[q * N + e] = S.item1[(q + 1) * N + e]; ITP(0, q) = ITP(0, q + 1); ITP(1, q) = ITP(1, q + 1); }
     ni--;
   }
   DEV void remove_heal(int k) {
-    for (int q = k; q + 1 < nh; ++q) { S.heal[q * N + e] = S.heal[(q + 1) * N + e]; S.healseq[q * N + e] = S.healseq[(q + 1) * N + e]; }
+    for (int q = k; q + 1 < nh; ++q) { S.heal[q * N + e] = S.heal[(q + 1) * N + e]; S.healseq[q * N + e] = S.healseq[(q + 1) * N + e]; HLP(0, q) = HLP(0, q + 1); HLP(1, q) = HLP(1, q + 1); }
     nh--;
   }
   DEV void add_item(float x, float y, float hx, float hy, int owner) {  // Item.drop sem:143-148
     if (ni >= BC) { overflow++; return; }
-    S.item0[ni * N + e] = make_float4(x, y, hx, hy);
+    S.item0[ni * N + e] = make_float4(x, y, hx, hy); ITP(0, ni) = x; ITP(1, ni) = y;
     S.item1[ni * N + e] = make_int2(owner, body_seq++);
     ni++;
   }
   DEV void add_heal(float x, float y) {
     if (nh >= HC) { overflow++; return; }
-    S.heal[nh * N + e] = make_float2(x, y);
+    S.heal[nh * N + e] = make_float2(x, y); HLP(0, nh) = x; HLP(1, nh) = y;
     S.healseq[nh * N + e] = body_seq++;
     nh++;
   }
@@ -1018,6 +1029,7 @@ struct Env {
     gsync();
     unsigned mv = 0;
     for (int i = g; i < C.A; i += G) if (AGF(i) & FL_MOVED) mv = 1u;
+    MSV_SOLVE_SYNC();
     if (or32(mv)) find_new_contacts();
   }
 
@@ -1375,9 +1387,9 @@ struct Env {
     t -= AC;
     if (t < BC) return mk2(BX(G_X, t), BX(G_Y, t));
     t -= BC;
-    if (t < BC) { float4 it = S.item0[t * N + e]; return mk2(it.x, it.y); }
+    if (t < BC) return mk2(ITP(0, t), ITP(1, t));
     t -= BC;
-    float2 h = S.heal[t * N + e]; return mk2(h.x, h.y);
+    return mk2(HLP(0, t), HLP(1, t));
   }
   // every lane is the camera of its own agents                      [all lanes]
   DEV void cameras() {
@@ -1539,8 +1551,8 @@ struct Env {
       for (int i = g; i < C.A; i += G) {
         if (!alive(i)) continue;
         f2 me = apos(i); bool any = false;
-        for (int k = 0; k < ni; ++k) { float4 it = S.item0[k * N + e]; f2 d = vsub(mk2(it.x, it.y), me); if (vdot(d, d) <= r2) any = true; }
-        for (int k = 0; k < nh; ++k) { float2 h = S.heal[k * N + e]; f2 d = vsub(mk2(h.x, h.y), me); if (vdot(d, d) <= r2) any = true; }
+        for (int k = 0; k < ni; ++k) { f2 d = vsub(mk2(ITP(0, k), ITP(1, k)), me); if (vdot(d, d) <= r2) any = true; }
+        for (int k = 0; k < nh; ++k) { f2 d = vsub(mk2(HLP(0, k), HLP(1, k)), me); if (vdot(d, d) <= r2) any = true; }
         if (any) near |= 1u << i;
       }
     }
@@ -1728,7 +1740,7 @@ struct Env {
     }
     for (int h = 0; h < C.H0; ++h) {
       int cell = perm[--top];
-      S.heal[h * N + e] = make_float2(C.grid_px[cell], C.grid_py[cell]);
+      S.heal[h * N + e] = make_float2(C.grid_px[cell], C.grid_py[cell]); HLP(0, h) = C.grid_px[cell]; HLP(1, h) = C.grid_py[cell];
       S.healseq[h * N + e] = body_seq++;
       nh++;
     }

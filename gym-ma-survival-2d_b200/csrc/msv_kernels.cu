@@ -7,6 +7,12 @@
 // k_reset : BaseEnv.reset (env:59-74) for every environment.
 // k_observe: fetch_observations only (after msv_set_state).
 // k_stats : flush_stats reduction.
+#ifndef MSV_NO_PHASE_SYNC
+#ifndef MSV_SYNC_MASK
+#define MSV_SYNC_MASK 0x3FF
+#endif
+#define MSV_SOLVE_SYNC() do { if ((MSV_SYNC_MASK >> 9) & 1) __syncthreads(); } while (0)
+#endif
 #include "msv_env.cuh"
 #include "msv_launch.h"
 
@@ -22,10 +28,13 @@ __device__ unsigned long long g_prof[32];   // [0..11] per-phase sums, [12] max 
 // thread -> (environment slot of the block, lane of the group)
 // keep the warps of a block in the same phase: they then share instruction-cache lines
 #define MSV_COLD_ON(env, call) do { auto c_ = env; c_.call; env.take(c_); } while (0)
+#ifndef MSV_SYNC_MASK
+#define MSV_SYNC_MASK 0x3FF
+#endif
 #ifdef MSV_NO_PHASE_SYNC
-#define PHASE_SYNC() do { } while (0)
+#define PHASE_SYNC(k) do { } while (0)
 #else
-#define PHASE_SYNC() __syncthreads()
+#define PHASE_SYNC(k) do { if ((MSV_SYNC_MASK >> (k)) & 1) __syncthreads(); } while (0)
 #endif
 #define MSV_GROUP_SETUP(G)                                                                       \
   const int T = MSV_TPB / (G), es = threadIdx.x / (G), g = threadIdx.x % (G);                    \
@@ -52,7 +61,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     for (int k = 0; k < AC * 6; ++k) act[k] = (real && k < C.A * 6) ? src[k] : (uint8_t)(k % 6 < 3 ? 1 : 0);
   }
   PROF(0);
-  PHASE_SYNC();
+  PHASE_SYNC(0);
   env.pre_motors(actions, real);           // sim:234-235
   env.gsync();
   if (env.lead) env.pre_use_give(act);
@@ -60,20 +69,21 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   env.share_counts();
   const int newfix = env.bc(env.newfix);
   if (env.bc(env.new_box)) env.share_bits();
+  PHASE_SYNC(6);
   env.pre_melee(act);
   PROF(1);
 #pragma unroll 1
   for (int sub = 0; sub < 2; ++sub) {      // sim:236-239: b2World::Step x2
     if (sub == 0 && newfix) { env.find_new_contacts(); env.newfix = 0; }  // b2World::Step: e_newFixture
     PROF(2);
-    PHASE_SYNC();
+    PHASE_SYNC(1);
     env.collide();
     PROF(3);
-    PHASE_SYNC();
+    PHASE_SYNC(2);
     const int first = env.bc(env.first_step);
     env.solve(C.dt, first ? 0.0f : C.dt_ratio1);
     PROF(4);
-    PHASE_SYNC();
+    PHASE_SYNC(3);
     env.solve_toi(C.dt);
     env.first_step = 0;
     PROF(5);
@@ -81,13 +91,14 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   if (env.lead) env.post_step_boxes();
   env.share_counts();
   PROF(6);
-  PHASE_SYNC();
+  PHASE_SYNC(4);
   env.cameras();
   PROF(7);
-  PHASE_SYNC();
+  PHASE_SYNC(5);
   int again = 0;
   env.post_step_rest();                    // sim:241-242
   PROF(8);
+  PHASE_SYNC(7);
   if (env.lead) {
     bool done = env.rewards_done(O);       // env:85-89
     if (done && C.auto_reset) {            // vector-env extension: the observation returned is the new episode's first
@@ -98,6 +109,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   }
   if (env.bc(again)) { env.share_counts(); env.cameras(); }
   PROF(9);
+  PHASE_SYNC(8);
   if (env.lead) env.store_obm();           // env:84: the observation tensors are gathered by k_obs
   PROF(10);
   env.store();
@@ -351,7 +363,7 @@ static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, con
                             const uint8_t* actions, cudaStream_t st) {
   const int epb = MSV_TPB / G;                       // environments per block
   const int blocks = C.N / epb;
-  size_t smem = (size_t)Env<AC, BC, HC, G>::SM_WORDS * epb * sizeof(float);
+  size_t smem = (size_t)Env<AC, BC, HC, G>::SM_WORDS * Env<AC, BC, HC, G>::T * sizeof(float);
   if (which == 3) {  // one-time: allow the dynamic shared memory the kernels need
     cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -12,6 +12,7 @@ def run(variant, N, steps=200, warm=50, prof=True):
     A = int(rec['n_agents'])
     h = _lib.Handle(rec, N, 0, 1, 0)
     h.reset()
+    torch.manual_seed(1234)   # identical action streams in every run: timing differences come from the code only
     acts = torch.randint(0, 2, (8, N, A, 6), dtype=torch.uint8, device='cuda')
     acts[..., 0:3] = torch.randint(0, 3, (8, N, A, 3), dtype=torch.uint8, device='cuda')
     for t in range(warm): h.step(acts[t % 8].data_ptr())
