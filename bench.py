@@ -216,7 +216,7 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': ncu_traffic(), 'kernel': 'k_step<4,4,4>', 'kernel_ms': kavg_ms,
+                     'traffic': ncu_traffic(), 'kernel': 'k_step<4,4,4,4>', 'kernel_ms': kavg_ms,
                      'algorithmic_bytes_per_env_step': kstep_bytes, 'whole_step_bytes_per_env_step': bytes_env,
                      'whole_step_gbs': bytes_env * N / (ms_per_step * 1e-3) / 1e9, 'peak_source': peak_src,
                      'note': 'latency/issue bound, not bandwidth bound: see DESIGN.md section 8'},

@@ -186,8 +186,6 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
     D->lidar_ang[r] = c->lidar_n > 1 ? r * (c->lidar_fov / (c->lidar_n - 1)) - c->lidar_fov / 2. : 0.0;
   D->seed_lo = (uint32_t)seed; D->seed_hi = (uint32_t)(seed >> 32);
   D->env_offset = (uint32_t)env_offset;
-  D->epw = 32;
-  if (const char* ev = getenv("MSV_EPW")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) D->epw = v; }
   return 0;
 }
 

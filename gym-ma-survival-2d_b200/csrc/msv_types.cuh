@@ -35,13 +35,12 @@ struct DevConst {
   double lidar_ang[MSV_MAX_LASERS];       // i*(fov/(n-1)) - fov/2, as Python doubles
   uint32_t seed_lo, seed_hi;
   uint32_t env_offset;
-  int epw;               // environments per warp (<= 32): fewer envs per warp = smaller union of divergent paths, more warps in flight
   int profile;           // debug: accumulate per-phase clock64() deltas into g_prof
 };
 
 // All per-environment state, structure-of-arrays: every array is
-// [slot][N] with the environment index fastest, so a warp of 32 consecutive
-// environments reads 32 consecutive float4/int4 (512 B) per field.
+// [slot][N] with the environment index fastest: the leader lanes of a warp's
+// consecutive environments read consecutive float4/int4 words of a field.
 struct DevState {
   float4* akin0;   // [AC][N]  x, y, angle, vx
   float4* akin1;   // [AC][N]  vy, omega, sleep_time, flags (int bits: 1 alive, 2 awake)
@@ -61,7 +60,7 @@ struct DevState {
   float4* zonecur; // [N] x, y, r, -
   int4* zoneint;   // [N] phase, t_cooldown, t_shrink, endgame
   int4* hdr0;      // [N] counts (nb | ni<<8 | nh<<16 | np<<24), steps, episode, body_seq
-  int4* hdr1;      // [N] contact_seq, first_step, overflow events, -
+  int4* hdr1;      // [N] contact_seq, first_step, overflow events, new-fixture flag
   unsigned long long* pex;  // [PW][N] pair exists
   unsigned long long* ptc;  // [PW][N] pair touching
   unsigned long long* pen;  // [PW][N] pair enabled
