@@ -80,10 +80,21 @@ struct Env {
   using PL = PairLayout<AC, BC>;
   static constexpr int P = PL::P, PW = PL::PW, NAA = PL::NAA;
   static constexpr int MAXC = AC <= 4 ? 16 : 24;
+  // ---- the leader's scalar state lives in the environment's shared-memory column
+  // (L_* words below, accessed through the LI/LF/LU accessors): plain LDS/STS, shared by the
+  // out-of-line cold paths without copying, no local-memory mirror.
+  enum { L_HEALTH = 0, L_CAUSE = L_HEALTH + AC, L_COOLDOWN = L_CAUSE + AC, L_INV = L_COOLDOWN + AC,
+         L_SREW = L_INV + AC, L_SKILLS = L_SREW + AC, L_SEENA = L_SKILLS + AC, L_SEENX = L_SEENA + AC,
+         L_KCAUSE = L_SEENX + AC,
+         L_NP = L_KCAUSE + AC, L_STEPS, L_EPISODE, L_BODYSEQ, L_CONTACTSEQ, L_FIRST, L_OVERFLOW, L_NEWFIX,
+         L_ZX, L_ZY, L_ZR, L_ZPHASE, L_ZTCOOL, L_ZTSHRINK, L_ZEND,
+         L_STSTEPS, L_STHEALS, L_STBOXES, L_STEPISODES, L_USEHEAL, L_USEBOX, L_NEWBOX,
+         L_PREALIVE, L_DMASK, L_NKILLS, L_COUNT };
   static constexpr int SLOTS = AC / G;               // agents per lane
   static constexpr int W_BOX = F_COUNT * AC, W_TC = W_BOX + G_COUNT * BC, W_MISC = W_TC + K_COUNT * MAXC;
   static constexpr int W_ITEM = W_MISC + 2, W_HEAL = W_ITEM + 2 * BC;   // floor item / heal positions (x then y)
-  static constexpr int SM_WORDS = W_HEAL + 2 * HC;
+  static constexpr int W_LEAD = W_HEAL + 2 * HC;
+  static constexpr int SM_WORDS = W_LEAD + L_COUNT;
   static constexpr int NR = 3;                       // contacts of a one-agent island kept in registers
   static_assert(AC % G == 0 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two dividing AC");
 
@@ -97,17 +108,6 @@ struct Env {
   unsigned gmask;         // the group's lanes within the warp
   bool lead;              // g == 0
 
-  // ---- registers that are only meaningful on the leader lane
-  int health[AC], cause[AC], cooldown[AC], inv[AC];
-  int np, steps, episode, body_seq, contact_seq, first_step, overflow;
-  int newfix;             // b2World::e_newFixture: bodies were created since the last Step (reset, placed box, injected state)
-  float zx, zy, zr; int zphase, ztcool, ztshrink, zend;
-  float st_reward[AC]; int st_kills[AC]; int st_steps, st_heals, st_boxes, st_episodes;
-  int use_heal, use_box;
-  int new_box;
-  unsigned seenA[AC];  // by PRE-death rank: bit j = agent j seen
-  unsigned seenX[AC];  // non-omniscient only: bits 0-15 heals, 16-23 boxes, 24-31 box items (list positions)
-  unsigned pre_alive;
   // ---- replicated on every lane of the group (kept equal by share_*())
   int nb, ni, nh;
   unsigned long long ex[PW], tc[PW], en[PW];
@@ -156,18 +156,7 @@ struct Env {
   // the hot code works on never has its address taken, so the compiler keeps
   // it in registers instead of spilling every field around the calls.
   DEV void take(const Env& o) {
-#pragma unroll
-    for (int i = 0; i < AC; ++i) {
-      health[i] = o.health[i]; cause[i] = o.cause[i]; cooldown[i] = o.cooldown[i]; inv[i] = o.inv[i];
-      st_reward[i] = o.st_reward[i]; st_kills[i] = o.st_kills[i]; seenA[i] = o.seenA[i]; seenX[i] = o.seenX[i];
-      kill_cause[i] = o.kill_cause[i];
-    }
-    np = o.np; steps = o.steps; episode = o.episode; body_seq = o.body_seq; contact_seq = o.contact_seq;
-    first_step = o.first_step; overflow = o.overflow; newfix = o.newfix;
-    zx = o.zx; zy = o.zy; zr = o.zr; zphase = o.zphase; ztcool = o.ztcool; ztshrink = o.ztshrink; zend = o.zend;
-    st_steps = o.st_steps; st_heals = o.st_heals; st_boxes = o.st_boxes; st_episodes = o.st_episodes;
-    use_heal = o.use_heal; use_box = o.use_box; new_box = o.new_box; pre_alive = o.pre_alive;
-    nb = o.nb; ni = o.ni; nh = o.nh; ntc = o.ntc; dmask = o.dmask; n_kills = o.n_kills;
+    nb = o.nb; ni = o.ni; nh = o.nh; ntc = o.ntc;
 #pragma unroll
     for (int w = 0; w < PW; ++w) { ex[w] = o.ex[w]; tc[w] = o.tc[w]; en[w] = o.en[w]; }
   }
@@ -183,6 +172,9 @@ struct Env {
   DEV int& NTC() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 0) * T + es]; }
   DEV float& ITP(int c, int k) { return msv_sm[(W_ITEM + c * BC + k) * T + es]; }
   DEV float& HLP(int c, int k) { return msv_sm[(W_HEAL + c * HC + k) * T + es]; }
+  DEV int& LI(int k) { return reinterpret_cast<int*>(msv_sm)[(W_LEAD + k) * T + es]; }
+  DEV unsigned& LU(int k) { return reinterpret_cast<unsigned*>(msv_sm)[(W_LEAD + k) * T + es]; }
+  DEV float& LF(int k) { return msv_sm[(W_LEAD + k) * T + es]; }
   DEV int& OVF() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 1) * T + es]; }
   DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
   DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
@@ -245,20 +237,20 @@ struct Env {
     if (lead) {
 #pragma unroll
       for (int i = 0; i < AC; ++i) {
-        if (i < C.A) { int4 ai = S.aint[i * N + e]; health[i] = ai.x; cause[i] = ai.y; cooldown[i] = ai.z; inv[i] = ai.w; }
-        else { health[i] = 0; cause[i] = MSV_CAUSE_NONE; cooldown[i] = 0; inv[i] = 0; }
-        st_reward[i] = S.sreward[i * N + e]; st_kills[i] = S.skills[i * N + e];
+        if (i < C.A) { int4 ai = S.aint[i * N + e]; LI(L_HEALTH + (i)) = ai.x; LI(L_CAUSE + (i)) = ai.y; LI(L_COOLDOWN + (i)) = ai.z; LI(L_INV + (i)) = ai.w; }
+        else { LI(L_HEALTH + (i)) = 0; LI(L_CAUSE + (i)) = MSV_CAUSE_NONE; LI(L_COOLDOWN + (i)) = 0; LI(L_INV + (i)) = 0; }
+        LF(L_SREW + (i)) = S.sreward[i * N + e]; LI(L_SKILLS + (i)) = S.skills[i * N + e];
       }
       int4 h0 = S.hdr0[e], h1 = S.hdr1[e];
-      nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; np = (h0.x >> 24) & 255;
-      steps = h0.y; episode = h0.z; body_seq = h0.w;
-      contact_seq = h1.x; first_step = h1.y; overflow = h1.z; newfix = h1.w;
+      nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; LI(L_NP) = (h0.x >> 24) & 255;
+      LI(L_STEPS) = h0.y; LI(L_EPISODE) = h0.z; LI(L_BODYSEQ) = h0.w;
+      LI(L_CONTACTSEQ) = h1.x; LI(L_FIRST) = h1.y; LI(L_OVERFLOW) = h1.z; LI(L_NEWFIX) = h1.w;
 #pragma unroll
       for (int w = 0; w < PW; ++w) { ex[w] = S.pex[w * N + e]; tc[w] = S.ptc[w * N + e]; en[w] = S.pen[w * N + e]; }
       float4 zc = S.zonecur[e]; int4 zi = S.zoneint[e];
-      zx = zc.x; zy = zc.y; zr = zc.z; zphase = zi.x; ztcool = zi.y; ztshrink = zi.z; zend = zi.w;
+      LF(L_ZX) = zc.x; LF(L_ZY) = zc.y; LF(L_ZR) = zc.z; LI(L_ZPHASE) = zi.x; LI(L_ZTCOOL) = zi.y; LI(L_ZTSHRINK) = zi.z; LI(L_ZEND) = zi.w;
       int4 sm_ = S.smisc[e];
-      st_steps = sm_.x; st_heals = sm_.y; st_boxes = sm_.z; st_episodes = sm_.w;
+      LI(L_STSTEPS) = sm_.x; LI(L_STHEALS) = sm_.y; LI(L_STBOXES) = sm_.z; LI(L_STEPISODES) = sm_.w;
       NTC() = 0; OVF() = 0;
     }
     ntc = 0;
@@ -282,17 +274,17 @@ struct Env {
     if (lead) {
 #pragma unroll
       for (int i = 0; i < AC; ++i) {
-        if (i < C.A) S.aint[i * N + e] = make_int4(health[i], cause[i], cooldown[i], inv[i]);
-        S.sreward[i * N + e] = st_reward[i]; S.skills[i * N + e] = st_kills[i];
+        if (i < C.A) S.aint[i * N + e] = make_int4(LI(L_HEALTH + (i)), LI(L_CAUSE + (i)), LI(L_COOLDOWN + (i)), LI(L_INV + (i)));
+        S.sreward[i * N + e] = LF(L_SREW + (i)); S.skills[i * N + e] = LI(L_SKILLS + (i));
       }
-      S.hdr0[e] = make_int4(nb | (ni << 8) | (nh << 16) | (np << 24), steps, episode, body_seq);
-      S.hdr1[e] = make_int4(contact_seq, first_step, overflow + OVF(), newfix);
+      S.hdr0[e] = make_int4(nb | (ni << 8) | (nh << 16) | (LI(L_NP) << 24), LI(L_STEPS), LI(L_EPISODE), LI(L_BODYSEQ));
+      S.hdr1[e] = make_int4(LI(L_CONTACTSEQ), LI(L_FIRST), LI(L_OVERFLOW) + OVF(), LI(L_NEWFIX));
       // box positions/shapes only change on spawn/despawn, which write through
 #pragma unroll
       for (int w = 0; w < PW; ++w) { S.pex[w * N + e] = ex[w]; S.ptc[w * N + e] = tc[w]; S.pen[w * N + e] = en[w]; }
-      S.zonecur[e] = make_float4(zx, zy, zr, 0.0f);
-      S.zoneint[e] = make_int4(zphase, ztcool, ztshrink, zend);
-      S.smisc[e] = make_int4(st_steps, st_heals, st_boxes, st_episodes);
+      S.zonecur[e] = make_float4(LF(L_ZX), LF(L_ZY), LF(L_ZR), 0.0f);
+      S.zoneint[e] = make_int4(LI(L_ZPHASE), LI(L_ZTCOOL), LI(L_ZTSHRINK), LI(L_ZEND));
+      S.smisc[e] = make_int4(LI(L_STSTEPS), LI(L_STHEALS), LI(L_STBOXES), LI(L_STEPISODES));
     }
   }
 
@@ -372,7 +364,7 @@ struct Env {
     if (!alive(i)) return;
     if (C.teams && cz == MSV_CAUSE_TEAM0 + team_of(i)) return;  // immunities sem:942-946
 #pragma unroll
-    for (int j = 0; j < AC; ++j) if (j == i) { health[j] += delta; cause[j] = cz; }
+    for (int j = 0; j < AC; ++j) if (j == i) { LI(L_HEALTH + (j)) += delta; LI(L_CAUSE + (j)) = cz; }
   }
   DEV void box_change_health(int k, int delta, int cz) {
     int4 b1 = S.box1[k * N + e];
@@ -381,18 +373,18 @@ struct Env {
     b1.x += delta; b1.z = cz;
     S.box1[k * N + e] = b1;
   }
-  DEV int inv_n(int i) { return inv[i] & 7; }
-  DEV int inv_kind(int i, int s) { return (inv[i] >> (4 + 2 * s)) & 3; }
+  DEV int inv_n(int i) { return LI(L_INV + (i)) & 7; }
+  DEV int inv_kind(int i, int s) { return (LI(L_INV + (i)) >> (4 + 2 * s)) & 3; }
   DEV void inv_push(int i, int kind, float4 payload) {
     int n = inv_n(i);
-    inv[i] = (inv[i] & ~(3 << (4 + 2 * n)) & ~7) | (kind << (4 + 2 * n)) | (n + 1);
+    LI(L_INV + (i)) = (LI(L_INV + (i)) & ~(3 << (4 + 2 * n)) & ~7) | (kind << (4 + 2 * n)) | (n + 1);
     if (kind == MSV_ITEM_BOX) S.ainv[(i * 4 + n) * N + e] = payload;
   }
   DEV int inv_pop(int i, float4& payload) {  // list.pop(-1)
     int n = inv_n(i) - 1;
     int kind = inv_kind(i, n);
     if (kind == MSV_ITEM_BOX) payload = S.ainv[(i * 4 + n) * N + e];
-    inv[i] = (inv[i] & ~7) | n;
+    LI(L_INV + (i)) = (LI(L_INV + (i)) & ~7) | n;
     return kind;
   }
 
@@ -430,15 +422,15 @@ struct Env {
     nh--;
   }
   DEV void add_item(float x, float y, float hx, float hy, int owner) {  // Item.drop sem:143-148
-    if (ni >= BC) { overflow++; return; }
+    if (ni >= BC) { LI(L_OVERFLOW)++; return; }
     S.item0[ni * N + e] = make_float4(x, y, hx, hy); ITP(0, ni) = x; ITP(1, ni) = y;
-    S.item1[ni * N + e] = make_int2(owner, body_seq++);
+    S.item1[ni * N + e] = make_int2(owner, LI(L_BODYSEQ)++);
     ni++;
   }
   DEV void add_heal(float x, float y) {
-    if (nh >= HC) { overflow++; return; }
+    if (nh >= HC) { LI(L_OVERFLOW)++; return; }
     S.heal[nh * N + e] = make_float2(x, y); HLP(0, nh) = x; HLP(1, nh) = y;
-    S.healseq[nh * N + e] = body_seq++;
+    S.healseq[nh * N + e] = LI(L_BODYSEQ)++;
     nh++;
   }
   DEV void kill_agent(int i) {  // b2World::DestroyBody for an agent
@@ -498,7 +490,7 @@ struct Env {
       if (best < 0) break;
       clrb(cand, best);
       setb(ex, best); setb(en, best); clrb(tc, best);
-      S.pseq[best * N + e] = (uint32_t)(++contact_seq);
+      S.pseq[best * N + e] = (uint32_t)(++LI(L_CONTACTSEQ));
       S.pimp[best * N + e] = make_float2(0.0f, 0.0f);
     }
   }
@@ -1086,7 +1078,7 @@ struct Env {
         }
         if (best < 0) break;
         setb(done, best);
-        if (nisl >= 8) { overflow++; break; }
+        if (nisl >= 8) { LI(L_OVERFLOW)++; break; }
         int a2, sid2, b2; decode(best, a2, sid2, b2);
         Manifold m; unsigned wk2 = 0;
         bool t2 = contact_update(best, a2, sid2, b2, false, wk2, &m);
@@ -1132,7 +1124,7 @@ struct Env {
       snap[F_COUNT + 6 * w + 2] = (unsigned)tc[w]; snap[F_COUNT + 6 * w + 3] = (unsigned)(tc[w] >> 32);
       snap[F_COUNT + 6 * w + 4] = (unsigned)en[w]; snap[F_COUNT + 6 * w + 5] = (unsigned)(en[w] >> 32);
     }
-    snap[SNAPW - 1] = (unsigned)contact_seq;
+    snap[SNAPW - 1] = (unsigned)LI(L_CONTACTSEQ);
     bool same = prevP == minP;
     for (int q = 0; q < SNAPW; ++q) { if (prev[q] != snap[q]) same = false; prev[q] = snap[q]; }
     prevP = minP;
@@ -1250,28 +1242,28 @@ struct Env {
   }
   // [leader] pending drops, UseLast, GiveLast
   DEV void pre_use_give(const uint8_t* act) {
-    use_heal = 0; use_box = 0; new_box = 0;
-    bool any = np > 0;                       // nothing to do unless a drop is pending or an agent with items uses/gives
+    LI(L_USEHEAL) = 0; LI(L_USEBOX) = 0; LI(L_NEWBOX) = 0;
+    bool any = LI(L_NP) > 0;                       // nothing to do unless a drop is pending or an agent with items uses/gives
 #pragma unroll
-    for (int i = 0; i < AC; ++i) if (i < C.A && (act[6 * i + 4] | act[6 * i + 5]) && (inv[i] & 7) != 0 && alive(i)) any = true;
+    for (int i = 0; i < AC; ++i) if (i < C.A && (act[6 * i + 4] | act[6 * i + 5]) && (LI(L_INV + (i)) & 7) != 0 && alive(i)) any = true;
     if (any) MSV_COLD(pre_use_give_body(act));
   }
   __device__ __noinline__ void pre_use_give_body(const uint8_t* act) {
     // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
-    for (int q = 0; q < np; ++q) {
+    for (int q = 0; q < LI(L_NP); ++q) {
       float4 p0 = S.pend0[q * N + e];
       add_item(p0.x, p0.y, p0.z, p0.w, S.pend1[q * N + e]);
     }
-    np = 0;
+    LI(L_NP) = 0;
     // agents/UseLast.pre_step (sem:300-309) -> Inventory.use (sem:206-213)
 #pragma unroll
     for (int i = 0; i < AC; ++i) {
       if (i >= C.A || !alive(i) || !act[6 * i + 4] || inv_n(i) == 0) continue;
       float4 pl; int kind = inv_pop(i, pl);
-      if (kind == MSV_ITEM_HEAL) { use_heal++; agent_change_health(i, C.healing, MSV_CAUSE_NONE); }  // sem:646-649
+      if (kind == MSV_ITEM_HEAL) { LI(L_USEHEAL)++; agent_change_health(i, C.healing, MSV_CAUSE_NONE); }  // sem:646-649
       else {  // ObjectItem.use (sem:830-836, 876-884)
-        use_box++;
-        if (nb >= BC) { overflow++; continue; }
+        LI(L_USEBOX)++;
+        if (nb >= BC) { LI(L_OVERFLOW)++; continue; }
         float L = C.box_item_offset;
         float qs = AG(F_QS, i), qc = AG(F_QC, i);
         f2 off = mk2(qc * L + (-qs) * 0.0f, qs * L + qc * 0.0f);
@@ -1279,10 +1271,10 @@ struct Env {
         int reh = __float_as_int(pl.w) & 1;
         S.box0[nb * N + e] = make_float4(x, y, pl.x, pl.y);
         S.box1[nb * N + e] = make_int4(0, reh << 1, MSV_CAUSE_NONE, C.box_ownership ? __float_as_int(pl.z) : MSV_CAUSE_NONE);
-        S.boxseq[nb * N + e] = body_seq++;
+        S.boxseq[nb * N + e] = LI(L_BODYSEQ)++;
         load_box(nb, nb);
         for (int j = 0; j < C.A; ++j) { int p = p_ab(j, nb); clrb(ex, p); clrb(tc, p); clrb(en, p); }
-        nb++; new_box = 1; newfix = 1;
+        nb++; LI(L_NEWBOX) = 1; LI(L_NEWFIX) = 1;
       }
     }
     // agents/GiveLast.pre_step (sem:335-370): taker = nearest body of any kind
@@ -1322,7 +1314,7 @@ struct Env {
 #pragma unroll
       for (int i = 0; i < AC; ++i) {
         if (i >= C.A || !alive(i)) continue;
-        bool on_cd = C.melee_cooldown >= 0 && cooldown[i] > 0;
+        bool on_cd = C.melee_cooldown >= 0 && LI(L_COOLDOWN + (i)) > 0;
         if (act[6 * i + 3] && !on_cd) raymask |= 1u << i;
       }
     }
@@ -1353,19 +1345,19 @@ struct Env {
           int cz = C.teams ? MSV_CAUSE_TEAM0 + team_of(i) : i;
           if (kind == KIND_AGENT) agent_change_health(tidx, -C.melee_damage, cz);
           else if (kind == KIND_BOX) box_change_health(tidx, -C.melee_damage, cz);
-          if (C.melee_cooldown >= 0) cooldown[i] = C.melee_cooldown;
+          if (C.melee_cooldown >= 0) LI(L_COOLDOWN + (i)) = C.melee_cooldown;
         }
       }
     }
     if (lead && C.melee_cooldown >= 0) {
 #pragma unroll
-      for (int i = 0; i < AC; ++i) if (cooldown[i] > 0) cooldown[i]--;
+      for (int i = 0; i < AC; ++i) if (LI(L_COOLDOWN + (i)) > 0) LI(L_COOLDOWN + (i))--;
     }
   }
 
   __device__ __noinline__ double philox_uniform(uint32_t step, uint32_t stream, uint32_t k) {
     uint32_t o[4];
-    philox4x32(C.env_offset + (uint32_t)e, (uint32_t)episode, step, (stream << 16) | (k >> 1), C.seed_lo, C.seed_hi, o);
+    philox4x32(C.env_offset + (uint32_t)e, (uint32_t)LI(L_EPISODE), step, (stream << 16) | (k >> 1), C.seed_lo, C.seed_hi, o);
     uint32_t a = o[(k & 1) * 2], b = o[(k & 1) * 2 + 1];
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
   }
@@ -1435,15 +1427,15 @@ struct Env {
       for (int j = 0; j < G; ++j) { saA[s * G + j] = from(saL[s], j); sxA[s * G + j] = from(sxL[s], j); }
     }
     if (lead) {
-      pre_alive = 0; int row = 0;
+      LU(L_PREALIVE) = 0; int row = 0;
 #pragma unroll
-      for (int i = 0; i < AC; ++i) { seenA[i] = 0; seenX[i] = 0; }
+      for (int i = 0; i < AC; ++i) { LU(L_SEENA + (i)) = 0; LU(L_SEENX + (i)) = 0; }
 #pragma unroll
       for (int i = 0; i < AC; ++i) {
         if (i >= C.A || !alive(i)) continue;
-        pre_alive |= 1u << i;
+        LU(L_PREALIVE) |= 1u << i;
 #pragma unroll
-        for (int r = 0; r < AC; ++r) if (r == row) { seenA[r] = saA[i]; seenX[r] = sxA[i]; }
+        for (int r = 0; r < AC; ++r) if (r == row) { LU(L_SEENA + (r)) = saA[i]; LU(L_SEENX + (r)) = sxA[i]; }
         row++;
       }
     }
@@ -1452,15 +1444,13 @@ struct Env {
   DEV void seen_remove(int first_bit, int width, int k) {
 #pragma unroll
     for (int r = 0; r < AC; ++r) {
-      unsigned field = (seenX[r] >> first_bit) & ((1u << width) - 1u);
+      unsigned field = (LU(L_SEENX + (r)) >> first_bit) & ((1u << width) - 1u);
       unsigned lowm = (1u << k) - 1u;
       field = (field & lowm) | ((field >> (k + 1)) << k);
-      seenX[r] = (seenX[r] & ~(((1u << width) - 1u) << first_bit)) | (field << first_bit);
+      LU(L_SEENX + (r)) = (LU(L_SEENX + (r)) & ~(((1u << width) - 1u) << first_bit)) | (field << first_bit);
     }
   }
 
-  unsigned dmask;          // agents that died this step (bit i); Health.post_step visits them in index order
-  int n_kills, kill_cause[AC];
 
   // [leader]
   __device__ __forceinline__ void post_step_boxes() {
@@ -1469,11 +1459,11 @@ struct Env {
       int4 b1 = S.box1[k * N + e];
       if (!(b1.y & 1)) { b1.y |= 1; b1.x = C.box_health; S.box1[k * N + e] = b1; }
       if (b1.x <= 0) {
-        if (np < BC) {
-          S.pend0[np * N + e] = make_float4(BX(G_X, k), BX(G_Y, k), BX(G_HX, k), BX(G_HY, k));
-          S.pend1[np * N + e] = C.box_ownership ? b1.z : MSV_CAUSE_NONE;
-          np++;
-        } else overflow++;
+        if (LI(L_NP) < BC) {
+          S.pend0[LI(L_NP) * N + e] = make_float4(BX(G_X, k), BX(G_Y, k), BX(G_HX, k), BX(G_HY, k));
+          S.pend1[LI(L_NP) * N + e] = C.box_ownership ? b1.z : MSV_CAUSE_NONE;
+          LI(L_NP)++;
+        } else LI(L_OVERFLOW)++;
         MSV_COLD(remove_box(k));
       } else ++k;
     }
@@ -1482,24 +1472,24 @@ struct Env {
   // [leader] agents/Health.post_step -> despawn(dead) (sem:429-448)
   __device__ __noinline__ void handle_deaths() {
     int total = 0;
-    for (int i = 0; i < C.A; ++i) if ((dmask >> i) & 1u) total += inv_n(i);
+    for (int i = 0; i < C.A; ++i) if ((LU(L_DMASK) >> i) & 1u) total += inv_n(i);
     int top = total;
     for (int i = 0; i < C.A; ++i) {         // DeathDrop.pre_despawn (sem:387-396)
-      if (!((dmask >> i) & 1u)) continue;
+      if (!((LU(L_DMASK) >> i) & 1u)) continue;
       f2 me = apos(i);
       int n = inv_n(i);
       for (int j = 0; j < n; ++j) {
-        double ang = 2 * 3.141592653589793 * philox_uniform((uint32_t)steps, STREAM_DEATH, (uint32_t)(--top));
+        double ang = 2 * 3.141592653589793 * philox_uniform((uint32_t)LI(L_STEPS), STREAM_DEATH, (uint32_t)(--top));
         f2 off = from_polar(C.drop_radius, (float)ang);
         float x = me.x + off.x, y = me.y + off.y;
         int kind = inv_kind(i, j);
         if (kind == MSV_ITEM_HEAL) add_heal(x, y);
         else { float4 pl = S.ainv[(i * 4 + j) * N + e]; add_item(x, y, pl.x, pl.y, __float_as_int(pl.z)); }
       }
-      inv[i] = 0;
+      LI(L_INV + (i)) = 0;
     }
-    for (int i = 0; i < C.A; ++i) if ((dmask >> i) & 1u) kill_cause[n_kills++] = cause[i];  // TrackKills sem:628-629
-    for (int i = 0; i < C.A; ++i) if ((dmask >> i) & 1u) kill_agent(i);
+    for (int i = 0; i < C.A; ++i) if ((LU(L_DMASK) >> i) & 1u) LI(L_KCAUSE + (LI(L_NKILLS)++)) = LI(L_CAUSE + (i));  // TrackKills sem:628-629
+    for (int i = 0; i < C.A; ++i) if ((LU(L_DMASK) >> i) & 1u) kill_agent(i);
   }
   // [leader] agents/AutoPickup.post_step (sem:278-283) for agent i: bodies in creation order
   __device__ __noinline__ void pickup_agent(int i) {
@@ -1538,10 +1528,10 @@ struct Env {
   __device__ __forceinline__ void post_step_rest() {
     int dflag = 0;
     if (lead) {
-      dmask = 0; n_kills = 0;
+      LU(L_DMASK) = 0; LI(L_NKILLS) = 0;
 #pragma unroll
-      for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && health[i] <= 0) dmask |= 1u << i;
-      if (dmask) { MSV_COLD(handle_deaths()); dflag = 1; }
+      for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && LI(L_HEALTH + (i)) <= 0) LU(L_DMASK) |= 1u << i;
+      if (LU(L_DMASK)) { MSV_COLD(handle_deaths()); dflag = 1; }
     }
     dflag = bc(dflag);
     if (dflag) { gsync(); share_counts(); }   // drops changed the lists, deaths the flags
@@ -1562,30 +1552,30 @@ struct Env {
     // agents/SafeZone.post_step (sem:758-768) + tick (sem:776-811)
     for (int i = 0; i < C.A; ++i) {
       if (!alive(i)) continue;
-      float dx = AG(F_CX, i) - zx, dy = AG(F_CY, i) - zy;
-      bool inside = dx * dx + dy * dy <= zr * zr;
-      if (zend || !inside) agent_change_health(i, -C.zone_damage, MSV_CAUSE_ZONE);
+      float dx = AG(F_CX, i) - LF(L_ZX), dy = AG(F_CY, i) - LF(L_ZY);
+      bool inside = dx * dx + dy * dy <= LF(L_ZR) * LF(L_ZR);
+      if (LI(L_ZEND) || !inside) agent_change_health(i, -C.zone_damage, MSV_CAUSE_ZONE);
     }
-    if (ztcool == 0) {
-      if (!zend) {
-        ztshrink -= 1;
-        if (ztshrink > 0) {
-          double t = (double)ztshrink / C.zone_cooldown;
-          double r1 = C.zone_radiuses[zphase], r2 = C.zone_radiuses[zphase + 1];
-          zr = (float)(t * r1 + (1 - t) * r2);
+    if (LI(L_ZTCOOL) == 0) {
+      if (!LI(L_ZEND)) {
+        LI(L_ZTSHRINK) -= 1;
+        if (LI(L_ZTSHRINK) > 0) {
+          double t = (double)LI(L_ZTSHRINK) / C.zone_cooldown;
+          double r1 = C.zone_radiuses[LI(L_ZPHASE)], r2 = C.zone_radiuses[LI(L_ZPHASE) + 1];
+          LF(L_ZR) = (float)(t * r1 + (1 - t) * r2);
           float t1 = (float)t, t2 = (float)(1 - t);
-          float2 c1 = S.zonec[zphase * N + e], c2 = S.zonec[(zphase + 1) * N + e];
-          zx = t1 * c1.x + t2 * c2.x; zy = t1 * c1.y + t2 * c2.y;
+          float2 c1 = S.zonec[LI(L_ZPHASE) * N + e], c2 = S.zonec[(LI(L_ZPHASE) + 1) * N + e];
+          LF(L_ZX) = t1 * c1.x + t2 * c2.x; LF(L_ZY) = t1 * c1.y + t2 * c2.y;
         } else {
-          ztcool = C.zone_cooldown; zphase += 1;
-          zr = C.zone_r32[zphase];
-          float2 cc = S.zonec[zphase * N + e]; zx = cc.x; zy = cc.y;
-          if (zphase == C.zone_phases - 1) zend = 1;
+          LI(L_ZTCOOL) = C.zone_cooldown; LI(L_ZPHASE) += 1;
+          LF(L_ZR) = C.zone_r32[LI(L_ZPHASE)];
+          float2 cc = S.zonec[LI(L_ZPHASE) * N + e]; LF(L_ZX) = cc.x; LF(L_ZY) = cc.y;
+          if (LI(L_ZPHASE) == C.zone_phases - 1) LI(L_ZEND) = 1;
         }
       }
     } else {
-      ztcool -= 1;
-      if (ztcool <= 0) ztshrink = C.zone_cooldown;
+      LI(L_ZTCOOL) -= 1;
+      if (LI(L_ZTCOOL) <= 0) LI(L_ZTSHRINK) = C.zone_cooldown;
     }
   }
 
@@ -1603,7 +1593,7 @@ struct Env {
       if (!alive(i)) continue;
       unsigned sr = 0;
 #pragma unroll
-      for (int q = 0; q < AC; ++q) if (q == r) sr = seenA[q];
+      for (int q = 0; q < AC; ++q) if (q == r) sr = LU(L_SEENA + (q));
       r++;
       for (int j = 0; j < C.A; ++j)
         if (j != i && alive(j) && ((sr >> j) & 1u)) bits |= 1ull << (i * AC + j);
@@ -1615,7 +1605,7 @@ struct Env {
         unsigned sx = 0;
         if (alive(i)) {
 #pragma unroll
-          for (int q = 0; q < AC; ++q) if (q == r2) sx = seenX[q];
+          for (int q = 0; q < AC; ++q) if (q == r2) sx = LU(L_SEENX + (q));
           r2++;
         }
         S.omask[i * N + e] = sx;
@@ -1640,22 +1630,22 @@ struct Env {
     if (!C.teams) {
 #pragma unroll
       for (int i = 0; i < AC; ++i) if (i < A) rew[i] += alive(i) ? C.r_alive : C.r_dead;
-      for (int k = 0; k < n_kills; ++k) {
-        int killer = kill_cause[k];
+      for (int k = 0; k < LI(L_NKILLS); ++k) {
+        int killer = LI(L_KCAUSE + (k));
         if (killer >= 0 && killer < A && alive(killer)) {
 #pragma unroll
           for (int i = 0; i < AC; ++i) if (i == killer) { rew[i] += C.r_kill; lk[i]++; }
         }
       }
-      if (dmask) {
+      if (LU(L_DMASK)) {
 #pragma unroll
-        for (int i = 0; i < AC; ++i) if ((dmask >> i) & 1u) rew[i] += C.r_death;
+        for (int i = 0; i < AC; ++i) if ((LU(L_DMASK) >> i) & 1u) rew[i] += C.r_death;
       }
     } else {
 #pragma unroll
       for (int i = 0; i < AC; ++i) if (i < A) rew[i] += (i < split ? ta0 : ta1) ? C.r_alive : C.r_dead;
-      for (int k = 0; k < n_kills; ++k) {
-        int cz = kill_cause[k];
+      for (int k = 0; k < LI(L_NKILLS); ++k) {
+        int cz = LI(L_KCAUSE + (k));
         if (cz != MSV_CAUSE_TEAM0 && cz != MSV_CAUSE_TEAM0 + 1) continue;
         int t = cz - MSV_CAUSE_TEAM0;
 #pragma unroll
@@ -1663,9 +1653,9 @@ struct Env {
 #pragma unroll
         for (int i = 0; i < 2; ++i) if (i == t) lk[i]++;
       }
-      if (dmask) {
+      if (LU(L_DMASK)) {
         for (int d = 0; d < A; ++d) {         // deaths in index order
-          if (!((dmask >> d) & 1u)) continue;
+          if (!((LU(L_DMASK) >> d) & 1u)) continue;
           int t = team_of(d);
 #pragma unroll
           for (int i = 0; i < AC; ++i) if (i < A && (i < split ? 0 : 1) == t) rew[i] += C.r_death;
@@ -1676,20 +1666,20 @@ struct Env {
     if (C.teams) n_alive = (int)ta0 + (int)ta1;
     else for (int i = 0; i < A; ++i) n_alive += alive(i);
     bool done = C.gameover_mode == MSV_GAMEOVER_ALLDEAD ? n_alive == 0 : n_alive <= 1;
-    steps += 1;
+    LI(L_STEPS) += 1;
     if (!C.teams) {
 #pragma unroll
-      for (int i = 0; i < AC; ++i) if (i < A) st_reward[i] += rew[i];
+      for (int i = 0; i < AC; ++i) if (i < A) LF(L_SREW + (i)) += rew[i];
     } else {
-      st_reward[0] += rew[0];
+      LF(L_SREW + (0)) += rew[0];
       float rs = 0.0f;
 #pragma unroll
       for (int i = 0; i < AC; ++i) if (i == split) rs = rew[i];
-      st_reward[1] += rs;
+      LF(L_SREW + (1)) += rs;
     }
 #pragma unroll
-    for (int i = 0; i < AC; ++i) if (i < (C.teams ? 2 : A)) st_kills[i] += lk[i];
-    st_steps += 1; st_heals += use_heal; st_boxes += use_box;
+    for (int i = 0; i < AC; ++i) if (i < (C.teams ? 2 : A)) LI(L_SKILLS + (i)) += lk[i];
+    LI(L_STSTEPS) += 1; LI(L_STHEALS) += LI(L_USEHEAL); LI(L_STBOXES) += LI(L_USEBOX);
 #pragma unroll
     for (int i = 0; i < AC; ++i) if (i < A) O.rewards[(size_t)e * A + i] = rew[i];
     O.dones[e] = done ? 1 : 0;
@@ -1704,7 +1694,7 @@ struct Env {
   // (sem:739-756).  The numpy Generator is replaced by counter-based
   // Philox4x32-10 keyed by (seed, global env id, episode).          [leader]
   __device__ __noinline__ void reset() {
-    episode += 1; steps = 0;
+    LI(L_EPISODE) += 1; LI(L_STEPS) = 0;
     int n = C.grid_n;
     unsigned char perm[64];
     for (int k = 0; k < n; ++k) perm[k] = (unsigned char)k;
@@ -1714,8 +1704,8 @@ struct Env {
       unsigned char t = perm[i]; perm[i] = perm[j]; perm[j] = t;
     }
     int top = n;
-    body_seq = 0; contact_seq = 0; first_step = 1; newfix = 1;
-    nb = 0; ni = 0; nh = 0; np = 0;
+    LI(L_BODYSEQ) = 0; LI(L_CONTACTSEQ) = 0; LI(L_FIRST) = 1; LI(L_NEWFIX) = 1;
+    nb = 0; ni = 0; nh = 0; LI(L_NP) = 0;
 #pragma unroll
     for (int w = 0; w < PW; ++w) { ex[w] = 0ull; tc[w] = 0ull; en[w] = 0ull; }
     for (int b = 0; b < C.B0; ++b) {
@@ -1734,17 +1724,17 @@ struct Env {
       int cell = perm[--top];
       S.box0[b * N + e] = make_float4(C.grid_px[cell], C.grid_py[cell], hx, hy);
       S.box1[b * N + e] = make_int4(C.box_health, 1, MSV_CAUSE_NONE, MSV_CAUSE_NONE);
-      S.boxseq[b * N + e] = body_seq++;
+      S.boxseq[b * N + e] = LI(L_BODYSEQ)++;
       load_box(b, b);
       nb++;
     }
     for (int h = 0; h < C.H0; ++h) {
       int cell = perm[--top];
       S.heal[h * N + e] = make_float2(C.grid_px[cell], C.grid_py[cell]); HLP(0, h) = C.grid_px[cell]; HLP(1, h) = C.grid_py[cell];
-      S.healseq[h * N + e] = body_seq++;
+      S.healseq[h * N + e] = LI(L_BODYSEQ)++;
       nh++;
     }
-    body_seq += 4;  // walls
+    LI(L_BODYSEQ) += 4;  // walls
     for (int i = 0; i < AC; ++i) {
       if (i < C.A) {
         int cell = perm[--top];
@@ -1754,9 +1744,9 @@ struct Env {
         AG(F_FAT0, i) = (x - r) - B2_AABB_EXT; AG(F_FAT1, i) = (y - r) - B2_AABB_EXT;
         AG(F_FAT2, i) = (x + r) + B2_AABB_EXT; AG(F_FAT3, i) = (y + r) + B2_AABB_EXT;
         AGF(i) = FL_ALIVE | FL_AWAKE;
-        health[i] = C.health; body_seq++;
-      } else { AGF(i) = 0; health[i] = 0; }
-      cause[i] = MSV_CAUSE_NONE; cooldown[i] = 0; inv[i] = 0;
+        LI(L_HEALTH + (i)) = C.health; LI(L_BODYSEQ)++;
+      } else { AGF(i) = 0; LI(L_HEALTH + (i)) = 0; }
+      LI(L_CAUSE + (i)) = MSV_CAUSE_NONE; LI(L_COOLDOWN + (i)) = 0; LI(L_INV + (i)) = 0;
     }
     if (C.zone_centers_random) {
       int d = 0;
@@ -1770,9 +1760,9 @@ struct Env {
       for (int z = 0; z < C.n_zones; ++z)
         S.zonec[z * N + e] = make_float2((float)C.zone_centers[z][0], (float)C.zone_centers[z][1]);
     }
-    ztcool = C.zone_cooldown; ztshrink = 0; zphase = 0; zend = 0;
-    zr = C.zone_r32[0];
-    float2 c0 = S.zonec[e]; zx = c0.x; zy = c0.y;
-    dmask = 0; n_kills = 0; use_heal = 0; use_box = 0;
+    LI(L_ZTCOOL) = C.zone_cooldown; LI(L_ZTSHRINK) = 0; LI(L_ZPHASE) = 0; LI(L_ZEND) = 0;
+    LF(L_ZR) = C.zone_r32[0];
+    float2 c0 = S.zonec[e]; LF(L_ZX) = c0.x; LF(L_ZY) = c0.y;
+    LU(L_DMASK) = 0; LI(L_NKILLS) = 0; LI(L_USEHEAL) = 0; LI(L_USEBOX) = 0;
   }
 };

@@ -67,25 +67,25 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   if (env.lead) env.pre_use_give(act);
   env.gsync();
   env.share_counts();
-  const int newfix = env.bc(env.newfix);
-  if (env.bc(env.new_box)) env.share_bits();
+  const int newfix = env.bc(env.LI(env.L_NEWFIX));
+  if (env.bc(env.LI(env.L_NEWBOX))) env.share_bits();
   PHASE_SYNC(6);
   env.pre_melee(act);
   PROF(1);
 #pragma unroll 1
   for (int sub = 0; sub < 2; ++sub) {      // sim:236-239: b2World::Step x2
-    if (sub == 0 && newfix) { env.find_new_contacts(); env.newfix = 0; }  // b2World::Step: e_newFixture
+    if (sub == 0 && newfix) { env.find_new_contacts(); env.LI(env.L_NEWFIX) = 0; }  // b2World::Step: e_newFixture
     PROF(2);
     PHASE_SYNC(1);
     env.collide();
     PROF(3);
     PHASE_SYNC(2);
-    const int first = env.bc(env.first_step);
+    const int first = env.bc(env.LI(env.L_FIRST));
     env.solve(C.dt, first ? 0.0f : C.dt_ratio1);
     PROF(4);
     PHASE_SYNC(3);
     env.solve_toi(C.dt);
-    env.first_step = 0;
+    env.LI(env.L_FIRST) = 0;
     PROF(5);
   }
   if (env.lead) env.post_step_boxes();
@@ -102,7 +102,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   if (env.lead) {
     bool done = env.rewards_done(O);       // env:85-89
     if (done && C.auto_reset) {            // vector-env extension: the observation returned is the new episode's first
-      env.st_episodes++;
+      env.LI(env.L_STEPISODES)++;
       MSV_COLD_ON(env, reset());
       again = 1;
     }
@@ -137,7 +137,7 @@ k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   Env<AC, BC, HC, G> env(C, S, es, g, gmask, e);
   env.load();
   if (env.lead) {
-    if (only_done) env.st_episodes++;
+    if (only_done) env.LI(env.L_STEPISODES)++;
     MSV_COLD_ON(env, reset());
   }
   env.share_counts();
