@@ -24,7 +24,7 @@
 enum { F_CX, F_CY, F_A, F_VX, F_VY, F_W, F_C0X, F_C0Y, F_A0, F_ALPHA0, F_SLEEP,
        F_FAT0, F_FAT1, F_FAT2, F_FAT3, F_FLAGS, F_QS, F_QC, F_COUNT };
 // shared-memory box fields
-enum { G_X, G_Y, G_HX, G_HY, G_AX, G_AY, G_ROT, G_COUNT };
+enum { G_X, G_Y, G_HX, G_HY, G_AX, G_AY, G_ROT, G_F0, G_F1, G_F2, G_F3, G_COUNT };   // G_F*: fat AABB (b2DynamicTree proxy)
 // shared-memory touching-contact fields (a b2Contact with a one-point manifold)
 enum { K_META, K_SEQ, K_MTYPE, K_LNX, K_LNY, K_LPX, K_LPY, K_NI, K_TI, K_COUNT };
 
@@ -263,6 +263,9 @@ struct Env {
     BX(G_X, dst) = b0.x; BX(G_Y, dst) = b0.y;
     SBox t; sb_set_shape(t, b0.z, b0.w, (b1.y >> 1) & 1);
     BX(G_HX, dst) = t.hx; BX(G_HY, dst) = t.hy; BX(G_AX, dst) = t.ax; BX(G_AY, dst) = t.ay; BXROT(dst) = t.rot;
+    t.px = b0.x; t.py = b0.y; t.qs = 0.0f; t.qc = 1.0f; t.ang = 0.0f;
+    float ft[4]; sb_fat(t, ft);                 // computed once per box and step instead of once per pair test
+    BX(G_F0, dst) = ft[0]; BX(G_F1, dst) = ft[1]; BX(G_F2, dst) = ft[2]; BX(G_F3, dst) = ft[3];
   }
   DEV void store() {
     gsync();
@@ -302,7 +305,7 @@ struct Env {
     return b;
   }
   DEV void static_fat(int sid, float out[4]) {
-    if (sid < BC) { SBox b = static_box(sid); sb_fat(b, out); }
+    if (sid < BC) { out[0] = BX(G_F0, sid); out[1] = BX(G_F1, sid); out[2] = BX(G_F2, sid); out[3] = BX(G_F3, sid); }
     else { const WallC& w = C.walls[sid - BC]; out[0] = w.fat[0]; out[1] = w.fat[1]; out[2] = w.fat[2]; out[3] = w.fat[3]; }
   }
   DEV void agent_fat(int i, float out[4]) {
@@ -363,8 +366,7 @@ struct Env {
   DEV void agent_change_health(int i, int delta, int cz) {
     if (!alive(i)) return;
     if (C.teams && cz == MSV_CAUSE_TEAM0 + team_of(i)) return;  // immunities sem:942-946
-#pragma unroll
-    for (int j = 0; j < AC; ++j) if (j == i) { LI(L_HEALTH + (j)) += delta; LI(L_CAUSE + (j)) = cz; }
+    LI(L_HEALTH + i) += delta; LI(L_CAUSE + i) = cz;
   }
   DEV void box_change_health(int k, int delta, int cz) {
     int4 b1 = S.box1[k * N + e];
@@ -410,6 +412,7 @@ struct Env {
       BX(G_X, q) = BX(G_X, q + 1); BX(G_Y, q) = BX(G_Y, q + 1); BX(G_HX, q) = BX(G_HX, q + 1);
       BX(G_HY, q) = BX(G_HY, q + 1); BX(G_AX, q) = BX(G_AX, q + 1); BX(G_AY, q) = BX(G_AY, q + 1);
       BXROT(q) = BXROT(q + 1);
+      BX(G_F0, q) = BX(G_F0, q + 1); BX(G_F1, q) = BX(G_F1, q + 1); BX(G_F2, q) = BX(G_F2, q + 1); BX(G_F3, q) = BX(G_F3, q + 1);
     }
     nb--;
   }
@@ -1299,8 +1302,7 @@ struct Env {
       if (C.teams && team_of(tidx) != team_of(i)) continue;            // strangers sem:344-349
       float4 pl = make_float4(0.f, 0.f, 0.f, 0.f); int kind = inv_pop(i, pl);
       if (inv_n(tidx) + 1 <= C.inv_slots) {
-#pragma unroll
-        for (int j = 0; j < AC; ++j) if (j == tidx) inv_push(j, kind, pl);
+        inv_push(tidx, kind, pl);
       }                                                                // else lost (Q6)
     }
   }
@@ -1434,8 +1436,7 @@ struct Env {
       for (int i = 0; i < AC; ++i) {
         if (i >= C.A || !alive(i)) continue;
         LU(L_PREALIVE) |= 1u << i;
-#pragma unroll
-        for (int r = 0; r < AC; ++r) if (r == row) { LU(L_SEENA + (r)) = saA[i]; LU(L_SEENX + (r)) = sxA[i]; }
+        LU(L_SEENA + row) = saA[i]; LU(L_SEENX + row) = sxA[i];
         row++;
       }
     }
@@ -1588,15 +1589,14 @@ struct Env {
   // [leader]
   DEV void store_obm() {
     unsigned long long bits = 0ull;
+    unsigned am = 0;                           // agents alive now (after this step's deaths)
+    for (int i = 0; i < C.A; ++i) if (alive(i)) am |= 1u << i;
     int r = 0;
     for (int i = 0; i < C.A; ++i) {
-      if (!alive(i)) continue;
-      unsigned sr = 0;
-#pragma unroll
-      for (int q = 0; q < AC; ++q) if (q == r) sr = LU(L_SEENA + (q));
+      if (!((am >> i) & 1u)) continue;
+      const unsigned sr = LU(L_SEENA + r);
       r++;
-      for (int j = 0; j < C.A; ++j)
-        if (j != i && alive(j) && ((sr >> j) & 1u)) bits |= 1ull << (i * AC + j);
+      bits |= (unsigned long long)(sr & am & ~(1u << i)) << (i * AC);
     }
     S.obm[e] = bits;
     if (!C.omniscient) {   // env:706-739: zip(agents.bodies, cameras.seen) -> same Q1 row remap
@@ -1604,8 +1604,7 @@ struct Env {
       for (int i = 0; i < C.A; ++i) {
         unsigned sx = 0;
         if (alive(i)) {
-#pragma unroll
-          for (int q = 0; q < AC; ++q) if (q == r2) sx = LU(L_SEENX + (q));
+          sx = LU(L_SEENX + r2);
           r2++;
         }
         S.omask[i * N + e] = sx;
