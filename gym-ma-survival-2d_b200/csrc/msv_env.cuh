@@ -1229,11 +1229,16 @@ struct Env {
   //                      SEMANTICS (pre_step / post_step)
   // ======================================================================
   // agents/DynamicMotors.pre_step (sim:407-424)                      [all lanes]
-  __device__ __forceinline__ void pre_motors(const uint8_t* actions, bool real) {
+  // Returns the group's action flags: bit i attack, bit 8+i use, bit 16+i give of agent i.
+  __device__ __forceinline__ unsigned pre_motors(const uint8_t* actions, bool real) {
+    unsigned flags = 0;
     for (int i = g; i < C.A; i += G) {
-      if (!alive(i)) continue;
       int a0 = 1, a1 = 1, a2 = 1;            // padding envs (N rounded up to the block size) get the no-op action
-      if (real) { const uint8_t* a = actions + ((size_t)e * C.A + i) * 6; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
+      if (real) {
+        const uint8_t* a = actions + ((size_t)e * C.A + i) * 6; a0 = a[0]; a1 = a[1]; a2 = a[2];
+        flags |= (a[3] ? 1u : 0u) << i | (a[4] ? 1u : 0u) << (8 + i) | (a[5] ? 1u : 0u) << (16 + i);
+      }
+      if (!alive(i)) continue;
       float s, c; rot_set(AG(F_A, i), s, c);
       AG(F_QS, i) = s; AG(F_QC, i) = c;
       float par = C.imp_par[a0], nor = C.imp_nor[a1];
@@ -1242,16 +1247,17 @@ struct Env {
       AG(F_VX, i) += C.inv_mass * ix; AG(F_VY, i) += C.inv_mass * iy;
       AG(F_W, i) += C.inv_I * C.imp_ang[a2];
     }
+    return or32(flags);
   }
   // [leader] pending drops, UseLast, GiveLast
-  DEV void pre_use_give(const uint8_t* act) {
+  DEV void pre_use_give(unsigned act) {
     LI(L_USEHEAL) = 0; LI(L_USEBOX) = 0; LI(L_NEWBOX) = 0;
     bool any = LI(L_NP) > 0;                       // nothing to do unless a drop is pending or an agent with items uses/gives
 #pragma unroll
-    for (int i = 0; i < AC; ++i) if (i < C.A && (act[6 * i + 4] | act[6 * i + 5]) && (LI(L_INV + (i)) & 7) != 0 && alive(i)) any = true;
+    for (int i = 0; i < AC; ++i) if (i < C.A && (((act >> (8 + i)) | (act >> (16 + i))) & 1u) && (LI(L_INV + (i)) & 7) != 0 && alive(i)) any = true;
     if (any) MSV_COLD(pre_use_give_body(act));
   }
-  __device__ __noinline__ void pre_use_give_body(const uint8_t* act) {
+  __device__ __noinline__ void pre_use_give_body(unsigned act) {
     // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
     for (int q = 0; q < LI(L_NP); ++q) {
       float4 p0 = S.pend0[q * N + e];
@@ -1261,7 +1267,7 @@ struct Env {
     // agents/UseLast.pre_step (sem:300-309) -> Inventory.use (sem:206-213)
 #pragma unroll
     for (int i = 0; i < AC; ++i) {
-      if (i >= C.A || !alive(i) || !act[6 * i + 4] || inv_n(i) == 0) continue;
+      if (i >= C.A || !alive(i) || !((act >> (8 + i)) & 1u) || inv_n(i) == 0) continue;
       float4 pl; int kind = inv_pop(i, pl);
       if (kind == MSV_ITEM_HEAL) { LI(L_USEHEAL)++; agent_change_health(i, C.healing, MSV_CAUSE_NONE); }  // sem:646-649
       else {  // ObjectItem.use (sem:830-836, 876-884)
@@ -1283,7 +1289,7 @@ struct Env {
     // agents/GiveLast.pre_step (sem:335-370): taker = nearest body of any kind
 #pragma unroll
     for (int i = 0; i < AC; ++i) {
-      if (i >= C.A || !alive(i) || !act[6 * i + 5] || inv_n(i) == 0) continue;
+      if (i >= C.A || !alive(i) || !((act >> (16 + i)) & 1u) || inv_n(i) == 0) continue;
       f2 me = apos(i); float r2 = C.give_r * C.give_r;
       float minDist = INFINITY; int tkind = KIND_NONE, tidx = -1;
       auto consider = [&](f2 o, int kind, int idx) {
@@ -1310,14 +1316,14 @@ struct Env {
   // rays only depend on geometry (boxes placed above included), which the
   // health changes do not alter: every lane casts its agents' rays, then the
   // leader applies the hits in agent order.                          [all lanes]
-  __device__ __forceinline__ void pre_melee(const uint8_t* act) {
+  __device__ __forceinline__ void pre_melee(unsigned act) {
     unsigned raymask = 0;
     if (lead) {
 #pragma unroll
       for (int i = 0; i < AC; ++i) {
         if (i >= C.A || !alive(i)) continue;
         bool on_cd = C.melee_cooldown >= 0 && LI(L_COOLDOWN + (i)) > 0;
-        if (act[6 * i + 3] && !on_cd) raymask |= 1u << i;
+        if (((act >> i) & 1u) && !on_cd) raymask |= 1u << i;
       }
     }
     raymask = bc(raymask);

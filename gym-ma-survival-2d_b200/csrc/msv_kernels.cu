@@ -55,14 +55,9 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
 #endif
   env.load();
   const bool real = e < C.n_real;   // padding envs (N rounded up to the block size) get the no-op action
-  uint8_t act[AC * 6];
-  if (env.lead) {
-    const uint8_t* src = actions + (size_t)e * C.A * 6;
-    for (int k = 0; k < AC * 6; ++k) act[k] = (real && k < C.A * 6) ? src[k] : (uint8_t)(k % 6 < 3 ? 1 : 0);
-  }
   PROF(0);
   PHASE_SYNC(0);
-  env.pre_motors(actions, real);           // sim:234-235
+  const unsigned act = env.pre_motors(actions, real);   // sim:234-235; every lane reads its own agent's action
   env.gsync();
   if (env.lead) env.pre_use_give(act);
   env.gsync();
