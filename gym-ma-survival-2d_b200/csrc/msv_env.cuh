@@ -457,16 +457,23 @@ struct Env {
   // fat AABBs overlap and that has no contact yet; new contacts are numbered
   // in ascending (proxyIdA, proxyIdB) order (creation sequence surrogate).
   // candidate pairs whose body B is agent j
-  DEV void candidates_of(int j, unsigned long long* cand) {
-    if (!alive(j)) return;
+  // only_moved: b2BroadPhase::UpdatePairs queries the proxies that moved in this solve; a pair
+  // neither of whose proxies moved cannot have started to overlap
+  DEV void candidates_of(int j, unsigned long long* cand, bool only_moved = false) {
+    const int fj_ = AGF(j);
+    if (!(fj_ & FL_ALIVE)) return;
+    const bool mj = !only_moved || (fj_ & FL_MOVED);
     float fj[4]; agent_fat(j, fj);
     for (int i = 0; i < j; ++i) {
-      if (!alive(i)) continue;
+      const int fi_ = AGF(i);
+      if (!(fi_ & FL_ALIVE)) continue;
+      if (!mj && !(fi_ & FL_MOVED)) continue;
       int p = p_aa(i, j);
       if (bit(ex, p)) continue;
       float fi[4]; agent_fat(i, fi);
       if (aabb_overlap(fi, fj)) setb(cand, p);
     }
+    if (!mj) return;
     for (int k = 0; k < BC + 4; ++k) {
       if (k < BC && k >= nb) continue;
       int p = k < BC ? p_ab(j, k) : p_aw(j, k - BC);
@@ -498,11 +505,11 @@ struct Env {
     }
   }
   // [all lanes] every lane tests the pairs of its own agents; the leader numbers the new contacts
-  DEV void find_new_contacts() {
+  DEV void find_new_contacts(bool only_moved = false) {
     unsigned long long cand[PW];
 #pragma unroll
     for (int w = 0; w < PW; ++w) cand[w] = 0ull;
-    for (int j = g; j < C.A; j += G) candidates_of(j, cand);
+    for (int j = g; j < C.A; j += G) candidates_of(j, cand, only_moved);
     bool any = false;
 #pragma unroll
     for (int w = 0; w < PW; ++w) { cand[w] = or64(cand[w]); any |= cand[w] != 0ull; }
@@ -1025,7 +1032,7 @@ struct Env {
     unsigned mv = 0;
     for (int i = g; i < C.A; i += G) if (AGF(i) & FL_MOVED) mv = 1u;
     MSV_SOLVE_SYNC();
-    if (or32(mv)) find_new_contacts();
+    if (or32(mv)) find_new_contacts(true);
   }
 
   // b2Body::Advance for agent i
