@@ -898,7 +898,7 @@ struct Env {
   // together (per-island contact order, position-iteration early-out and sleep
   // decision are kept).  [leader] generic version, used when some agent touches
   // another agent; works on a private copy of the shared contact list.
-  __device__ __noinline__ void solve_generic(float h, float dtRatio) {
+  __device__ __noinline__ void solve_generic(float h, float dtRatio, unsigned members) {
     TCon tcs[MAXC];
     for (int k = 0; k < ntc; ++k) {
       TCon& t = tcs[k];
@@ -912,11 +912,13 @@ struct Env {
     unsigned char order[MAXC], cisl[MAXC];
     int nisl = 0, nc = 0;
     unsigned multi = 0;                        // islands that contain an agent-agent contact
+    unsigned inisl = 0;                        // agents this call put into an island (others belong to their lanes)
     for (int seed = C.A - 1; seed >= 0; --seed) {
+      if (!((members >> seed) & 1u)) continue;
       int fs = AGF(seed);
       if (!(fs & FL_ALIVE) || (fs & FL_ISLAND) || !(fs & FL_AWAKE)) continue;
       int sc = 0;
-      stack[sc++] = seed; AGF(seed) |= FL_ISLAND;
+      stack[sc++] = seed; AGF(seed) |= FL_ISLAND; inisl |= 1u << seed;
       while (sc > 0) {
         int bI = stack[--sc];
         isl_of[bI] = nisl;
@@ -938,7 +940,7 @@ struct Env {
           if (t.a >= 0) {
             multi |= 1u << nisl;
             int other = t.a == bI ? t.b : t.a;
-            if (!(AGF(other) & FL_ISLAND)) { stack[sc++] = other; AGF(other) |= FL_ISLAND; }
+            if (!(AGF(other) & FL_ISLAND)) { stack[sc++] = other; AGF(other) |= FL_ISLAND; inisl |= 1u << other; }
           }
         }
       }
@@ -946,7 +948,7 @@ struct Env {
     }
     // ---- b2Island::Solve, all islands
     for (int i = 0; i < C.A; ++i) {
-      if (!(AGF(i) & FL_ISLAND)) continue;
+      if (!((inisl >> i) & 1u)) continue;
       AG(F_C0X, i) = AG(F_CX, i); AG(F_C0Y, i) = AG(F_CY, i); AG(F_A0, i) = AG(F_A, i);
       AG(F_VX, i) = C.damp * AG(F_VX, i); AG(F_VY, i) = C.damp * AG(F_VY, i);  // v *= 1/(1+h*damping)
       AG(F_W, i) *= C.damp;
@@ -975,7 +977,7 @@ struct Env {
       }
       for (int k = 0; k < nc; ++k) { const TCon& t = tcs[order[k]]; S.pimp[t.p * N + e] = make_float2(t.ni, t.ti); }
     }
-    for (int i = 0; i < C.A; ++i) if (AGF(i) & FL_ISLAND) integrate_position(i, h);
+    for (int i = 0; i < C.A; ++i) if ((inisl >> i) & 1u) integrate_position(i, h);
     solved = all_isl;
     for (int k0 = 0; k0 < nc;) {
       const int j = cisl[k0]; int k1 = k0;
@@ -1005,7 +1007,7 @@ struct Env {
       const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
       unsigned can_sleep = solved;             // islands with minSleepTime >= timeToSleep && positionSolved
       for (int i = 0; i < C.A; ++i) {
-        if (!(AGF(i) & FL_ISLAND)) continue;
+        if (!((inisl >> i) & 1u)) continue;
         float w = AG(F_W, i); f2 v = mk2(AG(F_VX, i), AG(F_VY, i));
         float st;
         if (w * w > angTol || vdot(v, v) > linTol) st = 0.0f; else st = AG(F_SLEEP, i) + h;
@@ -1014,20 +1016,29 @@ struct Env {
       }
       if (can_sleep)
         for (int i = 0; i < C.A; ++i)
-          if ((AGF(i) & FL_ISLAND) && ((can_sleep >> isl_of[i]) & 1u)) sleep_body(i);
+          if (((inisl >> i) & 1u) && ((can_sleep >> isl_of[i]) & 1u)) sleep_body(i);
     }
     for (int i = 0; i < C.A; ++i)
-      if (AGF(i) & FL_ISLAND) synchronize_fixtures(i);
+      if ((inisl >> i) & 1u) synchronize_fixtures(i);
   }
 
   // b2World::Solve                                                   [all lanes]
   __device__ __forceinline__ void solve(float h, float dtRatio) {
     for (int i = g; i < C.A; i += G) AGF(i) &= ~(FL_ISLAND | FL_MOVED);
-    bool aa = false;                           // does any agent touch another agent? (group-uniform)
-    { unsigned long long m = tc[0] & en[0]; if (NAA < 64) m &= (1ull << NAA) - 1ull; aa = m != 0ull; }
+    // agents with a touching, enabled agent-agent contact: their islands go to the leader's
+    // generic solver; every other awake agent is an island of its own, solved by its lane
+    unsigned multi = 0;
+    {
+      unsigned long long m = tc[0] & en[0]; if (NAA < 64) m &= (1ull << NAA) - 1ull;
+      while (m) {
+        int p = __ffsll((long long)m) - 1; m &= m - 1;
+        int a, sid, b; decode(p, a, sid, b);
+        multi |= (1u << a) | (1u << b);
+      }
+    }
     gsync();
-    if (aa) { if (lead) MSV_COLD(solve_generic(h, dtRatio)); }
-    else for (int i = g; i < C.A; i += G) solve_single(i, h, dtRatio);
+    if (multi && lead) MSV_COLD(solve_generic(h, dtRatio, multi));
+    for (int i = g; i < C.A; i += G) if (!((multi >> i) & 1u)) solve_single(i, h, dtRatio);
     gsync();
     unsigned mv = 0;
     for (int i = g; i < C.A; i += G) if (AGF(i) & FL_MOVED) mv = 1u;
