@@ -226,7 +226,7 @@ __device__ __forceinline__ float obs_value(const DevConst& C, const DevState& S,
   return v;
 }
 
-#define OBS_EPB 8   // environments per block
+#define OBS_EPB 4   // environments per block (measured: 1 -> 32.9, 2 -> 28.8, 4 -> 28.2, 8 -> 34.2, 16 -> 48.3 us for 16 384 envs of 2v2)
 __global__ void __launch_bounds__(256)
 k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC,
       const uint8_t* __restrict__ only_if) {
@@ -234,11 +234,18 @@ k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, co
   for (int el = threadIdx.x; el < Tb.n_elems; el += 256) {
     const ObsDesc d = Tb.desc[el];           // read once, reused for the block's environments
     const ObsKey k = Tb.keys[d.key];
+    // gather first, store afterwards: the state loads of the 8 environments are independent and
+    // overlap instead of being serialised behind the (possibly aliasing) output stores
+    float v[OBS_EPB]; bool on[OBS_EPB];
 #pragma unroll
     for (int j = 0; j < OBS_EPB; ++j) {
       const int e = e0 + j;
-      if (e < C.n_real && (!only_if || only_if[e])) k.base[(size_t)e * k.chunk + d.off] = obs_value(C, S, d, e, AC);
+      on[j] = e < C.n_real && (!only_if || only_if[e]);
+      v[j] = on[j] ? obs_value(C, S, d, e, AC) : 0.0f;
     }
+#pragma unroll
+    for (int j = 0; j < OBS_EPB; ++j)
+      if (on[j]) k.base[(size_t)(e0 + j) * k.chunk + d.off] = v[j];
   }
 }
 
