@@ -1,13 +1,23 @@
-"""Quick device-side timing of the step kernel (development aid; bench.py is
-the contract benchmark)."""
-import sys, time
-import numpy as np
-import parity
+"""Quick device-side timing of the whole step (development aid; bench.py is the contract benchmark).
+
+  python gpu_quickbench.py                      # 2v2, 16384 envs, 600 timed steps (seeded actions)
+  python gpu_quickbench.py ffa 32768 300 100    # variant, envs, timed steps, warm-up steps
+  python gpu_quickbench.py --sweep              # 2v2 at 1k .. 32k envs
+  python gpu_quickbench.py --all                # one line per BASELINE config shape
+  python gpu_quickbench.py --prof               # per-phase clock64() profile (needs `make PROFILE=1`)
+MSV_LIB=/path/to/other/libmasurv.so selects another build of the library (A/B runs).
+"""
+import sys
+import parity  # noqa: F401  (puts the package and the oracle on sys.path)
 from parity import make_config
 import torch
 from masurvival import _lib
 
-def run(variant, N, steps=200, warm=50, prof=True):
+PHASES = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest',
+          'rewards+reset', 'observe', 'store']
+
+
+def run(variant, N, steps=600, warm=100, prof=False):
     rec = make_config(variant, auto_reset=True)
     A = int(rec['n_agents'])
     h = _lib.Handle(rec, N, 0, 1, 0)
@@ -15,12 +25,15 @@ def run(variant, N, steps=200, warm=50, prof=True):
     torch.manual_seed(1234)   # identical action streams in every run: timing differences come from the code only
     acts = torch.randint(0, 2, (8, N, A, 6), dtype=torch.uint8, device='cuda')
     acts[..., 0:3] = torch.randint(0, 3, (8, N, A, 3), dtype=torch.uint8, device='cuda')
-    for t in range(warm): h.step(acts[t % 8].data_ptr())
+    for t in range(warm):
+        h.step(acts[t % 8].data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for t in range(steps): h.step(acts[t % 8].data_ptr())
-    e1.record(); torch.cuda.synchronize()
+    for t in range(steps):
+        h.step(acts[t % 8].data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     bps = h.bytes_per_env_step()
     st = h.flush_stats()
@@ -32,14 +45,26 @@ def run(variant, N, steps=200, warm=50, prof=True):
         L.msv_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         buf = (ctypes.c_ulonglong * 32)()
         L.msv_debug_profile(h.h, 1, buf)
-        for t in range(20): h.step(acts[t % 8].data_ptr())
+        for t in range(20):
+            h.step(acts[t % 8].data_ptr())
         L.msv_debug_profile(h.h, 0, buf)
-        print('   max over threads (any of 20 launches): total=%d; ' % buf[12] + ', '.join(f'{n}={buf[16+i]}' for i, n in enumerate(['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'observe', 'store'])))
-        names = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes', 'cameras', 'post_rest', 'rewards+reset', 'observe', 'store']
         tot = sum(buf[:12]) or 1
-        print('   phase cycles/thread/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(names)))
+        print('   slowest group (any of 20 launches): total=%d; ' % buf[12] + ', '.join(f'{n}={buf[16+i]}' for i, n in enumerate(PHASES)))
+        print('   leader-lane cycles/env/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(PHASES)))
     h.close()
 
+
 if __name__ == '__main__':
-    for v, N in (('2v2', 16384), ('1v1_heal_only', 4096), ('ffa', 8192), ('ffa_lidar', 32768)):
-        run(v, N)
+    a = sys.argv[1:]
+    if a and a[0] == '--sweep':
+        for N in (1024, 2048, 4096, 8192, 16384, 32768):
+            run('2v2', N, steps=500)
+    elif a and a[0] == '--all':
+        for v, N in (('2v2', 16384), ('1v1_heal_only', 4096), ('1v1', 16384), ('ffa', 32768), ('ffa_lidar', 32768)):
+            run(v, N, steps=500)
+    elif a and a[0] == '--prof':
+        run('2v2', 16384, prof=True)
+    else:
+        v = a[0] if a else '2v2'
+        N = int(a[1]) if len(a) > 1 else 16384
+        run(v, N, int(a[2]) if len(a) > 2 else 600, int(a[3]) if len(a) > 3 else 100)
