@@ -140,7 +140,9 @@ DEV bool ray_circle(f2 center, float radius, f2 p1, f2 p2, float& fraction) {
   return false;
 }
 // b2PolygonShape::RayCast with maxFraction = 1
-__device__ __noinline__ bool ray_box(const SBox& bx, f2 p1w, f2 p2w, float& fraction) {
+// (out-of-line functions take the box BY VALUE: by reference it would be spilled to the stack)
+// returns the hit fraction in [0, 1], or -1 for a miss (by value: no stack traffic at the call)
+__device__ __noinline__ float ray_box_f(const SBox bx, f2 p1w, f2 p2w) {
   f2 p1 = sb_mulT(bx, p1w), p2 = sb_mulT(bx, p2w);
   f2 d = vsub(p2, p1);
   float lower = 0.0f, upper = 1.0f;
@@ -151,15 +153,20 @@ __device__ __noinline__ bool ray_box(const SBox& bx, f2 p1w, f2 p2w, float& frac
     float numerator = vdot(n, vsub(sb_vert(bx, i), p1));
     float denominator = vdot(n, d);
     if (denominator == 0.0f) {
-      if (numerator < 0.0f) return false;
+      if (numerator < 0.0f) return -1.0f;
     } else {
       if (denominator < 0.0f && numerator < lower * denominator) { lower = numerator / denominator; index = i; }
       else if (denominator > 0.0f && numerator < upper * denominator) { upper = numerator / denominator; }
     }
-    if (upper < lower) return false;
+    if (upper < lower) return -1.0f;
   }
-  if (index >= 0) { fraction = lower; return true; }
-  return false;
+  if (index >= 0) return lower;
+  return -1.0f;
+}
+DEV bool ray_box(const SBox& bx, f2 p1w, f2 p2w, float& fraction) {
+  float f = ray_box_f(bx, p1w, p2w);
+  if (f < 0.0f) return false;
+  fraction = f; return true;
 }
 
 // ---------------------------------------------------------------- manifolds
@@ -237,7 +244,7 @@ DEV float simplex_metric(const SimplexV* v, int count) {
 }
 
 // b2Distance(useRadii = false): returns distance, updates the cache
-__device__ __noinline__ float gjk_distance(SimplexCache& cache, const SBox& A, f2 pB) {
+__device__ __noinline__ float gjk_distance(SimplexCache& cache, const SBox A, f2 pB) {
   SimplexV v[3]; int count = cache.count;
   for (int i = 0; i < count; ++i) {  // b2Simplex::ReadCache
     v[i].indexA = cache.indexA[i];
@@ -352,8 +359,9 @@ DEV f2 point_at(f2 c0, f2 c, float beta) { return vadd(vmul(1.0f - beta, c0), vm
 __device__ unsigned long long g_dbg[8];
 #endif
 // b2TimeOfImpact(proxyA = box, proxyB = circle centre), tMax = 1
-__device__ __noinline__ int time_of_impact(const SBox& A, f2 c0, f2 c, float rB, float& tOut) {
-  int state = 0; tOut = 1.0f;
+struct ToiOut { int state; float t; };
+__device__ __noinline__ ToiOut time_of_impact_v(const SBox A, f2 c0, f2 c, float rB) {
+  int state = 0; float tOut = 1.0f;
   const float tMax = 1.0f;
 #ifdef MSV_PROFILE
   long long dbg_t0 = clock64(); int dbg_roots = 0, dbg_push = 0;
@@ -373,7 +381,7 @@ __device__ __noinline__ int time_of_impact(const SBox& A, f2 c0, f2 c, float rB,
     f2 l = sb_mulT(A, c0);
     float dx = fmax_(fabsf(l.x) - A.hx, 0.0f), dy = fmax_(fabsf(l.y) - A.hy, 0.0f);
     float d = sqrtf(dx * dx + dy * dy);
-    if (d > 1e-3f && d < (target + tolerance) - 1e-3f) { tOut = 0.0f; return TOI_TOUCHING; }
+    if (d > 1e-3f && d < (target + tolerance) - 1e-3f) { ToiOut r0; r0.state = TOI_TOUCHING; r0.t = 0.0f; return r0; }
   }
   SimplexCache cache; cache.count = 0;
   for (;;) {
@@ -473,7 +481,12 @@ __device__ __noinline__ int time_of_impact(const SBox& A, f2 c0, f2 c, float rB,
   atomicMax(&g_dbg[3], (unsigned long long)dbg_push); atomicMax(&g_dbg[4], (unsigned long long)(clock64() - dbg_t0));
   atomicAdd(&g_dbg[5], (unsigned long long)(clock64() - dbg_t0));
 #endif
-  return state;
+  ToiOut r; r.state = state; r.t = tOut;
+  return r;
+}
+DEV int time_of_impact(const SBox& A, f2 c0, f2 c, float rB, float& tOut) {
+  ToiOut r = time_of_impact_v(A, c0, c, rB);
+  tOut = r.t; return r.state;
 }
 
 // ------------------------------------------------------------------ Philox
