@@ -58,11 +58,12 @@ DEV float fclamp_(float a, float lo, float hi) { return fmax_(lo, fmin_(a, hi));
 
 // b2Rot::Set: sinf/cosf evaluated in double and rounded (correctly rounded
 // float on every platform the oracle runs on).
-__device__ __noinline__ void rot_set(float angle, float& s, float& c) {
+__device__ __noinline__ f2 rot_sc(float angle) {   // (sin, cos), returned in registers
   double ds, dc;
   sincos((double)angle, &ds, &dc);
-  s = (float)ds; c = (float)dc;
+  return mk2((float)ds, (float)dc);
 }
+DEV void rot_set(float angle, float& s, float& c) { f2 r = rot_sc(angle); s = r.x; c = r.y; }
 DEV f2 qmul(float s, float c, f2 v) { return mk2(c * v.x - s * v.y, s * v.x + c * v.y); }
 DEV f2 qmulT(float s, float c, f2 v) { return mk2(c * v.x + s * v.y, -s * v.x + c * v.y); }
 

@@ -94,7 +94,8 @@ struct Env {
   static constexpr int W_BOX = F_COUNT * AC, W_TC = W_BOX + G_COUNT * BC, W_MISC = W_TC + K_COUNT * MAXC;
   static constexpr int W_ITEM = W_MISC + 2, W_HEAL = W_ITEM + 2 * BC;   // floor item / heal positions (x then y)
   static constexpr int W_LEAD = W_HEAL + 2 * HC;
-  static constexpr int SM_WORDS = W_LEAD + L_COUNT;
+  static constexpr int W_TOI = W_LEAD + L_COUNT;          // cached TOI per (agent, static body)
+  static constexpr int SM_WORDS = W_TOI + AC * (BC + 4);
   static constexpr int NR = 3;                       // contacts of a one-agent island kept in registers
   static_assert(AC % G == 0 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two dividing AC");
 
@@ -175,6 +176,7 @@ struct Env {
   DEV int& LI(int k) { return reinterpret_cast<int*>(msv_sm)[(W_LEAD + k) * T + es]; }
   DEV unsigned& LU(int k) { return reinterpret_cast<unsigned*>(msv_sm)[(W_LEAD + k) * T + es]; }
   DEV float& LF(int k) { return msv_sm[(W_LEAD + k) * T + es]; }
+  DEV float& TOIA(int i, int k) { return msv_sm[(W_TOI + i * (BC + 4) + k) * T + es]; }
   DEV int& OVF() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 1) * T + es]; }
   DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
   DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
@@ -1158,11 +1160,12 @@ struct Env {
   // the group picks the minimum; the leader runs the event.
   DEV void solve_toi(float dt) {
     for (int i = g; i < C.A; i += G) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
-    // per-contact toiCount: only contacts that produced events carry one (replicated on every lane)
-    int evP[8], evN[8], nev = 0;
-    // cached TOIs (b2Contact::e_toiFlag / m_toi) of this lane's contacts: valid until the agent is displaced
-    constexpr int MAXT = SLOTS * (BC + 4) < 12 ? SLOTS * (BC + 4) : 12;
-    int cP[MAXT]; float cAlpha[MAXT]; int ncache = 0;
+    // Per (own agent, static body k): the contact's toiCount (4 bits each) and the validity bit of
+    // its cached TOI (b2Contact::e_toiFlag / m_toi, the value sits in shared memory); both are
+    // only ever needed by the lane that owns the agent.
+    unsigned long long evcnt[SLOTS]; unsigned cvalid[SLOTS];
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) { evcnt[q] = 0ull; cvalid[q] = 0u; }
     unsigned prev[SNAPW]; int prevP = -1;      // leader: state after the previous event (compared only once prevP is set)
     for (int guard = 0; guard < 64; ++guard) {
       int minP = -1, minSeq = -1; float minAlpha = 1.0f;
@@ -1175,11 +1178,14 @@ struct Env {
           int p = w * 64 + __ffsll((long long)mbits) - 1; mbits &= mbits - 1;
           int a_, k, i; decode(p, a_, k, i);
           if (!alive(i) || !awake(i)) continue;
-          int cnt = 0; for (int q = 0; q < nev; ++q) if (evP[q] == p) cnt = evN[q];
+          unsigned long long ec = evcnt[0]; unsigned cv = cvalid[0];
+#pragma unroll
+          for (int q = 1; q < SLOTS; ++q) if (i / G == q) { ec = evcnt[q]; cv = cvalid[q]; }
+          const int cnt = (int)((ec >> (4 * k)) & 15ull);
           if (cnt > B2_MAX_SUBSTEPS) continue;
-          float alpha = 1.0f; bool have = false;
-          for (int q = 0; q < ncache; ++q) if (cP[q] == p) { alpha = cAlpha[q]; have = true; }
-          if (!have) {
+          float alpha = 1.0f; const bool have = (cv >> k) & 1u;
+          if (have) alpha = TOIA(i, k);
+          else {
             float beta;
             const SBox sbx = static_box(k);
             const f2 q0 = mk2(AG(F_C0X, i), AG(F_C0Y, i)), q1 = apos(i);
@@ -1199,7 +1205,9 @@ struct Env {
             if (may_touch) state = time_of_impact(sbx, q0, q1, C.agent_r, beta);
             float alpha0 = AG(F_ALPHA0, i);
             if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
-            if (ncache < MAXT) { cP[ncache] = p; cAlpha[ncache] = alpha; ncache++; }
+            TOIA(i, k) = alpha;
+#pragma unroll
+            for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || i / G == q) cvalid[q] |= 1u << k;
           }
           // the world contact list is newest first and the scan keeps the FIRST minimum:
           // on equal alpha the contact with the larger creation sequence wins
@@ -1216,29 +1224,36 @@ struct Env {
         if (op >= 0 && (oa < minAlpha || (oa == minAlpha && os > minSeq))) { minAlpha = oa; minP = op; minSeq = os; }
       }
       if (minP < 0 || 1.0f - 10.0f * B2_EPS < minAlpha) break;   // group-uniform
-      { int q = 0; while (q < ncache) { if (cP[q] == minP) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q; } }
+      int ea, ek, eb; decode(minP, ea, ek, eb);   // the event's contact: static body ek, agent eb
+      const bool mine = (eb % G) == g;
+      if (mine) {
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || eb / G == q) cvalid[q] &= ~(1u << ek);
+      }
       gsync();
       int r = 0;
       if (lead) { Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prev, prevP); take(c_); }
       gsync();
       r = bc(r);
       share_bits();
-      {
-        int q = 0; for (; q < nev; ++q) if (evP[q] == minP) break;
-        if (q == nev && nev < 8) { evP[nev] = minP; evN[nev] = 0; nev++; }
-        if (q < nev) evN[q]++;
-      }
-      if (!(r & 1)) continue;
-      {  // "Invalidate all contact TOIs on this displaced body"
-        int a3, s3, b; decode(minP, a3, s3, b);
-        int q = 0;
-        while (q < ncache) {
-          int a4, s4, b4; decode(cP[q], a4, s4, b4);
-          if (b4 == b) { cP[q] = cP[ncache - 1]; cAlpha[q] = cAlpha[ncache - 1]; ncache--; } else ++q;
+      if (mine) {                              // toiCount of the event's contact (saturating at 15 > b2_maxSubSteps)
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || eb / G == q) {
+          unsigned long long c4 = (evcnt[q] >> (4 * ek)) & 15ull;
+          if (c4 < 15ull) evcnt[q] += 1ull << (4 * ek);
         }
       }
-      if (r & 2)
-        for (int q = 0; q < nev; ++q) if (evP[q] == minP && evN[q] <= B2_MAX_SUBSTEPS) evN[q] = B2_MAX_SUBSTEPS + 1;
+      if (!(r & 1)) continue;
+      if (mine) {
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || eb / G == q) {
+          cvalid[q] = 0u;                      // "Invalidate all contact TOIs on this displaced body"
+          if (r & 2) {                         // identical repeat: jump the contact's toiCount past b2_maxSubSteps
+            unsigned long long c4 = (evcnt[q] >> (4 * ek)) & 15ull;
+            if (c4 <= (unsigned long long)B2_MAX_SUBSTEPS) evcnt[q] = (evcnt[q] & ~(15ull << (4 * ek))) | ((unsigned long long)(B2_MAX_SUBSTEPS + 1) << (4 * ek));
+          }
+        }
+      }
     }
     gsync();
   }
