@@ -388,6 +388,19 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
     if (dalloc(h, &dd, D.size())) { g_err = h->err; msv_destroy(h); return MSV_ERR_ALLOC; }
     cudaMemcpy(dd, D.data(), D.size() * sizeof(ObsDesc), cudaMemcpyHostToDevice);
     h->obs.desc = dd; h->obs.n_elems = (int)D.size();
+    {  // compute order: grouped by source kind (then slot, component) so that the lanes of a warp take the same branch
+      std::vector<ObsDesc> Cd(D);
+      for (size_t i = 0; i < Cd.size(); ++i) { Cd[i].key = (uint16_t)i; Cd[i].off = 0; }
+      std::stable_sort(Cd.begin(), Cd.end(), [](const ObsDesc& x, const ObsDesc& y) {
+        if (x.src != y.src) return x.src < y.src;
+        if (x.aux != y.aux) return x.aux < y.aux;
+        if (x.comp != y.comp) return x.comp < y.comp;
+        return x.slot < y.slot; });
+      ObsDesc* cd = nullptr;
+      if (dalloc(h, &cd, Cd.size())) { g_err = h->err; msv_destroy(h); return MSV_ERR_ALLOC; }
+      cudaMemcpy(cd, Cd.data(), Cd.size() * sizeof(ObsDesc), cudaMemcpyHostToDevice);
+      h->obs.cdesc = cd;
+    }
     h->obs_term = h->obs;
     if (cfg->auto_reset == 2) {
       for (int k = 0; k < MSV_OBS_KEYS; ++k) {

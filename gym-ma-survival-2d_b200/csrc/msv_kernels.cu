@@ -160,7 +160,8 @@ k_observe(const __grid_constant__ DevConst C, const __grid_constant__ DevState S
 
 // fetch_observations (env:510-657): one thread per output float, gathered from
 // the SoA state after k_step / k_reset / k_observe stored it.  A block covers
-// OBS_EPB consecutive environments: a thread reads its element descriptor once
+// OBS_EPB consecutive environments (evaluated in source-kind order into shared memory, then
+// written in output order): a thread reads its element descriptor once
 // and emits that element for each of them (their SoA words share sectors);
 // consecutive threads write consecutive floats of a key -> coalesced stores.
 // value of one observation element of environment e (see ObsDesc)
@@ -230,22 +231,25 @@ __device__ __forceinline__ float obs_value(const DevConst& C, const DevState& S,
 __global__ void __launch_bounds__(256)
 k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC,
       const uint8_t* __restrict__ only_if) {
-  const int e0 = blockIdx.x * OBS_EPB;
-  for (int el = threadIdx.x; el < Tb.n_elems; el += 256) {
-    const ObsDesc d = Tb.desc[el];           // read once, reused for the block's environments
-    const ObsKey k = Tb.keys[d.key];
-    // gather first, store afterwards: the state loads of the 8 environments are independent and
-    // overlap instead of being serialised behind the (possibly aliasing) output stores
-    float v[OBS_EPB]; bool on[OBS_EPB];
+  extern __shared__ float stage[];           // [OBS_EPB][n_elems] values in output order
+  const int e0 = blockIdx.x * OBS_EPB, n = Tb.n_elems;
+  bool on[OBS_EPB];
 #pragma unroll
-    for (int j = 0; j < OBS_EPB; ++j) {
-      const int e = e0 + j;
-      on[j] = e < C.n_real && (!only_if || only_if[e]);
-      v[j] = on[j] ? obs_value(C, S, d, e, AC) : 0.0f;
-    }
+  for (int j = 0; j < OBS_EPB; ++j) { const int e = e0 + j; on[j] = e < C.n_real && (!only_if || only_if[e]); }
+  // phase 1: evaluate the elements in source-kind order (the lanes of a warp take the same branch)
+  for (int t = threadIdx.x; t < n; t += 256) {
+    const ObsDesc d = Tb.cdesc[t];           // read once, reused for the block's environments
+#pragma unroll
+    for (int j = 0; j < OBS_EPB; ++j) stage[j * n + d.key] = on[j] ? obs_value(C, S, d, e0 + j, AC) : 0.0f;
+  }
+  __syncthreads();
+  // phase 2: write them out in output order: consecutive threads, consecutive floats of a key
+  for (int el = threadIdx.x; el < n; el += 256) {
+    const ObsDesc d = Tb.desc[el];
+    const ObsKey k = Tb.keys[d.key];
 #pragma unroll
     for (int j = 0; j < OBS_EPB; ++j)
-      if (on[j]) k.base[(size_t)(e0 + j) * k.chunk + d.off] = v[j];
+      if (on[j]) k.base[(size_t)(e0 + j) * k.chunk + d.off] = stage[j * n + el];
   }
 }
 
@@ -389,7 +393,7 @@ cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S,
 }
 
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, const uint8_t* only_if, cudaStream_t st) {
-  k_obs<<<(C.n_real + OBS_EPB - 1) / OBS_EPB, 256, 0, st>>>(C, S, T, AC, only_if);
+  k_obs<<<(C.n_real + OBS_EPB - 1) / OBS_EPB, 256, (size_t)OBS_EPB * T.n_elems * sizeof(float), st>>>(C, S, T, AC, only_if);
   return cudaPeekAtLastError();
 }
 

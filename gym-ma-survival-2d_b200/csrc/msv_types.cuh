@@ -107,4 +107,6 @@ enum ObsSrc : uint8_t {
 struct ObsDesc { uint8_t src, slot, comp, aux; uint16_t key; uint16_t off; };
 struct ObsKey { float* base; int chunk; };
 #define MSV_OBS_KEYS 14
-struct ObsTable { const ObsDesc* desc; int n_elems; ObsKey keys[MSV_OBS_KEYS]; };
+// desc: elements in output order (key, offset).  cdesc: the same elements sorted by source kind,
+// `key` holding the element's index in `desc` -- warps of the compute phase are homogeneous.
+struct ObsTable { const ObsDesc* desc; const ObsDesc* cdesc; int n_elems; ObsKey keys[MSV_OBS_KEYS]; };
