@@ -394,8 +394,8 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
       std::stable_sort(Cd.begin(), Cd.end(), [](const ObsDesc& x, const ObsDesc& y) {
         if (x.src != y.src) return x.src < y.src;
         if (x.aux != y.aux) return x.aux < y.aux;
-        if (x.comp != y.comp) return x.comp < y.comp;
-        return x.slot < y.slot; });
+        if (x.slot != y.slot) return x.slot < y.slot;   // same slot adjacent: the lanes share the 16-byte state word
+        return x.comp < y.comp; });
       ObsDesc* cd = nullptr;
       if (dalloc(h, &cd, Cd.size())) { g_err = h->err; msv_destroy(h); return MSV_ERR_ALLOC; }
       cudaMemcpy(cd, Cd.data(), Cd.size() * sizeof(ObsDesc), cudaMemcpyHostToDevice);
