@@ -40,6 +40,11 @@ struct msv_handle {
   std::vector<void*> allocs;
   std::map<std::string, TensorInfo> tensors;
   uint8_t* d_actions;       // staging for msv_step_host
+  // msv_step_host reads rewards/dones back on a second stream as soon as the step kernel is done,
+  // overlapping the copy with the observation kernels
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_step = nullptr, ev_copy = nullptr;
+  float* host_rewards = nullptr; uint8_t* host_dones = nullptr;   // destinations of the pending read-back (one step)
+  bool copy_pending = false;
   double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
   int64_t launches;
   ObsTable obs;
@@ -448,11 +453,34 @@ int msv_destroy(msv_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_step) cudaEventDestroy(h->ev_step);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
   delete h;
   return MSV_OK;
 }
 
 const char* msv_last_error(msv_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+// rewards and dones are final once the step kernel has run: copy them to the host buffers of a
+// pending msv_step_host on the copy stream while the observation kernels run on `st`
+static int readback(msv_handle* h, cudaStream_t st) {
+  if (!h->host_rewards && !h->host_dones) return MSV_OK;
+  size_t N = h->C.n_real, A = h->C.A;
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(h->ev_step, st));
+  CK(cudaStreamWaitEvent(h->copy_stream, h->ev_step, 0));
+  if (h->host_rewards) CK(cudaMemcpyAsync(h->host_rewards, h->O.rewards, N * A * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+  if (h->host_dones) CK(cudaMemcpyAsync(h->host_dones, h->O.dones, N, cudaMemcpyDeviceToHost, h->copy_stream));
+  CK(cudaEventRecord(h->ev_copy, h->copy_stream));
+  h->host_rewards = nullptr; h->host_dones = nullptr;
+  h->copy_pending = true;                       // launch() makes `st` wait for it after the observation kernels
+  return MSV_OK;
+}
 
 static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream) {
   int cur = -1;
@@ -463,16 +491,22 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
     // reset exactly the envs that finished (same Philox streams as the in-kernel reset)
     DevConst C0 = h->C; C0.auto_reset = 0;
     CK(msv_launch(h->cap, 0, C0, h->S, h->O, actions, st));
+    { int rc = readback(h, st); if (rc) return rc; }
     CK(msv_launch_obs(h->C, h->S, h->obs_term, h->AC, h->O.dones, st));
     CK(msv_launch(h->cap, 4, h->C, h->S, h->O, nullptr, st));
     h->launches += 3;
   } else {
     CK(msv_launch(h->cap, which, h->C, h->S, h->O, actions, st));
     h->launches += 1;
+    if (which == 0) { int rc = readback(h, st); if (rc) return rc; }
   }
   CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, nullptr, st));   // fetch_observations
   h->launches += 1;
   if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, (cudaStream_t)stream)); h->launches++; }
+  if (h->copy_pending) {                        // the read-back overlapped the kernels above; join it into `st`
+    h->copy_pending = false;
+    CK(cudaStreamWaitEvent(st, h->ev_copy, 0));
+  }
   return MSV_OK;
 }
 
@@ -517,11 +551,11 @@ int msv_step_host(msv_handle* h, const uint8_t* actions_host, float* rewards_hos
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(h->d_actions, actions_host, N * A * 6, cudaMemcpyHostToDevice, st));
+  h->host_rewards = rewards_host; h->host_dones = dones_host;   // read back right after the step kernel (readback())
   int rc = launch(h, 0, h->d_actions, stream);
+  h->host_rewards = nullptr; h->host_dones = nullptr;
   if (rc) return rc;
-  if (rewards_host) CK(cudaMemcpyAsync(rewards_host, h->O.rewards, N * A * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (dones_host) CK(cudaMemcpyAsync(dones_host, h->O.dones, N, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(st));                // st waits for the read-back (ev_copy) and runs the observation kernels
   return MSV_OK;
 }
 
