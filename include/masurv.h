@@ -234,7 +234,10 @@ int msv_step(msv_handle* h, const uint8_t* actions_dev, void* cuda_stream);
 
 /* Same, but actions come from HOST memory and rewards/dones are copied back
  * to host buffers inside the call (the end-to-end path bench.py times).
- * rewards_host: float[num_envs][n_agents]; dones_host: uint8[num_envs]. */
+ * rewards_host: float[num_envs][n_agents]; dones_host: uint8[num_envs].
+ * The read-back runs on an internal stream as soon as the step kernel is done,
+ * overlapped with the observation kernels; the call returns when both the host
+ * buffers and the observation tensors are complete. */
 int msv_step_host(msv_handle* h, const uint8_t* actions_host,
                   float* rewards_host, uint8_t* dones_host, void* cuda_stream);
 
