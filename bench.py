@@ -2,22 +2,34 @@
 """bench.py -- headline benchmark of the masurvival step path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload 2v2|1v1_heal_only|ffa|ffa_lidar]
 
-Workload (BASELINE.json configs[2], the config the metric is quoted on):
-default 2v2 (A=4, teams, melee cd 40, B=4, H=4, shrinking safe zone),
-16384 environments PER GPU, random actions, auto-reset.  One "step" = one
-MaSurvival.step of every environment of the batch (one kernel launch).
-Environments shard trivially: one process per GPU, no collective on the data
-path -> weak scaling.
+Default workload = BASELINE.json configs[2], the config the metric is quoted on:
+default 2v2 (A=4, teams, melee cd 40, B=4, H=4, shrinking safe zone), 16384
+environments PER GPU, random actions, auto-reset.  One "step" = one
+MaSurvival.step of every environment of the batch.  Environments shard
+trivially: one process per GPU, no collective on the data path (SURVEY.md
+section 8e) -> weak scaling.
+
+What is timed is the STATIONARY workload, whatever --steps/--warmup are: before
+the timed region every batch is pre-rolled `--preroll` (default 1500) untimed
+steps so that episode phases are de-synchronised (mean episode ~420 steps) and
+contacts, TOI events, melee hits, deaths, death-drops and in-kernel auto-resets
+all occur at their steady-state rates.  Then W warm-up steps, then R >= 5
+repeats of EXACTLY K steps, each repeat bracketed by barrier + synchronize and
+timed with CUDA events, MAX over ranks per repeat; `ms_per_step` is the MEDIAN
+repeat.  R is raised until the timed work exceeds 50 ms.
 
 Prints ONE JSON line (rank 0).  `value` = agent-steps/s with actions already
 resident in HBM; `e2e` = the same through the host-buffer C-ABI call
-(msv_step_host: H2D actions + D2H rewards/dones inside the timed region).
-`--impl reference` times the CPU oracle port (the reference's own pybox2d
-stack is not installable here) on all host threads.
+(H2D actions + D2H rewards/dones inside the timed region), `e2e_obs` with the
+observation tensors copied back as well.  `--impl reference` times the CPU
+oracle port (the reference's own pybox2d stack is not installable here,
+DESIGN.md) on all host threads, same pre-roll, same config block.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,22 +40,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, 'gym-ma-survival-2d_b200'))
 
-WORKLOAD = '2v2'
-ENVS_PER_GPU = 16384
 METRIC = 'agent_steps_per_sec'
 UNIT = 'agent-steps/s'
+L2_BYTES = 126e6
+
+# BASELINE.json `configs` made concrete (SURVEY.md section 8d / BASELINE.md section 3)
+WORKLOADS = {
+    '2v2': dict(variant='2v2', envs=16384, agents=4, kernel='k_step<4,4,4,4>',
+                label='configs[2]: default 2v2 (A=4 teams, melee cd40, B=4, H=4, safe zone), random actions, auto-reset'),
+    '1v1_heal_only': dict(variant='1v1_heal_only', envs=4096, agents=2, kernel='k_step<2,4,4,2>',
+                          label='configs[1]: 1v1 heal-only (A=2, B=0, H=4, melee damage 0), random actions, auto-reset'),
+    'ffa': dict(variant='ffa', envs=8192, agents=8, kernel='k_step<8,8,16,8>',
+                label='configs[3]: free-for-all max (A=8, B=8 randomized, H=16, grid 8), 65536 envs across 8 GPUs = 8192 per GPU, auto-reset'),
+    'ffa_lidar': dict(variant='ffa_lidar', envs=32768, agents=8, kernel='k_step<8,8,16,8>',
+                      label='configs[4]: ffa max + 32-ray lidar block (doubled rays), 32768 envs per GPU, auto-reset'),
+}
 
 
-def workload_config(auto_reset=True):
+def workload_config(name, auto_reset=True):
     from masurvival.config import merge_config, pack_config, variant
-    cfg, cm = merge_config(variant(WORKLOAD))
+    cfg, cm = merge_config(variant(WORKLOADS[name]['variant']))
     return pack_config(cfg, cm, auto_reset=auto_reset)
 
 
-def config_block(n_gpus, envs_per_gpu, l2):
-    return {'workload': 'configs[2]: default 2v2 (A=4 teams, melee cd40, B=4, H=4, safe zone), random actions, auto-reset',
-            'envs_per_gpu': envs_per_gpu, 'global_envs': envs_per_gpu * n_gpus, 'agents_per_env': 4,
-            'parallelism': f'{n_gpus} independent env shards (1 process/GPU, no collective)', 'l2': l2}
+def config_block(name, n_gpus, envs_per_gpu):
+    w = WORKLOADS[name]
+    return {'workload': w['label'], 'envs_per_gpu': envs_per_gpu, 'global_envs': envs_per_gpu * n_gpus,
+            'agents_per_env': w['agents'],
+            'parallelism': f'{n_gpus} independent env shards (1 process/GPU, no collective)'}
 
 
 def measured_peak():
@@ -53,11 +77,26 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-def ncu_traffic():
-    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+def ncu_counters(name):
+    """per-launch counters of the dominant kernel from the committed ncu --set full capture
+    (profiles/counters.json): DRAM traffic and warp instructions; None when not captured"""
+    p = os.path.join(ROOT, 'profiles', 'counters.json')
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get('dram_bytes_per_launch')
+            return json.load(open(p)).get(name, {})
+        except Exception:
+            return {}
+    return {}
+
+
+def ref_python_baseline(name):
+    """`ref-python-on-shim`: the reference's unmodified Python on the
+    Box2D/gym shims.  /root/reference does not exist on the GPU box, so this is the figure
+    measured in the build container by tests/golden/time_reference.py (committed)."""
+    p = os.path.join(ROOT, 'profiles', 'ref_python_on_shim.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(name)
         except Exception:
             return None
     return None
@@ -74,7 +113,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -82,7 +121,7 @@ class ClockSampler:
     def stop(self):
         if self.p is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.p.terminate()
         try:
             out, _ = self.p.communicate(timeout=5)
@@ -111,6 +150,7 @@ def run_ours(args):
     from masurvival.envs import MaSurvivalVec
     from masurvival.config import variant
 
+    W = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     if not torch.cuda.is_available():
@@ -119,29 +159,32 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     n_gpus = world
-    N, A = args.envs, 4
-    # ROT independent batches of N envs are stepped round-robin: their combined state +
-    # outputs (ROT x ~48 MB) exceed the 126 MB L2, so every step finds its data in HBM
-    # (timing rule: "inputs larger than L2") and no flush kernel perturbs the timed region.
-    ROT = args.rotate
-    envs = [MaSurvivalVec(variant(WORKLOAD), num_envs=N, device=local, seed=args.seed + r,
-                          env_offset=(rank * ROT + r) * N, auto_reset=True) for r in range(ROT)]
+    N, A = args.envs or W['envs'], W['agents']
+    dev = f'cuda:{local}'
+
+    def make_env(r):
+        return MaSurvivalVec(variant(W['variant']), num_envs=N, device=local, seed=args.seed + r,
+                             env_offset=(rank * 64 + r) * N, auto_reset=True)
+
+    # ROT independent batches of N envs are stepped round-robin: their combined state + outputs
+    # exceed the 126 MB L2, so every step finds its data in HBM (timing rule: "inputs larger
+    # than L2") and no flush kernel perturbs the timed region.
+    envs = [make_env(0)]
+    batch_bytes = envs[0].device_bytes()
+    ROT = args.rotate or int(min(32, max(2, math.ceil(1.3 * L2_BYTES / batch_bytes))))
+    envs += [make_env(r) for r in range(1, ROT)]
     for e_ in envs:
         e_.reset()
     env = envs[0]
-    dev = f'cuda:{local}'
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     NB = 8  # rotating pre-generated action batches
 
-    def gen_actions(device, generator=None):
-        a = torch.empty((NB, N, A, 6), dtype=torch.uint8, device=device)
-        a[..., 0:3] = torch.randint(0, 3, (NB, N, A, 3), dtype=torch.uint8, device=device, generator=generator)
-        a[..., 3:6] = torch.randint(0, 2, (NB, N, A, 3), dtype=torch.uint8, device=device, generator=generator)
-        return a
-    acts_dev = gen_actions(dev, g)
+    acts_dev = torch.empty((NB, N, A, 6), dtype=torch.uint8, device=dev)
+    acts_dev[..., 0:3] = torch.randint(0, 3, (NB, N, A, 3), dtype=torch.uint8, device=dev, generator=g)
+    acts_dev[..., 3:6] = torch.randint(0, 2, (NB, N, A, 3), dtype=torch.uint8, device=dev, generator=g)
     acts_host = acts_dev.cpu().pin_memory()
-    rew_host = torch.empty((N, A), dtype=torch.float32).pin_memory()
-    done_host = torch.empty((N,), dtype=torch.uint8).pin_memory()
+    rew_host = [torch.empty((N, A), dtype=torch.float32).pin_memory() for _ in range(ROT)]
+    done_host = [torch.empty((N,), dtype=torch.uint8).pin_memory() for _ in range(ROT)]
     stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
@@ -150,80 +193,167 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ------------------------------------------------
-    for t in range(args.warmup):
+    def max_over_ranks(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return ms
+
+    tick = [0]
+
+    def dev_step():
+        t = tick[0]; tick[0] += 1
         envs[t % ROT]._h.step(acts_dev[t % NB].data_ptr(), stream)
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, k):
+        """K calls of fn between barrier+synchronize, CUDA events on the launch stream, max over ranks"""
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record()
+        for _ in range(k):
+            fn()
+        t1.record()
+        barrier()
+        return max_over_ranks(float(t0.elapsed_time(t1)))
+
+    # ---- episode-phase profile: ms/step right after a synchronised reset (all envs at the same
+    # episode step), before the pre-roll de-synchronises them -----------------------------------
+    phase_ms = {}
+    if not args.no_phase:
+        marks = [(0, 50, 'steps 0-50 (post-reset transient)'), (150, 200, 'steps 150-200'), (350, 400, 'steps 350-400'), (700, 750, 'steps 700-750')]
+        t_ep = 0
+        for lo, hi, label in marks:
+            for _ in range((lo - t_ep) * ROT):
+                dev_step()
+            phase_ms[label] = timed(dev_step, (hi - lo) * ROT) / ((hi - lo) * ROT)
+            t_ep = hi
+        preroll_left = max(0, args.preroll - t_ep)
+    else:
+        preroll_left = args.preroll
+    # ---- pre-roll to the stationary episode mix ------------------------------------------------
+    for _ in range(preroll_left * ROT):
+        dev_step()
+    torch.cuda.synchronize()
+    st0 = [e_.flush_stats() for e_ in envs]   # zero the accumulators: stats below describe the timed region only
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    est = timed(dev_step, max(args.warmup, 3)) / max(args.warmup, 3)     # warm-up doubles as the duration estimate
+    R = int(max(args.repeats, math.ceil(50.0 / max(est * args.steps, 1e-6))))
+    R = min(R, 2000)
     clk = ClockSampler(local); clk.start()
-    barrier()
     l0 = sum(e_.kernel_launches() for e_ in envs)
-    t0.record()
-    for t in range(args.steps):
-        envs[t % ROT]._h.step(acts_dev[t % NB].data_ptr(), stream)
-    t1.record()
-    barrier()
-    launches = sum(e_.kernel_launches() for e_ in envs) - l0
+    reps = [timed(dev_step, args.steps) for _ in range(R)]
+    launches_per_rep = (sum(e_.kernel_launches() for e_ in envs) - l0) // R
     clocks = clk.stop()
-    total_ms = float(t0.elapsed_time(t1))
-    if world > 1:
-        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX); total_ms = float(tt.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = float(np.median(reps)) / args.steps
     value = n_gpus * N * A / (ms_per_step * 1e-3)
 
-    # ---- duration of the dominant kernel (k_step), CUDA events on the launch stream ----
-    ks = [torch.cuda.Event(enable_timing=True) for _ in range(64)]
-    ke = [torch.cuda.Event(enable_timing=True) for _ in range(64)]
-    for t in range(64):
-        ks[t].record()
-        envs[t % ROT]._h.step_kernel_only(acts_dev[t % NB].data_ptr(), stream)
-        ke[t].record()
-        envs[t % ROT]._h.observe_only(stream)
-    torch.cuda.synchronize()
-    kernel_ms = [s_.elapsed_time(e_) for s_, e_ in zip(ks, ke)]
+    # ---- the same loop with CUDA events around every kernel (roofline numerator) ---------------
+    for e_ in envs:
+        e_._h.kernel_timing(True)
+    reps_k = [timed(dev_step, args.steps) for _ in range(max(5, min(R, 50)))]
+    ksum, kn = np.zeros(3), 0
+    for e_ in envs:
+        ms3, n = e_._h.kernel_timing(False)
+        ksum += np.array(ms3) * n; kn += n
+    k_ms = ksum / max(kn, 1)                                   # mean ms of k_step, k_obs, k_lidar
+    ms_per_step_kt = float(np.median(reps_k)) / args.steps
+    stats = [e_.flush_stats() for e_ in envs]
+    tot_steps = sum(s['steps'] for s in stats); tot_eps = sum(s['episodes'] for s in stats)
 
-    # ---- end-to-end arm: host buffers through msv_step_host ------------------
-    for t in range(max(3, args.warmup // 4)):
-        envs[t % ROT].step_host(acts_host[t % NB], rew_host, done_host)
-    barrier()
-    w0 = time.perf_counter()
-    t0.record()
-    for t in range(args.steps):
-        envs[t % ROT].step_host(acts_host[t % NB], rew_host, done_host)   # H2D + kernels + D2H + stream sync
-    t1.record()
-    barrier()
-    e2e_ms = float(t0.elapsed_time(t1))
-    if world > 1:
-        tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_ms = float(tt.item())
-    e2e_value = n_gpus * N * A / (e2e_ms / args.steps * 1e-3)
-    checksum = float(rew_host.sum())
+    # ---- end-to-end arms: host buffers through the C ABI ---------------------------------------
+    def e2e_sync():      # H2D actions + kernels + D2H rewards/dones, host blocks until they arrived
+        t = tick[0]; tick[0] += 1
+        envs[t % ROT].step_host_async(acts_host[t % NB], rew_host[t % ROT], done_host[t % ROT])
+        envs[t % ROT].step_host_wait()
 
-    bytes_env = env.bytes_per_env_step()            # whole step (k_step + k_obs)
+    for _ in range(max(3, args.warmup)):
+        e2e_sync()
+    Re = int(max(5, min(R, 200)))
+    e2e_ms = float(np.median([timed(e2e_sync, args.steps) for _ in range(Re)])) / args.steps
+    e2e_value = n_gpus * N * A / (e2e_ms * 1e-3)
+    checksum = float(sum(float(r.sum()) for r in rew_host))
+
+    obs_bufs = [envs[r].host_obs_buffer() for r in range(ROT)]
+    obs_bytes_host = envs[0]._h.obs_host_bytes()
+
+    def e2e_obs_sync():  # ... + D2H of every observation tensor, one env group at a time
+        t = tick[0]; tick[0] += 1
+        envs[t % ROT].step_host_obs(acts_host[t % NB], obs_bufs[t % ROT][0], rew_host[t % ROT], done_host[t % ROT])
+
+    def e2e_obs_pipelined():  # the ROT env groups in flight: group r's copy-out overlaps group r+1's kernels
+        t = tick[0]; tick[0] += 1
+        envs[t % ROT].step_host_wait()      # results of this group's previous step (the policy would read them here)
+        envs[t % ROT].step_host_async(acts_host[t % NB], rew_host[t % ROT], done_host[t % ROT], obs_bufs[t % ROT][0])
+
+    for _ in range(max(3, args.warmup)):
+        e2e_obs_sync()
+    Ro = int(max(5, min(R, 50)))
+    e2e_obs_ms = float(np.median([timed(e2e_obs_sync, args.steps) for _ in range(Ro)])) / args.steps
+    for _ in range(max(3, args.warmup)):
+        e2e_obs_pipelined()
+    e2e_pipe_ms = float(np.median([timed(e2e_obs_pipelined, args.steps) for _ in range(Ro)])) / args.steps
+    for e_ in envs:
+        e_.step_host_wait()
+    obs_checksum = float(obs_bufs[0][1]['agent'][:, :, -6:].astype(np.float64).sum())
+
+    bytes_env = env.bytes_per_env_step()            # whole step (k_step + k_obs [+ k_lidar])
     obs_bytes = env.obs_bytes_per_env()             # written by k_obs
     kstep_bytes = bytes_env - obs_bytes + 8         # k_step: state r/w, actions, rewards, dones, 8 B mask word for k_obs
     peak, peak_src = measured_peak()
-    kavg_ms = float(np.mean(kernel_ms[8:]))
+    kavg_ms = float(k_ms[0])
     achieved = kstep_bytes * N / (kavg_ms * 1e-3) / 1e9
+    ctr = ncu_counters(args.workload)
+    sm_hz = (clocks.get('sm_mhz') or 1965.0) * 1e6
+    issue = None
+    if ctr.get('warp_inst_per_launch') and ctr.get('envs_per_launch'):
+        winst = ctr['warp_inst_per_launch'] * N / ctr['envs_per_launch']
+        issue = {'bound': 'issue', 'warp_inst_per_launch': winst, 'issue_slots_per_clk': 148 * 4, 'sm_hz': sm_hz,
+                 'min_ms_at_full_issue': winst / (148 * 4 * sm_hz) * 1e3,
+                 'frac': winst / (148 * 4 * sm_hz) * 1e3 / kavg_ms, 'source': ctr.get('source')}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': config_block(n_gpus, N, f'{ROT} batches of {N} envs stepped round-robin (state+outputs {ROT}x~48 MB > 126 MB L2): inputs larger than L2, no flush'),
+        'config': config_block(args.workload, n_gpus, N),
+        'l2': f'{ROT} batches of {N} envs stepped round-robin ({ROT} x {batch_bytes / 1e6:.0f} MB of state+outputs > 126 MB L2): inputs larger than L2, no flush',
+        'timing': {'method': 'median over repeats of K steps; each repeat: barrier+sync, CUDA events, max over ranks',
+                   'repeats': R, 'timed_ms_total': float(np.sum(reps)), 'rep_ms_min': float(np.min(reps)), 'rep_ms_max': float(np.max(reps)),
+                   'preroll_steps_per_batch': args.preroll, 'rotating_batches': ROT,
+                   'mean_episode_steps_in_timed_region': (tot_steps / tot_eps) if tot_eps else None,
+                   'episodes_finished_in_timed_region': int(tot_eps),
+                   'ms_per_step_with_kernel_events': ms_per_step_kt},
+        'ms_per_step_by_episode_phase': phase_ms,
         'env_steps_per_sec': value / A,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': N * A * 6, 'd2h_bytes_per_step': N * A * 4 + N,
-                'api': 'MaSurvivalVec.step_host -> msv_step_host (pinned host buffers)', 'reward_checksum': checksum},
-        'gpu_launches': int(launches),
+                'ms_per_step': e2e_ms, 'repeats': Re,
+                'api': 'MaSurvivalVec.step_host_async + step_host_wait -> msv_step_host_async/_wait (pinned host buffers; returns when rewards/dones are in host memory)',
+                'reward_checksum': checksum},
+        'e2e_obs': {'value': n_gpus * N * A / (e2e_obs_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': N * A * 6,
+                    'd2h_bytes_per_step': N * A * 4 + N + obs_bytes_host, 'ms_per_step': e2e_obs_ms,
+                    'd2h_gbs': (N * A * 4 + N + obs_bytes_host) / (e2e_obs_ms * 1e-3) / 1e9,
+                    'api': 'MaSurvivalVec.step_host_obs -> msv_step_host_obs: rewards, dones AND every observation tensor land in pinned host memory',
+                    'pipelined': {'value': n_gpus * N * A / (e2e_pipe_ms * 1e-3), 'ms_per_step': e2e_pipe_ms,
+                                  'how': f'{ROT} env groups in flight (msv_step_host_async/_wait): copy-out of one group overlaps the kernels of the next'},
+                    'obs_checksum': obs_checksum},
+        'gpu_launches': int(launches_per_rep),
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': ncu_traffic(), 'kernel': 'k_step<4,4,4,4>', 'kernel_ms': kavg_ms,
+                     'traffic': ctr.get('dram_bytes_per_launch'), 'kernel': W['kernel'], 'kernel_ms': kavg_ms,
+                     'kernel_ms_all': {'k_step': float(k_ms[0]), 'k_obs': float(k_ms[1]), 'k_lidar': float(k_ms[2])},
+                     'kernel_share_of_step': float(k_ms[0] / max(k_ms.sum(), 1e-9)),
                      'algorithmic_bytes_per_env_step': kstep_bytes, 'whole_step_bytes_per_env_step': bytes_env,
                      'whole_step_gbs': bytes_env * N / (ms_per_step * 1e-3) / 1e9, 'peak_source': peak_src,
+                     'issue': issue,
                      'note': 'latency/issue bound, not bandwidth bound: see DESIGN.md section 8'},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu:
-            line['cpu_baseline'] = cpu_baseline(sample_envs=8192, steps=600)   # ~10-20 s of host work
+            line['cpu_baseline'] = cpu_baseline(args.workload, sample_envs=min(N, 4096), steps=300, preroll=min(args.preroll, 600))
+            rp = ref_python_baseline(args.workload)
+            if rp:
+                line['cpu_baseline_ref_python'] = rp
         print(json.dumps(line))
     for e_ in envs:
         e_.close()
@@ -231,21 +361,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(sample_envs, steps, threads=None):
-    """The oracle port (reference semantics restated in C, oracle/) timed on
-    this box's host cores on a bounded sample of the same workload."""
+def _cpu_batch(name, seed, sample_envs, threads):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import pyoracle as po
-    threads = threads or os.cpu_count() or 1
-    rec = workload_config(auto_reset=True)
+    rec = workload_config(name, auto_reset=True)
     A = int(rec['n_agents'])
-    b = po.OracleBatch(rec, 1, sample_envs, threads)
+    b = po.OracleBatch(rec, seed, sample_envs, threads)
     b.reset()
     rng = np.random.default_rng(0)
     acts = np.zeros((4, sample_envs, A, 6), dtype=np.uint8)
     acts[..., 0:3] = rng.integers(0, 3, size=(4, sample_envs, A, 3))
     acts[..., 3:6] = rng.integers(0, 2, size=(4, sample_envs, A, 3))
-    for t in range(10):
+    return b, acts, A
+
+
+def cpu_baseline(name, sample_envs, steps, preroll, threads=None):
+    """The oracle port (reference semantics restated in C, oracle/) timed on this box's host
+    cores on a bounded sample of the same stationary workload."""
+    threads = threads or os.cpu_count() or 1
+    b, acts, A = _cpu_batch(name, 1, sample_envs, threads)
+    for t in range(preroll):
         b.step(acts[t % 4])
     t0 = time.perf_counter()
     for t in range(steps):
@@ -253,7 +388,7 @@ def cpu_baseline(sample_envs, steps, threads=None):
     dt = time.perf_counter() - t0
     b.close()
     return {'value': sample_envs * steps * A / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-            'sample': f'{sample_envs} envs x {steps} steps of the 2v2 workload, {threads} host threads, C oracle (oracle/masurv_oracle.c)',
+            'sample': f'{sample_envs} envs x {steps} steps of the {name} workload after a {preroll}-step pre-roll, {threads} host threads, C oracle (oracle/masurv_oracle.c)',
             'seconds': dt}
 
 
@@ -261,52 +396,63 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import pyoracle as po
+    W = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     n_gpus = int(os.environ.get('WORLD_SIZE', args.gpus))
-    # bounded sample of the workload: 4096 envs per "step" keeps K steps + W warm-up within minutes
-    sample = min(args.envs, 4096)
-    rec = workload_config(auto_reset=True)
-    A = int(rec['n_agents'])
-    b = po.OracleBatch(rec, args.seed, sample, threads)
-    b.reset()
-    rng = np.random.default_rng(0)
-    acts = np.zeros((4, sample, A, 6), dtype=np.uint8)
-    acts[..., 0:3] = rng.integers(0, 3, size=(4, sample, A, 3))
-    acts[..., 3:6] = rng.integers(0, 2, size=(4, sample, A, 3))
+    N = args.envs or W['envs']
+    # bounded sample of the workload: at most 4096 envs per "step" keeps pre-roll + K steps within minutes
+    sample = min(N, 4096)
+    b, acts, A = _cpu_batch(args.workload, args.seed, sample, threads)
+    preroll = min(args.preroll, 1500)
+    for t in range(preroll):                      # the same stationary episode mix as the GPU arm
+        b.step(acts[t % 4])
     for t in range(args.warmup):
         b.step(acts[t % 4])
-    t0 = time.perf_counter()
-    for t in range(args.steps):
-        b.step(acts[t % 4])
-    dt = time.perf_counter() - t0
+    reps = []
+    R = max(args.repeats, 5)
+    for _ in range(R):
+        t0 = time.perf_counter()
+        for t in range(args.steps):
+            b.step(acts[t % 4])
+        reps.append(time.perf_counter() - t0)
+        if sum(reps) > 60.0 and len(reps) >= 5:
+            break
     b.close()
+    dt = float(np.median(reps))
     value = sample * args.steps * A / dt
     cb = {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-          'sample': f'{sample} envs per step (bounded sample of the {args.envs}-env workload), {threads} host threads, C oracle port; '
-                    'the reference\'s own pybox2d stack is not installable in this image'}
-    print(json.dumps({
+          'sample': f'{sample} envs per step (bounded sample of the {N}-env workload), {preroll}-step pre-roll, median of {len(reps)} repeats, '
+                    f'{threads} host threads, C oracle port; the reference\'s own pybox2d stack is not installable in this image'}
+    line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': config_block(n_gpus, args.envs, 'n/a (CPU)'),
+        'config': config_block(args.workload, n_gpus, N),
+        'sample_envs_per_step': sample,
         'cpu_baseline': cb,
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }))
+    }
+    rp = ref_python_baseline(args.workload)
+    if rp:
+        line['cpu_baseline_ref_python'] = rp
+    print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=1000)
-    ap.add_argument('--warmup', type=int, default=100)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='environments per GPU')
+    ap.add_argument('--workload', default='2v2', choices=sorted(WORKLOADS))
+    ap.add_argument('--envs', type=int, default=0, help='environments per GPU (default: the workload\'s BASELINE count)')
     ap.add_argument('--seed', type=int, default=0)
-    ap.add_argument('--rotate', type=int, default=4, help='independent env batches stepped round-robin (working set > L2)')
+    ap.add_argument('--preroll', type=int, default=1500, help='untimed steps per batch before the timed region (stationary episode mix)')
+    ap.add_argument('--repeats', type=int, default=5, help='minimum number of timed repeats of K steps (median reported)')
+    ap.add_argument('--rotate', type=int, default=0, help='independent env batches stepped round-robin (0: enough to exceed L2)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-phase', action='store_true', help='skip the per-episode-phase timing')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

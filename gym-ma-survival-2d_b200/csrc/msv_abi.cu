@@ -40,11 +40,17 @@ struct msv_handle {
   std::vector<void*> allocs;
   std::map<std::string, TensorInfo> tensors;
   uint8_t* d_actions;       // staging for msv_step_host
-  // msv_step_host reads rewards/dones back on a second stream as soon as the step kernel is done,
-  // overlapping the copy with the observation kernels
-  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_step = nullptr, ev_copy = nullptr;
-  float* host_rewards = nullptr; uint8_t* host_dones = nullptr;   // destinations of the pending read-back (one step)
-  bool copy_pending = false;
+  // msv_step_host* read rewards/dones back on a second stream as soon as the step kernel is done
+  // (overlapping the copy with the observation kernels) and the observation arena after them
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_step = nullptr, ev_obs = nullptr, ev_copy = nullptr;
+  float* host_rewards = nullptr; uint8_t* host_dones = nullptr; void* host_obs = nullptr;   // destinations of the pending read-back (one step)
+  bool copy_pending = false;     // ev_copy was recorded and nobody waited for it yet
+  // every output tensor lives in ONE device arena: [rewards | dones | observation keys | lidar]
+  char* arena = nullptr; size_t arena_bytes = 0, obs_begin = 0, obs_end = 0;
+  size_t device_bytes = 0;
+  bool zombie = false;           // msv_destroy was called while DLPack exports were alive
+  // debug: CUDA-event timing of the kernels of msv_step (bench.py's roofline numerator)
+  bool timing = false; std::vector<cudaEvent_t> tev; size_t tev_used = 0;
   double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
   int64_t launches;
   ObsTable obs;
@@ -63,6 +69,16 @@ struct msv_handle {
   } while (0)
 
 static thread_local std::string g_err;
+
+// the calling thread's current device is restored when a DevGuard goes out of scope
+struct DevGuard {
+  int prev = -1; bool switched = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 
 // ---- host float32 helpers (same arithmetic as the reference's pybox2d calls)
 static void h_rot(float angle, float* s, float* c) { *s = (float)sin((double)angle); *c = (float)cos((double)angle); }
@@ -116,6 +132,7 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
   D->zone_phases = c->zone_phases; D->zone_cooldown = c->zone_cooldown; D->zone_damage = c->zone_damage;
   D->n_zones = c->zone_n_radiuses + 1; D->zone_centers_random = c->zone_centers_random;
   D->lidar_n = c->lidar_n; D->auto_reset = c->auto_reset; D->grid_n = c->grid_size * c->grid_size;
+  D->immunity_cooldown = c->immunity_cooldown; D->battle_royale = c->battle_royale; D->b2_variant = c->b2_variant;
   D->r_alive = c->r_alive; D->r_dead = c->r_dead; D->r_kill = c->r_kill; D->r_death = c->r_death;
   D->agent_r = (float)(c->agent_size / 2);          // semantics.py:16-18
   D->heal_r = (float)(c->heal_item_size / 2);       // semantics.py:24-25
@@ -133,7 +150,11 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
   D->friction = sqrtf(0.2f * 0.2f);                  // b2MixFriction of the fixture default
   D->dt = (float)(1.0 / 60);                         // simulation.py:219
   D->dt_ratio1 = (1.0f / D->dt) * D->dt;
-  D->damp = 1.0f / (1.0f + D->dt * (float)0.8);      // simulation.py:118, Pade damping
+  D->damp = 1.0f / (1.0f + D->dt * (float)0.8);      // simulation.py:118, Pade damping (b2Island::Solve, Box2D >= 2.3.0)
+  if (c->b2_variant & MSV_B2_CLAMP_DAMPING) {        // Box2D <= 2.2: v *= b2Clamp(1 - h * damping, 0, 1)
+    float d = 1.0f - D->dt * (float)0.8;
+    D->damp = d < 0.0f ? 0.0f : (d > 1.0f ? 1.0f : d);
+  }
   static const double dtab[3] = {-1., 0., 1.};       // env:742
   for (int a = 0; a < 3; ++a) {
     D->imp_par[a] = (float)(dtab[a] * c->motor_impulse[0]);
@@ -201,6 +222,7 @@ template <typename T> static int dalloc(msv_handle* h, T** p, size_t count) {
   if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return MSV_ERR_ALLOC; }
   cudaMemset(q, 0, bytes);
   h->allocs.push_back(q);
+  h->device_bytes += bytes;
   *p = (T*)q;
   return 0;
 }
@@ -220,39 +242,46 @@ struct Mirror {
   std::vector<float2> heal, zonec, pimp;
   std::vector<unsigned long long> pex, ptc, pen;
   std::vector<uint32_t> pseq;
-  std::vector<float> sreward;
+  std::vector<float> sreward, epret;
 };
-template <typename T> static cudaError_t dl(std::vector<T>& v, const T* d, size_t n) {
-  v.resize(n); return cudaMemcpy(v.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost);
+// Only the columns [first, first+count) of every [slots][N] array cross the bus: the mirror's
+// arrays are [slots][count] (a checkpoint of k envs costs O(k), not O(N)).
+struct Slice { size_t first, count, N; };
+template <typename T> static cudaError_t dl(std::vector<T>& v, const T* d, size_t slots, const Slice& sl) {
+  v.resize(slots * sl.count);
+  return cudaMemcpy2D(v.data(), sl.count * sizeof(T), d + sl.first, sl.N * sizeof(T), sl.count * sizeof(T), slots, cudaMemcpyDeviceToHost);
 }
-template <typename T> static cudaError_t ul(const std::vector<T>& v, T* d) {
-  return cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+template <typename T> static cudaError_t ul(const std::vector<T>& v, T* d, const Slice& sl) {
+  const size_t slots = v.size() / sl.count;
+  return cudaMemcpy2D(d + sl.first, sl.N * sizeof(T), v.data(), sl.count * sizeof(T), sl.count * sizeof(T), slots, cudaMemcpyHostToDevice);
 }
-static int download(msv_handle* h, Mirror& m) {
-  const size_t N = h->C.N, AC = h->AC, BC = h->BC, HC = h->HC, P = h->P, PW = h->PW;
+static int download(msv_handle* h, Mirror& m, const Slice& sl) {
+  const size_t AC = h->AC, BC = h->BC, HC = h->HC, P = h->P, PW = h->PW;
   DevState& S = h->S;
-  CK(cudaSetDevice(h->device)); CK(cudaDeviceSynchronize());
-  CK(dl(m.akin0, S.akin0, AC * N)); CK(dl(m.akin1, S.akin1, AC * N)); CK(dl(m.afat, S.afat, AC * N));
-  CK(dl(m.aint, S.aint, AC * N)); CK(dl(m.ainv, S.ainv, AC * 4 * N));
-  CK(dl(m.box0, S.box0, BC * N)); CK(dl(m.box1, S.box1, BC * N)); CK(dl(m.boxseq, S.boxseq, BC * N));
-  CK(dl(m.item0, S.item0, BC * N)); CK(dl(m.item1, S.item1, BC * N));
-  CK(dl(m.heal, S.heal, HC * N)); CK(dl(m.healseq, S.healseq, HC * N));
-  CK(dl(m.pend0, S.pend0, BC * N)); CK(dl(m.pend1, S.pend1, BC * N));
-  CK(dl(m.zonec, S.zonec, (size_t)MSV_MAX_ZONES * N)); CK(dl(m.zonecur, S.zonecur, N)); CK(dl(m.zoneint, S.zoneint, N));
-  CK(dl(m.hdr0, S.hdr0, N)); CK(dl(m.hdr1, S.hdr1, N));
-  CK(dl(m.pex, S.pex, PW * N)); CK(dl(m.ptc, S.ptc, PW * N)); CK(dl(m.pen, S.pen, PW * N));
-  CK(dl(m.pseq, S.pseq, P * N)); CK(dl(m.pimp, S.pimp, P * N));
-  CK(dl(m.sreward, S.sreward, AC * N)); CK(dl(m.skills, S.skills, AC * N)); CK(dl(m.smisc, S.smisc, N));
+  CK(cudaDeviceSynchronize());
+  CK(dl(m.akin0, S.akin0, AC, sl)); CK(dl(m.akin1, S.akin1, AC, sl)); CK(dl(m.afat, S.afat, AC, sl));
+  CK(dl(m.aint, S.aint, AC, sl)); CK(dl(m.ainv, S.ainv, AC * 4, sl));
+  CK(dl(m.box0, S.box0, BC, sl)); CK(dl(m.box1, S.box1, BC, sl)); CK(dl(m.boxseq, S.boxseq, BC, sl));
+  CK(dl(m.item0, S.item0, BC, sl)); CK(dl(m.item1, S.item1, BC, sl));
+  CK(dl(m.heal, S.heal, HC, sl)); CK(dl(m.healseq, S.healseq, HC, sl));
+  CK(dl(m.pend0, S.pend0, BC, sl)); CK(dl(m.pend1, S.pend1, BC, sl));
+  CK(dl(m.zonec, S.zonec, (size_t)MSV_MAX_ZONES, sl)); CK(dl(m.zonecur, S.zonecur, 1, sl)); CK(dl(m.zoneint, S.zoneint, 1, sl));
+  CK(dl(m.hdr0, S.hdr0, 1, sl)); CK(dl(m.hdr1, S.hdr1, 1, sl));
+  CK(dl(m.pex, S.pex, PW, sl)); CK(dl(m.ptc, S.ptc, PW, sl)); CK(dl(m.pen, S.pen, PW, sl));
+  CK(dl(m.pseq, S.pseq, P, sl)); CK(dl(m.pimp, S.pimp, P, sl));
+  CK(dl(m.sreward, S.sreward, AC, sl)); CK(dl(m.skills, S.skills, AC, sl)); CK(dl(m.smisc, S.smisc, 1, sl));
+  CK(dl(m.epret, S.epret, AC, sl));
   return MSV_OK;
 }
-static int upload(msv_handle* h, const Mirror& m) {
+static int upload(msv_handle* h, const Mirror& m, const Slice& sl) {
   DevState& S = h->S;
-  CK(ul(m.akin0, S.akin0)); CK(ul(m.akin1, S.akin1)); CK(ul(m.afat, S.afat)); CK(ul(m.aint, S.aint)); CK(ul(m.ainv, S.ainv));
-  CK(ul(m.box0, S.box0)); CK(ul(m.box1, S.box1)); CK(ul(m.boxseq, S.boxseq)); CK(ul(m.item0, S.item0)); CK(ul(m.item1, S.item1));
-  CK(ul(m.heal, S.heal)); CK(ul(m.healseq, S.healseq)); CK(ul(m.pend0, S.pend0)); CK(ul(m.pend1, S.pend1));
-  CK(ul(m.zonec, S.zonec)); CK(ul(m.zonecur, S.zonecur)); CK(ul(m.zoneint, S.zoneint)); CK(ul(m.hdr0, S.hdr0)); CK(ul(m.hdr1, S.hdr1));
-  CK(ul(m.pex, S.pex)); CK(ul(m.ptc, S.ptc)); CK(ul(m.pen, S.pen)); CK(ul(m.pseq, S.pseq)); CK(ul(m.pimp, S.pimp));
-  CK(ul(m.sreward, S.sreward)); CK(ul(m.skills, S.skills)); CK(ul(m.smisc, S.smisc));
+  CK(ul(m.akin0, S.akin0, sl)); CK(ul(m.akin1, S.akin1, sl)); CK(ul(m.afat, S.afat, sl)); CK(ul(m.aint, S.aint, sl)); CK(ul(m.ainv, S.ainv, sl));
+  CK(ul(m.box0, S.box0, sl)); CK(ul(m.box1, S.box1, sl)); CK(ul(m.boxseq, S.boxseq, sl)); CK(ul(m.item0, S.item0, sl)); CK(ul(m.item1, S.item1, sl));
+  CK(ul(m.heal, S.heal, sl)); CK(ul(m.healseq, S.healseq, sl)); CK(ul(m.pend0, S.pend0, sl)); CK(ul(m.pend1, S.pend1, sl));
+  CK(ul(m.zonec, S.zonec, sl)); CK(ul(m.zonecur, S.zonecur, sl)); CK(ul(m.zoneint, S.zoneint, sl)); CK(ul(m.hdr0, S.hdr0, sl)); CK(ul(m.hdr1, S.hdr1, sl));
+  CK(ul(m.pex, S.pex, sl)); CK(ul(m.ptc, S.ptc, sl)); CK(ul(m.pen, S.pen, sl)); CK(ul(m.pseq, S.pseq, sl)); CK(ul(m.pimp, S.pimp, sl));
+  CK(ul(m.sreward, S.sreward, sl)); CK(ul(m.skills, S.skills, sl)); CK(ul(m.smisc, S.smisc, sl));
+  CK(ul(m.epret, S.epret, sl));
   return MSV_OK;
 }
 static inline int f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
@@ -288,6 +317,7 @@ int msv_default_config(msv_config* c) {  // env:140-238
   c->motor_impulse[0] = 0.25; c->motor_impulse[1] = 0.25; c->motor_impulse[2] = 0.0125;
   c->box_min_w = 0.1; c->box_min_h = 0.1;
   c->lidar_n = 0; c->lidar_fov = 0.8 * M_PI; c->lidar_depth = 10;
+  c->immunity_cooldown = -1; c->battle_royale = 0; c->b2_variant = 0;
   return MSV_OK;
 }
 
@@ -298,7 +328,8 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
       cfg->n_heals < 0 || cfg->n_heals > MSV_MAX_HEALS || cfg->grid_size < 1 || cfg->grid_size > 8 ||
       cfg->n_agents + cfg->n_boxes + cfg->n_heals > cfg->grid_size * cfg->grid_size ||
       cfg->inv_slots < 1 || cfg->inv_slots > MSV_MAX_SLOTS || cfg->zone_n_radiuses + 1 > MSV_MAX_ZONES ||
-      cfg->zone_phases > cfg->zone_n_radiuses + 1 || cfg->lidar_n < 0 || cfg->lidar_n > MSV_MAX_LASERS)
+      cfg->zone_phases > cfg->zone_n_radiuses + 1 || cfg->lidar_n < 0 || cfg->lidar_n > MSV_MAX_LASERS ||
+      cfg->zone_phases < 1 || env_offset < 0 || env_offset + (int64_t)num_envs > (int64_t)1 << 32)   // Philox counter word 0 is 32 bits
     return MSV_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
@@ -307,7 +338,8 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   }
   msv_handle* h = new msv_handle();
   h->cfg = *cfg; h->device = device; h->launches = 0; h->exported = 0;
-  if (cudaSetDevice(device) != cudaSuccess) { delete h; return MSV_ERR_CUDA; }
+  DevGuard guard(device);
+  { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != device) { delete h; return MSV_ERR_CUDA; } }
   build_const(cfg, num_envs, seed, env_offset, &h->C);
   h->cap = (cfg->n_agents <= 2 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 0
          : (cfg->n_agents <= 4 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 1 : 2;
@@ -330,15 +362,32 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   rc |= dalloc(h, &S.pseq, P * N); rc |= dalloc(h, &S.pimp, P * N);
   rc |= dalloc(h, &S.sreward, AC * N); rc |= dalloc(h, &S.skills, AC * N); rc |= dalloc(h, &S.smisc, N);
   const size_t A = cfg->n_agents, B = cfg->n_boxes, H = cfg->n_heals, Sw = h->C.S, L = cfg->lidar_n;
-  rc |= dalloc(h, &O.agent, N * A * Sw); rc |= dalloc(h, &O.others, N * A * (A - 1) * Sw);
-  rc |= dalloc(h, &O.others_mask, N * A * (A - 1)); rc |= dalloc(h, &O.zone, N * 6);
-  rc |= dalloc(h, &O.heals, N * H * 2); rc |= dalloc(h, &O.heals_mask, N * A * H);
-  rc |= dalloc(h, &O.heal_slot, N * A); rc |= dalloc(h, &O.heal_slot_mask, N * A);
-  rc |= dalloc(h, &O.boxes, N * B * 11); rc |= dalloc(h, &O.boxes_mask, N * A * B);
-  rc |= dalloc(h, &O.box_items, N * B * 10); rc |= dalloc(h, &O.box_items_mask, N * A * B);
-  rc |= dalloc(h, &O.box_slot, N * A * 8); rc |= dalloc(h, &O.box_slot_mask, N * A);
-  rc |= dalloc(h, &O.lidar_frac, N * A * L); rc |= dalloc(h, &O.lidar_hit, N * A * L);
-  rc |= dalloc(h, &O.rewards, N * A); rc |= dalloc(h, &O.dones, N);
+  rc |= dalloc(h, &S.epret, AC * N);
+  {  // one arena for every output tensor, so that msv_step_host_obs reads the observations back in ONE copy
+    struct Slot { void** p; size_t bytes; };
+    const size_t f = sizeof(float);
+    Slot slots[] = {
+      {(void**)&O.rewards, N * A * f}, {(void**)&O.dones, N}, {(void**)&O.episode_return, N * A * f},
+      {(void**)&O.episode_length, N * sizeof(int)}, {(void**)&O.immune, N}, {(void**)&O.br_over, N}, {(void**)&O.br_results, N * A},
+      // ---- observation block (obs_begin .. obs_end)
+      {(void**)&O.agent, N * A * Sw * f}, {(void**)&O.others, N * A * (A - 1) * Sw * f}, {(void**)&O.others_mask, N * A * (A - 1) * f},
+      {(void**)&O.zone, N * 6 * f}, {(void**)&O.heals, N * H * 2 * f}, {(void**)&O.heals_mask, N * A * H * f},
+      {(void**)&O.heal_slot, N * A * f}, {(void**)&O.heal_slot_mask, N * A * f}, {(void**)&O.boxes, N * B * 11 * f},
+      {(void**)&O.boxes_mask, N * A * B * f}, {(void**)&O.box_items, N * B * 10 * f}, {(void**)&O.box_items_mask, N * A * B * f},
+      {(void**)&O.box_slot, N * A * 8 * f}, {(void**)&O.box_slot_mask, N * A * f},
+      {(void**)&O.lidar_frac, N * A * L * f}, {(void**)&O.lidar_hit, N * A * L * sizeof(int)},
+    };
+    const int n_slots = (int)(sizeof slots / sizeof slots[0]), first_obs = 7;
+    size_t off = 0; std::vector<size_t> offs;
+    for (int k = 0; k < n_slots; ++k) {
+      if (k == first_obs) h->obs_begin = off;
+      offs.push_back(off);
+      off += (slots[k].bytes + 255) / 256 * 256;
+    }
+    h->obs_end = off; h->arena_bytes = off;
+    rc |= dalloc(h, &h->arena, off);
+    if (!rc) for (int k = 0; k < n_slots; ++k) *slots[k].p = h->arena + offs[k];
+  }
   rc |= dalloc(h, &S.obm, N); rc |= dalloc(h, &S.omask, AC * N);
   rc |= dalloc(h, &h->d_actions, N * A * 6);
   rc |= dalloc(h, &h->d_stat_reward, (size_t)MSV_MAX_AGENTS); rc |= dalloc(h, &h->d_stat_kills, (size_t)MSV_MAX_AGENTS);
@@ -432,6 +481,10 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   if (L > 0) { reg(h, "lidar_frac", O.lidar_frac, 0, {n, a, l}); reg(h, "lidar_hit", O.lidar_hit, 2, {n, a, l}); }
   reg(h, "rewards", O.rewards, 0, {n, a});
   reg(h, "dones", O.dones, 1, {n});
+  reg(h, "episode_return", O.episode_return, 0, {n, a});
+  reg(h, "episode_length", O.episode_length, 2, {n});
+  if (cfg->immunity_cooldown >= 0) reg(h, "immune", O.immune, 1, {n});
+  if (cfg->battle_royale) { reg(h, "br_over", O.br_over, 1, {n}); reg(h, "br_results", O.br_results, 1, {n, a}); }
   if (cfg->auto_reset == 2) {   // same shapes, "terminal_" prefix
     std::map<std::string, TensorInfo> extra;
     static const char* names[MSV_OBS_KEYS] = {"agent", "others", "others_mask", "zone", "heals", "heals_mask", "heal_slot",
@@ -448,44 +501,86 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   return MSV_OK;
 }
 
-int msv_destroy(msv_handle* h) {
-  if (!h) return MSV_ERR_INVALID;
-  cudaSetDevice(h->device);
+static void really_destroy(msv_handle* h) {
+  DevGuard g(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_step) cudaEventDestroy(h->ev_step);
+  if (h->ev_obs) cudaEventDestroy(h->ev_obs);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   delete h;
+}
+
+int msv_destroy(msv_handle* h) {
+  if (!h || h->zombie) return MSV_ERR_INVALID;
+  if (h->exported > 0) {          // tensors handed out through DLPack are still alive: their
+    DevGuard g(h->device);        // storage (and the handle their deleter refers to) stays until
+    cudaDeviceSynchronize();      // the last one is deleted (dl_deleter)
+    h->zombie = true;
+    return MSV_OK;
+  }
+  really_destroy(h);
   return MSV_OK;
 }
 
 const char* msv_last_error(msv_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
+// ---- host read-back (msv_step_host*) ----------------------------------------
+static int copy_setup(msv_handle* h) {
+  if (h->copy_stream) return MSV_OK;
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_obs, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  return MSV_OK;
+}
 // rewards and dones are final once the step kernel has run: copy them to the host buffers of a
 // pending msv_step_host on the copy stream while the observation kernels run on `st`
 static int readback(msv_handle* h, cudaStream_t st) {
   if (!h->host_rewards && !h->host_dones) return MSV_OK;
   size_t N = h->C.n_real, A = h->C.A;
-  if (!h->copy_stream) {
-    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-  }
   CK(cudaEventRecord(h->ev_step, st));
   CK(cudaStreamWaitEvent(h->copy_stream, h->ev_step, 0));
   if (h->host_rewards) CK(cudaMemcpyAsync(h->host_rewards, h->O.rewards, N * A * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
   if (h->host_dones) CK(cudaMemcpyAsync(h->host_dones, h->O.dones, N, cudaMemcpyDeviceToHost, h->copy_stream));
-  CK(cudaEventRecord(h->ev_copy, h->copy_stream));
-  h->host_rewards = nullptr; h->host_dones = nullptr;
-  h->copy_pending = true;                       // launch() makes `st` wait for it after the observation kernels
+  return MSV_OK;
+}
+// the observation arena, once the observation kernels are done
+static int readback_obs(msv_handle* h, cudaStream_t st) {
+  if (h->host_obs) {
+    CK(cudaEventRecord(h->ev_obs, st));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_obs, 0));
+    CK(cudaMemcpyAsync(h->host_obs, h->arena + h->obs_begin, h->obs_end - h->obs_begin, cudaMemcpyDeviceToHost, h->copy_stream));
+  }
+  if (h->host_obs || h->host_rewards || h->host_dones) {
+    CK(cudaEventRecord(h->ev_copy, h->copy_stream));
+    h->copy_pending = true;
+  }
   return MSV_OK;
 }
 
+// debug kernel timing: one event before and one after every kernel of a step
+static void tmark(msv_handle* h, cudaStream_t st) {
+  if (!h->timing) return;
+  if (h->tev_used >= h->tev.size()) {
+    if (h->tev.size() >= 4 * 8192) { h->timing = false; return; }
+    cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) { h->timing = false; return; }
+    h->tev.push_back(e);
+  }
+  cudaEventRecord(h->tev[h->tev_used++], st);
+}
+
 static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream) {
-  int cur = -1;
-  if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) CK(cudaSetDevice(h->device));
+  DevGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->copy_pending) {                        // a read-back of the previous step may still be reading the arena
+    h->copy_pending = false;
+    CK(cudaStreamWaitEvent(st, h->ev_copy, 0));
+  }
+  const bool timed = h->timing && which == 0;
+  if (timed) tmark(h, st);
   if (which == 0 && h->cfg.auto_reset == 2) {
     // step without the in-kernel reset, keep the finished episodes' last observation, then
     // reset exactly the envs that finished (same Philox streams as the in-kernel reset)
@@ -500,13 +595,13 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
     h->launches += 1;
     if (which == 0) { int rc = readback(h, st); if (rc) return rc; }
   }
+  if (timed) tmark(h, st);
   CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, nullptr, st));   // fetch_observations
   h->launches += 1;
+  if (timed) tmark(h, st);
   if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, (cudaStream_t)stream)); h->launches++; }
-  if (h->copy_pending) {                        // the read-back overlapped the kernels above; join it into `st`
-    h->copy_pending = false;
-    CK(cudaStreamWaitEvent(st, h->ev_copy, 0));
-  }
+  if (timed) tmark(h, st);
+  if (which == 0) { int rc = readback_obs(h, st); if (rc) return rc; }
   return MSV_OK;
 }
 
@@ -514,7 +609,7 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
  * lists) any env has recorded since its last set_state -- must stay 0 */
 int64_t msv_debug_overflow(msv_handle* h) {
   if (!h) return -1;
-  cudaSetDevice(h->device); cudaDeviceSynchronize();
+  DevGuard g(h->device); cudaDeviceSynchronize();
   std::vector<int4> v((size_t)h->C.N);
   if (cudaMemcpy(v.data(), h->S.hdr1, v.size() * sizeof(int4), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   int64_t tot = 0;
@@ -544,18 +639,93 @@ int msv_step(msv_handle* h, const uint8_t* actions_dev, void* stream) {
   return launch(h, 0, actions_dev, stream);
 }
 
-int msv_step_host(msv_handle* h, const uint8_t* actions_host, float* rewards_host, uint8_t* dones_host, void* stream) {
+int msv_step_host_async(msv_handle* h, const uint8_t* actions_host, float* rewards_host, uint8_t* dones_host, void* obs_host,
+                        void* stream) {
   if (!h || !actions_host) return MSV_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   size_t N = h->C.n_real, A = h->C.A;
-  int cur = -1;
-  if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(h->d_actions, actions_host, N * A * 6, cudaMemcpyHostToDevice, st));
-  h->host_rewards = rewards_host; h->host_dones = dones_host;   // read back right after the step kernel (readback())
-  int rc = launch(h, 0, h->d_actions, stream);
-  h->host_rewards = nullptr; h->host_dones = nullptr;
+  DevGuard g(h->device);
+  { int rc = copy_setup(h); if (rc) return rc; }
+  if (h->copy_pending) {       // d_actions / the arena are reused: order this step after the previous read-back
+    h->copy_pending = false;
+    CK(cudaStreamWaitEvent(st, h->ev_copy, 0));
+  }
+  cudaError_t ce = cudaMemcpyAsync(h->d_actions, actions_host, N * A * 6, cudaMemcpyHostToDevice, st);
+  int rc = MSV_OK;
+  if (ce != cudaSuccess) { h->err = std::string("cudaMemcpyAsync(actions): ") + cudaGetErrorString(ce); rc = MSV_ERR_CUDA; }
+  if (!rc) {
+    h->host_rewards = rewards_host; h->host_dones = dones_host; h->host_obs = obs_host;
+    rc = launch(h, 0, h->d_actions, stream);
+    h->host_rewards = nullptr; h->host_dones = nullptr; h->host_obs = nullptr;
+  }
+  if (rc) {                    // nothing may still be writing into the caller's buffers after an error return
+    cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(st);
+    h->copy_pending = false;
+  }
+  return rc;
+}
+
+int msv_step_host_wait(msv_handle* h) {
+  if (!h) return MSV_ERR_INVALID;
+  if (!h->copy_stream || !h->copy_pending) return MSV_OK;
+  DevGuard g(h->device);
+  // spin on the copy-out event: no blocking stream synchronize on the launch stream
+  for (;;) {
+    cudaError_t e = cudaEventQuery(h->ev_copy);
+    if (e == cudaSuccess) break;
+    if (e != cudaErrorNotReady) { h->err = std::string("cudaEventQuery: ") + cudaGetErrorString(e); h->copy_pending = false; return MSV_ERR_CUDA; }
+  }
+  // copy_pending stays set: the next launch on the handle makes its stream wait for the (completed) event
+  return MSV_OK;
+}
+
+int msv_step_host(msv_handle* h, const uint8_t* actions_host, float* rewards_host, uint8_t* dones_host, void* stream) {
+  int rc = msv_step_host_async(h, actions_host, rewards_host, dones_host, nullptr, stream);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(st));                // st waits for the read-back (ev_copy) and runs the observation kernels
+  rc = msv_step_host_wait(h);
+  if (rc) return rc;
+  DevGuard g(h->device);
+  CK(cudaStreamSynchronize((cudaStream_t)stream));   // observation tensors complete as well (documented contract)
+  return MSV_OK;
+}
+
+int msv_step_host_obs(msv_handle* h, const uint8_t* actions_host, float* rewards_host, uint8_t* dones_host, void* obs_host,
+                      void* stream) {
+  if (!obs_host) return MSV_ERR_INVALID;
+  int rc = msv_step_host_async(h, actions_host, rewards_host, dones_host, obs_host, stream);
+  if (rc) return rc;
+  return msv_step_host_wait(h);
+}
+
+int64_t msv_obs_host_bytes(msv_handle* h) { return h ? (int64_t)(h->obs_end - h->obs_begin) : 0; }
+int64_t msv_obs_host_offset(msv_handle* h, const char* name) {
+  if (!h || !name) return -1;
+  auto it = h->tensors.find(name);
+  if (it == h->tensors.end()) return -1;
+  const char* p = (const char*)it->second.ptr;
+  if (p < h->arena + h->obs_begin || p >= h->arena + h->obs_end) return -1;
+  return (int64_t)(p - (h->arena + h->obs_begin));
+}
+int64_t msv_device_bytes(msv_handle* h) { return h ? (int64_t)h->device_bytes : 0; }
+
+/* debug/bench: CUDA-event timing of the kernels msv_step launches.  enable=1 starts recording (one
+ * event pair per kernel and step, up to 8192 steps); enable=0 stops, synchronises and returns the
+ * mean milliseconds of [k_step (+ terminal capture), k_obs, k_lidar] and the number of steps. */
+int msv_debug_kernel_timing(msv_handle* h, int enable, double out_ms[3], int64_t* n_steps) {
+  if (!h) return MSV_ERR_INVALID;
+  DevGuard g(h->device);
+  if (enable) { h->tev_used = 0; h->timing = true; return MSV_OK; }
+  h->timing = false;
+  CK(cudaDeviceSynchronize());
+  double sum[3] = {0, 0, 0}; int64_t n = (int64_t)(h->tev_used / 4);
+  for (int64_t t = 0; t < n; ++t)
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.0f; CK(cudaEventElapsedTime(&ms, h->tev[4 * t + k], h->tev[4 * t + k + 1]));
+      sum[k] += ms;
+    }
+  if (out_ms) for (int k = 0; k < 3; ++k) out_ms[k] = n ? sum[k] / (double)n : 0.0;
+  if (n_steps) *n_steps = n;
+  h->tev_used = 0;
   return MSV_OK;
 }
 
@@ -578,7 +748,11 @@ static void dl_deleter(DLManagedTensor* m) {
   if (!m) return;
   DLCtx* c = (DLCtx*)m->manager_ctx;
   // the library owns the memory for the handle's lifetime: only drop the count
-  if (c) { c->h->exported--; delete c; }
+  if (c) {
+    msv_handle* h = c->h;
+    delete c;
+    if (--h->exported == 0 && h->zombie) really_destroy(h);
+  }
   delete m;
 }
 
@@ -607,10 +781,13 @@ int msv_tensor(msv_handle* h, const char* name, struct DLManagedTensor** out) {
 
 int msv_get_state(msv_handle* h, int32_t first, int32_t count, msv_env_state* out) {
   if (!h || !out || first < 0 || count < 0 || first + count > h->C.n_real) return MSV_ERR_INVALID;
-  Mirror m; int rc = download(h, m); if (rc) return rc;
-  const size_t N = h->C.N; const int AC = h->AC, BC = h->BC, A = h->C.A, NAA = AC * (AC - 1) / 2;
+  if (count == 0) return MSV_OK;
+  DevGuard g(h->device);
+  const Slice sl{(size_t)first, (size_t)count, (size_t)h->C.N};
+  Mirror m; int rc = download(h, m, sl); if (rc) return rc;
+  const size_t N = (size_t)count; const int AC = h->AC, BC = h->BC, A = h->C.A, NAA = AC * (AC - 1) / 2;
   for (int q = 0; q < count; ++q) {
-    size_t e = (size_t)first + q; msv_env_state& s = out[q];
+    size_t e = (size_t)q; msv_env_state& s = out[q];
     memset(&s, 0, sizeof s);
     for (int i = 0; i < A; ++i) {
       float4 k0 = m.akin0[i * N + e], k1 = m.akin1[i * N + e], ft = m.afat[i * N + e]; int4 ai = m.aint[i * N + e];
@@ -666,18 +843,33 @@ int msv_get_state(msv_handle* h, int32_t first, int32_t count, msv_env_state* ou
     }
     s.first_step = h1.y; s.steps = h0.y; s.episode = h0.z; s.body_seq = h0.w; s.contact_seq = h1.x;
     for (int i = 0; i < AC; ++i) { s.stat_reward[i] = m.sreward[i * N + e]; s.stat_kills[i] = m.skills[i * N + e]; }
-    int4 sm = m.smisc[e]; s.stat_steps = sm.x; s.stat_heals_used = sm.y; s.stat_boxes_placed = sm.z;
+    int4 sm = m.smisc[e]; s.stat_steps = sm.x; s.stat_heals_used = sm.y; s.stat_boxes_placed = sm.z; s.stat_episodes = sm.w;
+    for (int i = 0; i < A; ++i) s.ep_return[i] = m.epret[i * N + e];
   }
   return MSV_OK;
 }
 
 int msv_set_state(msv_handle* h, int32_t first, int32_t count, const msv_env_state* in) {
   if (!h || !in || first < 0 || count < 0 || first + count > h->C.n_real) return MSV_ERR_INVALID;
-  Mirror m; int rc = download(h, m); if (rc) return rc;
-  const size_t N = h->C.N; const int AC = h->AC, BC = h->BC, HC = h->HC, A = h->C.A, NAA = AC * (AC - 1) / 2;
+  if (count == 0) return MSV_OK;
+  const int AC = h->AC, BC = h->BC, HC = h->HC, A = h->C.A, NAA = AC * (AC - 1) / 2;
+  for (int q = 0; q < count; ++q) {   // validate everything before touching the device
+    const msv_env_state& s = in[q];
+    bool ok = s.n_boxes >= 0 && s.n_boxes <= BC && s.n_items >= 0 && s.n_items <= BC && s.n_heals >= 0 && s.n_heals <= HC &&
+              s.n_pending >= 0 && s.n_pending <= BC && s.zone_phase >= 0 && s.zone_phase < h->C.zone_phases &&
+              s.n_boxes + s.n_pending <= 255;
+    for (int i = 0; ok && i < A; ++i) {
+      ok = s.inv_n[i] >= 0 && s.inv_n[i] <= h->C.inv_slots;
+      for (int k = 0; ok && k < s.inv_n[i]; ++k) ok = s.inv_kind[i][k] == MSV_ITEM_HEAL || s.inv_kind[i][k] == MSV_ITEM_BOX;
+    }
+    if (!ok) { h->err = "msv_set_state: list length / inventory / zone phase out of range in env record " + std::to_string(q); return MSV_ERR_INVALID; }
+  }
+  DevGuard g(h->device);
+  const Slice sl{(size_t)first, (size_t)count, (size_t)h->C.N};
+  Mirror m; int rc = download(h, m, sl); if (rc) return rc;
+  const size_t N = (size_t)count;
   for (int q = 0; q < count; ++q) {
-    size_t e = (size_t)first + q; const msv_env_state& s = in[q];
-    if (s.n_boxes > BC || s.n_items > BC || s.n_heals > HC || s.n_pending > BC) return MSV_ERR_INVALID;
+    size_t e = (size_t)q; const msv_env_state& s = in[q];
     for (int i = 0; i < A; ++i) {
       int fl = (s.alive[i] ? 1 : 0) | (s.alive[i] && s.awake[i] ? 2 : 0);
       m.akin0[i * N + e] = make_float4(s.x[i], s.y[i], s.angle[i], s.vx[i]);
@@ -723,14 +915,16 @@ int msv_set_state(msv_handle* h, int32_t first, int32_t count, const msv_env_sta
       for (int k = 0; k < 4; ++k) set_pair(NAA + AC * BC + i * 4 + k, s.pair_aw[i][k]);
     }
     for (int i = 0; i < AC; ++i) { m.sreward[i * N + e] = s.stat_reward[i]; m.skills[i * N + e] = s.stat_kills[i]; }
-    m.smisc[e] = make_int4(s.stat_steps, s.stat_heals_used, s.stat_boxes_placed, 0);
+    m.smisc[e] = make_int4(s.stat_steps, s.stat_heals_used, s.stat_boxes_placed, s.stat_episodes);
+    for (int i = 0; i < AC; ++i) m.epret[i * N + e] = i < A ? s.ep_return[i] : 0.0f;
   }
-  return upload(h, m);
+  return upload(h, m, sl);
 }
 
 int msv_flush_stats(msv_handle* h, msv_stats* out) {
   if (!h || !out) return MSV_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  DevGuard g(h->device);
+  CK(cudaDeviceSynchronize());   // k_stats runs on stream 0: steps queued on non-blocking streams must be complete
   CK(cudaMemset(h->d_stat_reward, 0, sizeof(double) * MSV_MAX_AGENTS));
   CK(cudaMemset(h->d_stat_kills, 0, sizeof(unsigned long long) * MSV_MAX_AGENTS));
   CK(cudaMemset(h->d_stat_misc, 0, sizeof(unsigned long long) * 4));
@@ -771,7 +965,7 @@ int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }
  * the stable ABI; used by tests/gpu_quickbench.py) */
 int msv_debug_profile(msv_handle* h, int enable, unsigned long long out[32]) {
   if (!h) return MSV_ERR_INVALID;
-  CK(cudaSetDevice(h->device)); CK(cudaDeviceSynchronize());
+  DevGuard g(h->device); CK(cudaDeviceSynchronize());
   if (out) CK(msv_read_profile(out, 1));
   h->C.profile = enable;
   return MSV_OK;

@@ -85,8 +85,8 @@ struct Env {
   // out-of-line cold paths without copying, no local-memory mirror.
   enum { L_HEALTH = 0, L_CAUSE = L_HEALTH + AC, L_COOLDOWN = L_CAUSE + AC, L_INV = L_COOLDOWN + AC,
          L_SREW = L_INV + AC, L_SKILLS = L_SREW + AC, L_SEENA = L_SKILLS + AC, L_SEENX = L_SEENA + AC,
-         L_KCAUSE = L_SEENX + AC,
-         L_NP = L_KCAUSE + AC, L_STEPS, L_EPISODE, L_BODYSEQ, L_CONTACTSEQ, L_FIRST, L_OVERFLOW, L_NEWFIX,
+         L_KCAUSE = L_SEENX + AC, L_EPRET = L_KCAUSE + AC,
+         L_NP = L_EPRET + AC, L_STEPS, L_EPISODE, L_BODYSEQ, L_CONTACTSEQ, L_FIRST, L_OVERFLOW, L_NEWFIX,
          L_ZX, L_ZY, L_ZR, L_ZPHASE, L_ZTCOOL, L_ZTSHRINK, L_ZEND,
          L_STSTEPS, L_STHEALS, L_STBOXES, L_STEPISODES, L_USEHEAL, L_USEBOX, L_NEWBOX,
          L_PREALIVE, L_DMASK, L_NKILLS, L_COUNT };
@@ -242,6 +242,7 @@ struct Env {
         if (i < C.A) { int4 ai = S.aint[i * N + e]; LI(L_HEALTH + (i)) = ai.x; LI(L_CAUSE + (i)) = ai.y; LI(L_COOLDOWN + (i)) = ai.z; LI(L_INV + (i)) = ai.w; }
         else { LI(L_HEALTH + (i)) = 0; LI(L_CAUSE + (i)) = MSV_CAUSE_NONE; LI(L_COOLDOWN + (i)) = 0; LI(L_INV + (i)) = 0; }
         LF(L_SREW + (i)) = S.sreward[i * N + e]; LI(L_SKILLS + (i)) = S.skills[i * N + e];
+        LF(L_EPRET + (i)) = S.epret[i * N + e];
       }
       int4 h0 = S.hdr0[e], h1 = S.hdr1[e];
       nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; LI(L_NP) = (h0.x >> 24) & 255;
@@ -281,6 +282,7 @@ struct Env {
       for (int i = 0; i < AC; ++i) {
         if (i < C.A) S.aint[i * N + e] = make_int4(LI(L_HEALTH + (i)), LI(L_CAUSE + (i)), LI(L_COOLDOWN + (i)), LI(L_INV + (i)));
         S.sreward[i * N + e] = LF(L_SREW + (i)); S.skills[i * N + e] = LI(L_SKILLS + (i));
+        S.epret[i * N + e] = LF(L_EPRET + (i));
       }
       S.hdr0[e] = make_int4(nb | (ni << 8) | (nh << 16) | (LI(L_NP) << 24), LI(L_STEPS), LI(L_EPISODE), LI(L_BODYSEQ));
       S.hdr1[e] = make_int4(LI(L_CONTACTSEQ), LI(L_FIRST), LI(L_OVERFLOW) + OVF(), LI(L_NEWFIX));
@@ -1268,7 +1270,8 @@ struct Env {
     for (int i = g; i < C.A; i += G) {
       int a0 = 1, a1 = 1, a2 = 1;            // padding envs (N rounded up to the block size) get the no-op action
       if (real) {
-        const uint8_t* a = actions + ((size_t)e * C.A + i) * 6; a0 = a[0]; a1 = a[1]; a2 = a[2];
+        const uint8_t* a = actions + ((size_t)e * C.A + i) * 6;
+        a0 = min((int)a[0], 2); a1 = min((int)a[1], 2); a2 = min((int)a[2], 2);   // env:80 asserts the range; never index past the tables
         flags |= (a[3] ? 1u : 0u) << i | (a[4] ? 1u : 0u) << (8 + i) | (a[5] ? 1u : 0u) << (16 + i);
       }
       if (!alive(i)) continue;
@@ -1719,8 +1722,18 @@ struct Env {
     for (int i = 0; i < AC; ++i) if (i < (C.teams ? 2 : A)) LI(L_SKILLS + (i)) += lk[i];
     LI(L_STSTEPS) += 1; LI(L_STHEALS) += LI(L_USEHEAL); LI(L_STBOXES) += LI(L_USEBOX);
 #pragma unroll
-    for (int i = 0; i < AC; ++i) if (i < A) O.rewards[(size_t)e * A + i] = rew[i];
+    for (int i = 0; i < AC; ++i) if (i < A) { O.rewards[(size_t)e * A + i] = rew[i]; LF(L_EPRET + (i)) += rew[i]; }
     O.dones[e] = done ? 1 : 0;
+    if (done) {   // per-env episode statistics of the episode that just ended (rows valid where dones)
+#pragma unroll
+      for (int i = 0; i < AC; ++i) if (i < A) O.episode_return[(size_t)e * A + i] = LF(L_EPRET + (i));
+      O.episode_length[e] = LI(L_STEPS);
+    }
+    if (C.battle_royale) {   // BattleRoyale.post_step (sem:41-46): runs last, on the post-death body list
+      int na = 0;
+      for (int i = 0; i < A; ++i) { const bool al = alive(i); na += al; O.br_results[(size_t)e * A + i] = al ? 1 : 0; }
+      O.br_over[e] = na <= 1 ? 1 : 0;
+    }
     return done;
   }
 
@@ -1802,5 +1815,12 @@ struct Env {
     LF(L_ZR) = C.zone_r32[0];
     float2 c0 = S.zonec[e]; LF(L_ZX) = c0.x; LF(L_ZY) = c0.y;
     LU(L_DMASK) = 0; LI(L_NKILLS) = 0; LI(L_USEHEAL) = 0; LI(L_USEBOX) = 0;
+    for (int i = 0; i < AC; ++i) LF(L_EPRET + (i)) = 0.0f;
+  }
+  // ImmunityPhase (sem:652-674): Health.immune is True from reset until max(cooldown, 1) steps have run  [leader]
+  DEV void store_immune(DevOut& O) {
+    if (C.immunity_cooldown < 0) return;
+    const int cd = C.immunity_cooldown < 1 ? 1 : C.immunity_cooldown;
+    O.immune[e] = LI(L_STEPS) < cd ? 1 : 0;
   }
 };

@@ -101,6 +101,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
       MSV_COLD_ON(env, reset());
       again = 1;
     }
+    env.store_immune(O);
   }
   if (env.bc(again)) { env.share_counts(); env.cameras(); }
   PROF(9);
@@ -139,9 +140,11 @@ k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   env.cameras();
   if (env.lead) {
     env.store_obm();
+    env.store_immune(O);
     if (!only_done) {
       for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
       O.dones[e] = 0;
+      if (C.battle_royale) O.br_over[e] = 0;   // BattleRoyale.post_reset (sem:38-39)
     }
   }
   env.store();

@@ -18,6 +18,7 @@ struct DevConst {
   int box_ownership, box_randomized, box_health, healing, inv_slots;
   int zone_phases, zone_cooldown, zone_damage, n_zones, zone_centers_random;
   int lidar_n, auto_reset, grid_n;  // grid_n = grid_size^2
+  int immunity_cooldown, battle_royale, b2_variant;
   float r_alive, r_dead, r_kill, r_death;
   float agent_r, heal_r, item_r, box_h;
   float inv_mass, inv_I, friction, dt, dt_ratio1, damp;
@@ -34,7 +35,7 @@ struct DevConst {
   double box_avg_w, box_std_w, box_avg_h, box_std_h, box_min_w, box_min_h;
   double lidar_ang[MSV_MAX_LASERS];       // i*(fov/(n-1)) - fov/2, as Python doubles
   uint32_t seed_lo, seed_hi;
-  uint32_t env_offset;
+  uint32_t env_offset;       // global index of env 0 (Philox counter word 0); msv_create rejects ids >= 2^32
   int profile;           // debug: accumulate per-phase clock64() deltas into g_prof
 };
 
@@ -69,6 +70,7 @@ struct DevState {
   float* sreward;  // [AC][N]
   int* skills;     // [AC][N]
   int4* smisc;     // [N] steps, heals_used, boxes_placed, episodes
+  float* epret;    // [AC][N] running return of the current episode, per agent
   unsigned long long* obm;  // [N] others_mask bits (observer i sees agent j: bit i*AC+j)
   unsigned* omask;          // [AC][N] non-omniscient: per observer, seen heals (bits 0-15), boxes (16-23), box items (24-31)
 };
@@ -92,6 +94,11 @@ struct DevOut {
   int* lidar_hit;        // [N][A][L]
   float* rewards;        // [N][A]
   uint8_t* dones;        // [N]
+  float* episode_return; // [N][A]  return of the episode that just ended (rows valid where dones)
+  int* episode_length;   // [N]     its length in steps
+  uint8_t* immune;       // [N]     Health.immune as driven by ImmunityPhase (semantics.py:652-674)
+  uint8_t* br_over;      // [N]     BattleRoyale.over (semantics.py:31-46)
+  uint8_t* br_results;   // [N][A]  BattleRoyale.results (valid where br_over)
 };
 
 // ---- observation writer (k_obs) ------------------------------------------

@@ -19,7 +19,8 @@ ERRORS = {-1: 'MSV_ERR_INVALID', -2: 'MSV_ERR_CUDA', -3: 'MSV_ERR_NO_DEVICE',
 EXPORTS = [
     'msv_abi_version', 'msv_sizeof_config', 'msv_sizeof_env_state', 'msv_sizeof_stats',
     'msv_default_config', 'msv_create', 'msv_destroy', 'msv_reset', 'msv_step',
-    'msv_step_host', 'msv_tensor', 'msv_tensor_info', 'msv_get_state', 'msv_set_state',
+    'msv_step_host', 'msv_step_host_obs', 'msv_step_host_async', 'msv_step_host_wait', 'msv_obs_host_bytes',
+    'msv_obs_host_offset', 'msv_device_bytes', 'msv_tensor', 'msv_tensor_info', 'msv_get_state', 'msv_set_state',
     'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_obs_bytes_per_env', 'msv_kernel_launches',
     'msv_last_error', 'msv_philox4x32',
 ]
@@ -53,6 +54,16 @@ def load():
     L.msv_reset.argtypes = [vp, vp]
     L.msv_step.argtypes = [vp, vp, vp]
     L.msv_step_host.argtypes = [vp, vp, vp, vp, vp]
+    L.msv_step_host_obs.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.msv_step_host_async.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.msv_step_host_wait.argtypes = [vp]
+    L.msv_obs_host_bytes.argtypes = [vp]
+    L.msv_obs_host_bytes.restype = i64
+    L.msv_obs_host_offset.argtypes = [vp, ctypes.c_char_p]
+    L.msv_obs_host_offset.restype = i64
+    L.msv_device_bytes.argtypes = [vp]
+    L.msv_device_bytes.restype = i64
+    L.msv_debug_kernel_timing.argtypes = [vp, ctypes.c_int, vp, vp]
     L.msv_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
     L.msv_tensor_info.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(i32),
                                   ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32)]
@@ -73,7 +84,7 @@ def load():
     L.msv_debug_obs_kernel.argtypes = [vp, vp]
     L.msv_debug_overflow.argtypes = [vp]
     L.msv_debug_overflow.restype = i64
-    if L.msv_abi_version() != 1:
+    if L.msv_abi_version() != 2:
         raise MasurvError('libmasurv.so ABI version mismatch')
     for name, dt in (('msv_sizeof_config', CONFIG_DT), ('msv_sizeof_env_state', STATE_DT),
                      ('msv_sizeof_stats', STATS_DT)):
@@ -109,6 +120,8 @@ class Handle:
         self._tensors = {}
 
     def close(self):
+        """msv_destroy.  Tensors already handed out stay valid: the library keeps the
+        device memory they alias until the last of them is garbage-collected."""
         if getattr(self, 'h', None):
             self._tensors.clear()
             load().msv_destroy(self.h)
@@ -151,6 +164,32 @@ class Handle:
 
     def step_host(self, actions, rewards, dones, stream=0):
         check(load().msv_step_host(self.h, actions, rewards, dones, stream), self.h)
+
+    def step_host_obs(self, actions, rewards, dones, obs, stream=0):
+        check(load().msv_step_host_obs(self.h, actions, rewards, dones, obs, stream), self.h)
+
+    def step_host_async(self, actions, rewards, dones, obs=None, stream=0):
+        check(load().msv_step_host_async(self.h, actions, rewards, dones, obs, stream), self.h)
+
+    def step_host_wait(self):
+        check(load().msv_step_host_wait(self.h), self.h)
+
+    def obs_host_bytes(self):
+        return int(load().msv_obs_host_bytes(self.h))
+
+    def obs_host_offset(self, name):
+        return int(load().msv_obs_host_offset(self.h, name.encode()))
+
+    def device_bytes(self):
+        return int(load().msv_device_bytes(self.h))
+
+    def kernel_timing(self, enable):
+        """debug: start (True) / stop (False) CUDA-event timing of the kernels of step(); stopping
+        returns (mean ms of [k_step, k_obs, k_lidar], number of steps recorded)."""
+        out = (ctypes.c_double * 3)()
+        n = ctypes.c_int64()
+        check(load().msv_debug_kernel_timing(self.h, 1 if enable else 0, out, ctypes.byref(n)), self.h)
+        return [float(x) for x in out], int(n.value)
 
     def get_state(self, first=0, count=None):
         count = self.num_envs - first if count is None else count

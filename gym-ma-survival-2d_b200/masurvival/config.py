@@ -74,6 +74,12 @@ def default_config():
         # extension (the reference's Lidars module, simulation.py:357-392, is
         # not wired into its env; off by default here as well)
         'lidars': {'n_lasers': 0, 'fov': 0.8 * math.pi, 'depth': 10},
+        # modules the reference ships but never instantiates (env:322,336): opt-in.
+        # ImmunityPhase takes its cooldown from 'immunity_phase' above (env:157).
+        'modules': {'immunity_phase': False, 'battle_royale': False},
+        # Box2D build details that cannot be pinned in this image:
+        # bit 0 clamp damping, bit 1 squared weld tolerance, bit 2 toiCount >= maxSubSteps
+        'box2d': {'variant': 0},
     }
 
 
@@ -169,6 +175,10 @@ def pack_config(cfg, continuous_melee=False, auto_reset=False):
     rec['lidar_n'] = lid.get('n_lasers', 0)
     rec['lidar_fov'] = lid.get('fov', 0.8 * math.pi)
     rec['lidar_depth'] = lid.get('depth', 10)
+    mods = cfg.get('modules', {})
+    rec['immunity_cooldown'] = int(cfg.get('immunity_phase', {}).get('cooldown', 300)) if mods.get('immunity_phase') else -1
+    rec['battle_royale'] = int(bool(mods.get('battle_royale', False)))
+    rec['b2_variant'] = int(cfg.get('box2d', {}).get('variant', 0))
     # False/0 off, True/1 in-kernel reset, 'terminal'/2 reset + terminal observation capture
     rec['auto_reset'] = 2 if auto_reset in ('terminal', 2) else int(bool(auto_reset))
     validate(rec)

@@ -49,6 +49,8 @@ class MaSurvivalVec:
         self.action_space = self.compute_action_space()
         self.steps = 0
         self._act_buf = None
+        self._done_bool = None
+        self._host_obs = None
 
     # ---- reference properties (env:245-291) --------------------------------
     @property
@@ -137,6 +139,10 @@ class MaSurvivalVec:
         import torch
         N, A = self.num_envs, self.n_agents
         if isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.uint8:
+            # consumed in place; out-of-range components are clamped by the kernel (the
+            # reference asserts, env:80: validating on the device would cost a sync per step)
+            if actions.device.index != self.device:
+                raise ValueError(f'actions live on {actions.device}, the environments on cuda:{self.device}')
             a = actions.contiguous()
         else:
             arr = np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions)
@@ -150,22 +156,96 @@ class MaSurvivalVec:
         self._h.step(a.data_ptr(), self._stream())
         self.steps += 1
         info = {'terminal_observation': self._obs('terminal_')} if self._terminal else {}
-        return self._obs(), self._h.tensor('rewards'), self._h.tensor('dones').bool(), info
+        # per-env episode statistics (rows valid where done): what a trainer logs at episode end
+        info['episode_return'] = self._h.tensor('episode_return')
+        info['episode_length'] = self._h.tensor('episode_length')
+        for k in ('immune', 'br_over', 'br_results'):
+            if self._h.has_tensor(k):
+                info[k] = self._h.tensor(k)
+        dones = self._h.tensor('dones')
+        if self._done_bool is None or self._done_bool.data_ptr() != dones.data_ptr():
+            self._done_bool = dones.view(torch.bool)      # zero-copy: uint8 0/1 reinterpreted, no per-step allocation
+        return self._obs(), self._h.tensor('rewards'), self._done_bool, info
 
     def step_host(self, actions, rewards_out=None, dones_out=None):
         """End-to-end step from HOST buffers: actions uint8[N,A,6] (numpy or
         pinned torch CPU tensor) -> rewards float32[N,A], dones uint8[N] in
         host memory; copies happen inside the call."""
+        a, rewards_out, dones_out = self._host_args(actions, rewards_out, dones_out)
+        self._h.step_host(self._ptr(a), self._ptr(rewards_out), self._ptr(dones_out), self._stream())
+        self.steps += 1
+        return rewards_out, dones_out
+
+    @staticmethod
+    def _ptr(t):
+        return t.ctypes.data if isinstance(t, np.ndarray) else t.data_ptr()
+
+    @staticmethod
+    def _check_host(name, t, dtype, numel):
+        """raw pointers cross the C ABI: dtype, size and contiguity are checked here"""
+        import torch
+        if isinstance(t, np.ndarray):
+            ok = t.dtype == np.dtype(dtype) and t.size == numel and t.flags['C_CONTIGUOUS']
+        elif isinstance(t, torch.Tensor):
+            ok = (not t.is_cuda) and t.dtype == getattr(torch, np.dtype(dtype).name) and t.numel() == numel and t.is_contiguous()
+        else:
+            ok = False
+        if not ok:
+            raise ValueError(f'{name} must be a C-contiguous host {np.dtype(dtype).name} array/tensor with {numel} elements')
+
+    def _host_args(self, actions, rewards_out, dones_out):
         N, A = self.num_envs, self.n_agents
         a = np.ascontiguousarray(actions, dtype=np.uint8) if isinstance(actions, np.ndarray) else actions
         if rewards_out is None:
             rewards_out = np.empty((N, A), dtype=np.float32)
         if dones_out is None:
             dones_out = np.empty((N,), dtype=np.uint8)
-        ptr = lambda t: t.ctypes.data if isinstance(t, np.ndarray) else t.data_ptr()
-        self._h.step_host(ptr(a), ptr(rewards_out), ptr(dones_out), self._stream())
+        self._check_host('actions', a, np.uint8, N * A * 6)
+        self._check_host('rewards_out', rewards_out, np.float32, N * A)
+        self._check_host('dones_out', dones_out, np.uint8, N)
+        return a, rewards_out, dones_out
+
+    def host_obs_buffer(self, pinned=True):
+        """A host buffer for step_host_obs (page-locked by default) and the dict of
+        zero-copy numpy views into it, one per observation key (library layout:
+        `zone/heals/boxes/box_items` once per env, see _obs)."""
+        import torch
+        nbytes = self._h.obs_host_bytes()
+        buf = torch.empty(nbytes, dtype=torch.uint8)
+        if pinned:
+            buf = buf.pin_memory()
+        raw = buf.numpy()
+        views, N, A = {}, self.num_envs, self.n_agents
+        for k, shp in self.obs_shapes().items():
+            off = self._h.obs_host_offset(k)
+            if k in ('zone', 'heals', 'boxes', 'box_items'):
+                shp = shp[1:]
+            dt = np.int32 if k == 'lidar_hit' else np.float32
+            n = int(np.prod(shp)) * N
+            views[k] = raw[off:off + 4 * n].view(dt).reshape((N,) + tuple(shp))
+        return buf, views
+
+    def step_host_obs(self, actions, obs_buf, rewards_out=None, dones_out=None):
+        """step_host that also lands the observations in `obs_buf` (from
+        host_obs_buffer()): H2D actions, kernels, D2H rewards/dones/observations."""
+        a, rewards_out, dones_out = self._host_args(actions, rewards_out, dones_out)
+        self._check_host('obs_buf', obs_buf, np.uint8, self._h.obs_host_bytes())
+        self._h.step_host_obs(self._ptr(a), self._ptr(rewards_out), self._ptr(dones_out), self._ptr(obs_buf), self._stream())
         self.steps += 1
         return rewards_out, dones_out
+
+    def step_host_async(self, actions, rewards_out, dones_out, obs_buf=None):
+        """Enqueue a host-buffer step and return; step_host_wait() blocks until the host
+        buffers are complete.  Lets a caller keep several env groups in flight."""
+        a, rewards_out, dones_out = self._host_args(actions, rewards_out, dones_out)
+        if obs_buf is not None:
+            self._check_host('obs_buf', obs_buf, np.uint8, self._h.obs_host_bytes())
+        self._h.step_host_async(self._ptr(a), self._ptr(rewards_out), self._ptr(dones_out),
+                                None if obs_buf is None else self._ptr(obs_buf), self._stream())
+        self.steps += 1
+
+    def step_host_wait(self):
+        self._h.step_host_wait()
 
     def observe(self):
         self._h.observe(self._stream())
@@ -200,6 +280,9 @@ class MaSurvivalVec:
     def kernel_launches(self):
         return self._h.kernel_launches()
 
+    def device_bytes(self):
+        return self._h.device_bytes()
+
     def render(self, mode='human'):
         raise NotImplementedError('rendering is outside the accelerated step path (SURVEY.md section 2)')
 
@@ -226,4 +309,4 @@ class MaSurvival(MaSurvivalVec):
         actions = tuple(a for a in actions)
         assert self.action_space.contains(actions), f'Invalid action {actions}.'
         obs, rew, done, info = super().step(np.asarray(actions, dtype=np.int64).reshape(1, self.n_agents, 6))
-        return self._np_obs(obs), rew[0].cpu().numpy(), bool(done[0].item()), info
+        return self._np_obs(obs), rew[0].cpu().numpy(), bool(done[0].item()), {}   # env:90 returns an empty info dict

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSV_ABI_VERSION 1
+#define MSV_ABI_VERSION 2
 
 /* Compile-time capacities (per environment). */
 #define MSV_MAX_AGENTS 8
@@ -107,7 +107,21 @@ typedef struct msv_config {
   double zone_radiuses[MSV_MAX_ZONES];
   double zone_centers[MSV_MAX_ZONES][2]; /* used when !zone_centers_random */
   double lidar_fov, lidar_depth;
+  /* ---- modules the reference ships but its env never instantiates (env:322,336) ---- */
+  int32_t immunity_cooldown; /* ImmunityPhase(cooldown), semantics.py:652-674; <0 = module absent.
+                                Health.immune is written by it and read by nothing (semantics.py:490-500),
+                                so only the "immune" tensor changes */
+  int32_t battle_royale;     /* BattleRoyale, semantics.py:31-46: "br_over"/"br_results" tensors */
+  /* Box2D details that differ between 2.3.x builds (the real pybox2d cannot be run here, DESIGN.md
+   * section 4): bit 0 = clamp damping v *= clamp(1 - h*d, 0, 1) instead of the Pade form
+   * v *= 1/(1 + h*d); bit 1 = b2PolygonShape::Set weld tolerance (0.5*linearSlop)^2 instead of
+   * 2.3.0's 0.5*linearSlop; bit 2 = SolveTOI gives up at toiCount >= b2_maxSubSteps instead of >. */
+  int32_t b2_variant;
+  int32_t reserved0;
 } msv_config;
+#define MSV_B2_CLAMP_DAMPING 1
+#define MSV_B2_WELD_SQUARED 2
+#define MSV_B2_SUBSTEPS_GE 4
 
 /*
  * One contact-pair record.  A pair "exists" while the two bodies' fat AABBs
@@ -192,6 +206,9 @@ typedef struct msv_env_state {
   float stat_reward[MSV_MAX_AGENTS];
   int32_t stat_kills[MSV_MAX_AGENTS];
   int32_t stat_steps, stat_heals_used, stat_boxes_placed;
+  int32_t stat_episodes;  /* auto-resets since the last flush (vector-env extension) */
+  /* ---- running return / length of the current episode (per-env view of env:483-508) ---- */
+  float ep_return[MSV_MAX_AGENTS];
 } msv_env_state;
 
 /* Sum over envs of the reference's flush_stats() dict (env:471-480). */
@@ -222,6 +239,9 @@ int msv_default_config(msv_config* cfg);
  * sharding: rank r passes r*num_envs) and only keys the Philox streams. */
 int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device,
                uint64_t seed, int64_t env_offset, msv_handle** out);
+/* Frees the handle.  Device memory that is still referenced by live DLPack
+ * exports (msv_tensor) stays allocated until the last of them is deleted, so
+ * a tensor that outlives its environment never dangles. */
 int msv_destroy(msv_handle* h);
 
 /* Replaces BaseEnv.reset (env:59-74) for every env; stream-ordered. */
@@ -237,9 +257,32 @@ int msv_step(msv_handle* h, const uint8_t* actions_dev, void* cuda_stream);
  * rewards_host: float[num_envs][n_agents]; dones_host: uint8[num_envs].
  * The read-back runs on an internal stream as soon as the step kernel is done,
  * overlapped with the observation kernels; the call returns when both the host
- * buffers and the observation tensors are complete. */
+ * buffers and the observation tensors are complete.  The host buffers should be
+ * page-locked (cudaHostAlloc / torch pin_memory): with pageable memory the
+ * copies are staged by the driver and do not overlap the kernels. */
 int msv_step_host(msv_handle* h, const uint8_t* actions_host,
                   float* rewards_host, uint8_t* dones_host, void* cuda_stream);
+
+/* The same step returning the OBSERVATIONS as well (env:84,90: the step's main
+ * result).  obs_host receives msv_obs_host_bytes() bytes: every observation
+ * tensor (and the lidar block) in the library's de-duplicated layout, tensor
+ * `name` at byte offset msv_obs_host_offset(name), row-major with the shape
+ * msv_tensor_info reports.  One device->host copy on the internal stream after
+ * the observation kernels. */
+int msv_step_host_obs(msv_handle* h, const uint8_t* actions_host,
+                      float* rewards_host, uint8_t* dones_host, void* obs_host,
+                      void* cuda_stream);
+/* Split form for callers that keep several handles in flight (double-buffered
+ * env groups): _async enqueues copy-in, kernels and copy-out and returns;
+ * _wait blocks (spinning on an event, no stream synchronize) until the host
+ * buffers of the last _async call are complete.  The next step on the same
+ * handle is ordered after the copy-out by the library.  obs_host may be NULL. */
+int msv_step_host_async(msv_handle* h, const uint8_t* actions_host,
+                        float* rewards_host, uint8_t* dones_host, void* obs_host,
+                        void* cuda_stream);
+int msv_step_host_wait(msv_handle* h);
+int64_t msv_obs_host_bytes(msv_handle* h);
+int64_t msv_obs_host_offset(msv_handle* h, const char* name); /* -1: unknown */
 
 /* Zero-copy export of a library-owned device tensor as DLPack.  Names are the
  * reference's observation keys (env:391-447) plus "rewards", "dones",
@@ -262,7 +305,8 @@ int msv_set_state(msv_handle* h, int32_t first, int32_t count,
  * (fetch_observations, env:510-657), e.g. after msv_set_state. */
 int msv_observe(msv_handle* h, void* cuda_stream);
 
-/* flush_stats (env:471-480) summed over all envs; zeroes the accumulators. */
+/* flush_stats (env:471-480) summed over all envs; zeroes the accumulators.
+ * Synchronises the device first (work queued on any stream is complete). */
 int msv_flush_stats(msv_handle* h, msv_stats* out);
 
 /* Algorithmic HBM bytes one msv_step moves per env (state read+write,
@@ -271,6 +315,7 @@ int64_t msv_bytes_per_env_step(msv_handle* h);
 /* The part of it written by the observation gather kernel (k_obs). */
 int64_t msv_obs_bytes_per_env(msv_handle* h);
 int64_t msv_kernel_launches(msv_handle* h); /* launches since create */
+int64_t msv_device_bytes(msv_handle* h);    /* HBM allocated by the handle */
 
 const char* msv_last_error(msv_handle* h);
 

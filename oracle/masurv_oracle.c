@@ -63,6 +63,7 @@ struct oracle_env {
   float stat_reward[MA]; int stat_kills[MA]; int stat_steps, stat_heals, stat_boxes;
   int64_t stat_episodes;
   float last_rewards[MA]; int last_kills[MA];
+  float ep_return[MA];   /* running return of the current episode (per-env view of env:483-508) */
 };
 
 /* ------------------------------------------------------------------ Philox */
@@ -230,6 +231,7 @@ static void lidar_update(oracle_env* e);
 void orc_reset(oracle_env* e, orc_out* out) {
   const msv_config* c = &e->cfg;
   e->episode += 1; e->steps = 0;
+  memset(e->ep_return, 0, sizeof e->ep_return);
   b2l_world_clear(e->w);
   /* SpawnGrid.reset (sem:71-74) + square_grid (sem:987-992) */
   int g = c->grid_size, n = g * g;
@@ -315,7 +317,11 @@ void orc_reset(oracle_env* e, orc_out* out) {
     e->zone_x = e->zone_cx[0]; e->zone_y = e->zone_cy[0];
   }
   e->n_deaths = 0; e->n_kills = 0; e->use_heal = 0; e->use_box = 0;
-  if (out) { orc_observe(e, out); memset(out->rewards, 0, sizeof out->rewards); out->done = 0; }
+  if (out) {
+    orc_observe(e, out); memset(out->rewards, 0, sizeof out->rewards); out->done = 0;
+    out->immune = c->immunity_cooldown >= 0;   /* ImmunityPhase.post_reset (sem:661-665) */
+    out->br_over = 0;                          /* BattleRoyale.post_reset (sem:38-39) */
+  }
 }
 
 /* -------------------------------------------------------------- sensors --- */
@@ -664,11 +670,23 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
   for (int i = 0; i < (c->teams ? 2 : A); ++i) e->stat_kills[i] += e->last_kills[i];
   e->stat_steps += 1; e->stat_heals += e->use_heal; e->stat_boxes += e->use_box;
   memcpy(e->last_rewards, rewards, sizeof rewards);
-  if (out) { memcpy(out->rewards, rewards, sizeof rewards); out->done = done; out->n_toi_events = w->n_toi_events; }
+  for (int i = 0; i < A; ++i) e->ep_return[i] += rewards[i];
+  if (out) {
+    memcpy(out->rewards, rewards, sizeof rewards); out->done = done; out->n_toi_events = w->n_toi_events;
+    if (done) { memcpy(out->episode_return, e->ep_return, sizeof e->ep_return); out->episode_length = e->steps; }
+    /* BattleRoyale.post_step (sem:41-46): last module of the agents group, sees the post-death body list */
+    out->br_over = c->battle_royale && n_agents_alive(e) <= 1;
+    for (int i = 0; i < MA; ++i) out->br_results[i] = i < A && e->a_slot[i] >= 0;
+    /* ImmunityPhase.post_step (sem:667-674): Health.immune stays True for max(cooldown, 1) steps */
+    { int cd = c->immunity_cooldown < 1 ? 1 : c->immunity_cooldown; out->immune = c->immunity_cooldown >= 0 && e->steps < cd; }
+  }
   if (done && c->auto_reset) {
     e->stat_episodes++;
     orc_reset(e, 0);
-    if (out) { float r[MA]; memcpy(r, out->rewards, sizeof r); orc_observe(e, out); memcpy(out->rewards, r, sizeof r); out->done = 1; }
+    if (out) {
+      float r[MA]; memcpy(r, out->rewards, sizeof r); orc_observe(e, out); memcpy(out->rewards, r, sizeof r); out->done = 1;
+      out->immune = c->immunity_cooldown >= 0;   /* the new episode's flag; br_* and episode_* describe the finished one */
+    }
   }
 }
 
@@ -838,6 +856,8 @@ void orc_get_state(oracle_env* e, msv_env_state* s) {
   s->body_seq = w->body_seq; s->contact_seq = w->contact_seq;
   for (int i = 0; i < MA; ++i) { s->stat_reward[i] = e->stat_reward[i]; s->stat_kills[i] = e->stat_kills[i]; }
   s->stat_steps = e->stat_steps; s->stat_heals_used = e->stat_heals; s->stat_boxes_placed = e->stat_boxes;
+  s->stat_episodes = (int32_t)e->stat_episodes;
+  for (int i = 0; i < MA; ++i) s->ep_return[i] = i < e->cfg.n_agents ? e->ep_return[i] : 0.0f;
 }
 
 static void force_seq(b2l_world* w, int slot, int seq) { w->bodies[slot].seq = seq; }
@@ -937,6 +957,8 @@ void orc_set_state(oracle_env* e, const msv_env_state* s) {
   w->body_seq = s->body_seq; w->contact_seq = s->contact_seq;
   for (int i = 0; i < MA; ++i) { e->stat_reward[i] = s->stat_reward[i]; e->stat_kills[i] = s->stat_kills[i]; }
   e->stat_steps = s->stat_steps; e->stat_heals = s->stat_heals_used; e->stat_boxes = s->stat_boxes_placed;
+  e->stat_episodes = s->stat_episodes;
+  for (int i = 0; i < MA; ++i) e->ep_return[i] = s->ep_return[i];
   /* sensors are recomputed from the injected world (Cameras.post_reset analogue) */
   cameras_update(e);
   lidar_update(e);

@@ -44,6 +44,11 @@ typedef struct orc_out {
   float rewards[MSV_MAX_AGENTS];
   int32_t done;
   int32_t n_toi_events;
+  float episode_return[MSV_MAX_AGENTS]; /* valid when done: per-agent return of the finished episode */
+  int32_t episode_length;               /* valid when done */
+  int32_t immune;                       /* Health.immune under ImmunityPhase (sem:652-674) */
+  int32_t br_over;                      /* BattleRoyale.over / .results (sem:31-46) */
+  int32_t br_results[MSV_MAX_AGENTS];
 } orc_out;
 
 #define ORC_KIND_AGENT 1

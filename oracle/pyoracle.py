@@ -93,6 +93,11 @@ def unpack_out(cfg, out):
     res['rewards'] = np.array(out['rewards'][:A])
     res['done'] = bool(out['done'])
     res['n_toi_events'] = int(out['n_toi_events'])
+    res['episode_return'] = np.array(out['episode_return'][:A])
+    res['episode_length'] = int(out['episode_length'])
+    res['immune'] = int(out['immune'])
+    res['br_over'] = int(out['br_over'])
+    res['br_results'] = np.array(out['br_results'][:A])
     return res
 
 

@@ -27,11 +27,12 @@ def run(variant='2v2', n_envs=64, steps=300, seed=7, auto_reset=True, verbose=Tr
     h = _lib.Handle(rec, n_envs, device=0, seed=seed, env_offset=0)
     orcs = [po.OracleEnv(rec, seed=seed, env_id=e) for e in range(n_envs)]
     keys = list(po.obs_dims(rec).keys())
+    extra = [k for k in ('immune', 'br_over', 'br_results') if h.has_tensor(k)]
 
     def gpu_obs():
         torch.cuda.synchronize()
         out = {}
-        for k in keys + ['rewards', 'dones']:
+        for k in keys + ['rewards', 'dones', 'episode_return', 'episode_length'] + extra:
             out[k] = h.tensor(k).cpu().numpy()
         return out
 
@@ -41,7 +42,7 @@ def run(variant='2v2', n_envs=64, steps=300, seed=7, auto_reset=True, verbose=Tr
         return arr
 
     report = {'state_exact_mismatch': 0, 'state_fail': 0, 'obs_exact_mismatch': 0, 'obs_fail': 0,
-              'env_steps': 0, 'toi_events': 0, 'dones': 0, 'details': []}
+              'env_steps': 0, 'toi_events': 0, 'dones': 0, 'episode_stats_checked': 0, 'details': []}
 
     def check(tag, oouts):
         g = gpu_obs()
@@ -53,6 +54,14 @@ def run(variant='2v2', n_envs=64, steps=300, seed=7, auto_reset=True, verbose=Tr
             og['rewards'] = g['rewards'][e]
             og['done'] = bool(g['dones'][e])
             oo = dict(oouts[e])
+            if tag != 'reset':
+                if oo['done']:   # per-env episode statistics: rows valid where done
+                    og['episode_return'] = g['episode_return'][e]; og['episode_length'] = int(g['episode_length'][e])
+                    report['episode_stats_checked'] += 1
+                for k in extra:
+                    og[k] = g[k][e] if k == 'br_results' else int(g[k][e])
+            elif 'immune' in extra:
+                og['immune'] = int(g['immune'][e])
             oex, ofl = compare_obs(og, oo)
             report['state_exact_mismatch'] += bool(ex)
             report['state_fail'] += bool(fl)

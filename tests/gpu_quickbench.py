@@ -49,7 +49,7 @@ def run(variant, N, steps=600, warm=100, prof=False):
             h.step(acts[t % 8].data_ptr())
         L.msv_debug_profile(h.h, 0, buf)
         tot = sum(buf[:12]) or 1
-        print('   slowest group (any of 20 launches): total=%d; ' % buf[12] + ', '.join(f'{n}={buf[16+i]}' for i, n in enumerate(PHASES)))
+        print('   slowest group (any of 20 launches): total=%d cycles, env %d; ' % (buf[12], buf[13]) + ', '.join(f'{n}={buf[16+i]}' for i, n in enumerate(PHASES)))
         print('   leader-lane cycles/env/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(PHASES)))
     h.close()
 
@@ -63,7 +63,7 @@ if __name__ == '__main__':
         for v, N in (('2v2', 16384), ('1v1_heal_only', 4096), ('1v1', 16384), ('ffa', 32768), ('ffa_lidar', 32768)):
             run(v, N, steps=500)
     elif a and a[0] == '--prof':
-        run('2v2', 16384, prof=True)
+        run(a[1] if len(a) > 1 else '2v2', int(a[2]) if len(a) > 2 else 16384, steps=400, warm=1500, prof=True)   # stationary episode mix
     else:
         v = a[0] if a else '2v2'
         N = int(a[1]) if len(a) > 1 else 16384

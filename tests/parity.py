@@ -100,7 +100,8 @@ def compare_states(a, b, rel_tol=REL_TOL):
 
 
 DISCRETE_KEYS = ('others_mask', 'heals_mask', 'boxes_mask', 'box_items_mask', 'heal_slot',
-                 'heal_slot_mask', 'box_slot_mask', 'lidar_hit', 'rewards', 'done')
+                 'heal_slot_mask', 'box_slot_mask', 'lidar_hit', 'rewards', 'done',
+                 'episode_return', 'episode_length', 'immune', 'br_over', 'br_results')
 
 
 def compare_obs(a, b, rel_tol=REL_TOL):

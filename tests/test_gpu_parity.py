@@ -214,39 +214,46 @@ def test_golden_fixtures_on_gpu():
 
 
 def test_terminal_observation_capture():
-    """auto_reset='terminal': same trajectory as the in-kernel reset, and the finished
-    episode's last observation equals what an env without auto-reset returns"""
+    """auto_reset='terminal': same trajectory as the in-kernel reset, and the finished episode's
+    last observation equals the observation the ORACLE (stepped without auto-reset) returns on the
+    step its episode ends"""
     import torch
+    import pyoracle as po
     from masurvival.envs import MaSurvivalVec
-    from masurvival.config import variant
-    N = 512
-    cfg = parity.apply_overrides(variant('2v2'), {'safe_zone': {'cooldown': 6}, 'health': {'health': 10}})
+    N = 96
+    over = {'safe_zone': {'cooldown': 6}, 'health': {'health': 10}}
+    cfg = parity.apply_overrides(parity.variant('2v2'), over)
+    rec0 = make_config('2v2', auto_reset=False, **over)
     et = MaSurvivalVec(cfg, N, seed=9, auto_reset='terminal')
     e1 = MaSurvivalVec(cfg, N, seed=9, auto_reset=True)
-    e0 = MaSurvivalVec(cfg, N, seed=9, auto_reset=False)
-    for e in (et, e1, e0):
-        e.reset()
+    orcs = [po.OracleEnv(rec0, seed=9, env_id=e) for e in range(N)]
+    et.reset(); e1.reset()
+    for o in orcs:
+        o.reset()
+    keys = [k for k in po.obs_dims(rec0)]
     rng = np.random.default_rng(1)
-    fresh = torch.ones(N, dtype=torch.bool, device='cuda')     # e0 envs still in their first episode
     checked = 0
     for t in range(90):
-        a = torch.as_tensor(random_actions(rng, N, 4)).cuda()
+        act = random_actions(rng, N, 4)
+        a = torch.as_tensor(act).cuda()
         ot, rt, dt, info = et.step(a)
         o1, r1, d1, _ = e1.step(a)
-        o0, r0, d0, _ = e0.step(a)
         for k in o1:
             assert torch.equal(ot[k], o1[k]), k
         assert torch.equal(rt, r1) and torch.equal(dt, d1)
-        sel = dt & fresh
-        if sel.any():
-            for k, v in info['terminal_observation'].items():
-                assert torch.equal(v[sel], o0[k][sel]), k
-            checked += int(sel.sum())
-        fresh &= ~d0
+        dn = dt.cpu().numpy()
+        term = {k: v.cpu().numpy() for k, v in info['terminal_observation'].items()}
+        for e in range(N):
+            oo = orcs[e].step(act[e])
+            assert bool(dn[e]) == oo['done'], (t, e)
+            if oo['done']:
+                for k in keys:
+                    assert np.array_equal(term[k][e], oo[k]), (t, e, k)     # the oracle's last observation of the episode
+                checked += 1
+                orcs[e].reset()                                             # oracle episode n+1 == the GPU's auto-reset episode
     assert et.get_state().tobytes() == e1.get_state().tobytes()
-    assert checked > 100
-    for e in (et, e1, e0):
-        e.close()
+    assert checked > 60
+    et.close(); e1.close()
 
 
 def test_abi_tensor_info_errors_and_lifetime():
@@ -289,3 +296,112 @@ def test_abi_tensor_info_errors_and_lifetime():
     with pytest.raises(_lib.MasurvError):
         h.get_state(first=100, count=1)
     h.close()
+
+
+def test_step_host_obs_and_async_pipeline():
+    """msv_step_host_obs lands every observation tensor in host memory (one copy of the output
+    arena) and equals the device tensors; the async/wait split keeps two env groups in flight."""
+    import torch
+    from masurvival.envs import MaSurvivalVec
+    from masurvival.config import variant
+    N = 300
+    for name in ('2v2', 'ffa_lidar'):
+        A = 4 if name == '2v2' else 8
+        e1 = MaSurvivalVec(variant(name), N, seed=4)
+        e2 = MaSurvivalVec(variant(name), N, seed=4)
+        e1.reset(); e2.reset()
+        buf, views = e2.host_obs_buffer()
+        rew = torch.empty((N, A), dtype=torch.float32).pin_memory(); done = torch.empty((N,), dtype=torch.uint8).pin_memory()
+        rng = np.random.default_rng(3)
+        for t in range(25):
+            a = random_actions(rng, N, A)
+            obs, r1, d1, _ = e1.step(torch.as_tensor(a).cuda())
+            if t % 2:
+                e2.step_host_obs(a, buf, rew, done)
+            else:
+                e2.step_host_async(a, rew, done, buf); e2.step_host_wait()
+            torch.cuda.synchronize()
+            assert np.array_equal(r1.cpu().numpy(), rew.numpy()) and np.array_equal(d1.cpu().numpy(), done.numpy().astype(bool))
+            for k, v in views.items():
+                dv = e1._h.tensor(k).cpu().numpy()
+                assert v.shape == dv.shape and np.array_equal(v, dv), (name, t, k)
+        with pytest.raises(ValueError):
+            e2.step_host(np.zeros((N, A, 6), dtype=np.int64), rew, done)       # wrong dtype must not reach the C ABI
+        with pytest.raises(ValueError):
+            e2.step_host(np.zeros((N - 1, A, 6), dtype=np.uint8), rew, done)   # wrong size
+        e1.close(); e2.close()
+
+
+def test_tensor_outlives_environment():
+    """closing an env while DLPack tensors are alive must not free their storage"""
+    import gc
+    import torch
+    from masurvival.envs import MaSurvivalVec
+    from masurvival.config import variant
+    e = MaSurvivalVec(variant('2v2'), 128, seed=1)
+    obs = e.reset()
+    keep = obs['agent']; ref = keep.clone()
+    rew = e._h.tensor('rewards')
+    e.close()
+    junk = [torch.empty(1 << 20, device='cuda').fill_(7.0) for _ in range(8)]   # would reuse freed blocks
+    torch.cuda.synchronize()
+    assert torch.equal(keep, ref) and float(rew.abs().sum()) == 0.0
+    del keep, rew, obs, junk
+    gc.collect()                                   # last export dropped -> the library frees the handle now
+    e2 = MaSurvivalVec(variant('2v2'), 128, seed=1)
+    assert torch.equal(e2.reset()['agent'], ref)
+    e2.close()
+
+
+def test_set_state_validation_and_out_of_range_actions():
+    import torch
+    from masurvival import _lib
+    rec = make_config('2v2', auto_reset=False)
+    h = _lib.Handle(rec, 8, 0, 1, 0)
+    h.reset()
+    s = h.get_state()
+    for field, val in (('n_boxes', 9), ('n_heals', -1), ('zone_phase', 7), ('inv_n', 5)):
+        bad = s.copy()
+        if field == 'inv_n':
+            bad[field][2][1] = val
+        else:
+            bad[field][2] = val
+        with pytest.raises(_lib.MasurvError, match='INVALID'):
+            h.set_state(bad)
+    bad = s.copy(); bad['inv_n'][0][0] = 1; bad['inv_kind'][0][0][0] = 3
+    with pytest.raises(_lib.MasurvError, match='INVALID'):
+        h.set_state(bad)
+    assert h.get_state().tobytes() == s.tobytes()          # nothing was written by the rejected calls
+    # partial get/set: only the requested columns move
+    part = h.get_state(first=3, count=2)
+    assert part.tobytes() == s[3:5].tobytes()
+    h.set_state(s[5:6], first=1)
+    s2 = h.get_state()
+    assert s2[1].tobytes() == s[5].tobytes() and s2[0].tobytes() == s[0].tobytes() and s2[2].tobytes() == s[2].tobytes()
+    # action bytes outside MultiDiscrete([3,3,3,2,2,2]) are clamped, never index past the impulse tables
+    h.reset()
+    a = torch.full((8, 4, 6), 255, dtype=torch.uint8, device='cuda')
+    b = torch.zeros((8, 4, 6), dtype=torch.uint8, device='cuda'); b[..., :3] = 2; b[..., 3:] = 1
+    h2 = _lib.Handle(rec, 8, 0, 1, 0); h2.reset()
+    for _ in range(5):
+        h.step(a.data_ptr()); h2.step(b.data_ptr())
+    torch.cuda.synchronize()
+    assert h.get_state().tobytes() == h2.get_state().tobytes()
+    h.close(); h2.close()
+    with pytest.raises(_lib.MasurvError, match='INVALID'):
+        _lib.Handle(rec, 8, 0, 1, (1 << 32) - 4)           # global env ids must fit the 32-bit Philox counter word
+
+
+def test_unwired_modules_and_episode_stats():
+    """ImmunityPhase / BattleRoyale (semantics.py:652-674, 31-46) behind config keys, and the per-env
+    episode_return / episode_length buffers, lock-step against the oracle"""
+    import gpu_lockstep
+    r = gpu_lockstep.run('1v1', 48, 160, verbose=False, modules={'immunity_phase': True, 'battle_royale': True},
+                         immunity_phase={'cooldown': 7}, safe_zone={'cooldown': 6}, health={'health': 9},
+                         reward_scheme={'r_alive': 0.5, 'r_dead': -0.25, 'r_kill': 3, 'r_death': -1})
+    _assert_clean(r)
+    assert r['episode_stats_checked'] > 40
+    r = gpu_lockstep.run('2v2', 32, 120, verbose=False, modules={'immunity_phase': True, 'battle_royale': True},
+                         immunity_phase={'cooldown': 0}, safe_zone={'cooldown': 6}, health={'health': 9}, gameover={'mode': 'lastalive'})
+    _assert_clean(r)
+    assert r['episode_stats_checked'] > 20
