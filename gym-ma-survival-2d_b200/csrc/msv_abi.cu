@@ -35,7 +35,7 @@ struct msv_handle {
   DevConst C;
   DevState S;
   DevOut O;
-  int cap, AC, BC, HC, P, PW;
+  int cap, AC, BC, HC, P, PW, sm_words;
   int device;
   std::vector<void*> allocs;
   std::map<std::string, TensorInfo> tensors;
@@ -123,7 +123,7 @@ static void h_polygon_set4(const float vin[4][2], float vout[4][2], float nout[4
 
 static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_offset, DevConst* D) {
   memset(D, 0, sizeof *D);
-  D->N = (N + MSV_TPB - 1) / MSV_TPB * MSV_TPB; D->n_real = N; D->A = c->n_agents; D->B0 = c->n_boxes; D->H0 = c->n_heals;
+  D->N = N; D->epb = 0; D->n_real = N;   /* N (the padded SoA stride) and epb are set by plan_blocks() */ D->A = c->n_agents; D->B0 = c->n_boxes; D->H0 = c->n_heals;
   D->S = 8 + (c->teams ? 1 : 0);
   D->teams = c->teams; D->omniscient = c->omniscient; D->gameover_mode = c->gameover_mode;
   D->health = c->health; D->melee_damage = c->melee_damage; D->melee_cooldown = c->melee_cooldown;
@@ -213,6 +213,34 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
   D->seed_lo = (uint32_t)seed; D->seed_hi = (uint32_t)(seed >> 32);
   D->env_offset = (uint32_t)env_offset;
   return 0;
+}
+
+// Grid shape of k_step: a block is a tile of `epb` environments (epb * G threads, G = agent capacity
+// = lanes per environment).  All blocks should be resident at once (the step is one long dependent
+// chain per environment, so a second wave would double the time): take the largest tile for which
+// ceil(blocks / SMs) blocks fit on an SM (registers, shared memory).  MSV_EPB overrides (development).
+static void plan_blocks(msv_handle* h, int device) {
+  cudaDeviceProp pr; int sms = 148; size_t smem_sm = 227 * 1024, regs_sm = 65536;
+  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) { sms = pr.multiProcessorCount; smem_sm = pr.sharedMemPerMultiprocessor; regs_sm = (size_t)pr.regsPerMultiprocessor; }
+  const int G = h->AC, wpe = 32 / G, epb_max = MSV_TPB / G, n = h->C.n_real;
+  int best = epb_max; long best_load = -1;
+  for (int epb = epb_max; epb >= wpe; epb -= wpe) {
+    const long blocks = (n + epb - 1) / epb;
+    const size_t smem_blk = (size_t)h->sm_words * epb * sizeof(float) + 1024;
+    long res = (long)(smem_sm / smem_blk);
+    const long by_regs = (long)(regs_sm / (128 * (size_t)epb * G));
+    if (by_regs < res) res = by_regs;
+    if (res > 32) res = 32;
+    if (res < 1) continue;
+    const long per_sm = (blocks + sms - 1) / sms;
+    if (per_sm > res) continue;                    // would need a second wave
+    (void)best_load;
+    best = epb; break;                             // the largest tile that still runs as a single wave (measured, 2v2 16 384 envs,
+  }                                                // stationary mix: 64 envs/block 222 us, 56: 225, 40: 247, 32: 271, 16: 314 -- the
+                                                   // warps of a block share the instruction stream, so bigger tiles win over a balanced grid)
+  if (const char* ov = getenv("MSV_EPB")) { int v = atoi(ov); if (v >= wpe && v <= epb_max && v % wpe == 0) best = v; }
+  h->C.epb = best;
+  h->C.N = (n + best - 1) / best * best;
 }
 
 template <typename T> static int dalloc(msv_handle* h, T** p, size_t count) {
@@ -343,7 +371,8 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   build_const(cfg, num_envs, seed, env_offset, &h->C);
   h->cap = (cfg->n_agents <= 2 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 0
          : (cfg->n_agents <= 4 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 1 : 2;
-  msv_capacity(h->cap, &h->AC, &h->BC, &h->HC, &h->P, &h->PW);
+  msv_capacity(h->cap, &h->AC, &h->BC, &h->HC, &h->P, &h->PW, &h->sm_words);
+  plan_blocks(h, device);
   if (msv_launch(h->cap, 3, h->C, h->S, h->O, nullptr, 0) != cudaSuccess) {
     g_err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; delete h; return MSV_ERR_CUDA;
   }
@@ -963,7 +992,7 @@ int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }
 
 /* debug: enable / read the per-phase cycle profile of k_step (not part of
  * the stable ABI; used by tests/gpu_quickbench.py) */
-int msv_debug_profile(msv_handle* h, int enable, unsigned long long out[32]) {
+int msv_debug_profile(msv_handle* h, int enable, unsigned long long out[64]) {
   if (!h) return MSV_ERR_INVALID;
   DevGuard g(h->device); CK(cudaDeviceSynchronize());
   if (out) CK(msv_read_profile(out, 1));

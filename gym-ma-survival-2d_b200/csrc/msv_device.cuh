@@ -358,6 +358,14 @@ DEV f2 point_at(f2 c0, f2 c, float beta) { return vadd(vmul(1.0f - beta, c0), vm
 
 #ifdef MSV_PROFILE
 __device__ unsigned long long g_dbg[8];
+// rare-path census: [2k] number of calls, [2k+1] clock64() cycles spent in them (k: 0 generic island solve,
+// 1 TOI event, 2 reset, 3 deaths, 4 pickups, 5 use/give, 6 contact numbering, 7 box removal)
+__device__ unsigned long long g_cnt[16];
+#define RARE_BEGIN() long long rare_t0_ = clock64()
+#define RARE_END(k) do { atomicAdd(&g_cnt[2 * (k)], 1ull); atomicAdd(&g_cnt[2 * (k) + 1], (unsigned long long)(clock64() - rare_t0_)); } while (0)
+#else
+#define RARE_BEGIN() do { } while (0)
+#define RARE_END(k) do { } while (0)
 #endif
 // b2TimeOfImpact(proxyA = box, proxyB = circle centre), tMax = 1
 struct ToiOut { int state; float t; };

@@ -26,7 +26,10 @@ enum { F_CX, F_CY, F_A, F_VX, F_VY, F_W, F_C0X, F_C0Y, F_A0, F_ALPHA0, F_SLEEP,
 // shared-memory box fields
 enum { G_X, G_Y, G_HX, G_HY, G_AX, G_AY, G_ROT, G_F0, G_F1, G_F2, G_F3, G_COUNT };   // G_F*: fat AABB (b2DynamicTree proxy)
 // shared-memory touching-contact fields (a b2Contact with a one-point manifold)
-enum { K_META, K_SEQ, K_MTYPE, K_LNX, K_LNY, K_LPX, K_LPY, K_NI, K_TI, K_COUNT };
+enum { K_META, K_SEQ, K_MTYPE, K_LNX, K_LNY, K_LPX, K_LPY, K_NI, K_TI, K_NM, K_TM, K_COUNT };
+// the same words while solve_island() works on a contact (its list entry is dead once the island order is fixed):
+// world normal, plane point (static body A) or rA (agent-agent), rB, effective masses
+enum { KS_NX = K_SEQ, KS_NY = K_MTYPE, KS_PX = K_LNX, KS_PY = K_LNY, KS_RBX = K_LPX, KS_RBY = K_LPY };
 
 #define FL_ALIVE 1
 #define FL_AWAKE 2
@@ -71,9 +74,6 @@ struct BodyS { f2 c; float a; f2 v; float w; float invM, invI; };
 // the block's dynamic shared memory (addressed as shared, not through a generic pointer)
 extern __shared__ float msv_sm[];
 
-#ifndef MSV_SOLVE_SYNC
-#define MSV_SOLVE_SYNC() do { } while (0)
-#endif
 
 template <int AC, int BC, int HC, int G>
 struct Env {
@@ -95,17 +95,18 @@ struct Env {
   static constexpr int W_ITEM = W_MISC + 2, W_HEAL = W_ITEM + 2 * BC;   // floor item / heal positions (x then y)
   static constexpr int W_LEAD = W_HEAL + 2 * HC;
   static constexpr int W_TOI = W_LEAD + L_COUNT;          // cached TOI per (agent, static body)
-  static constexpr int SM_WORDS = W_TOI + AC * (BC + 4);
+  static constexpr int SM_USED = W_TOI + AC * (BC + 4);
+  // Shared memory is environment-major: word w of environment slot s sits at msv_sm[s * SM_WORDS + w].
+  // SM_WORDS == G (mod 32): the G lanes of a group (same slot, words of G different agents) and the
+  // 32/G slots of a warp then fall into 32 different banks, whatever the block size.
+  static constexpr int SM_WORDS = SM_USED + ((G - SM_USED % 32) + 32) % 32;
   static constexpr int NR = 3;                       // contacts of a one-agent island kept in registers
   static_assert(AC % G == 0 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two dividing AC");
 
   const DevConst& C;
   const DevState& S;
-  static constexpr int EPB = MSV_TPB / G;  // environment slots per block
-  // shared-memory word stride: EPB + 32/G, so that the G lanes of a group (same slot, words of
-  // different agents) and the 32/G slots of a warp fall into 32 different banks
-  static constexpr int T = EPB + 32 / G;
-  int es, g, e, N;        // es: my slot; g: my lane in the group
+  int es, g, e, N;        // es: my slot in the block (blockDim.x / G slots); g: my lane in the group
+  int sb;                 // es * SM_WORDS: base of my environment's shared-memory column
   unsigned gmask;         // the group's lanes within the warp
   bool lead;              // g == 0
 
@@ -116,7 +117,7 @@ struct Env {
   int ntc;
 
   __device__ __forceinline__ Env(const DevConst& c, const DevState& s, int es_, int g_, unsigned gmask_, int e_)
-      : C(c), S(s), es(es_), g(g_), e(e_), N(c.N), gmask(gmask_), lead(g_ == 0) {
+      : C(c), S(s), es(es_), g(g_), e(e_), N(c.N), sb(es_ * SM_WORDS), gmask(gmask_), lead(g_ == 0) {
 #pragma unroll
     for (int w = 0; w < PW; ++w) own[w] = 0ull;
     for (int i = g; i < AC; i += G) {
@@ -164,20 +165,20 @@ struct Env {
 #define MSV_COLD(call) do { Env c_(*this); c_.call; take(c_); } while (0)
 
   // ---- shared-memory accessors
-  DEV float& AG(int f, int i) { return msv_sm[(f * AC + i) * T + es]; }
-  DEV int& AGF(int i) { return reinterpret_cast<int*>(msv_sm)[(F_FLAGS * AC + i) * T + es]; }
-  DEV float& BX(int f, int k) { return msv_sm[(W_BOX + f * BC + k) * T + es]; }
-  DEV int& BXROT(int k) { return reinterpret_cast<int*>(msv_sm)[(W_BOX + G_ROT * BC + k) * T + es]; }
-  DEV float& KF(int f, int k) { return msv_sm[(W_TC + f * MAXC + k) * T + es]; }
-  DEV int& KI(int f, int k) { return reinterpret_cast<int*>(msv_sm)[(W_TC + f * MAXC + k) * T + es]; }
-  DEV int& NTC() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 0) * T + es]; }
-  DEV float& ITP(int c, int k) { return msv_sm[(W_ITEM + c * BC + k) * T + es]; }
-  DEV float& HLP(int c, int k) { return msv_sm[(W_HEAL + c * HC + k) * T + es]; }
-  DEV int& LI(int k) { return reinterpret_cast<int*>(msv_sm)[(W_LEAD + k) * T + es]; }
-  DEV unsigned& LU(int k) { return reinterpret_cast<unsigned*>(msv_sm)[(W_LEAD + k) * T + es]; }
-  DEV float& LF(int k) { return msv_sm[(W_LEAD + k) * T + es]; }
-  DEV float& TOIA(int i, int k) { return msv_sm[(W_TOI + i * (BC + 4) + k) * T + es]; }
-  DEV int& OVF() { return reinterpret_cast<int*>(msv_sm)[(W_MISC + 1) * T + es]; }
+  DEV float& AG(int f, int i) { return msv_sm[sb + (f * AC + i)]; }
+  DEV int& AGF(int i) { return reinterpret_cast<int*>(msv_sm)[sb + (F_FLAGS * AC + i)]; }
+  DEV float& BX(int f, int k) { return msv_sm[sb + (W_BOX + f * BC + k)]; }
+  DEV int& BXROT(int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_BOX + G_ROT * BC + k)]; }
+  DEV float& KF(int f, int k) { return msv_sm[sb + (W_TC + f * MAXC + k)]; }
+  DEV int& KI(int f, int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_TC + f * MAXC + k)]; }
+  DEV int& NTC() { return reinterpret_cast<int*>(msv_sm)[sb + (W_MISC + 0)]; }
+  DEV float& ITP(int c, int k) { return msv_sm[sb + (W_ITEM + c * BC + k)]; }
+  DEV float& HLP(int c, int k) { return msv_sm[sb + (W_HEAL + c * HC + k)]; }
+  DEV int& LI(int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_LEAD + k)]; }
+  DEV unsigned& LU(int k) { return reinterpret_cast<unsigned*>(msv_sm)[sb + (W_LEAD + k)]; }
+  DEV float& LF(int k) { return msv_sm[sb + (W_LEAD + k)]; }
+  DEV float& TOIA(int i, int k) { return msv_sm[sb + (W_TOI + i * (BC + 4) + k)]; }
+  DEV int& OVF() { return reinterpret_cast<int*>(msv_sm)[sb + (W_MISC + 1)]; }
   DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
   DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
   DEV f2 apos(int i) { return mk2(AG(F_CX, i), AG(F_CY, i)); }
@@ -259,6 +260,30 @@ struct Env {
     ntc = 0;
     gsync();
     share_counts(); share_bits();
+    prefetch_cold();
+  }
+  // The cold per-pair / per-body words (contact sequence numbers, warm-start impulses, creation
+  // sequences, zone centres) are read in the middle of the step, one dependent load at a time; ask
+  // L2 for them now so that those loads do not wait for HBM.
+  DEV static void pf(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+  DEV void prefetch_cold() {
+#ifndef MSV_NO_PREFETCH
+#pragma unroll
+    for (int w = 0; w < PW; ++w) {
+      unsigned long long m = ex[w] & own[w];
+      while (m) {
+        int p = w * 64 + __ffsll((long long)m) - 1; m &= m - 1;
+        pf(&S.pseq[p * N + e]); pf(&S.pimp[p * N + e]);
+      }
+    }
+    for (int k = g; k < nb; k += G) pf(&S.boxseq[k * N + e]);
+    for (int k = g; k < ni; k += G) pf(&S.item1[k * N + e]);
+    for (int k = g; k < nh; k += G) pf(&S.healseq[k * N + e]);
+    if (lead) {
+      const int ph = LI(L_ZPHASE);
+      pf(&S.zonec[ph * N + e]); pf(&S.zonec[(ph + 1 < MSV_MAX_ZONES ? ph + 1 : ph) * N + e]);
+    }
+#endif
   }
   // read box at global slot `src` into shared slot `dst`
   DEV void load_box(int dst, int src) {
@@ -518,7 +543,7 @@ struct Env {
 #pragma unroll
     for (int w = 0; w < PW; ++w) { cand[w] = or64(cand[w]); any |= cand[w] != 0ull; }
     if (any) {                               // group-uniform
-      if (lead) { unsigned long long cc[PW]; for (int w = 0; w < PW; ++w) cc[w] = cand[w]; MSV_COLD(number_candidates(cc)); }
+      if (lead) { RARE_BEGIN(); unsigned long long cc[PW]; for (int w = 0; w < PW; ++w) cc[w] = cand[w]; MSV_COLD(number_candidates(cc)); RARE_END(6); }
       share_bits();
     }
   }
@@ -895,158 +920,222 @@ struct Env {
     else island_single<BC + 4>(i, cnt, ord, h, dtRatio);
   }
 
-  // b2World::Solve: islands by DFS over touching contacts, seeds in body-list
-  // order (newest body first = highest agent index first), contact edges
-  // newest first; each island solved by b2Island::Solve.  Islands touch
-  // disjoint bodies, so all islands are built first and then advanced
-  // together (per-island contact order, position-iteration early-out and sleep
-  // decision are kept).  [leader] generic version, used when some agent touches
-  // another agent; works on a private copy of the shared contact list.
-  __device__ __noinline__ void solve_generic(float h, float dtRatio, unsigned members) {
-    TCon tcs[MAXC];
-    for (int k = 0; k < ntc; ++k) {
-      TCon& t = tcs[k];
-      meta_unpack(KI(K_META, k), t.p, t.a, t.sid, t.b);
-      if (t.a >= 0) t.sid = -1;
-      t.seq = KI(K_SEQ, k); t.flags = 0; t.m.type = KI(K_MTYPE, k);
-      t.m.localNormal = mk2(KF(K_LNX, k), KF(K_LNY, k)); t.m.localPoint = mk2(KF(K_LPX, k), KF(K_LPY, k));
-      t.ni = KF(K_NI, k); t.ti = KF(K_TI, k);
-    }
-    int stack[AC], isl_of[AC];
-    unsigned char order[MAXC], cisl[MAXC];
-    int nisl = 0, nc = 0;
-    unsigned multi = 0;                        // islands that contain an agent-agent contact
-    unsigned inisl = 0;                        // agents this call put into an island (others belong to their lanes)
-    for (int seed = C.A - 1; seed >= 0; --seed) {
-      if (!((members >> seed) & 1u)) continue;
-      int fs = AGF(seed);
-      if (!(fs & FL_ALIVE) || (fs & FL_ISLAND) || !(fs & FL_AWAKE)) continue;
-      int sc = 0;
-      stack[sc++] = seed; AGF(seed) |= FL_ISLAND; inisl |= 1u << seed;
+  // b2World::Solve for ONE island that contains agent-agent contacts, executed by the lane of the
+  // island's seed (the highest-index awake agent of the component: Box2D seeds in body-list order,
+  // newest body first): DFS over touching contacts, contact edges newest first, then
+  // b2Island::Solve.  Everything lives in the environment's shared-memory column -- body state in
+  // the agent fields, solver constants and impulses in the island's own contact-list entries
+  // (KS_*) -- so several islands of one environment are solved concurrently by different lanes and
+  // nothing goes through local memory.  Contacts against static bodies use the routines that drop
+  // the exact no-ops of a massless body A (same arithmetic as the two-body form).
+  struct Ord { unsigned long long lo, hi; };   // island contact order: list slots, 5 bits each
+  DEV static int ord_get(const Ord& o, int k) { return k < 12 ? (int)((o.lo >> (5 * k)) & 31ull) : (int)((o.hi >> (5 * (k - 12))) & 31ull); }
+  DEV static void ord_put(Ord& o, int k, int v) { if (k < 12) o.lo |= (unsigned long long)v << (5 * k); else o.hi |= (unsigned long long)v << (5 * (k - 12)); }
+  __device__ __noinline__ void solve_island(int seed, float h, float dtRatio) {
+    Ord ord; ord.lo = 0ull; ord.hi = 0ull;
+    int nc = 0; unsigned taken = 0, inisl = 1u << seed;
+    {
+      unsigned stack = (unsigned)seed; int sc = 1;    // agent indices, 4 bits each
+      AGF(seed) |= FL_ISLAND;
       while (sc > 0) {
-        int bI = stack[--sc];
-        isl_of[bI] = nisl;
+        --sc;
+        const int bI = (int)((stack >> (4 * sc)) & 15u);
         wake(bI);
-        if (ntc == 0) continue;
         for (;;) {  // contact edges of bI, newest (largest seq) first
-          int best = -1, bestSeq = -1;
+          int best = -1, bestSeq = -1, bestMeta = 0;
           for (int k = 0; k < ntc; ++k) {
-            const TCon& t = tcs[k];
-            if (t.flags & 1) continue;
-            if (t.a != bI && t.b != bI) continue;
-            if (!bit(en, t.p) || !bit(tc, t.p)) continue;
-            if (t.seq > bestSeq) { bestSeq = t.seq; best = k; }
+            if ((taken >> k) & 1u) continue;
+            const int meta = KI(K_META, k);
+            int p, a_, sid, b_; meta_unpack(meta, p, a_, sid, b_);
+            if (a_ != bI && b_ != bI) continue;
+            if (!bit(en, p) || !bit(tc, p)) continue;
+            const int sq = KI(K_SEQ, k);
+            if (sq > bestSeq) { bestSeq = sq; best = k; bestMeta = meta; }
           }
           if (best < 0) break;
-          tcs[best].flags |= 1;
-          order[nc] = (unsigned char)best; cisl[nc] = (unsigned char)nisl; nc++;
-          const TCon& t = tcs[best];
-          if (t.a >= 0) {
-            multi |= 1u << nisl;
-            int other = t.a == bI ? t.b : t.a;
-            if (!(AGF(other) & FL_ISLAND)) { stack[sc++] = other; AGF(other) |= FL_ISLAND; inisl |= 1u << other; }
+          taken |= 1u << best;
+          ord_put(ord, nc, best); nc++;
+          int p, a_, sid, b_; meta_unpack(bestMeta, p, a_, sid, b_);
+          if (a_ >= 0) {
+            const int other = a_ == bI ? b_ : a_;
+            if (!(AGF(other) & FL_ISLAND)) {
+              stack = (stack & ~(15u << (4 * sc))) | ((unsigned)other << (4 * sc)); sc++;
+              AGF(other) |= FL_ISLAND; inisl |= 1u << other;
+            }
           }
         }
       }
-      nisl++;
     }
-    // ---- b2Island::Solve, all islands
+    // ---- b2Island::Solve
     for (int i = 0; i < C.A; ++i) {
       if (!((inisl >> i) & 1u)) continue;
       AG(F_C0X, i) = AG(F_CX, i); AG(F_C0Y, i) = AG(F_CY, i); AG(F_A0, i) = AG(F_A, i);
       AG(F_VX, i) = C.damp * AG(F_VX, i); AG(F_VY, i) = C.damp * AG(F_VY, i);  // v *= 1/(1+h*damping)
       AG(F_W, i) *= C.damp;
     }
-    unsigned solved = 0;                       // per-island positionSolved
-    const unsigned all_isl = nisl >= 32 ? 0xFFFFFFFFu : ((1u << nisl) - 1u);
-    if (nc > 0) {
-      for (int k = 0; k < nc; ++k) { TCon& t = tcs[order[k]]; t.ni = dtRatio * t.ni; t.ti = dtRatio * t.ti; }
-      for (int k = 0; k < nc; ++k) init_velocity(tcs[order[k]]);
-      for (int k0 = 0; k0 < nc;) {             // one island = one contiguous run of `order`
-        const int j = cisl[k0]; int k1 = k0;
-        while (k1 < nc && cisl[k1] == j) ++k1;
-        if ((multi >> j) & 1u) {               // agents touching agents: generic two-body updates
-          for (int k = k0; k < k1; ++k) warm_start(tcs[order[k]]);
-          for (int it = 0; it < 10; ++it)
-            for (int k = k0; k < k1; ++k) solve_velocity(tcs[order[k]]);
-        } else {                               // one agent against static bodies: state in registers
-          const int i = tcs[order[k0]].b;
-          f2 vB = mk2(AG(F_VX, i), AG(F_VY, i)); float wB = AG(F_W, i);
-          for (int k = k0; k < k1; ++k) { TCon& t = tcs[order[k]]; warm_start_static(t.normal, t.rB, t.ni, t.ti, vB, wB); }
-          for (int it = 0; it < 10; ++it)
-            for (int k = k0; k < k1; ++k) { TCon& t = tcs[order[k]]; solve_velocity_static(t.normal, t.rB, t.normalMass, t.tangentMass, t.ni, t.ti, vB, wB); }
-          AG(F_VX, i) = vB.x; AG(F_VY, i) = vB.y; AG(F_W, i) = wB;
-        }
-        k0 = k1;
+    // b2ContactSolver::InitializeVelocityConstraints (+ the warm-start scaling of b2ContactSolver's constructor)
+    for (int k = 0; k < nc; ++k) {
+      const int s = ord_get(ord, k);
+      int p, a_, sid, b_; meta_unpack(KI(K_META, s), p, a_, sid, b_);
+      const f2 ln = mk2(KF(K_LNX, s), KF(K_LNY, s)), lp = mk2(KF(K_LPX, s), KF(K_LPY, s));
+      KF(K_NI, s) = dtRatio * KF(K_NI, s); KF(K_TI, s) = dtRatio * KF(K_TI, s);
+      f2 normal, px, rB; float nm, tm;
+      if (a_ >= 0) {   // two dynamic circles (b2WorldManifold::Initialize, e_circles)
+        const f2 cA = apos(a_), cB = apos(b_);
+        normal = mk2(1.0f, 0.0f);
+        if (vlen2(vsub(cA, cB)) > B2_EPS * B2_EPS) { normal = vsub(cB, cA); vnormalize(normal); }
+        const f2 pA = vadd(cA, vmul(C.agent_r, normal)), pB = vsub(cB, vmul(C.agent_r, normal));
+        const f2 point = vmul(0.5f, vadd(pA, pB));
+        px = vsub(point, cA); rB = vsub(point, cB);                      // px := rA
+        const float rnA = vcross(px, normal), rnB = vcross(rB, normal);
+        const float kNormal = C.inv_mass + C.inv_mass + C.inv_I * rnA * rnA + C.inv_I * rnB * rnB;
+        nm = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+        const f2 tangent = cross_vs(normal, 1.0f);
+        const float rtA = vcross(px, tangent), rtB = vcross(rB, tangent);
+        const float kTangent = C.inv_mass + C.inv_mass + C.inv_I * rtA * rtA + C.inv_I * rtB * rtB;
+        tm = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+      } else {
+        init_velocity_static(sid, ln, lp, apos(b_), normal, px, rB, nm, tm);   // px := plane point
       }
-      for (int k = 0; k < nc; ++k) { const TCon& t = tcs[order[k]]; S.pimp[t.p * N + e] = make_float2(t.ni, t.ti); }
+      KF(KS_NX, s) = normal.x; KF(KS_NY, s) = normal.y; KF(KS_PX, s) = px.x; KF(KS_PY, s) = px.y;
+      KF(KS_RBX, s) = rB.x; KF(KS_RBY, s) = rB.y; KF(K_NM, s) = nm; KF(K_TM, s) = tm;
+    }
+    // warm start, then 10 velocity iterations, contacts in island order
+    for (int it = -1; it < 10; ++it) {
+      for (int k = 0; k < nc; ++k) {
+        const int s = ord_get(ord, k);
+        int p, a_, sid, b_; meta_unpack(KI(K_META, s), p, a_, sid, b_);
+        const f2 normal = mk2(KF(KS_NX, s), KF(KS_NY, s)), rB = mk2(KF(KS_RBX, s), KF(KS_RBY, s));
+        float ni_ = KF(K_NI, s), ti_ = KF(K_TI, s);
+        f2 vB = mk2(AG(F_VX, b_), AG(F_VY, b_)); float wB = AG(F_W, b_);
+        if (a_ < 0) {
+          if (it < 0) warm_start_static(normal, rB, ni_, ti_, vB, wB);
+          else solve_velocity_static(normal, rB, KF(K_NM, s), KF(K_TM, s), ni_, ti_, vB, wB);
+        } else {
+          const f2 rA = mk2(KF(KS_PX, s), KF(KS_PY, s)), tangent = cross_vs(normal, 1.0f);
+          f2 vA = mk2(AG(F_VX, a_), AG(F_VY, a_)); float wA = AG(F_W, a_);
+          const float mA = C.inv_mass, iA = C.inv_I, mB = C.inv_mass, iB = C.inv_I;
+          if (it < 0) {   // b2ContactSolver::WarmStart
+            const f2 Pv = vadd(vmul(ni_, normal), vmul(ti_, tangent));
+            wA -= iA * vcross(rA, Pv); vA = vsub(vA, vmul(mA, Pv));
+            wB += iB * vcross(rB, Pv); vB = vadd(vB, vmul(mB, Pv));
+          } else {        // b2ContactSolver::SolveVelocityConstraints: friction, then the normal constraint
+            {
+              const f2 dv = vsub(vsub(vadd(vB, cross_sv(wB, rB)), vA), cross_sv(wA, rA));
+              const float vt = vdot(dv, tangent) - 0.0f;
+              float lambda = KF(K_TM, s) * (-vt);
+              const float maxFriction = C.friction * ni_;
+              const float newImpulse = fclamp_(ti_ + lambda, -maxFriction, maxFriction);
+              lambda = newImpulse - ti_; ti_ = newImpulse;
+              const f2 Pv = vmul(lambda, tangent);
+              vA = vsub(vA, vmul(mA, Pv)); wA -= iA * vcross(rA, Pv);
+              vB = vadd(vB, vmul(mB, Pv)); wB += iB * vcross(rB, Pv);
+            }
+            {
+              const f2 dv = vsub(vsub(vadd(vB, cross_sv(wB, rB)), vA), cross_sv(wA, rA));
+              const float vn = vdot(dv, normal);
+              float lambda = -KF(K_NM, s) * (vn - 0.0f);
+              const float newImpulse = fmax_(ni_ + lambda, 0.0f);
+              lambda = newImpulse - ni_; ni_ = newImpulse;
+              const f2 Pv = vmul(lambda, normal);
+              vA = vsub(vA, vmul(mA, Pv)); wA -= iA * vcross(rA, Pv);
+              vB = vadd(vB, vmul(mB, Pv)); wB += iB * vcross(rB, Pv);
+            }
+          }
+          AG(F_VX, a_) = vA.x; AG(F_VY, a_) = vA.y; AG(F_W, a_) = wA;
+        }
+        AG(F_VX, b_) = vB.x; AG(F_VY, b_) = vB.y; AG(F_W, b_) = wB;
+        KF(K_NI, s) = ni_; KF(K_TI, s) = ti_;
+      }
+    }
+    for (int k = 0; k < nc; ++k) {   // b2ContactSolver::StoreImpulses
+      const int s = ord_get(ord, k);
+      S.pimp[(KI(K_META, s) & 255) * N + e] = make_float2(KF(K_NI, s), KF(K_TI, s));
     }
     for (int i = 0; i < C.A; ++i) if ((inisl >> i) & 1u) integrate_position(i, h);
-    solved = all_isl;
-    for (int k0 = 0; k0 < nc;) {
-      const int j = cisl[k0]; int k1 = k0;
-      while (k1 < nc && cisl[k1] == j) ++k1;
-      bool ok = false;
-      if ((multi >> j) & 1u) {
-        for (int it = 0; it < 10 && !ok; ++it) {
-          float minSep = 0.0f;
-          for (int k = k0; k < k1; ++k) minSep = fmin_(minSep, solve_position(tcs[order[k]], false, -1));
-          ok = minSep >= -3.0f * B2_LINEAR_SLOP;
+    bool ok = false;
+    for (int it = 0; it < 10 && !ok; ++it) {   // b2ContactSolver::SolvePositionConstraints
+      float minSep = 0.0f;
+      for (int k = 0; k < nc; ++k) {
+        const int s = ord_get(ord, k);
+        int p, a_, sid, b_; meta_unpack(KI(K_META, s), p, a_, sid, b_);
+        f2 cB = apos(b_);
+        float separation;
+        if (a_ < 0) {
+          separation = solve_position_static(mk2(KF(KS_NX, s), KF(KS_NY, s)), mk2(KF(KS_PX, s), KF(KS_PY, s)), cB, false);
+        } else {       // circles: the manifold point is the midpoint, normal along the centres
+          f2 cA = apos(a_); float aA = AG(F_A, a_), aB = AG(F_A, b_);
+          const float mA = C.inv_mass, iA = C.inv_I, mB = C.inv_mass, iB = C.inv_I;
+          f2 normal = vsub(cB, cA); vnormalize(normal);
+          const f2 point = vmul(0.5f, vadd(cA, cB));
+          separation = vdot(vsub(cB, cA), normal) - C.agent_r - C.agent_r;
+          const f2 rA = vsub(point, cA), rB = vsub(point, cB);
+          const float Cc = fclamp_(B2_BAUMGARTE * (separation + B2_LINEAR_SLOP), -B2_MAX_LIN_CORR, 0.0f);
+          const float rnA = vcross(rA, normal), rnB = vcross(rB, normal);
+          const float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+          const float impulse = K > 0.0f ? -Cc / K : 0.0f;
+          const f2 Pv = vmul(impulse, normal);
+          cA = vsub(cA, vmul(mA, Pv)); aA -= iA * vcross(rA, Pv);
+          cB = vadd(cB, vmul(mB, Pv)); aB += iB * vcross(rB, Pv);
+          AG(F_CX, a_) = cA.x; AG(F_CY, a_) = cA.y; AG(F_A, a_) = aA; AG(F_A, b_) = aB;
         }
-      } else {
-        const int i = tcs[order[k0]].b;
-        f2 cB = apos(i);
-        for (int k = k0; k < k1; ++k) { TCon& t = tcs[order[k]]; static_plane(t, t.normal, t.rA); }  // rA := plane point
-        for (int it = 0; it < 10 && !ok; ++it) {
-          float minSep = 0.0f;
-          for (int k = k0; k < k1; ++k) { const TCon& t = tcs[order[k]]; minSep = fmin_(minSep, solve_position_static(t.normal, t.rA, cB, false)); }
-          ok = minSep >= -3.0f * B2_LINEAR_SLOP;
-        }
-        AG(F_CX, i) = cB.x; AG(F_CY, i) = cB.y;
+        AG(F_CX, b_) = cB.x; AG(F_CY, b_) = cB.y;
+        minSep = fmin_(minSep, separation);
       }
-      if (!ok) solved &= ~(1u << j);
-      k0 = k1;
+      ok = minSep >= -3.0f * B2_LINEAR_SLOP;
     }
     {
       const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
-      unsigned can_sleep = solved;             // islands with minSleepTime >= timeToSleep && positionSolved
+      bool can_sleep = ok;                       // minSleepTime >= timeToSleep && positionSolved
       for (int i = 0; i < C.A; ++i) {
         if (!((inisl >> i) & 1u)) continue;
         float w = AG(F_W, i); f2 v = mk2(AG(F_VX, i), AG(F_VY, i));
         float st;
         if (w * w > angTol || vdot(v, v) > linTol) st = 0.0f; else st = AG(F_SLEEP, i) + h;
         AG(F_SLEEP, i) = st;
-        if (!(st >= B2_TIME_TO_SLEEP)) can_sleep &= ~(1u << isl_of[i]);
+        if (!(st >= B2_TIME_TO_SLEEP)) can_sleep = false;
       }
       if (can_sleep)
-        for (int i = 0; i < C.A; ++i)
-          if (((inisl >> i) & 1u) && ((can_sleep >> isl_of[i]) & 1u)) sleep_body(i);
+        for (int i = 0; i < C.A; ++i) if ((inisl >> i) & 1u) sleep_body(i);
     }
     for (int i = 0; i < C.A; ++i)
       if ((inisl >> i) & 1u) synchronize_fixtures(i);
   }
 
   // b2World::Solve                                                   [all lanes]
+  // Agents with a touching, enabled agent-agent contact form islands of several bodies: each such
+  // island is solved by the lane of its seed agent (solve_island); every other awake agent is an
+  // island of its own, solved by its lane (solve_single).
   __device__ __forceinline__ void solve(float h, float dtRatio) {
-    for (int i = g; i < C.A; i += G) AGF(i) &= ~(FL_ISLAND | FL_MOVED);
-    // agents with a touching, enabled agent-agent contact: their islands go to the leader's
-    // generic solver; every other awake agent is an island of its own, solved by its lane
-    unsigned multi = 0;
-    {
-      unsigned long long m = tc[0] & en[0]; if (NAA < 64) m &= (1ull << NAA) - 1ull;
-      while (m) {
-        int p = __ffsll((long long)m) - 1; m &= m - 1;
-        int a, sid, b; decode(p, a, sid, b);
-        multi |= (1u << a) | (1u << b);
+    unsigned awk = 0;
+    for (int i = g; i < C.A; i += G) { AGF(i) &= ~(FL_ISLAND | FL_MOVED); if ((AGF(i) & (FL_ALIVE | FL_AWAKE)) == (FL_ALIVE | FL_AWAKE)) awk |= 1u << i; }
+    unsigned long long aa = tc[0] & en[0]; if (NAA < 64) aa &= (1ull << NAA) - 1ull;   // touching agent-agent pairs
+    awk = or32(awk);                           // one consistent snapshot of the awake flags (islands wake bodies)
+    gsync();
+    for (int i = g; i < C.A; i += G) {
+      if (aa == 0ull) { solve_single(i, h, dtRatio); continue; }    // group-uniform: nobody touches another agent
+      // connected component of agent i over the touching agent-agent contacts
+      unsigned comp = 1u << i;
+      for (int it = 0; it < AC; ++it) {
+        unsigned grown = comp;
+        for (int j = 0; j < C.A; ++j) {
+          if (!((comp >> j) & 1u)) continue;
+          for (int a = 0; a < j; ++a) if ((aa >> p_aa(a, j)) & 1ull) grown |= 1u << a;
+          for (int b = j + 1; b < C.A; ++b) if ((aa >> p_aa(j, b)) & 1ull) grown |= 1u << b;
+        }
+        if (grown == comp) break;
+        comp = grown;
       }
+      if (comp == (1u << i)) { solve_single(i, h, dtRatio); continue; }
+      const unsigned cand = comp & awk;          // no awake member: the island is not simulated
+      if (cand != 0u && (31 - __clz((int)cand)) == i) { RARE_BEGIN(); MSV_COLD(solve_island(i, h, dtRatio)); RARE_END(0); }
     }
     gsync();
-    if (multi && lead) MSV_COLD(solve_generic(h, dtRatio, multi));
-    for (int i = g; i < C.A; i += G) if (!((multi >> i) & 1u)) solve_single(i, h, dtRatio);
-    gsync();
+  }
+  // b2ContactManager::FindNewContacts after the solve (the kernel puts a phase barrier in between)
+  __device__ __forceinline__ void solve_find_new() {
     unsigned mv = 0;
     for (int i = g; i < C.A; i += G) if (AGF(i) & FL_MOVED) mv = 1u;
-    MSV_SOLVE_SYNC();
     if (or32(mv)) find_new_contacts(true);
   }
 
@@ -1234,7 +1323,7 @@ struct Env {
       }
       gsync();
       int r = 0;
-      if (lead) { Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prev, prevP); take(c_); }
+      if (lead) { RARE_BEGIN(); Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prev, prevP); take(c_); RARE_END(1); }
       gsync();
       r = bc(r);
       share_bits();
@@ -1291,7 +1380,7 @@ struct Env {
     bool any = LI(L_NP) > 0;                       // nothing to do unless a drop is pending or an agent with items uses/gives
 #pragma unroll
     for (int i = 0; i < AC; ++i) if (i < C.A && (((act >> (8 + i)) | (act >> (16 + i))) & 1u) && (LI(L_INV + (i)) & 7) != 0 && alive(i)) any = true;
-    if (any) MSV_COLD(pre_use_give_body(act));
+    if (any) { RARE_BEGIN(); MSV_COLD(pre_use_give_body(act)); RARE_END(5); }
   }
   __device__ __noinline__ void pre_use_give_body(unsigned act) {
     // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
@@ -1507,7 +1596,7 @@ struct Env {
           S.pend1[LI(L_NP) * N + e] = C.box_ownership ? b1.z : MSV_CAUSE_NONE;
           LI(L_NP)++;
         } else LI(L_OVERFLOW)++;
-        MSV_COLD(remove_box(k));
+        { RARE_BEGIN(); MSV_COLD(remove_box(k)); RARE_END(7); }
       } else ++k;
     }
   }
@@ -1574,7 +1663,7 @@ struct Env {
       LU(L_DMASK) = 0; LI(L_NKILLS) = 0;
 #pragma unroll
       for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && LI(L_HEALTH + (i)) <= 0) LU(L_DMASK) |= 1u << i;
-      if (LU(L_DMASK)) { MSV_COLD(handle_deaths()); dflag = 1; }
+      if (LU(L_DMASK)) { RARE_BEGIN(); MSV_COLD(handle_deaths()); dflag = 1; RARE_END(3); }
     }
     dflag = bc(dflag);
     if (dflag) { gsync(); share_counts(); }   // drops changed the lists, deaths the flags
@@ -1591,7 +1680,7 @@ struct Env {
     }
     near = or32(near);
     if (!lead) return;
-    for (int i = 0; i < C.A; ++i) if ((near >> i) & 1u) MSV_COLD(pickup_agent(i));
+    for (int i = 0; i < C.A; ++i) if ((near >> i) & 1u) { RARE_BEGIN(); MSV_COLD(pickup_agent(i)); RARE_END(4); }
     // agents/SafeZone.post_step (sem:758-768) + tick (sem:776-811)
     for (int i = 0; i < C.A; ++i) {
       if (!alive(i)) continue;
@@ -1731,8 +1820,9 @@ struct Env {
     }
     if (C.battle_royale) {   // BattleRoyale.post_step (sem:41-46): runs last, on the post-death body list
       int na = 0;
-      for (int i = 0; i < A; ++i) { const bool al = alive(i); na += al; O.br_results[(size_t)e * A + i] = al ? 1 : 0; }
+      for (int i = 0; i < A; ++i) na += alive(i);
       O.br_over[e] = na <= 1 ? 1 : 0;
+      for (int i = 0; i < A; ++i) O.br_results[(size_t)e * A + i] = (na <= 1 && alive(i)) ? 1 : 0;   // .results only exists once over
     }
     return done;
   }

@@ -11,18 +11,21 @@
 #ifndef MSV_SYNC_MASK
 #define MSV_SYNC_MASK 0x3FF
 #endif
-#define MSV_SOLVE_SYNC() do { if ((MSV_SYNC_MASK >> 9) & 1) __syncthreads(); } while (0)
 #endif
 #include "msv_env.cuh"
 #include "msv_launch.h"
 
 // debug phase profile (make PROFILE=1 + msv_debug_profile): sum over the
 // leader lanes of the clock64() cycles spent in each phase of k_step
-__device__ unsigned long long g_prof[32];   // [0..11] per-phase sums, [12] max total, [16+k] phases of the slowest group
+// [0..11] per-phase work sums, [12] max total, [13] its env, [16+k] phases of the slowest group,
+// [32+k] time spent waiting at phase barrier k (sum), [48+k] the slowest group's waits
+__device__ unsigned long long g_prof[64];
 #ifdef MSV_PROFILE
 #define PROF(k) do { if (C.profile) { long long _t = clock64(); ph[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
+#define PROFW(k) do { if (C.profile) { long long _t = clock64(); wt[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
 #else
 #define PROF(k) do { } while (0)
+#define PROFW(k) do { } while (0)
 #endif
 
 // thread -> (environment slot of the block, lane of the group)
@@ -34,11 +37,11 @@ __device__ unsigned long long g_prof[32];   // [0..11] per-phase sums, [12] max 
 #ifdef MSV_NO_PHASE_SYNC
 #define PHASE_SYNC(k) do { } while (0)
 #else
-#define PHASE_SYNC(k) do { if ((MSV_SYNC_MASK >> (k)) & 1) __syncthreads(); } while (0)
+#define PHASE_SYNC(k) do { if ((MSV_SYNC_MASK >> (k)) & 1) __syncthreads(); PROFW(k); } while (0)
 #endif
 #define MSV_GROUP_SETUP(G)                                                                       \
-  const int T = MSV_TPB / (G), es = threadIdx.x / (G), g = threadIdx.x % (G);                    \
-  const int e = blockIdx.x * T + es;  /* C.N is a multiple of MSV_TPB, hence of T */             \
+  const int es = threadIdx.x / (G), g = threadIdx.x % (G);                                       \
+  const int e = blockIdx.x * (blockDim.x / (G)) + es;  /* C.N >= gridDim.x * environments per block */ \
   const unsigned gmask = (((G) >= 32) ? 0xffffffffu : ((1u << (G)) - 1u)) << ((threadIdx.x & 31) & ~((G) - 1))
 
 template <int AC, int BC, int HC, int G>
@@ -52,6 +55,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   long long t_last = C.profile ? clock64() : 0;
   const long long t_begin = t_last;
   unsigned long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long wt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   env.load();
   const bool real = e < C.n_real;   // padding envs (N rounded up to the block size) get the no-op action
@@ -78,6 +82,9 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     const int first = env.bc(env.LI(env.L_FIRST));
     env.solve(C.dt, first ? 0.0f : C.dt_ratio1);
     PROF(4);
+    PHASE_SYNC(9);
+    env.solve_find_new();
+    PROF(2);
     PHASE_SYNC(3);
     env.solve_toi(C.dt);
     env.LI(env.L_FIRST) = 0;
@@ -98,7 +105,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     bool done = env.rewards_done(O);       // env:85-89
     if (done && C.auto_reset) {            // vector-env extension: the observation returned is the new episode's first
       env.LI(env.L_STEPISODES)++;
-      MSV_COLD_ON(env, reset());
+      { RARE_BEGIN(); MSV_COLD_ON(env, reset()); RARE_END(2); }
       again = 1;
     }
     env.store_immune(O);
@@ -112,11 +119,11 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   PROF(11);
 #ifdef MSV_PROFILE
   if (C.profile && env.lead) {
-    for (int k = 0; k < 12; ++k) atomicAdd(&g_prof[k], ph[k]);
+    for (int k = 0; k < 12; ++k) { atomicAdd(&g_prof[k], ph[k]); atomicAdd(&g_prof[32 + k], wt[k]); }
     unsigned long long tot = (unsigned long long)(clock64() - t_begin);
     unsigned long long prev = atomicMax(&g_prof[12], tot);
     if (tot > prev) {   // (racy, indicative) phase breakdown + identity of the slowest group so far
-      for (int k = 0; k < 12; ++k) g_prof[16 + k] = ph[k];
+      for (int k = 0; k < 12; ++k) { g_prof[16 + k] = ph[k]; g_prof[48 + k] = wt[k]; }
       g_prof[13] = (unsigned long long)e;
     }
   }
@@ -144,7 +151,7 @@ k_reset(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
     if (!only_done) {
       for (int i = 0; i < C.A; ++i) O.rewards[(size_t)e * C.A + i] = 0.0f;
       O.dones[e] = 0;
-      if (C.battle_royale) O.br_over[e] = 0;   // BattleRoyale.post_reset (sem:38-39)
+      if (C.battle_royale) { O.br_over[e] = 0; for (int i = 0; i < C.A; ++i) O.br_results[(size_t)e * C.A + i] = 0; }   // BattleRoyale.post_reset (sem:38-39)
     }
   }
   env.store();
@@ -370,19 +377,20 @@ __global__ void k_stats(int N, int stride, int AC, float* sreward, int* skills, 
 template <int AC, int BC, int HC, int G>
 static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, const DevOut& O,
                             const uint8_t* actions, cudaStream_t st) {
-  const int epb = MSV_TPB / G;                       // environments per block
-  const int blocks = C.N / epb;
-  size_t smem = (size_t)Env<AC, BC, HC, G>::SM_WORDS * Env<AC, BC, HC, G>::T * sizeof(float);
+  const int epb = C.epb;                             // environments per block (runtime: msv_plan_blocks)
+  const int blocks = C.N / epb, tpb = epb * G;
+  size_t smem = (size_t)Env<AC, BC, HC, G>::SM_WORDS * epb * sizeof(float);
+  const size_t smem_max = (size_t)Env<AC, BC, HC, G>::SM_WORDS * (MSV_TPB / G) * sizeof(float);
   if (which == 3) {  // one-time: allow the dynamic shared memory the kernels need
-    cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_observe<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_observe<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     return e;
   }
-  if (which == 0) k_step<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O, actions);
-  else if (which == 1) k_reset<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 0);
-  else if (which == 4) k_reset<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O, 1);
-  else k_observe<AC, BC, HC, G><<<blocks, MSV_TPB, smem, st>>>(C, S, O);
+  if (which == 0) k_step<AC, BC, HC, G><<<blocks, tpb, smem, st>>>(C, S, O, actions);
+  else if (which == 1) k_reset<AC, BC, HC, G><<<blocks, tpb, smem, st>>>(C, S, O, 0);
+  else if (which == 4) k_reset<AC, BC, HC, G><<<blocks, tpb, smem, st>>>(C, S, O, 1);
+  else k_observe<AC, BC, HC, G><<<blocks, tpb, smem, st>>>(C, S, O);
   return cudaPeekAtLastError();
 }
 
@@ -406,11 +414,11 @@ cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut&
   return cudaPeekAtLastError();
 }
 
-void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW) {
+void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW, int* sm_words) {
   switch (cap) {
-    case 0: *AC = 2; *BC = 4; *HC = 4; *P = PairLayout<2, 4>::P; *PW = PairLayout<2, 4>::PW; break;
-    case 1: *AC = 4; *BC = 4; *HC = 4; *P = PairLayout<4, 4>::P; *PW = PairLayout<4, 4>::PW; break;
-    default: *AC = 8; *BC = 8; *HC = 16; *P = PairLayout<8, 8>::P; *PW = PairLayout<8, 8>::PW; break;
+    case 0: *AC = 2; *BC = 4; *HC = 4; *P = PairLayout<2, 4>::P; *PW = PairLayout<2, 4>::PW; *sm_words = Env<2, 4, 4, 2>::SM_WORDS; break;
+    case 1: *AC = 4; *BC = 4; *HC = 4; *P = PairLayout<4, 4>::P; *PW = PairLayout<4, 4>::PW; *sm_words = Env<4, 4, 4, 4>::SM_WORDS; break;
+    default: *AC = 8; *BC = 8; *HC = 16; *P = PairLayout<8, 8>::P; *PW = PairLayout<8, 8>::PW; *sm_words = Env<8, 8, 16, 8>::SM_WORDS; break;
   }
 }
 
@@ -420,12 +428,17 @@ cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* ski
   return cudaPeekAtLastError();
 }
 
-cudaError_t msv_read_profile(unsigned long long out[32], int reset) {
-  cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 32);
+cudaError_t msv_read_profile(unsigned long long out[64], int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 64);
   if (e != cudaSuccess) return e;
 #ifdef MSV_PROFILE
-  { unsigned long long d[8]; cudaMemcpyFromSymbol(d, g_dbg, sizeof d); out[28] = d[0]; out[29] = d[1]; out[30] = d[2]; out[31] = d[4]; unsigned long long z8[8] = {0}; if (reset) cudaMemcpyToSymbol(g_dbg, z8, sizeof z8); }
+  { unsigned long long d[8]; cudaMemcpyFromSymbol(d, g_dbg, sizeof d); out[28] = d[0]; out[29] = d[1]; out[30] = d[2]; out[31] = d[5]; unsigned long long z8[8] = {0}; if (reset) cudaMemcpyToSymbol(g_dbg, z8, sizeof z8); }
+  { unsigned long long d[16]; cudaMemcpyFromSymbol(d, g_cnt, sizeof d); for (int k = 0; k < 4; ++k) out[44 + k] = 0; for (int k = 0; k < 16; ++k) if (k < 4) out[44 + k] = d[k]; 
+    // [44..47] generic solve / TOI event (calls, cycles); the rest go to [60..63] and the slowest-wait slots that are unused ([58],[59])
+    out[58] = d[4]; out[59] = d[5]; out[60] = d[6]; out[61] = d[7]; out[62] = d[8]; out[63] = d[9];
+    out[14] = d[10]; out[15] = d[11]; out[42] = d[12]; out[43] = d[13];
+    unsigned long long z16[16] = {0}; if (reset) cudaMemcpyToSymbol(g_cnt, z16, sizeof z16); }
 #endif
-  if (reset) { unsigned long long z[32] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof z); }
+  if (reset) { unsigned long long z[64] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof z); }
   return e;
 }

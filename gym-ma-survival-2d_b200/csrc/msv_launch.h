@@ -3,14 +3,14 @@
 #pragma once
 #include "msv_types.cuh"
 #ifndef MSV_TPB
-#define MSV_TPB 256
+#define MSV_TPB 256   // maximum threads per block of k_step / k_reset / k_observe (the actual size is a runtime choice)
 #endif
 // cap: capacity class 0 = <2,4,4>, 1 = <4,4,4>, 2 = <8,8,16>; which: 0 step, 1 reset, 2 observe, 3 one-time kernel attribute setup, 4 reset only the envs whose done flag is set
 cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S, const DevOut& O,
                        const uint8_t* actions, cudaStream_t st);
-void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW);
+void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW, int* sm_words);
 cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* skills, int4* smisc, double* out_reward,
                              unsigned long long* out_kills, unsigned long long* out_misc, cudaStream_t st);
-cudaError_t msv_read_profile(unsigned long long out[32], int reset);
+cudaError_t msv_read_profile(unsigned long long out[64], int reset);
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, const uint8_t* only_if, cudaStream_t st);
 cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut& O, int BC, cudaStream_t st);

@@ -10,7 +10,8 @@
 struct WallC { float px, py, qs, qc, ang; float fat[4]; };
 
 struct DevConst {
-  int N;                 // environments on this device, padded to a multiple of the block size (SoA stride)
+  int N;                 // environments on this device, padded to blocks * epb (SoA stride)
+  int epb;               // environments per thread block of k_step (block = epb * G threads)
   int n_real;            // environments the caller asked for
   int A, B0, H0;         // n_agents, n_boxes, n_heals at reset
   int S;                 // agent row width: 8 (+1 with teams)

@@ -676,7 +676,7 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
     if (done) { memcpy(out->episode_return, e->ep_return, sizeof e->ep_return); out->episode_length = e->steps; }
     /* BattleRoyale.post_step (sem:41-46): last module of the agents group, sees the post-death body list */
     out->br_over = c->battle_royale && n_agents_alive(e) <= 1;
-    for (int i = 0; i < MA; ++i) out->br_results[i] = i < A && e->a_slot[i] >= 0;
+    for (int i = 0; i < MA; ++i) out->br_results[i] = out->br_over && i < A && e->a_slot[i] >= 0;   /* .results only exists once over */
     /* ImmunityPhase.post_step (sem:667-674): Health.immune stays True for max(cooldown, 1) steps */
     { int cd = c->immunity_cooldown < 1 ? 1 : c->immunity_cooldown; out->immune = c->immunity_cooldown >= 0 && e->steps < cd; }
   }
@@ -684,7 +684,11 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
     e->stat_episodes++;
     orc_reset(e, 0);
     if (out) {
-      float r[MA]; memcpy(r, out->rewards, sizeof r); orc_observe(e, out); memcpy(out->rewards, r, sizeof r); out->done = 1;
+      orc_out keep = *out;                       /* orc_observe clears the record */
+      orc_observe(e, out);
+      memcpy(out->rewards, keep.rewards, sizeof keep.rewards); out->done = 1; out->n_toi_events = keep.n_toi_events;
+      memcpy(out->episode_return, keep.episode_return, sizeof keep.episode_return); out->episode_length = keep.episode_length;
+      out->br_over = keep.br_over; memcpy(out->br_results, keep.br_results, sizeof keep.br_results);
       out->immune = c->immunity_cooldown >= 0;   /* the new episode's flag; br_* and episode_* describe the finished one */
     }
   }

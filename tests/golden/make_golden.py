@@ -83,7 +83,8 @@ class PhiloxGenerator:
 
 def ref_config(name, over):
     user = parity.apply_overrides(parity.variant(name), over)
-    user.pop('lidars', None)
+    for k in ('lidars', 'modules', 'box2d'):       # extension keys of the product config: not part of the reference's
+        user.pop(k, None)
     import masurvival.simulation as rsim          # the reference wants b2CircleShape objects (env:222-227)
     for k in ('auto_pickup', 'give'):
         if k in user and not hasattr(user[k].get('shape'), 'radius'):
@@ -139,10 +140,60 @@ def scripted_actions(obs, t, rng, A):
     return acts
 
 
+def wire_unused_modules(env, rec):
+    """Append the modules the reference ships but never instantiates to its `agents` group, at the
+    places its own source marks (commented lines env:336,338; Lidars has no marked place and goes
+    last: it then scans the state the observation describes).  Nothing in /root/reference is
+    modified: the instances are added to the live env object."""
+    import masurvival.simulation as rsim
+    import masurvival.semantics as rsem
+    mods = env.simulation.groups['agents'].modules
+    extra = {}
+    if int(rec['immunity_cooldown']) >= 0:
+        i = [k for k, m in enumerate(mods) if isinstance(m, rsem.SafeZone)][0] + 1      # env:336
+        extra['immunity'] = rsem.ImmunityPhase(int(rec['immunity_cooldown']))
+        mods.insert(i, extra['immunity'])
+    if int(rec['battle_royale']):
+        i = [k for k, m in enumerate(mods) if isinstance(m, (rsem.Melee, rsem.ContinuousMelee))][0] + 1   # env:338
+        extra['br'] = rsem.BattleRoyale()
+        mods.insert(i, extra['br'])
+    if int(rec['lidar_n']) > 0:
+        extra['lidars'] = rsim.Lidars(int(rec['lidar_n']), float(rec['lidar_fov']), float(rec['lidar_depth']))
+        mods.append(extra['lidars'])
+    return extra
+
+
+KIND = {'agents': 1, 'boxes': 2, 'box_items': 3, 'heals': 4, 'walls': 5}
+
+
+def ref_lidar(env, lid, A, L):
+    """Lidars.scans (simulation.py:377-383) -> per agent INDEX arrays: fraction (1 where the ray hit
+    nothing or the agent is dead) and kind << 8 | position of the hit body in its group's list
+    (agents: their stable IndexBodies slot)."""
+    import masurvival.simulation as rsim
+    groups = env.simulation.groups
+    agents = groups['agents']
+    index = agents.get(rsim.IndexBodies)[0].bodies
+    frac = np.ones((A, L), dtype=np.float32); hit = np.zeros((A, L), dtype=np.int32)
+    for row, body in enumerate(agents.bodies):
+        i = index.index(body)
+        for r, scan in enumerate(lid.scans[row]):
+            if scan is None:
+                continue
+            fixture, f = scan
+            hb = fixture.body
+            grp = rsim.Group.body_group(hb)
+            gname = [k for k, v in groups.items() if v is grp][0]
+            idx = index.index(hb) if gname == 'agents' else grp.bodies.index(hb)
+            frac[i, r] = np.float32(f); hit[i, r] = (KIND[gname] << 8) | idx
+    return frac, hit
+
+
 def run_case(name, over, seed, env_id, steps, policy='scripted'):
-    rec = parity.make_config(name, auto_reset=False, **{k: dict(v) for k, v in over.items() if k != 'lidars'})
+    rec = parity.make_config(name, auto_reset=False, **{k: dict(v) for k, v in over.items()})
     A = int(rec['n_agents'])
     env = MaSurvival(ref_config(name, over))
+    extra = wire_unused_modules(env, rec)
     gen = PhiloxGenerator(seed, env_id)
     env.np_random = gen
     orc = po.OracleEnv(rec, seed=seed, env_id=env_id)
@@ -150,10 +201,32 @@ def run_case(name, over, seed, env_id, steps, policy='scripted'):
     keys = [k for k in po.obs_dims(rec) if not k.startswith('lidar')]
     log = {k: [] for k in keys}
     log.update(kind=[], rewards=[], done=[], actions=[])
+    xkeys = (['lidar_frac', 'lidar_hit'] if 'lidars' in extra else []) + (['immune'] if 'immunity' in extra else []) + \
+            (['br_over', 'br_results'] if 'br' in extra else [])
+    log.update({k: [] for k in xkeys})
+    L = int(rec['lidar_n'])
 
-    def record(kind, obs, rew, done, act):
+    def extras(oo, tag):
+        """state of the extra modules, read off the reference objects and checked against the oracle"""
+        x = {}
+        if 'lidars' in extra:
+            x['lidar_frac'], x['lidar_hit'] = ref_lidar(env, extra['lidars'], A, L)
+        if 'immunity' in extra:
+            x['immune'] = np.int32(bool(env.simulation.groups['agents'].get(type(extra['immunity']))[0].health.immune))
+        if 'br' in extra:
+            br = extra['br']
+            x['br_over'] = np.int32(bool(br.over))
+            x['br_results'] = np.array(br.results if br.over else [0] * A, dtype=np.int32)   # .results only exists once over
+        for k, v in x.items():
+            if not np.array_equal(np.asarray(v), np.asarray(oo[k])):
+                raise AssertionError(f'{name} {tag}: {k} differs: ref {v} oracle {oo[k]}')
+        return x
+
+    def record(kind, obs, rew, done, act, x={}):
         for k in keys:
             log[k].append(np.asarray(obs[k], dtype=np.float32))
+        for k in xkeys:
+            log[k].append(np.asarray(x[k]))
         log['kind'].append(kind); log['rewards'].append(np.asarray(rew, dtype=np.float32))
         log['done'].append(done); log['actions'].append(act)
 
@@ -173,7 +246,7 @@ def run_case(name, over, seed, env_id, steps, policy='scripted'):
         obs = env.reset()
         oo = orc.reset()
         check('reset', obs, oo)
-        record(0, obs, np.zeros(A, np.float32), False, np.zeros((A, 6), np.uint8))
+        record(0, obs, np.zeros(A, np.float32), False, np.zeros((A, 6), np.uint8), extras(oo, 'reset'))
         return obs
 
     obs = reset()
@@ -185,7 +258,12 @@ def run_case(name, over, seed, env_id, steps, policy='scripted'):
         oo = orc.step(act)
         check(f'step {t}', obs, oo, rew, done)
         counters['toi'] += oo['n_toi_events']
-        record(1, obs, rew, done, act)
+        x = extras(oo, f'step {t}')
+        if 'lidar_hit' in x:
+            for kk, nm in KIND.items():
+                counters['lidar_' + kk] = counters.get('lidar_' + kk, 0) + int(((x['lidar_hit'] >> 8) == nm).sum())
+            counters['lidar_dead_rows'] = counters.get('lidar_dead_rows', 0) + int((obs['agent'][:, -7] == 0).sum())
+        record(1, obs, rew, done, act, x)
         if done:
             counters['dones'] += 1
             st = env.flush_stats()
@@ -223,11 +301,23 @@ CASES = [
     ('g_exotic_noheals', '1v1', parity.EXOTIC_B, 22, 11, 500, 'scripted'),
     ('g_2v2_partial_obs', '2v2', {'observation': {'omniscent': False}, 'safe_zone': {'cooldown': 40}}, 19, 8, 900, 'scripted'),
     ('g_ffa_partial_obs', 'ffa', {'observation': {'omniscent': False}, 'health': {'health': 60}}, 20, 9, 300, 'scripted'),
+    # the reference's own Lidars module (simulation.py:357-392) appended to its agents group: 32 and 9 rays
+    ('g_ffa_lidar', 'ffa_lidar', {'health': {'health': 50}, 'safe_zone': {'cooldown': 30}}, 23, 12, 400, 'scripted'),
+    ('g_2v2_lidar9', '2v2', {'lidars': {'n_lasers': 9, 'fov': 0.8 * math.pi, 'depth': 2.0}, 'safe_zone': {'cooldown': 25}, 'health': {'health': 30}},
+     24, 13, 500, 'scripted'),
+    # ImmunityPhase (semantics.py:652-674) and BattleRoyale (semantics.py:31-46) wired at env:336,338
+    ('g_1v1_modules', '1v1', {'modules': {'immunity_phase': True, 'battle_royale': True}, 'immunity_phase': {'cooldown': 12},
+                              'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}, 25, 14, 500, 'scripted'),
+    ('g_ffa_modules', 'ffa', {'modules': {'immunity_phase': True, 'battle_royale': True}, 'immunity_phase': {'cooldown': 0},
+                              'gameover': {'mode': 'lastalive'}, 'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}, 26, 15, 300, 'scripted'),
 ]
 
 
 def main():
+    only = sys.argv[1:]
     for fname, name, over, seed, env_id, steps, policy in CASES:
+        if only and fname not in only:
+            continue
         out, counters = run_case(name, over, seed, env_id, steps, policy)
         path = os.path.join(HERE, fname + '.npz')
         np.savez_compressed(path, **out)

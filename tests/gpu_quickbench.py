@@ -7,6 +7,7 @@
   python gpu_quickbench.py --prof               # per-phase clock64() profile (needs `make PROFILE=1`)
 MSV_LIB=/path/to/other/libmasurv.so selects another build of the library (A/B runs).
 """
+import os
 import sys
 import parity  # noqa: F401  (puts the package and the oracle on sys.path)
 from parity import make_config
@@ -20,38 +21,55 @@ PHASES = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes
 def run(variant, N, steps=600, warm=100, prof=False):
     rec = make_config(variant, auto_reset=True)
     A = int(rec['n_agents'])
-    h = _lib.Handle(rec, N, 0, 1, 0)
-    h.reset()
+    ROT = int(os.environ.get('QB_ROT', '1'))     # QB_ROT=4: four batches round-robin (working set > L2, as bench.py)
+    hs = [_lib.Handle(rec, N, 0, 1 + r, r * N) for r in range(ROT)]
+    h = hs[0]
+    for x in hs:
+        x.reset()
     torch.manual_seed(1234)   # identical action streams in every run: timing differences come from the code only
     acts = torch.randint(0, 2, (8, N, A, 6), dtype=torch.uint8, device='cuda')
     acts[..., 0:3] = torch.randint(0, 3, (8, N, A, 3), dtype=torch.uint8, device='cuda')
-    for t in range(warm):
-        h.step(acts[t % 8].data_ptr())
+    for t in range(warm * ROT):
+        hs[t % ROT].step(acts[t % 8].data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(steps):
-        h.step(acts[t % 8].data_ptr())
+        hs[t % ROT].step(acts[t % 8].data_ptr())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     bps = h.bytes_per_env_step()
     st = h.flush_stats()
-    print(f'{variant} N={N}: {ms*1e3:.1f} us/step, {N/ms*1e3:.3e} env-steps/s, {N*A/ms*1e3:.3e} agent-steps/s, '
+    tag = os.environ.get('MSV_LIB', 'default').split('/')[-1] + (' EPB=' + os.environ['MSV_EPB'] if 'MSV_EPB' in os.environ else '') + f' rot={ROT}'
+    print(f'[{tag}] {variant} N={N}: {ms*1e3:.1f} us/step, {N/ms*1e3:.3e} env-steps/s, {N*A/ms*1e3:.3e} agent-steps/s, '
           f'{bps} B/env-step -> {N*bps/ms/1e6:.1f} GB/s, episodes={int(st["episodes"])}')
     if prof:
         import ctypes
         L = _lib.load()
         L.msv_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
-        buf = (ctypes.c_ulonglong * 32)()
-        L.msv_debug_profile(h.h, 1, buf)
-        for t in range(20):
-            h.step(acts[t % 8].data_ptr())
+        buf = (ctypes.c_ulonglong * 64)()
+        for x in hs:
+            L.msv_debug_profile(x.h, 1, buf)
+        for t in range(20 * ROT):
+            hs[t % ROT].step(acts[t % 8].data_ptr())
+        for x in hs[1:]:
+            L.msv_debug_profile(x.h, 0, None)
         L.msv_debug_profile(h.h, 0, buf)
-        tot = sum(buf[:12]) or 1
+        N = N * ROT   # the sums below cover every batch
+        tot = (sum(buf[:12]) + sum(buf[32:44])) or 1
+        SYNCS = ['0 after load', '1 before collide', '2 before solve', '3 before toi', '4 before cameras', '5 before post_rest', '6 before melee', '7 before rewards', '8 before store_obm', '9 in solve']
         print('   slowest group (any of 20 launches): total=%d cycles, env %d; ' % (buf[12], buf[13]) + ', '.join(f'{n}={buf[16+i]}' for i, n in enumerate(PHASES)))
         print('   leader-lane cycles/env/step: ' + ', '.join(f'{n}={buf[i]/N/20:.0f} ({buf[i]/tot:.0%})' for i, n in enumerate(PHASES)))
-    h.close()
+        print('   barrier waits cycles/env/step: ' + ', '.join(f'[{n}]={buf[32+i]/N/20:.0f} ({buf[32+i]/tot:.0%})' for i, n in enumerate(SYNCS)))
+        print('   slowest group waits: ' + ', '.join(f'[{n}]={buf[48+i]}' for i, n in enumerate(SYNCS)))
+        print('   total cycles/env/step %.0f' % (tot / N / 20))
+        rare = [('generic island solve', 44), ('TOI event', 46), ('reset', 58), ('deaths', 60), ('pickups', 62), ('use/give', 14), ('contact numbering', 42)]
+        print('   rare paths (calls per 1000 env-steps, mean cycles per call): ' +
+              ', '.join(f'{n}: {buf[i] / (N * 20) * 1000:.2f} x {buf[i + 1] / max(buf[i], 1):.0f}' for n, i in rare))
+        print('   b2TimeOfImpact calls per 1000 env-steps: %.1f, mean cycles %.0f' % (buf[28] / (N * 20) * 1000, buf[31] / max(buf[28], 1)))
+    for x in hs:
+        x.close()
 
 
 if __name__ == '__main__':
@@ -67,4 +85,4 @@ if __name__ == '__main__':
     else:
         v = a[0] if a else '2v2'
         N = int(a[1]) if len(a) > 1 else 16384
-        run(v, N, int(a[2]) if len(a) > 2 else 600, int(a[3]) if len(a) > 3 else 100)
+        run(v, N, int(a[2]) if len(a) > 2 else 600, int(a[3]) if len(a) > 3 else 1500)   # default warm-up: stationary episode mix

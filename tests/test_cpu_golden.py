@@ -2,6 +2,7 @@
 own Python (tests/golden/make_golden.py): every observation key, reward and
 done flag must be bit-identical."""
 import glob
+import math
 import os
 
 import numpy as np
@@ -26,7 +27,15 @@ CASE_CFG = {
     'g_exotic_noheals': ('1v1', parity.EXOTIC_B),
     'g_2v2_partial_obs': ('2v2', {'observation': {'omniscent': False}, 'safe_zone': {'cooldown': 40}}),
     'g_ffa_partial_obs': ('ffa', {'observation': {'omniscent': False}, 'health': {'health': 60}}),
+    # the reference's own Lidars / ImmunityPhase / BattleRoyale modules appended to its agents group (make_golden.wire_unused_modules)
+    'g_ffa_lidar': ('ffa_lidar', {'health': {'health': 50}, 'safe_zone': {'cooldown': 30}}),
+    'g_2v2_lidar9': ('2v2', {'lidars': {'n_lasers': 9, 'fov': 0.8 * math.pi, 'depth': 2.0}, 'safe_zone': {'cooldown': 25}, 'health': {'health': 30}}),
+    'g_1v1_modules': ('1v1', {'modules': {'immunity_phase': True, 'battle_royale': True}, 'immunity_phase': {'cooldown': 12},
+                              'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}),
+    'g_ffa_modules': ('ffa', {'modules': {'immunity_phase': True, 'battle_royale': True}, 'immunity_phase': {'cooldown': 0},
+                              'gameover': {'mode': 'lastalive'}, 'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}),
 }
+EXTRA_KEYS = ('lidar_frac', 'lidar_hit', 'immune', 'br_over', 'br_results')
 
 
 def case_config(path):
@@ -56,5 +65,12 @@ def test_oracle_reproduces_reference(path):
             assert out['done'] == bool(g['done'][r]), r
             n_done += out['done']
         for k in keys:
-            assert np.array_equal(out[k], g[k][r]), (os.path.basename(path), r, k)
+            if k in g.files:                      # (the lidar block is only recorded by the lidar cases)
+                assert np.array_equal(out[k], g[k][r]), (os.path.basename(path), r, k)
+        for k in EXTRA_KEYS:
+            if k in g.files:
+                assert np.array_equal(np.asarray(out[k]), g[k][r]), (os.path.basename(path), r, k)
     assert n_done == int(g['done'].sum())
+    if 'lidar_hit' in g.files:                    # every body kind was hit, and dead agents were scanned as "no hit"
+        kinds = set((g['lidar_hit'] >> 8).ravel().tolist())
+        assert {0, 1, 2, 3, 4, 5} <= kinds, kinds

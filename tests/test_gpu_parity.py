@@ -202,7 +202,9 @@ def test_golden_fixtures_on_gpu():
                 a = torch.as_tensor(g['actions'][r][None]).cuda()
                 h.step(a.data_ptr())
             torch.cuda.synchronize()
-            for k in keys:
+            for k in keys + list(tg.EXTRA_KEYS):
+                if k not in g.files:
+                    continue
                 v = h.tensor(k).cpu().numpy()[0]
                 if k in ('zone', 'heals', 'boxes', 'box_items'):
                     v = np.broadcast_to(v[None], (A,) + v.shape)
@@ -326,7 +328,7 @@ def test_step_host_obs_and_async_pipeline():
                 dv = e1._h.tensor(k).cpu().numpy()
                 assert v.shape == dv.shape and np.array_equal(v, dv), (name, t, k)
         with pytest.raises(ValueError):
-            e2.step_host(np.zeros((N, A, 6), dtype=np.int64), rew, done)       # wrong dtype must not reach the C ABI
+            e2.step_host(torch.zeros((N, A, 6), dtype=torch.int64), rew, done)   # wrong dtype must not reach the C ABI (numpy input is converted)
         with pytest.raises(ValueError):
             e2.step_host(np.zeros((N - 1, A, 6), dtype=np.uint8), rew, done)   # wrong size
         e1.close(); e2.close()
@@ -379,7 +381,8 @@ def test_set_state_validation_and_out_of_range_actions():
     s2 = h.get_state()
     assert s2[1].tobytes() == s[5].tobytes() and s2[0].tobytes() == s[0].tobytes() and s2[2].tobytes() == s[2].tobytes()
     # action bytes outside MultiDiscrete([3,3,3,2,2,2]) are clamped, never index past the impulse tables
-    h.reset()
+    h.close()
+    h = _lib.Handle(rec, 8, 0, 1, 0); h.reset()
     a = torch.full((8, 4, 6), 255, dtype=torch.uint8, device='cuda')
     b = torch.zeros((8, 4, 6), dtype=torch.uint8, device='cuda'); b[..., :3] = 2; b[..., 3:] = 1
     h2 = _lib.Handle(rec, 8, 0, 1, 0); h2.reset()
