@@ -43,6 +43,7 @@ sys.path.insert(0, os.path.join(ROOT, 'gym-ma-survival-2d_b200'))
 METRIC = 'agent_steps_per_sec'
 UNIT = 'agent-steps/s'
 L2_BYTES = 126e6
+NB_CPU = 61   # pre-generated random action batches of the CPU arms (same cycling rule as the GPU arm)
 
 # BASELINE.json `configs` made concrete (SURVEY.md section 8d / BASELINE.md section 3)
 WORKLOADS = {
@@ -177,7 +178,11 @@ def run_ours(args):
         e_.reset()
     env = envs[0]
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-    NB = 8  # rotating pre-generated action batches
+    # Random policy (demo.py:18-22: action_space.sample() every step).  NB pre-generated action batches;
+    # batch r's k-th step uses batch (k * 7 + r * 13) mod NB with NB prime, so every env sees all NB
+    # batches in a scrambled order before any repeats (a short cycle would act like a constant drift:
+    # agents pile into the walls and the contact/TOI rates are no longer those of a random policy).
+    NB = 61
 
     acts_dev = torch.empty((NB, N, A, 6), dtype=torch.uint8, device=dev)
     acts_dev[..., 0:3] = torch.randint(0, 3, (NB, N, A, 3), dtype=torch.uint8, device=dev, generator=g)
@@ -202,9 +207,12 @@ def run_ours(args):
 
     tick = [0]
 
+    def abatch(t):
+        return ((t // ROT) * 7 + (t % ROT) * 13) % NB
+
     def dev_step():
         t = tick[0]; tick[0] += 1
-        envs[t % ROT]._h.step(acts_dev[t % NB].data_ptr(), stream)
+        envs[t % ROT]._h.step(acts_dev[abatch(t)].data_ptr(), stream)
 
     def timed(fn, k):
         """K calls of fn between barrier+synchronize, CUDA events on the launch stream, max over ranks"""
@@ -238,10 +246,17 @@ def run_ours(args):
     st0 = [e_.flush_stats() for e_ in envs]   # zero the accumulators: stats below describe the timed region only
 
     # ---- device-resident arm -------------------------------------------------------------------
-    est = timed(dev_step, max(args.warmup, 3)) / max(args.warmup, 3)     # warm-up doubles as the duration estimate
-    R = int(max(args.repeats, math.ceil(50.0 / max(est * args.steps, 1e-6))))
+    clk = ClockSampler(local)
+    if not os.environ.get('BENCH_NO_SMI'):
+        clk.start()
+    est = timed(dev_step, max(args.warmup, 3)) / max(args.warmup, 3)     # the W warm-up steps double as the duration estimate
+    R = int(max(args.repeats, math.ceil(60.0 / max(est * args.steps, 1e-6))))
     R = min(R, 2000)
-    clk = ClockSampler(local); clk.start()
+    # The host-side pauses above (stats read-back, sampler start) let the GPU idle for a few ms, after which
+    # the first ~40 ms of work run up to 35 % slower (measured: 20-step repeats of 4.0, 3.5, 3.4, 3.1, 2.9, 2.9 ...
+    # ms, identical from run to run): keep the device busy for 150 ms right before the timed repeats.
+    for _ in range(int(math.ceil(150.0 / max(est, 1e-6)))):
+        dev_step()
     l0 = sum(e_.kernel_launches() for e_ in envs)
     reps = [timed(dev_step, args.steps) for _ in range(R)]
     launches_per_rep = (sum(e_.kernel_launches() for e_ in envs) - l0) // R
@@ -265,7 +280,7 @@ def run_ours(args):
     # ---- end-to-end arms: host buffers through the C ABI ---------------------------------------
     def e2e_sync():      # H2D actions + kernels + D2H rewards/dones, host blocks until they arrived
         t = tick[0]; tick[0] += 1
-        envs[t % ROT].step_host_async(acts_host[t % NB], rew_host[t % ROT], done_host[t % ROT])
+        envs[t % ROT].step_host_async(acts_host[abatch(t)], rew_host[t % ROT], done_host[t % ROT])
         envs[t % ROT].step_host_wait()
 
     for _ in range(max(3, args.warmup)):
@@ -280,12 +295,12 @@ def run_ours(args):
 
     def e2e_obs_sync():  # ... + D2H of every observation tensor, one env group at a time
         t = tick[0]; tick[0] += 1
-        envs[t % ROT].step_host_obs(acts_host[t % NB], obs_bufs[t % ROT][0], rew_host[t % ROT], done_host[t % ROT])
+        envs[t % ROT].step_host_obs(acts_host[abatch(t)], obs_bufs[t % ROT][0], rew_host[t % ROT], done_host[t % ROT])
 
     def e2e_obs_pipelined():  # the ROT env groups in flight: group r's copy-out overlaps group r+1's kernels
         t = tick[0]; tick[0] += 1
         envs[t % ROT].step_host_wait()      # results of this group's previous step (the policy would read them here)
-        envs[t % ROT].step_host_async(acts_host[t % NB], rew_host[t % ROT], done_host[t % ROT], obs_bufs[t % ROT][0])
+        envs[t % ROT].step_host_async(acts_host[abatch(t)], rew_host[t % ROT], done_host[t % ROT], obs_bufs[t % ROT][0])
 
     for _ in range(max(3, args.warmup)):
         e2e_obs_sync()
@@ -320,6 +335,7 @@ def run_ours(args):
         'l2': f'{ROT} batches of {N} envs stepped round-robin ({ROT} x {batch_bytes / 1e6:.0f} MB of state+outputs > 126 MB L2): inputs larger than L2, no flush',
         'timing': {'method': 'median over repeats of K steps; each repeat: barrier+sync, CUDA events, max over ranks',
                    'repeats': R, 'timed_ms_total': float(np.sum(reps)), 'rep_ms_min': float(np.min(reps)), 'rep_ms_max': float(np.max(reps)),
+                   'rep_ms': [round(float(x), 4) for x in reps[:64]],
                    'preroll_steps_per_batch': args.preroll, 'rotating_batches': ROT,
                    'mean_episode_steps_in_timed_region': (tot_steps / tot_eps) if tot_eps else None,
                    'episodes_finished_in_timed_region': int(tot_eps),
@@ -354,6 +370,9 @@ def run_ours(args):
             rp = ref_python_baseline(args.workload)
             if rp:
                 line['cpu_baseline_ref_python'] = rp
+            c1 = {k: ref_python_baseline(k) for k in ('1v1_default', '2v2')}     # BASELINE.json configs[0]: 1 env, 1000 steps, demo.py loop
+            if all(c1.values()):
+                line['cpu_baseline_config1'] = c1
         print(json.dumps(line))
     for e_ in envs:
         e_.close()
@@ -369,9 +388,9 @@ def _cpu_batch(name, seed, sample_envs, threads):
     b = po.OracleBatch(rec, seed, sample_envs, threads)
     b.reset()
     rng = np.random.default_rng(0)
-    acts = np.zeros((4, sample_envs, A, 6), dtype=np.uint8)
-    acts[..., 0:3] = rng.integers(0, 3, size=(4, sample_envs, A, 3))
-    acts[..., 3:6] = rng.integers(0, 2, size=(4, sample_envs, A, 3))
+    acts = np.zeros((NB_CPU, sample_envs, A, 6), dtype=np.uint8)
+    acts[..., 0:3] = rng.integers(0, 3, size=(NB_CPU, sample_envs, A, 3))
+    acts[..., 3:6] = rng.integers(0, 2, size=(NB_CPU, sample_envs, A, 3))
     return b, acts, A
 
 
@@ -381,10 +400,10 @@ def cpu_baseline(name, sample_envs, steps, preroll, threads=None):
     threads = threads or os.cpu_count() or 1
     b, acts, A = _cpu_batch(name, 1, sample_envs, threads)
     for t in range(preroll):
-        b.step(acts[t % 4])
+        b.step(acts[(t * 7) % NB_CPU])
     t0 = time.perf_counter()
     for t in range(steps):
-        b.step(acts[t % 4])
+        b.step(acts[(t * 7) % NB_CPU])
     dt = time.perf_counter() - t0
     b.close()
     return {'value': sample_envs * steps * A / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
@@ -405,15 +424,15 @@ def run_reference(args):
     b, acts, A = _cpu_batch(args.workload, args.seed, sample, threads)
     preroll = min(args.preroll, 1500)
     for t in range(preroll):                      # the same stationary episode mix as the GPU arm
-        b.step(acts[t % 4])
+        b.step(acts[(t * 7) % NB_CPU])
     for t in range(args.warmup):
-        b.step(acts[t % 4])
+        b.step(acts[(t * 7) % NB_CPU])
     reps = []
     R = max(args.repeats, 5)
     for _ in range(R):
         t0 = time.perf_counter()
         for t in range(args.steps):
-            b.step(acts[t % 4])
+            b.step(acts[(t * 7) % NB_CPU])
         reps.append(time.perf_counter() - t0)
         if sum(reps) > 60.0 and len(reps) >= 5:
             break

@@ -75,6 +75,35 @@ struct BodyS { f2 c; float a; f2 v; float w; float invM, invI; };
 extern __shared__ float msv_sm[];
 
 
+#ifndef MSV_INLINE_MASK
+#define MSV_INLINE_MASK 0
+#endif
+#if (MSV_INLINE_MASK >> 0) & 1
+#define COLD0 __device__ __forceinline__
+#else
+#define COLD0 __device__ __noinline__
+#endif
+#if (MSV_INLINE_MASK >> 1) & 1
+#define COLD1 __device__ __forceinline__
+#else
+#define COLD1 __device__ __noinline__
+#endif
+#if (MSV_INLINE_MASK >> 2) & 1
+#define COLD2 __device__ __forceinline__
+#else
+#define COLD2 __device__ __noinline__
+#endif
+#if (MSV_INLINE_MASK >> 3) & 1
+#define COLD3 __device__ __forceinline__
+#else
+#define COLD3 __device__ __noinline__
+#endif
+#if (MSV_INLINE_MASK >> 4) & 1
+#define COLD4 __device__ __forceinline__
+#else
+#define COLD4 __device__ __noinline__
+#endif
+
 template <int AC, int BC, int HC, int G>
 struct Env {
   using PL = PairLayout<AC, BC>;
@@ -163,6 +192,12 @@ struct Env {
     for (int w = 0; w < PW; ++w) { ex[w] = o.ex[w]; tc[w] = o.tc[w]; en[w] = o.en[w]; }
   }
 #define MSV_COLD(call) do { Env c_(*this); c_.call; take(c_); } while (0)
+  // MSV_INLINE_MASK (development): bit k set -> the cold functions of class k are inlined into the
+  // kernel instead (0 islands, 1 TOI events, 2 contact numbering, 3 deaths/pickups/use-give/box removal, 4 reset)
+#ifndef MSV_INLINE_MASK
+#define MSV_INLINE_MASK 0
+#endif
+#define MSV_COLDK(k, call) do { if ((MSV_INLINE_MASK >> (k)) & 1) { call; } else { Env c_(*this); c_.call; take(c_); } } while (0)
 
   // ---- shared-memory accessors
   DEV float& AG(int f, int i) { return msv_sm[sb + (f * AC + i)]; }
@@ -421,7 +456,7 @@ struct Env {
 
   // ---- list maintenance (stable compaction, sim:185-189)            [leader]
   // shift the AB pair column k+1.. down by one for every agent
-  __device__ __noinline__ void remove_box(int k) {
+  COLD3 void remove_box(int k) {
     for (int i = 0; i < C.A; ++i) {   // b2World::DestroyBody -> contacts die, touching ones wake
       int p = p_ab(i, k);
       if (bit(ex, p) && bit(tc, p)) wake(i);
@@ -512,7 +547,7 @@ struct Env {
     }
   }
   // [leader] create the candidate contacts in proxy-pair order
-  __device__ __noinline__ void number_candidates(unsigned long long* cand) {
+  COLD2 void number_candidates(unsigned long long* cand) {
     for (;;) {
       int best = -1; unsigned bestKey = 0xFFFFFFFFu;
       for (int w = 0; w < PW; ++w) {
@@ -543,12 +578,12 @@ struct Env {
 #pragma unroll
     for (int w = 0; w < PW; ++w) { cand[w] = or64(cand[w]); any |= cand[w] != 0ull; }
     if (any) {                               // group-uniform
-      if (lead) { RARE_BEGIN(); unsigned long long cc[PW]; for (int w = 0; w < PW; ++w) cc[w] = cand[w]; MSV_COLD(number_candidates(cc)); RARE_END(6); }
+      if (lead) { RARE_BEGIN(); unsigned long long cc[PW]; for (int w = 0; w < PW; ++w) cc[w] = cand[w]; MSV_COLDK(2, number_candidates(cc)); RARE_END(6); }
       share_bits();
     }
   }
   // [leader] the same, sequentially (inside TOI events)
-  __device__ __noinline__ void find_new_contacts_seq() {
+  COLD1 void find_new_contacts_seq() {
     unsigned long long cand[PW];
 #pragma unroll
     for (int w = 0; w < PW; ++w) cand[w] = 0ull;
@@ -931,7 +966,7 @@ struct Env {
   struct Ord { unsigned long long lo, hi; };   // island contact order: list slots, 5 bits each
   DEV static int ord_get(const Ord& o, int k) { return k < 12 ? (int)((o.lo >> (5 * k)) & 31ull) : (int)((o.hi >> (5 * (k - 12))) & 31ull); }
   DEV static void ord_put(Ord& o, int k, int v) { if (k < 12) o.lo |= (unsigned long long)v << (5 * k); else o.hi |= (unsigned long long)v << (5 * (k - 12)); }
-  __device__ __noinline__ void solve_island(int seed, float h, float dtRatio) {
+  COLD0 void solve_island(int seed, float h, float dtRatio) {
     Ord ord; ord.lo = 0ull; ord.hi = 0ull;
     int nc = 0; unsigned taken = 0, inisl = 1u << seed;
     {
@@ -1128,7 +1163,7 @@ struct Env {
       }
       if (comp == (1u << i)) { solve_single(i, h, dtRatio); continue; }
       const unsigned cand = comp & awk;          // no awake member: the island is not simulated
-      if (cand != 0u && (31 - __clz((int)cand)) == i) { RARE_BEGIN(); MSV_COLD(solve_island(i, h, dtRatio)); RARE_END(0); }
+      if (cand != 0u && (31 - __clz((int)cand)) == i) { RARE_BEGIN(); MSV_COLDK(0, solve_island(i, h, dtRatio)); RARE_END(0); }
     }
     gsync();
   }
@@ -1154,7 +1189,7 @@ struct Env {
   // Returns bit 0: the contact was touching at the TOI (the sub-step ran);
   // bit 1: the event left everything exactly as the previous one on minP did.
   static constexpr int SNAPW = F_COUNT + 6 * PW + 1;
-  __device__ __noinline__ int toi_event(int minP, float minAlpha, float dt, unsigned* prev, int& prevP) {
+  COLD1 int toi_event(int minP, float minAlpha, float dt, unsigned* prev, int& prevP) {
     int a, sid, b; decode(minP, a, sid, b);
     // backup the agent's sweep, advance to the TOI, re-evaluate the contact
     float bk[7] = {AG(F_C0X, b), AG(F_C0Y, b), AG(F_CX, b), AG(F_CY, b), AG(F_A0, b), AG(F_A, b), AG(F_ALPHA0, b)};
@@ -1323,7 +1358,12 @@ struct Env {
       }
       gsync();
       int r = 0;
-      if (lead) { RARE_BEGIN(); Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prev, prevP); take(c_); RARE_END(1); }
+      if (lead) {
+        RARE_BEGIN();
+        if ((MSV_INLINE_MASK >> 1) & 1) r = toi_event(minP, minAlpha, dt, prev, prevP);
+        else { Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prev, prevP); take(c_); }
+        RARE_END(1);
+      }
       gsync();
       r = bc(r);
       share_bits();
@@ -1380,9 +1420,9 @@ struct Env {
     bool any = LI(L_NP) > 0;                       // nothing to do unless a drop is pending or an agent with items uses/gives
 #pragma unroll
     for (int i = 0; i < AC; ++i) if (i < C.A && (((act >> (8 + i)) | (act >> (16 + i))) & 1u) && (LI(L_INV + (i)) & 7) != 0 && alive(i)) any = true;
-    if (any) { RARE_BEGIN(); MSV_COLD(pre_use_give_body(act)); RARE_END(5); }
+    if (any) { RARE_BEGIN(); MSV_COLDK(3, pre_use_give_body(act)); RARE_END(5); }
   }
-  __device__ __noinline__ void pre_use_give_body(unsigned act) {
+  COLD3 void pre_use_give_body(unsigned act) {
     // boxes/Object.pre_step (sem:853-856, 902-905): pending drops become items
     for (int q = 0; q < LI(L_NP); ++q) {
       float4 p0 = S.pend0[q * N + e];
@@ -1596,13 +1636,13 @@ struct Env {
           S.pend1[LI(L_NP) * N + e] = C.box_ownership ? b1.z : MSV_CAUSE_NONE;
           LI(L_NP)++;
         } else LI(L_OVERFLOW)++;
-        { RARE_BEGIN(); MSV_COLD(remove_box(k)); RARE_END(7); }
+        { RARE_BEGIN(); MSV_COLDK(3, remove_box(k)); RARE_END(7); }
       } else ++k;
     }
   }
   // agents/Cameras.post_step (sim:333-334) runs between the two halves
   // [leader] agents/Health.post_step -> despawn(dead) (sem:429-448)
-  __device__ __noinline__ void handle_deaths() {
+  COLD3 void handle_deaths() {
     int total = 0;
     for (int i = 0; i < C.A; ++i) if ((LU(L_DMASK) >> i) & 1u) total += inv_n(i);
     int top = total;
@@ -1624,7 +1664,7 @@ struct Env {
     for (int i = 0; i < C.A; ++i) if ((LU(L_DMASK) >> i) & 1u) kill_agent(i);
   }
   // [leader] agents/AutoPickup.post_step (sem:278-283) for agent i: bodies in creation order
-  __device__ __noinline__ void pickup_agent(int i) {
+  COLD3 void pickup_agent(int i) {
     const float r2 = C.pickup_r * C.pickup_r;
     f2 me = apos(i);
     int lastSeq = -1;
@@ -1663,7 +1703,7 @@ struct Env {
       LU(L_DMASK) = 0; LI(L_NKILLS) = 0;
 #pragma unroll
       for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && LI(L_HEALTH + (i)) <= 0) LU(L_DMASK) |= 1u << i;
-      if (LU(L_DMASK)) { RARE_BEGIN(); MSV_COLD(handle_deaths()); dflag = 1; RARE_END(3); }
+      if (LU(L_DMASK)) { RARE_BEGIN(); MSV_COLDK(3, handle_deaths()); dflag = 1; RARE_END(3); }
     }
     dflag = bc(dflag);
     if (dflag) { gsync(); share_counts(); }   // drops changed the lists, deaths the flags
@@ -1680,7 +1720,7 @@ struct Env {
     }
     near = or32(near);
     if (!lead) return;
-    for (int i = 0; i < C.A; ++i) if ((near >> i) & 1u) { RARE_BEGIN(); MSV_COLD(pickup_agent(i)); RARE_END(4); }
+    for (int i = 0; i < C.A; ++i) if ((near >> i) & 1u) { RARE_BEGIN(); MSV_COLDK(3, pickup_agent(i)); RARE_END(4); }
     // agents/SafeZone.post_step (sem:758-768) + tick (sem:776-811)
     for (int i = 0; i < C.A; ++i) {
       if (!alive(i)) continue;
@@ -1834,7 +1874,7 @@ struct Env {
   // RandomizeBoxShapes (sem:97-120), ThickRoomWalls, SafeZone.post_reset
   // (sem:739-756).  The numpy Generator is replaced by counter-based
   // Philox4x32-10 keyed by (seed, global env id, episode).          [leader]
-  __device__ __noinline__ void reset() {
+  COLD4 void reset() {
     LI(L_EPISODE) += 1; LI(L_STEPS) = 0;
     int n = C.grid_n;
     unsigned char perm[64];

@@ -30,7 +30,7 @@ __device__ unsigned long long g_prof[64];
 
 // thread -> (environment slot of the block, lane of the group)
 // keep the warps of a block in the same phase: they then share instruction-cache lines
-#define MSV_COLD_ON(env, call) do { auto c_ = env; c_.call; env.take(c_); } while (0)
+#define MSV_COLD_ON(env, call) do { if ((MSV_INLINE_MASK >> 4) & 1) { env.call; } else { auto c_ = env; c_.call; env.take(c_); } } while (0)
 #ifndef MSV_SYNC_MASK
 #define MSV_SYNC_MASK 0x3FF
 #endif

@@ -64,6 +64,7 @@ struct oracle_env {
   int64_t stat_episodes;
   float last_rewards[MA]; int last_kills[MA];
   float ep_return[MA];   /* running return of the current episode (per-env view of env:483-508) */
+  int64_t ev[ORC_EV_COUNT]; /* event-coverage census (orc_get_events) */
 };
 
 /* ------------------------------------------------------------------ Philox */
@@ -456,6 +457,7 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
     b2l_body* b = &w->bodies[e->a_slot[i]];
     if (it.kind == MSV_ITEM_HEAL) {
       e->use_heal++;
+      if (e->health[i] <= 0) e->ev[ORC_EV_Q10_SAVED_BY_HEAL]++;   /* zone damage brought it to <= 0 after last step's death check */
       agent_change_health(e, i, c->healing, MSV_CAUSE_NONE); /* sem:646-649 */
     } else {
       e->use_box++;
@@ -466,6 +468,7 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
       e->box_slot[k] = spawn_box_body(e, b->p.x + off.x, b->p.y + off.y, &it.shape);
       e->box_has_health[k] = 0; e->box_health[k] = 0; e->box_cause[k] = MSV_CAUSE_NONE;
       e->box_owner[k] = c->box_ownership ? it.owner : MSV_CAUSE_NONE; /* sem:876-884 */
+      e->ev[ORC_EV_BOX_PLACED]++;
     }
   }
   /* agents/GiveLast.pre_step (sem:335-370) */
@@ -488,11 +491,12 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
     for (int i = 0; i < A; ++i) {
       if (e->a_slot[i] < 0 || !actions[6 * i + 5] || taker[i] < 0) continue;
       int tidx; int kind = classify(e, taker[i], &tidx);
-      if (kind != ORC_KIND_AGENT) continue;   /* no Inventory module: sem:196-198 */
-      if (c->teams && team_of(e, tidx) != team_of(e, i)) continue; /* strangers sem:344-349 */
+      if (kind != ORC_KIND_AGENT) { if (e->inv_n[i] > 0) e->ev[ORC_EV_GIVE_BLOCKED_BY_BODY]++; continue; }   /* no Inventory module: sem:196-198 (Q6) */
+      if (c->teams && team_of(e, tidx) != team_of(e, i)) { if (e->inv_n[i] > 0) e->ev[ORC_EV_GIVE_STRANGER]++; continue; } /* strangers sem:344-349 */
       if (e->inv_n[i] == 0) continue;          /* IndexError sem:199-202 */
       inv_item it = e->inv[i][--e->inv_n[i]];
-      if (e->inv_n[tidx] + 1 <= c->inv_slots) e->inv[tidx][e->inv_n[tidx]++] = it; /* else lost, Q6 */
+      if (e->inv_n[tidx] + 1 <= c->inv_slots) { e->inv[tidx][e->inv_n[tidx]++] = it; e->ev[ORC_EV_GIVE_OK]++; } /* else lost, Q6 */
+      else e->ev[ORC_EV_GIVE_TO_FULL]++;
     }
   }
   /* agents/Melee.pre_step (sem:584-617) / ContinuousMelee (sem:531-554) */
@@ -513,8 +517,16 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
       if (target[i] >= 0 && attack && !on_cooldown) {
         int cause = c->teams ? MSV_CAUSE_TEAM0 + team_of(e, i) : i;
         int tidx; int kind = classify(e, target[i], &tidx);
-        if (kind == ORC_KIND_AGENT) agent_change_health(e, tidx, -c->melee_damage, cause);
-        else if (kind == ORC_KIND_BOX) box_change_health(e, tidx, -c->melee_damage, cause);
+        if (kind == ORC_KIND_AGENT) {
+          e->ev[ORC_EV_MELEE_HIT_AGENT]++;
+          if (c->teams && team_of(e, tidx) == team_of(e, i)) e->ev[ORC_EV_MELEE_TEAMMATE_IMMUNE]++;
+          agent_change_health(e, tidx, -c->melee_damage, cause);
+        } else if (kind == ORC_KIND_BOX) {
+          e->ev[ORC_EV_MELEE_HIT_BOX]++;
+          if (!e->box_has_health[tidx]) e->ev[ORC_EV_Q9_FRESH_BOX_HIT]++;
+          else if (e->box_owner[tidx] != MSV_CAUSE_NONE && cause != e->box_owner[tidx]) e->ev[ORC_EV_OWNED_BOX_PROTECTED]++;
+          box_change_health(e, tidx, -c->melee_damage, cause);
+        } else e->ev[ORC_EV_Q3_COOLDOWN_BURNT]++;   /* wall / item hit: only the cooldown is consumed */
         if (c->melee_cooldown >= 0) e->cooldown[i] = c->melee_cooldown;
       }
     }
@@ -537,6 +549,7 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
       e->pend_x[q] = b->p.x; e->pend_y[q] = b->p.y;
       e->pend_shape[q] = e->box_shape[k]; e->pend_shape[q].rehulled = 1; /* sim.prototype -> copy_shape */
       e->pend_owner[q] = c->box_ownership ? e->box_cause[k] : MSV_CAUSE_NONE; /* sem:911-912 */
+      e->ev[ORC_EV_BOX_DESTROYED]++;
       remove_box(e, k);
     } else ++k;
   }
@@ -549,6 +562,16 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
     if (nd > 0) {
       /* TrackDeaths (sim:281-284) */
       for (int k = 0; k < nd; ++k) e->deaths[e->n_deaths++] = dead[k];
+      e->ev[ORC_EV_DEATH] += nd;
+      if (nd >= 2) e->ev[ORC_EV_MULTI_DEATH_STEP]++;
+      for (int k = 0; k < nd; ++k) {
+        if (e->inv_n[dead[k]] >= 2) e->ev[ORC_EV_DEATHDROP_2PLUS]++;
+        else if (e->inv_n[dead[k]] == 1) e->ev[ORC_EV_DEATHDROP_1]++;
+        if (e->cause[dead[k]] == MSV_CAUSE_ZONE) e->ev[ORC_EV_DEATH_BY_ZONE]++;
+        else if (e->cause[dead[k]] != MSV_CAUSE_NONE) e->ev[ORC_EV_DEATH_BY_MELEE]++;
+        /* Q1: a survivor listed AFTER the dead agent reads a neighbour's stale seen-row this step */
+        for (int j = dead[k] + 1; j < A; ++j) if (e->a_slot[j] >= 0 && e->health[j] > 0) { e->ev[ORC_EV_Q1_STALE_SEEN_ROW]++; break; }
+      }
       /* DeathDrop.pre_despawn (sem:387-396) */
       int total = 0; for (int k = 0; k < nd; ++k) total += e->inv_n[dead[k]];
       double angles[MA * MS];
@@ -587,10 +610,11 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
       if (e->a_slot[i] < 0) continue;
       for (int k = 0; k < nf[i]; ++k) {
         int slot = b2l_slot_of(w, found[i][k]);
-        if (slot < 0) continue;  /* Q7: already taken by an earlier agent */
+        if (slot < 0) { e->ev[ORC_EV_Q7_DOUBLE_PICKUP]++; continue; }  /* Q7: already taken by an earlier agent */
         int idx; int kind = classify(e, slot, &idx);
         if (kind != ORC_KIND_HEAL && kind != ORC_KIND_ITEM) continue;
-        if (e->inv_n[i] + 1 > c->inv_slots) continue; /* sem:184-185 */
+        if (e->inv_n[i] + 1 > c->inv_slots) { e->ev[ORC_EV_PICKUP_FULL]++; continue; } /* sem:184-185 */
+        e->ev[kind == ORC_KIND_HEAL ? ORC_EV_PICKUP_HEAL : ORC_EV_PICKUP_BOX]++;
         inv_item it; memset(&it, 0, sizeof it);
         if (kind == ORC_KIND_HEAL) { it.kind = MSV_ITEM_HEAL; it.owner = MSV_CAUSE_NONE; remove_heal(e, idx); }
         else { it.kind = MSV_ITEM_BOX; it.shape = e->item_shape[idx]; it.owner = e->item_owner[idx]; remove_item(e, idx); }
@@ -640,7 +664,8 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
     for (int i = 0; i < A; ++i) rewards[i] += e->a_slot[i] >= 0 ? c->r_alive : c->r_dead;
     for (int k = 0; k < e->n_kills; ++k) {
       int killer = e->kill_cause[k];
-      if (killer >= 0 && killer < A && e->a_slot[killer] >= 0) { rewards[killer] += c->r_kill; e->last_kills[killer]++; }
+      if (killer >= 0 && killer < A && e->a_slot[killer] >= 0) { rewards[killer] += c->r_kill; e->last_kills[killer]++; e->ev[ORC_EV_KILL_FFA]++; }
+      else if (killer >= 0 && killer < A) e->ev[ORC_EV_Q5_DEAD_KILLER]++;     /* kill credit needs a living killer (env:777-780) */
     }
     for (int k = 0; k < e->n_deaths; ++k) rewards[e->deaths[k]] += c->r_death;
   } else { /* env:783-801 */
@@ -654,7 +679,7 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
       if (cz != MSV_CAUSE_TEAM0 && cz != MSV_CAUSE_TEAM0 + 1) continue;
       int t = cz - MSV_CAUSE_TEAM0;
       for (int i = (t ? split : 0); i < (t ? A : split); ++i) rewards[i] += c->r_kill;
-      e->last_kills[t]++;
+      e->last_kills[t]++; e->ev[ORC_EV_KILL_TEAM]++;
     }
     for (int k = 0; k < e->n_deaths; ++k) {
       int t = team_of(e, e->deaths[k]);
@@ -680,6 +705,8 @@ void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
     /* ImmunityPhase.post_step (sem:667-674): Health.immune stays True for max(cooldown, 1) steps */
     { int cd = c->immunity_cooldown < 1 ? 1 : c->immunity_cooldown; out->immune = c->immunity_cooldown >= 0 && e->steps < cd; }
   }
+  if (done) e->ev[ORC_EV_EPISODE_END]++;
+  e->ev[ORC_EV_TOI_EVENT] += w->n_toi_events;
   if (done && c->auto_reset) {
     e->stat_episodes++;
     orc_reset(e, 0);
@@ -966,6 +993,10 @@ void orc_set_state(oracle_env* e, const msv_env_state* s) {
   /* sensors are recomputed from the injected world (Cameras.post_reset analogue) */
   cameras_update(e);
   lidar_update(e);
+}
+
+void orc_get_events(oracle_env* e, int64_t* out, int32_t n) {
+  for (int k = 0; k < n && k < ORC_EV_COUNT; ++k) out[k] = e->ev[k];
 }
 
 void orc_flush_stats(oracle_env* e, msv_stats* out) {

@@ -66,6 +66,21 @@ typedef struct orc_draws {
   const double* death_u;   /* uniforms for DeathDrop, rng.random(n) order */
 } orc_draws;
 
+/* Event-coverage census: how often each rule / quirk of SURVEY.md 8a fired in
+ * this env since it was created.  Test infrastructure: the golden generator and the lock-step
+ * drivers sum these and assert that every one of them was exercised. */
+enum {
+  ORC_EV_DEATH, ORC_EV_DEATH_BY_ZONE, ORC_EV_DEATH_BY_MELEE, ORC_EV_MULTI_DEATH_STEP,
+  ORC_EV_KILL_FFA, ORC_EV_KILL_TEAM, ORC_EV_Q5_DEAD_KILLER,
+  ORC_EV_GIVE_OK, ORC_EV_GIVE_TO_FULL, ORC_EV_GIVE_STRANGER, ORC_EV_GIVE_BLOCKED_BY_BODY,
+  ORC_EV_DEATHDROP_1, ORC_EV_DEATHDROP_2PLUS,
+  ORC_EV_PICKUP_HEAL, ORC_EV_PICKUP_BOX, ORC_EV_PICKUP_FULL, ORC_EV_Q7_DOUBLE_PICKUP,
+  ORC_EV_BOX_PLACED, ORC_EV_BOX_DESTROYED, ORC_EV_Q9_FRESH_BOX_HIT, ORC_EV_OWNED_BOX_PROTECTED,
+  ORC_EV_MELEE_HIT_AGENT, ORC_EV_MELEE_HIT_BOX, ORC_EV_MELEE_TEAMMATE_IMMUNE, ORC_EV_Q3_COOLDOWN_BURNT,
+  ORC_EV_Q1_STALE_SEEN_ROW, ORC_EV_Q10_SAVED_BY_HEAL, ORC_EV_TOI_EVENT, ORC_EV_EPISODE_END,
+  ORC_EV_COUNT
+};
+
 typedef struct oracle_env oracle_env;
 
 oracle_env* orc_create(const msv_config* cfg, uint64_t seed, int64_t env_id);
@@ -77,6 +92,7 @@ void orc_observe(oracle_env* e, orc_out* out);
 void orc_get_state(oracle_env* e, msv_env_state* s);
 void orc_set_state(oracle_env* e, const msv_env_state* s);
 void orc_flush_stats(oracle_env* e, msv_stats* out);
+void orc_get_events(oracle_env* e, int64_t* out, int32_t n); /* ORC_EV_* counters */
 
 /* multi-env, multi-thread driver used as the CPU baseline: n envs, `steps`
  * steps each with Philox actions, auto-reset on done.  Returns env-steps. */

@@ -48,6 +48,7 @@ def lib():
         L.orc_get_state.argtypes = [vp, vp]
         L.orc_set_state.argtypes = [vp, vp]
         L.orc_flush_stats.argtypes = [vp, vp]
+        L.orc_get_events.argtypes = [vp, vp, i32]
         L.orc_rollout.restype = i64
         L.orc_rollout.argtypes = [vp, u64, i32, i32, i32]
         L.orc_batch_create.restype = vp
@@ -66,6 +67,16 @@ def lib():
 class _Draws(ctypes.Structure):
     _fields_ = [('shuffle_u', ctypes.c_void_p), ('box_z', ctypes.c_void_p),
                 ('zone_u', ctypes.c_void_p), ('death_u', ctypes.c_void_p)]
+
+
+def _event_names():
+    import re
+    txt = open(os.path.join(_HERE, 'masurv_oracle.h')).read()
+    body = re.search(r'enum \{\s*(ORC_EV_DEATH.*?)ORC_EV_COUNT', txt, flags=re.S).group(1)
+    return [n.strip()[len('ORC_EV_'):].lower() for n in body.split(',') if n.strip()]
+
+
+EVENT_NAMES = _event_names()
 
 
 def obs_dims(cfg):
@@ -160,6 +171,12 @@ class OracleEnv:
         s = np.zeros(1, dtype=STATS_DT)
         lib().orc_flush_stats(self.h, s.ctypes.data)
         return s[0]
+
+    def events(self):
+        """event-coverage census: dict name -> count since creation (ORC_EV_* of masurv_oracle.h)"""
+        buf = np.zeros(len(EVENT_NAMES), dtype=np.int64)
+        lib().orc_get_events(self.h, buf.ctypes.data, len(buf))
+        return dict(zip(EVENT_NAMES, (int(v) for v in buf)))
 
 
 def rollout(cfg, seed, n_envs, steps, n_threads):

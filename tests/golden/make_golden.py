@@ -92,7 +92,7 @@ def ref_config(name, over):
     return user
 
 
-def scripted_actions(obs, t, rng, A):
+def scripted_actions(obs, t, rng, A, p_attack=0.6, p_use_heal=0.5, p_use_box=0.2, p_give=0.08):
     """seek-and-interact policy so that pickups, heals, box placement, melee
     kills, death drops and gives all happen within a few hundred steps"""
     acts = np.zeros((A, 6), dtype=np.uint8)
@@ -131,12 +131,12 @@ def scripted_actions(obs, t, rng, A):
             acts[i, 0] = 2 if abs(bearing) < 1.0 else 1
             acts[i, 1] = 1
             acts[i, 2] = 2 if bearing > 0.05 else (0 if bearing < -0.05 else 1)
-        acts[i, 3] = rng.random() < 0.6
+        acts[i, 3] = rng.random() < p_attack
         has_heal = 'heal_slot_mask' in obs and obs['heal_slot_mask'][i][0] == 0
         has_box = 'box_slot_mask' in obs and obs['box_slot_mask'][i][0] == 0
         hp = row[off - 1]
-        acts[i, 4] = (has_heal and hp < 70 and rng.random() < 0.5) or (has_box and rng.random() < 0.2) or rng.random() < 0.03
-        acts[i, 5] = rng.random() < 0.08
+        acts[i, 4] = (has_heal and hp < 70 and rng.random() < p_use_heal) or (has_box and rng.random() < p_use_box) or rng.random() < 0.03
+        acts[i, 5] = rng.random() < p_give
     return acts
 
 
@@ -189,7 +189,7 @@ def ref_lidar(env, lid, A, L):
     return frac, hit
 
 
-def run_case(name, over, seed, env_id, steps, policy='scripted'):
+def run_case(name, over, seed, env_id, steps, policy='scripted', pol={}):
     rec = parity.make_config(name, auto_reset=False, **{k: dict(v) for k, v in over.items()})
     A = int(rec['n_agents'])
     env = MaSurvival(ref_config(name, over))
@@ -252,7 +252,7 @@ def run_case(name, over, seed, env_id, steps, policy='scripted'):
     obs = reset()
     counters = dict(dones=0, heals_used=0, boxes_placed=0, kills=0, toi=0)
     for t in range(steps):
-        act = scripted_actions(obs, t, rng, A) if policy == 'scripted' else parity.random_actions(rng, 1, A)[0]
+        act = scripted_actions(obs, t, rng, A, **pol) if policy == 'scripted' else parity.random_actions(rng, 1, A)[0]
         gen.step = env.steps
         obs, rew, done, _ = env.step(tuple(tuple(int(v) for v in a) for a in act))
         oo = orc.step(act)
@@ -283,6 +283,7 @@ def run_case(name, over, seed, env_id, steps, policy='scripted'):
     out['kind'] = np.array(log['kind'], dtype=np.uint8)
     out['done'] = np.array(log['done'], dtype=np.uint8)
     out['meta'] = np.array([seed, env_id, steps], dtype=np.int64)
+    counters['events'] = {k: v for k, v in orc.events().items() if v}     # rule / quirk census of this trajectory (oracle/masurv_oracle.h ORC_EV_*)
     return out, counters
 
 
@@ -310,15 +311,33 @@ CASES = [
                               'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}, 25, 14, 500, 'scripted'),
     ('g_ffa_modules', 'ffa', {'modules': {'immunity_phase': True, 'battle_royale': True}, 'immunity_phase': {'cooldown': 0},
                               'gameover': {'mode': 'lastalive'}, 'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}, 26, 15, 300, 'scripted'),
+    # cases found by searching (oracle only) for the rules the cases above never fire -- see COVERAGE below
+    ('g_4v4_crowd', 'ffa', {'teams': {'twoteams': True}, 'inventory': {'slots': 1}, 'give': {'shape': 3.0}, 'spawn_grid': {'grid_size': 8, 'floor_size': 14},
+                            'safe_zone': {'cooldown': 80, 'radiuses': [7, 4, 2, 1]}, 'health': {'health': 80}}, 32, 12, 600, 'scripted',
+     dict(p_give=0.5, p_use_heal=0.02, p_use_box=0.02, p_attack=0.3)),                                   # give to a full taker, give blocked by a stranger, pickup with a full inventory
+    ('g_ffa_brawl', 'ffa', {'safe_zone': {'cooldown': 15, 'damage': 3}, 'health': {'health': 30}, 'melee': {'damage': 30, 'cooldown': 3, 'range': 2.5}},
+     31, 11, 800, 'scripted', dict(p_attack=0.95)),                                                       # Q5: kill by an attacker who is dead at reward time
+    ('g_ffa_hoard', 'ffa', {'inventory': {'slots': 3}, 'safe_zone': {'cooldown': 40, 'damage': 2}, 'health': {'health': 60}, 'melee': {'damage': 30, 'cooldown': 10}},
+     33, 13, 800, 'scripted', dict(p_give=0.02, p_use_heal=0.02, p_use_box=0.02, p_attack=0.9)),          # death drop of a 2+ item inventory
+    ('g_2v2_owned_attack', '2v2', {'boxes': {'ownership': True, 'health': 20}, 'safe_zone': {'cooldown': 150}, 'melee': {'cooldown': 5}},
+     32, 12, 800, 'scripted', dict(p_attack=0.9, p_use_box=0.6)),                                         # owned box hit by a non-owner
 ]
+
+# every rule / quirk of SURVEY.md 8a that must fire somewhere in the committed fixtures (Q7, two agents on
+# one item in the same step, cannot: the reference destroys the body twice there -- documented deviation)
+COVERAGE = ['death_by_zone', 'death_by_melee', 'multi_death_step', 'kill_ffa', 'kill_team', 'q5_dead_killer', 'give_ok', 'give_to_full',
+            'give_stranger', 'give_blocked_by_body', 'deathdrop_1', 'deathdrop_2plus', 'pickup_heal', 'pickup_box', 'pickup_full',
+            'box_placed', 'box_destroyed', 'q9_fresh_box_hit', 'owned_box_protected', 'melee_hit_agent', 'melee_hit_box',
+            'melee_teammate_immune', 'q3_cooldown_burnt', 'q1_stale_seen_row', 'q10_saved_by_heal', 'toi_event', 'episode_end']
 
 
 def main():
     only = sys.argv[1:]
-    for fname, name, over, seed, env_id, steps, policy in CASES:
+    for case in CASES:
+        fname, name, over, seed, env_id, steps, policy = case[:7]
         if only and fname not in only:
             continue
-        out, counters = run_case(name, over, seed, env_id, steps, policy)
+        out, counters = run_case(name, over, seed, env_id, steps, policy, case[7] if len(case) > 7 else {})
         path = os.path.join(HERE, fname + '.npz')
         np.savez_compressed(path, **out)
         print(f'{fname}: {len(out["kind"])} records, {os.path.getsize(path) / 1024:.0f} KiB, {counters}')

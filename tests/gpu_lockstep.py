@@ -96,6 +96,11 @@ def run(variant='2v2', n_envs=64, steps=300, seed=7, auto_reset=True, verbose=Tr
                               'episodes': int(sum(s['episodes'] for s in so)),
                               'kills': [int(sum(s['kills'][i] for s in so)) for i in range(A)]}
     report['overflow_events'] = h.overflow_events()
+    ev = {}
+    for o in orcs:                                   # which rules / quirks this lock-step run exercised (oracle census)
+        for k, v in o.events().items():
+            ev[k] = ev.get(k, 0) + v
+    report['events'] = {k: v for k, v in ev.items() if v}
     h.close()
     if verbose:
         print(json.dumps(report, default=str, indent=1))

@@ -27,15 +27,16 @@ def run(variant, N, steps=600, warm=100, prof=False):
     for x in hs:
         x.reset()
     torch.manual_seed(1234)   # identical action streams in every run: timing differences come from the code only
-    acts = torch.randint(0, 2, (8, N, A, 6), dtype=torch.uint8, device='cuda')
-    acts[..., 0:3] = torch.randint(0, 3, (8, N, A, 3), dtype=torch.uint8, device='cuda')
+    NB = 61   # prime: every batch sees all of them in a scrambled order (see bench.py)
+    acts = torch.randint(0, 2, (NB, N, A, 6), dtype=torch.uint8, device='cuda')
+    acts[..., 0:3] = torch.randint(0, 3, (NB, N, A, 3), dtype=torch.uint8, device='cuda')
     for t in range(warm * ROT):
-        hs[t % ROT].step(acts[t % 8].data_ptr())
+        hs[t % ROT].step(acts[((t // ROT) * 7 + (t % ROT) * 13) % NB].data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(steps):
-        hs[t % ROT].step(acts[t % 8].data_ptr())
+        hs[t % ROT].step(acts[((t // ROT) * 7 + (t % ROT) * 13) % NB].data_ptr())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -52,7 +53,7 @@ def run(variant, N, steps=600, warm=100, prof=False):
         for x in hs:
             L.msv_debug_profile(x.h, 1, buf)
         for t in range(20 * ROT):
-            hs[t % ROT].step(acts[t % 8].data_ptr())
+            hs[t % ROT].step(acts[((t // ROT) * 7 + (t % ROT) * 13) % NB].data_ptr())
         for x in hs[1:]:
             L.msv_debug_profile(x.h, 0, None)
         L.msv_debug_profile(h.h, 0, buf)

@@ -34,7 +34,20 @@ CASE_CFG = {
                               'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}),
     'g_ffa_modules': ('ffa', {'modules': {'immunity_phase': True, 'battle_royale': True}, 'immunity_phase': {'cooldown': 0},
                               'gameover': {'mode': 'lastalive'}, 'safe_zone': {'cooldown': 10}, 'health': {'health': 25}}),
+    # cases that fire the rules the others never do (tests/golden/make_golden.py COVERAGE)
+    'g_4v4_crowd': ('ffa', {'teams': {'twoteams': True}, 'inventory': {'slots': 1}, 'give': {'shape': 3.0}, 'spawn_grid': {'grid_size': 8, 'floor_size': 14},
+                            'safe_zone': {'cooldown': 80, 'radiuses': [7, 4, 2, 1]}, 'health': {'health': 80}}),
+    'g_ffa_brawl': ('ffa', {'safe_zone': {'cooldown': 15, 'damage': 3}, 'health': {'health': 30}, 'melee': {'damage': 30, 'cooldown': 3, 'range': 2.5}}),
+    'g_ffa_hoard': ('ffa', {'inventory': {'slots': 3}, 'safe_zone': {'cooldown': 40, 'damage': 2}, 'health': {'health': 60}, 'melee': {'damage': 30, 'cooldown': 10}}),
+    'g_2v2_owned_attack': ('2v2', {'boxes': {'ownership': True, 'health': 20}, 'safe_zone': {'cooldown': 150}, 'melee': {'cooldown': 5}}),
 }
+# every rule / quirk of SURVEY.md 8a that must fire somewhere in the committed fixtures (Q7 -- two agents on one item in
+# the same step -- cannot: the reference destroys the body twice there; documented deviation)
+COVERAGE = ['death_by_zone', 'death_by_melee', 'multi_death_step', 'kill_ffa', 'kill_team', 'q5_dead_killer', 'give_ok', 'give_to_full',
+            'give_stranger', 'give_blocked_by_body', 'deathdrop_1', 'deathdrop_2plus', 'pickup_heal', 'pickup_box', 'pickup_full',
+            'box_placed', 'box_destroyed', 'q9_fresh_box_hit', 'owned_box_protected', 'melee_hit_agent', 'melee_hit_box',
+            'melee_teammate_immune', 'q3_cooldown_burnt', 'q1_stale_seen_row', 'q10_saved_by_heal', 'toi_event', 'episode_end']
+EVENTS = {}     # summed over the replayed fixtures by test_oracle_reproduces_reference
 EXTRA_KEYS = ('lidar_frac', 'lidar_hit', 'immune', 'br_over', 'br_results')
 
 
@@ -71,6 +84,17 @@ def test_oracle_reproduces_reference(path):
             if k in g.files:
                 assert np.array_equal(np.asarray(out[k]), g[k][r]), (os.path.basename(path), r, k)
     assert n_done == int(g['done'].sum())
+    for k, v in orc.events().items():
+        EVENTS[k] = EVENTS.get(k, 0) + v
     if 'lidar_hit' in g.files:                    # every body kind was hit, and dead agents were scanned as "no hit"
         kinds = set((g['lidar_hit'] >> 8).ravel().tolist())
         assert {0, 1, 2, 3, 4, 5} <= kinds, kinds
+
+
+def test_zz_event_coverage():
+    """the fixtures (recorded from the reference's own Python) exercise every rule and quirk of SURVEY.md 8a"""
+    if len(EVENTS) == 0:
+        pytest.skip('runs after the replay tests of this module')
+    missing = [k for k in COVERAGE if EVENTS.get(k, 0) == 0]
+    assert not missing, (missing, EVENTS)
+    assert EVENTS['kill_ffa'] >= 10 and EVENTS['kill_team'] >= 4 and EVENTS['death'] >= 200
