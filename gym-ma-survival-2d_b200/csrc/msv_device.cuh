@@ -244,38 +244,46 @@ DEV float simplex_metric(const SimplexV* v, int count) {
   return 0.0f;
 }
 
-// b2Distance(useRadii = false): returns distance, updates the cache
-__device__ __noinline__ float gjk_distance(SimplexCache& cache, const SBox A, f2 pB) {
-  SimplexV v[3]; int count = cache.count;
-  for (int i = 0; i < count; ++i) {  // b2Simplex::ReadCache
-    v[i].indexA = cache.indexA[i];
-    v[i].wA = sb_mul(A, sb_vert(A, v[i].indexA));
-    v[i].w = vsub(pB, v[i].wA);
-    v[i].a = 0.0f;
+// b2Distance(useRadii = false): returns distance, updates the cache.  The simplex (at most three
+// box vertices against the one point) is three named records, every branch of b2Simplex::Solve2 /
+// Solve3 addresses them statically, so the whole state stays in registers (an indexed SimplexV[3]
+// lived in local memory); the arithmetic and the order of operations are those of b2Distance.
+struct SimplexV3 { SimplexV v0, v1, v2; int count; };
+DEV float simplex_metric3(const SimplexV3& s) {
+  if (s.count == 2) return vlen(vsub(s.v0.w, s.v1.w));
+  if (s.count == 3) return vcross(vsub(s.v1.w, s.v0.w), vsub(s.v2.w, s.v0.w));
+  return 0.0f;
+}
+DEV SimplexV simplex_vertex(const SBox& A, f2 pB, int indexA, float a) {
+  SimplexV v; v.indexA = indexA; v.wA = sb_mul(A, sb_vert(A, indexA)); v.w = vsub(pB, v.wA); v.a = a;
+  return v;
+}
+DEV float gjk_distance(SimplexCache& cache, const SBox& A, f2 pB) {
+  SimplexV3 s; s.count = cache.count;
+  s.v0 = simplex_vertex(A, pB, 0, 0.0f); s.v1 = s.v0; s.v2 = s.v0;
+  if (s.count > 0) s.v0 = simplex_vertex(A, pB, cache.indexA[0], 0.0f);   // b2Simplex::ReadCache
+  if (s.count > 1) s.v1 = simplex_vertex(A, pB, cache.indexA[1], 0.0f);
+  if (s.count > 2) s.v2 = simplex_vertex(A, pB, cache.indexA[2], 0.0f);
+  if (s.count > 1) {
+    float metric1 = cache.metric, metric2 = simplex_metric3(s);
+    if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < B2_EPS) s.count = 0;
   }
-  if (count > 1) {
-    float metric1 = cache.metric, metric2 = simplex_metric(v, count);
-    if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < B2_EPS) count = 0;
-  }
-  if (count == 0) {
-    v[0].indexA = 0; v[0].wA = sb_mul(A, sb_vert(A, 0)); v[0].w = vsub(pB, v[0].wA); v[0].a = 1.0f;
-    count = 1;
-  }
-  int saveA[3], saveCount = 0, iter = 0;
+  if (s.count == 0) { s.v0 = simplex_vertex(A, pB, 0, 1.0f); s.count = 1; }
+  int iter = 0;
   while (iter < 20) {
-    saveCount = count;
-    for (int i = 0; i < saveCount; ++i) saveA[i] = v[i].indexA;
-    if (count == 2) {  // b2Simplex::Solve2
-      f2 w1 = v[0].w, w2 = v[1].w, e12 = vsub(w2, w1);
+    const int saveCount = s.count;
+    const int save0 = s.v0.indexA, save1 = s.v1.indexA, save2 = s.v2.indexA;
+    if (s.count == 2) {  // b2Simplex::Solve2
+      f2 w1 = s.v0.w, w2 = s.v1.w, e12 = vsub(w2, w1);
       float d12_2 = -vdot(w1, e12);
-      if (d12_2 <= 0.0f) { v[0].a = 1.0f; count = 1; }
+      if (d12_2 <= 0.0f) { s.v0.a = 1.0f; s.count = 1; }
       else {
         float d12_1 = vdot(w2, e12);
-        if (d12_1 <= 0.0f) { v[1].a = 1.0f; count = 1; v[0] = v[1]; }
-        else { float inv = 1.0f / (d12_1 + d12_2); v[0].a = d12_1 * inv; v[1].a = d12_2 * inv; }
+        if (d12_1 <= 0.0f) { s.v1.a = 1.0f; s.count = 1; s.v0 = s.v1; }
+        else { float inv = 1.0f / (d12_1 + d12_2); s.v0.a = d12_1 * inv; s.v1.a = d12_2 * inv; }
       }
-    } else if (count == 3) {  // b2Simplex::Solve3
-      f2 w1 = v[0].w, w2 = v[1].w, w3 = v[2].w;
+    } else if (s.count == 3) {  // b2Simplex::Solve3
+      f2 w1 = s.v0.w, w2 = s.v1.w, w3 = s.v2.w;
       f2 e12 = vsub(w2, w1);
       float w1e12 = vdot(w1, e12), w2e12 = vdot(w2, e12);
       float d12_1 = w2e12, d12_2 = -w1e12;
@@ -289,52 +297,51 @@ __device__ __noinline__ float gjk_distance(SimplexCache& cache, const SBox A, f2
       float d123_1 = n123 * vcross(w2, w3);
       float d123_2 = n123 * vcross(w3, w1);
       float d123_3 = n123 * vcross(w1, w2);
-      if (d12_2 <= 0.0f && d13_2 <= 0.0f) { v[0].a = 1.0f; count = 1; }
+      if (d12_2 <= 0.0f && d13_2 <= 0.0f) { s.v0.a = 1.0f; s.count = 1; }
       else if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
-        float inv = 1.0f / (d12_1 + d12_2); v[0].a = d12_1 * inv; v[1].a = d12_2 * inv; count = 2;
+        float inv = 1.0f / (d12_1 + d12_2); s.v0.a = d12_1 * inv; s.v1.a = d12_2 * inv; s.count = 2;
       } else if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
-        float inv = 1.0f / (d13_1 + d13_2); v[0].a = d13_1 * inv; v[2].a = d13_2 * inv; count = 2; v[1] = v[2];
-      } else if (d12_1 <= 0.0f && d23_2 <= 0.0f) { v[1].a = 1.0f; count = 1; v[0] = v[1]; }
-      else if (d13_1 <= 0.0f && d23_1 <= 0.0f) { v[2].a = 1.0f; count = 1; v[0] = v[2]; }
+        float inv = 1.0f / (d13_1 + d13_2); s.v0.a = d13_1 * inv; s.v2.a = d13_2 * inv; s.count = 2; s.v1 = s.v2;
+      } else if (d12_1 <= 0.0f && d23_2 <= 0.0f) { s.v1.a = 1.0f; s.count = 1; s.v0 = s.v1; }
+      else if (d13_1 <= 0.0f && d23_1 <= 0.0f) { s.v2.a = 1.0f; s.count = 1; s.v0 = s.v2; }
       else if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
-        float inv = 1.0f / (d23_1 + d23_2); v[1].a = d23_1 * inv; v[2].a = d23_2 * inv; count = 2; v[0] = v[2];
+        float inv = 1.0f / (d23_1 + d23_2); s.v1.a = d23_1 * inv; s.v2.a = d23_2 * inv; s.count = 2; s.v0 = s.v2;
       } else {
         float inv = 1.0f / (d123_1 + d123_2 + d123_3);
-        v[0].a = d123_1 * inv; v[1].a = d123_2 * inv; v[2].a = d123_3 * inv; count = 3;
+        s.v0.a = d123_1 * inv; s.v1.a = d123_2 * inv; s.v2.a = d123_3 * inv; s.count = 3;
       }
     }
-    if (count == 3) break;
+    if (s.count == 3) break;
     f2 d;  // b2Simplex::GetSearchDirection
-    if (count == 1) d = vneg(v[0].w);
+    if (s.count == 1) d = vneg(s.v0.w);
     else {
-      f2 e12 = vsub(v[1].w, v[0].w);
-      float sgn = vcross(e12, vneg(v[0].w));
+      f2 e12 = vsub(s.v1.w, s.v0.w);
+      float sgn = vcross(e12, vneg(s.v0.w));
       d = sgn > 0.0f ? cross_sv(1.0f, e12) : cross_vs(e12, 1.0f);
     }
     if (vlen2(d) < B2_EPS * B2_EPS) break;
-    SimplexV& nv = v[count];
-    nv.indexA = box_support(A, qmulT(A.qs, A.qc, vneg(d)));
-    nv.wA = sb_mul(A, sb_vert(A, nv.indexA));
-    nv.w = vsub(pB, nv.wA);
+    const SimplexV nv = simplex_vertex(A, pB, box_support(A, qmulT(A.qs, A.qc, vneg(d))), 0.0f);   // (its .a is set by the next Solve)
     ++iter;
-    bool duplicate = false;
-    for (int i = 0; i < saveCount; ++i) if (nv.indexA == saveA[i]) { duplicate = true; break; }
+    bool duplicate = (saveCount > 0 && nv.indexA == save0) || (saveCount > 1 && nv.indexA == save1) || (saveCount > 2 && nv.indexA == save2);
     if (duplicate) break;
-    ++count;
+    if (s.count == 1) { const float a1 = s.v1.a; s.v1 = nv; s.v1.a = a1; } else { const float a2 = s.v2.a; s.v2 = nv; s.v2.a = a2; }   // vertex[count] keeps its stale weight, as in b2Distance
+    ++s.count;
   }
   f2 pointA, pointB;  // b2Simplex::GetWitnessPoints
-  if (count == 1) { pointA = v[0].wA; pointB = pB; }
-  else if (count == 2) {
-    pointA = vadd(vmul(v[0].a, v[0].wA), vmul(v[1].a, v[1].wA));
-    pointB = vadd(vmul(v[0].a, pB), vmul(v[1].a, pB));
+  if (s.count == 1) { pointA = s.v0.wA; pointB = pB; }
+  else if (s.count == 2) {
+    pointA = vadd(vmul(s.v0.a, s.v0.wA), vmul(s.v1.a, s.v1.wA));
+    pointB = vadd(vmul(s.v0.a, pB), vmul(s.v1.a, pB));
   } else {
-    pointA = vadd(vadd(vmul(v[0].a, v[0].wA), vmul(v[1].a, v[1].wA)), vmul(v[2].a, v[2].wA));
+    pointA = vadd(vadd(vmul(s.v0.a, s.v0.wA), vmul(s.v1.a, s.v1.wA)), vmul(s.v2.a, s.v2.wA));
     pointB = pointA;
   }
   float distance = vlen(vsub(pointA, pointB));
-  cache.metric = simplex_metric(v, count);
-  cache.count = count;
-  for (int i = 0; i < count; ++i) cache.indexA[i] = v[i].indexA;
+  cache.metric = simplex_metric3(s);
+  cache.count = s.count;
+  cache.indexA[0] = s.v0.indexA;
+  if (s.count > 1) cache.indexA[1] = s.v1.indexA;
+  if (s.count > 2) cache.indexA[2] = s.v2.indexA;
   return distance;
 }
 

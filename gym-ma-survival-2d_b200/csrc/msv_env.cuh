@@ -582,13 +582,25 @@ struct Env {
       share_bits();
     }
   }
-  // [leader] the same, sequentially (inside TOI events)
-  COLD1 void find_new_contacts_seq() {
+  // [leader] the same inside a TOI event: only agent b's proxy moved (b2BroadPhase::UpdatePairs queries the
+  // moved proxies), so only pairs with b can have started to overlap
+  DEV void find_new_contacts_of(int b) {
     unsigned long long cand[PW];
 #pragma unroll
     for (int w = 0; w < PW; ++w) cand[w] = 0ull;
-    for (int j = 0; j < C.A; ++j) candidates_of(j, cand);
-    number_candidates(cand);
+    candidates_of(b, cand);                      // (i < b, b) and b against the static bodies
+    float fb[4]; agent_fat(b, fb);
+    for (int j = b + 1; j < C.A; ++j) {          // (b, j > b)
+      if (!(AGF(j) & FL_ALIVE)) continue;
+      const int p = p_aa(b, j);
+      if (bit(ex, p)) continue;
+      float fj[4]; agent_fat(j, fj);
+      if (aabb_overlap(fb, fj)) setb(cand, p);
+    }
+    bool any = false;
+#pragma unroll
+    for (int w = 0; w < PW; ++w) any |= cand[w] != 0ull;
+    if (any) number_candidates(cand);
   }
 
   // evaluate the manifold of pair (a|sid, b) at the bodies' current transforms
@@ -1188,95 +1200,122 @@ struct Env {
   // [leader] one TOI event of b2World::SolveTOI on contact minP at minAlpha.
   // Returns bit 0: the contact was touching at the TOI (the sub-step ran);
   // bit 1: the event left everything exactly as the previous one on minP did.
+  // The mini island (the TOI contact, then the agent's other touching contacts against static
+  // bodies, newest first) keeps its solver constants in the dead touching-contact list (KS_* words of
+  // slots 0..TOI_ISL-1; the list is rebuilt by the next Collide), the state snapshot of the previous
+  // event in slots 8.., so nothing of the event goes through local memory.
   static constexpr int SNAPW = F_COUNT + 6 * PW + 1;
-  COLD1 int toi_event(int minP, float minAlpha, float dt, unsigned* prev, int& prevP) {
+  static constexpr int TOI_ISL = 8;
+  static_assert(SNAPW <= K_COUNT * (MAXC - TOI_ISL), "snapshot does not fit the scratch slots");
+  DEV unsigned& SNAP(int q) { return reinterpret_cast<unsigned*>(msv_sm)[sb + (W_TC + (q / (MAXC - TOI_ISL)) * MAXC + TOI_ISL + q % (MAXC - TOI_ISL))]; }
+  COLD1 int toi_event(int minP, float minAlpha, float dt, int prevP) {
     int a, sid, b; decode(minP, a, sid, b);
     // backup the agent's sweep, advance to the TOI, re-evaluate the contact
-    float bk[7] = {AG(F_C0X, b), AG(F_C0Y, b), AG(F_CX, b), AG(F_CY, b), AG(F_A0, b), AG(F_A, b), AG(F_ALPHA0, b)};
+    const float bk0 = AG(F_C0X, b), bk1 = AG(F_C0Y, b), bk2 = AG(F_CX, b), bk3 = AG(F_CY, b), bk4 = AG(F_A0, b), bk5 = AG(F_A, b), bk6 = AG(F_ALPHA0, b);
     advance(b, minAlpha);
-    Manifold m_min; unsigned wk = 0;
-    bool touching = contact_update(minP, a, sid, b, false, wk, &m_min);
-    wake_all(wk);
-    if (!touching) {
-      clrb(en, minP);
-      AG(F_C0X, b) = bk[0]; AG(F_C0Y, b) = bk[1]; AG(F_CX, b) = bk[2]; AG(F_CY, b) = bk[3];
-      AG(F_A0, b) = bk[4]; AG(F_A, b) = bk[5]; AG(F_ALPHA0, b) = bk[6];
-      return 0;
-    }
-    wake(b);
-    // mini island: the TOI contact first, then the agent's other touching
-    // contacts against statics, newest first
-    TCon isl[8]; int nisl = 0;
+    int nisl = 0;
+    auto isl_add = [&](int sid_, const Manifold& m) {   // world normal and plane point of the face contact (constant while solving)
+      SBox bx = static_box(sid_);
+      const f2 normal = qmul(bx.qs, bx.qc, m.localNormal), planePoint = sb_mul(bx, m.localPoint);
+      KF(KS_NX, nisl) = normal.x; KF(KS_NY, nisl) = normal.y; KF(KS_PX, nisl) = planePoint.x; KF(KS_PY, nisl) = planePoint.y;
+      nisl++;
+    };
     {
-      TCon& t = isl[nisl++];
-      t.p = minP; t.seq = 0; t.a = -1; t.sid = sid; t.b = b; t.flags = 0; t.m = m_min; t.ni = 0.0f; t.ti = 0.0f;
+      Manifold m_min; unsigned wk = 0;
+      bool touching = contact_update(minP, a, sid, b, false, wk, &m_min);
+      wake_all(wk);
+      if (!touching) {
+        clrb(en, minP);
+        AG(F_C0X, b) = bk0; AG(F_C0Y, b) = bk1; AG(F_CX, b) = bk2; AG(F_CY, b) = bk3;
+        AG(F_A0, b) = bk4; AG(F_A, b) = bk5; AG(F_ALPHA0, b) = bk6;
+        return 0;
+      }
+      wake(b);
+      isl_add(sid, m_min);
     }
     {
-      unsigned long long done[PW];
+      // the agent's other existing contacts against static bodies, newest (largest creation sequence) first;
+      // the sequence numbers are fetched together (one memory latency), then ranked in registers
+      int sq[BC + 4];
 #pragma unroll
-      for (int w = 0; w < PW; ++w) done[w] = 0ull;
-      setb(done, minP);
+      for (int k = 0; k < BC + 4; ++k) {
+        const int p = k < BC ? p_ab(b, k) : p_aw(b, k - BC);
+        sq[k] = ((k < BC && k >= nb) || p == minP || !bit(ex, p)) ? -1 : (int)S.pseq[p * N + e];
+      }
       for (;;) {
         int best = -1, bestSeq = -1;
-        for (int k = 0; k < BC + 4; ++k) {
-          if (k < BC && k >= nb) continue;
-          int p = k < BC ? p_ab(b, k) : p_aw(b, k - BC);
-          if (!bit(ex, p) || bit(done, p)) continue;
-          int sq = (int)S.pseq[p * N + e];
-          if (sq > bestSeq) { bestSeq = sq; best = p; }
-        }
+#pragma unroll
+        for (int k = 0; k < BC + 4; ++k) if (sq[k] > bestSeq) { bestSeq = sq[k]; best = k; }
         if (best < 0) break;
-        setb(done, best);
-        if (nisl >= 8) { LI(L_OVERFLOW)++; break; }
-        int a2, sid2, b2; decode(best, a2, sid2, b2);
+#pragma unroll
+        for (int k = 0; k < BC + 4; ++k) if (k == best) sq[k] = -1;
+        if (nisl >= TOI_ISL) { LI(L_OVERFLOW)++; break; }
+        const int p2 = best < BC ? p_ab(b, best) : p_aw(b, best - BC);
         Manifold m; unsigned wk2 = 0;
-        bool t2 = contact_update(best, a2, sid2, b2, false, wk2, &m);
+        bool t2 = contact_update(p2, -1, best, b, false, wk2, &m);
         wake_all(wk2);
-        if (!t2) continue;
-        TCon& t = isl[nisl++];
-        t.p = best; t.seq = 0; t.a = -1; t.sid = sid2; t.b = b; t.flags = 0; t.m = m; t.ni = 0.0f; t.ti = 0.0f;
+        if (t2) isl_add(best, m);
       }
     }
-    float subdt = (1.0f - minAlpha) * dt;
+    const float subdt = (1.0f - minAlpha) * dt;
     // b2Island::SolveTOI -- every contact of the mini island has a static body A
     {
       f2 cB = apos(b);
-      for (int k = 0; k < nisl; ++k) static_plane(isl[k], isl[k].normal, isl[k].rA);  // rA := plane point
       for (int it = 0; it < 20; ++it) {
         float minSep = 0.0f;
-        for (int k = 0; k < nisl; ++k) minSep = fmin_(minSep, solve_position_static(isl[k].normal, isl[k].rA, cB, true));
+        for (int k = 0; k < nisl; ++k)
+          minSep = fmin_(minSep, solve_position_static(mk2(KF(KS_NX, k), KF(KS_NY, k)), mk2(KF(KS_PX, k), KF(KS_PY, k)), cB, true));
         if (minSep >= -1.5f * B2_LINEAR_SLOP) break;
       }
       AG(F_CX, b) = cB.x; AG(F_CY, b) = cB.y;
     }
     AG(F_C0X, b) = AG(F_CX, b); AG(F_C0Y, b) = AG(F_CY, b); AG(F_A0, b) = AG(F_A, b);
-    for (int k = 0; k < nisl; ++k) init_velocity(isl[k]);
     {
+      // b2ContactSolver::InitializeVelocityConstraints at the corrected position (impulses start at zero, no warm start)
+      const f2 cB = apos(b);
+      for (int k = 0; k < nisl; ++k) {
+        const f2 normal = mk2(KF(KS_NX, k), KF(KS_NY, k)), planePoint = mk2(KF(KS_PX, k), KF(KS_PY, k));
+        const f2 pA = vadd(cB, vmul(B2_POLY_RADIUS - vdot(vsub(cB, planePoint), normal), normal));
+        const f2 pB = vsub(cB, vmul(C.agent_r, normal));
+        const f2 point = vmul(0.5f, vadd(pA, pB));
+        const f2 rB = vsub(point, cB);
+        const float rnB = vcross(rB, normal);
+        const float kNormal = C.inv_mass + C.inv_I * rnB * rnB;
+        const f2 tangent = cross_vs(normal, 1.0f);
+        const float rtB = vcross(rB, tangent);
+        const float kTangent = C.inv_mass + C.inv_I * rtB * rtB;
+        KF(KS_RBX, k) = rB.x; KF(KS_RBY, k) = rB.y;
+        KF(K_NM, k) = kNormal > 0.0f ? 1.0f / kNormal : 0.0f; KF(K_TM, k) = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+        KF(K_NI, k) = 0.0f; KF(K_TI, k) = 0.0f;
+      }
       f2 vB = mk2(AG(F_VX, b), AG(F_VY, b)); float wB = AG(F_W, b);
       for (int it = 0; it < 10; ++it)
-        for (int k = 0; k < nisl; ++k) { TCon& t = isl[k]; solve_velocity_static(t.normal, t.rB, t.normalMass, t.tangentMass, t.ni, t.ti, vB, wB); }
+        for (int k = 0; k < nisl; ++k) {
+          float ni_ = KF(K_NI, k), ti_ = KF(K_TI, k);
+          solve_velocity_static(mk2(KF(KS_NX, k), KF(KS_NY, k)), mk2(KF(KS_RBX, k), KF(KS_RBY, k)), KF(K_NM, k), KF(K_TM, k), ni_, ti_, vB, wB);
+          KF(K_NI, k) = ni_; KF(K_TI, k) = ti_;
+        }
       AG(F_VX, b) = vB.x; AG(F_VY, b) = vB.y; AG(F_W, b) = wB;
     }
     integrate_position(b, subdt);
     AGF(b) &= ~FL_MOVED;
     synchronize_fixtures(b);
-    if (AGF(b) & FL_MOVED) find_new_contacts_seq();
+    if (AGF(b) & FL_MOVED) find_new_contacts_of(b);
     // A TOI event is a pure function of (agent b's sweep/velocity/AABB words, the pair
     // bit-matrices, the contact counter).  If this event left all of them exactly as the
     // previous event on the same contact did, every further event on it would repeat
     // verbatim and only count up to b2_maxSubSteps (a body wedged between two static
     // bodies does this): the caller jumps the contact's toiCount there instead of replaying them.
-    unsigned snap[SNAPW];
-    for (int f = 0; f < F_COUNT; ++f) snap[f] = __float_as_uint(AG(f, b));
-    for (int w = 0; w < PW; ++w) {
-      snap[F_COUNT + 6 * w + 0] = (unsigned)ex[w]; snap[F_COUNT + 6 * w + 1] = (unsigned)(ex[w] >> 32);
-      snap[F_COUNT + 6 * w + 2] = (unsigned)tc[w]; snap[F_COUNT + 6 * w + 3] = (unsigned)(tc[w] >> 32);
-      snap[F_COUNT + 6 * w + 4] = (unsigned)en[w]; snap[F_COUNT + 6 * w + 5] = (unsigned)(en[w] >> 32);
-    }
-    snap[SNAPW - 1] = (unsigned)LI(L_CONTACTSEQ);
     bool same = prevP == minP;
-    for (int q = 0; q < SNAPW; ++q) { if (prev[q] != snap[q]) same = false; prev[q] = snap[q]; }
-    prevP = minP;
+    auto snap = [&](int q, unsigned v) { if (SNAP(q) != v) same = false; SNAP(q) = v; };
+    for (int f = 0; f < F_COUNT; ++f) snap(f, __float_as_uint(AG(f, b)));
+#pragma unroll
+    for (int w = 0; w < PW; ++w) {
+      snap(F_COUNT + 6 * w + 0, (unsigned)ex[w]); snap(F_COUNT + 6 * w + 1, (unsigned)(ex[w] >> 32));
+      snap(F_COUNT + 6 * w + 2, (unsigned)tc[w]); snap(F_COUNT + 6 * w + 3, (unsigned)(tc[w] >> 32));
+      snap(F_COUNT + 6 * w + 4, (unsigned)en[w]); snap(F_COUNT + 6 * w + 5, (unsigned)(en[w] >> 32));
+    }
+    snap(SNAPW - 1, (unsigned)LI(L_CONTACTSEQ));
     return 1 | (same ? 2 : 0);
   }
 
@@ -1292,7 +1331,7 @@ struct Env {
     unsigned long long evcnt[SLOTS]; unsigned cvalid[SLOTS];
 #pragma unroll
     for (int q = 0; q < SLOTS; ++q) { evcnt[q] = 0ull; cvalid[q] = 0u; }
-    unsigned prev[SNAPW]; int prevP = -1;      // leader: state after the previous event (compared only once prevP is set)
+    int prevP = -1;                            // leader: contact of the previous event that ran (its state snapshot sits in shared memory)
     for (int guard = 0; guard < 64; ++guard) {
       int minP = -1, minSeq = -1; float minAlpha = 1.0f;
 #pragma unroll
@@ -1360,8 +1399,9 @@ struct Env {
       int r = 0;
       if (lead) {
         RARE_BEGIN();
-        if ((MSV_INLINE_MASK >> 1) & 1) r = toi_event(minP, minAlpha, dt, prev, prevP);
-        else { Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prev, prevP); take(c_); }
+        if ((MSV_INLINE_MASK >> 1) & 1) r = toi_event(minP, minAlpha, dt, prevP);
+        else { Env c_(*this); r = c_.toi_event(minP, minAlpha, dt, prevP); take(c_); }
+        if (r & 1) prevP = minP;
         RARE_END(1);
       }
       gsync();

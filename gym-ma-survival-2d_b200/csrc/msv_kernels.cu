@@ -264,6 +264,126 @@ k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, co
 }
 
 
+// fetch_observations, fast path (every environment, no row filter).  The descriptor-driven kernel
+// above evaluates one output float per thread (~100 instructions each); this one works SOURCE-major:
+// a warp takes one source item -- agent j, box k, floor item k, heal k, the zone -- for 32
+// consecutive environments (lane = environment: the SoA loads are fully coalesced), builds
+// everything that item contributes (an agent row goes to `agent` and to the `others` block of every
+// other observer; observer j's mask rows and inventory-slot views) and scatters it into a
+// shared-memory stage laid out exactly like the 32-environment slice of each output tensor.  The
+// stage is then copied out with 16-byte stores, one contiguous run per tensor.
+#define OBS2_E 32
+__global__ void __launch_bounds__(1024)
+k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC) {
+  extern __shared__ float stage[];
+  __shared__ int koff[MSV_OBS_KEYS + 1];
+  const int A = C.A, B = C.B0, H = C.H0, Sw = C.S, N = C.N;
+  const int e0 = blockIdx.x * OBS2_E, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int k = 0; k < MSV_OBS_KEYS; ++k) { koff[k] = o; o += OBS2_E * Tb.keys[k].chunk; }
+    koff[MSV_OBS_KEYS] = o;
+  }
+  __syncthreads();
+  const int e = e0 + lane;
+  const bool live = e < N;                       // rows past the padded batch do not exist
+  const int n_items = A + 2 * B + H + 1;
+  auto put = [&](int key, int off, float v) { stage[koff[key] + lane * Tb.keys[key].chunk + off] = v; };
+  auto vert = [&](float hx, float hy, int rot, int comp) {   // b2PolygonShape vertex order (Q8)
+    int j = ((comp >> 1) + rot) & 3;
+    return (comp & 1) ? ((j >= 2) ? hy : -hy) : ((j == 1 || j == 2) ? hx : -hx);
+  };
+  const int nwarps = blockDim.x >> 5;
+  for (int it = warp; it < n_items; it += nwarps) {
+    if (it < A) {                                // ---- agent j: its row everywhere + observer j's own views
+      const int j = it;
+      int inv = 0; bool al = false; unsigned long long obm = 0ull; unsigned om = 0u; int cnts = 0;
+      float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+      float r_id = 0.f, r_team = 0.f, r_hp = 0.f, r_x = 0.f, r_y = 0.f, r_a = 0.f, r_vx = 0.f, r_vy = 0.f, r_w = 0.f;   // env:659-691
+      if (live) {
+        const float4 k0 = S.akin0[j * N + e], k1 = S.akin1[j * N + e]; const int4 ai = S.aint[j * N + e];
+        al = (__float_as_int(k1.w) & 1) != 0; inv = ai.w; obm = S.obm[e]; cnts = S.hdr0[e].x;
+        if (!C.omniscient) om = S.omask[j * N + e];
+        r_id = (float)j; r_team = (float)(j < A / 2 ? 0 : 1);
+        if (al) { r_hp = (float)ai.x; r_x = k0.x; r_y = k0.y; r_a = k0.z; r_vx = k0.w; r_vy = k1.x; r_w = k1.y; }
+        const int n = inv & 7;
+        if (al && n > 0 && ((inv >> (4 + 2 * (n - 1))) & 3) == MSV_ITEM_BOX) pl = S.ainv[(j * 4 + n - 1) * N + e];
+      }
+      const int tm = C.teams ? 1 : 0;
+      auto emit = [&](int key, int base) {         // [id, (team), health, x, y, angle, vx, vy, omega]
+        put(key, base, r_id); if (tm) put(key, base + 1, r_team);
+        put(key, base + tm + 1, r_hp); put(key, base + tm + 2, r_x); put(key, base + tm + 3, r_y); put(key, base + tm + 4, r_a);
+        put(key, base + tm + 5, r_vx); put(key, base + tm + 6, r_vy); put(key, base + tm + 7, r_w);
+      };
+      emit(0, j * Sw);
+      for (int i = 0; i < A; ++i) {              // others[i][k]: agents in index order skipping the observer (env:529-534)
+        if (i == j) continue;
+        emit(1, (i * (A - 1) + (j < i ? j : j - 1)) * Sw);
+      }
+      for (int q = 0; q < A; ++q) {              // others_mask[j][k]: 0 = seen by observer j's camera (env:692-703)
+        if (q == j) continue;
+        const int k = q < j ? q : q - 1;
+        put(2, j * (A - 1) + k, ((obm >> (j * AC + q)) & 1ull) ? 0.0f : 1.0f);
+      }
+      const int nb = cnts & 255, ni = (cnts >> 8) & 255, nh = (cnts >> 16) & 255;
+      const int n = inv & 7; const int top = n > 0 ? (inv >> (4 + 2 * (n - 1))) & 3 : 0;
+      if (H > 0) {
+        for (int k = 0; k < H; ++k) {
+          const bool seen = C.omniscient ? k < nh : (k < nh && al && ((om >> k) & 1u));      // env:564-568 / 706-739
+          put(5, j * H + k, (live && seen) ? 0.0f : 1.0f);
+        }
+        const bool has = al && top == MSV_ITEM_HEAL;
+        put(6, j, has ? (float)C.healing : 0.0f); put(7, j, has ? 0.0f : 1.0f);
+      }
+      if (B > 0) {
+        for (int k = 0; k < B; ++k) {
+          const bool sb_ = C.omniscient ? k < nb : (k < nb && al && ((om >> (16 + k)) & 1u));
+          const bool si_ = C.omniscient ? k < ni : (k < ni && al && ((om >> (24 + k)) & 1u));
+          put(9, j * B + k, (live && sb_) ? 0.0f : 1.0f); put(11, j * B + k, (live && si_) ? 0.0f : 1.0f);
+        }
+        const bool has = al && top == MSV_ITEM_BOX;
+        for (int c = 0; c < 8; ++c) put(12, j * 8 + c, has ? vert(pl.x, pl.y, __float_as_int(pl.w) & 1, c) : 0.0f);
+        put(13, j, has ? 0.0f : 1.0f);
+      }
+    } else if (it < A + B) {                     // ---- box k (env:570-591)
+      const int k = it - A;
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f); int rot = 0; bool on = false;
+      if (live && k < (S.hdr0[e].x & 255)) { b0 = S.box0[k * N + e]; rot = (S.box1[k * N + e].y >> 1) & 1; on = true; }
+      for (int c = 0; c < 8; ++c) put(8, k * 11 + c, on ? vert(b0.z, b0.w, rot, c) : 0.0f);
+      put(8, k * 11 + 8, on ? b0.x : 0.0f); put(8, k * 11 + 9, on ? b0.y : 0.0f); put(8, k * 11 + 10, 0.0f);
+    } else if (it < A + 2 * B) {                 // ---- floor box item k (env:593-619)
+      const int k = it - A - B;
+      float4 i0 = make_float4(0.f, 0.f, 0.f, 0.f); bool on = false;
+      if (live && k < ((S.hdr0[e].x >> 8) & 255)) { i0 = S.item0[k * N + e]; on = true; }
+      for (int c = 0; c < 8; ++c) put(10, k * 10 + c, on ? vert(i0.z, i0.w, 1, c) : 0.0f);
+      put(10, k * 10 + 8, on ? i0.x : 0.0f); put(10, k * 10 + 9, on ? i0.y : 0.0f);
+    } else if (it < A + 2 * B + H) {             // ---- heal k (env:552-568)
+      const int k = it - A - 2 * B;
+      float2 hh = make_float2(0.f, 0.f);
+      if (live && k < ((S.hdr0[e].x >> 16) & 255)) hh = S.heal[k * N + e];
+      put(4, 2 * k, hh.x); put(4, 2 * k + 1, hh.y);
+    } else {                                     // ---- zone (env:537-550)
+      float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        const float4 zc = S.zonecur[e]; const int ph = S.zoneint[e].x;
+        z[0] = zc.x; z[1] = zc.y; z[2] = zc.z;
+        if (ph < C.zone_phases - 1) { const float2 c2 = S.zonec[(ph + 1) * N + e]; z[3] = c2.x; z[4] = c2.y; z[5] = C.zone_r32[ph + 1]; }
+      }
+      for (int c = 0; c < 6; ++c) put(3, c, z[c]);
+    }
+  }
+  __syncthreads();
+  int rows = N - e0; if (rows > OBS2_E) rows = OBS2_E;         // N is a multiple of 4: every run below is a whole number of float4
+  for (int k = 0; k < MSV_OBS_KEYS; ++k) {
+    const int chunk = Tb.keys[k].chunk;
+    if (chunk <= 0 || (k >= 4 && k <= 7 && H == 0) || (k >= 8 && B == 0)) continue;   // key groups the config does not have
+    const int n4 = rows * chunk / 4;
+    const float4* src = reinterpret_cast<const float4*>(stage + koff[k]);
+    float4* dst = reinterpret_cast<float4*>(Tb.keys[k].base + (size_t)e0 * chunk);
+    for (int q = threadIdx.x; q < n4; q += blockDim.x) dst[q] = src[q];
+  }
+}
+
 // Lidars._update (simulation.py:377-392) as an extension observation block,
 // scanned on the state the observation describes.  ONE WARP PER AGENT: the
 // rays go across the lanes; when there are fewer than 32 rays each ray is
@@ -404,6 +524,17 @@ cudaError_t msv_launch(int cap, int which, const DevConst& C, const DevState& S,
 }
 
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, const uint8_t* only_if, cudaStream_t st) {
+#ifndef MSV_OBS_GENERIC
+  if (!only_if) {                                // every row: the source-major kernel
+    size_t smem = 0;
+    for (int k = 0; k < MSV_OBS_KEYS; ++k) smem += (size_t)OBS2_E * T.keys[k].chunk * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_obs2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    const int threads = smem <= 56 * 1024 ? 256 : 1024;     // small stage: several blocks per SM; large (ffa): one block of 32 warps
+    k_obs2<<<(C.n_real + OBS2_E - 1) / OBS2_E, threads, smem, st>>>(C, S, T, AC);
+    return cudaPeekAtLastError();
+  }
+#endif
   k_obs<<<(C.n_real + OBS_EPB - 1) / OBS_EPB, 256, (size_t)OBS_EPB * T.n_elems * sizeof(float), st>>>(C, S, T, AC, only_if);
   return cudaPeekAtLastError();
 }
