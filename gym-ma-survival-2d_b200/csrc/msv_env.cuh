@@ -253,83 +253,86 @@ struct Env {
   }
 
   // ---- global state I/O -------------------------------------------------
+  // Every global load of the environment is issued before the first shared-memory store: the state
+  // pointers are generic, so a store to shared memory orders the loads behind it and the load phase
+  // would pay the HBM latency once per field group instead of once.
   DEV void load() {
-    for (int i = g; i < AC; i += G) {        // every lane: its agents' kinematics
-      if (i < C.A) {
-        float4 k0 = S.akin0[i * N + e], k1 = S.akin1[i * N + e], ft = S.afat[i * N + e];
-        AG(F_CX, i) = k0.x; AG(F_CY, i) = k0.y; AG(F_A, i) = k0.z; AG(F_VX, i) = k0.w;
-        AG(F_VY, i) = k1.x; AG(F_W, i) = k1.y; AG(F_SLEEP, i) = k1.z; AGF(i) = __float_as_int(k1.w) & 3;
-        AG(F_FAT0, i) = ft.x; AG(F_FAT1, i) = ft.y; AG(F_FAT2, i) = ft.z; AG(F_FAT3, i) = ft.w;
-        AG(F_C0X, i) = k0.x; AG(F_C0Y, i) = k0.y; AG(F_A0, i) = k0.z; AG(F_ALPHA0, i) = 0.0f;
-        AG(F_QS, i) = 0.0f; AG(F_QC, i) = 1.0f;
-      } else AGF(i) = 0;
+    static_assert(SLOTS == 1, "one agent per lane");
+    constexpr int BL = (BC + G - 1) / G, HL = (HC + G - 1) / G;   // boxes / heals per lane
+    const int i = g;
+    const bool mine = i < C.A;
+    float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, ft = k0;
+    if (mine) { k0 = S.akin0[i * N + e]; k1 = S.akin1[i * N + e]; ft = S.afat[i * N + e]; }
+    float4 b0[BL], it0[BL]; int4 b1[BL]; float2 hl[HL];
+#pragma unroll
+    for (int q = 0; q < BL; ++q) {               // slots past the list lengths hold stale data that is never read
+      const int k = g + q * G;
+      if (k < BC) { b0[q] = S.box0[k * N + e]; b1[q] = S.box1[k * N + e]; it0[q] = S.item0[k * N + e]; }
     }
-    for (int k = g; k < BC; k += G) {          // slots past the list lengths hold stale data that is never read
-      load_box(k, k);
-      float4 it = S.item0[k * N + e]; ITP(0, k) = it.x; ITP(1, k) = it.y;
+#pragma unroll
+    for (int q = 0; q < HL; ++q) { const int k = g + q * G; if (k < HC) hl[q] = S.heal[k * N + e]; }
+    int4 ai[AC]; float srw[AC], epr[AC]; int skl[AC];
+    int4 h0 = make_int4(0, 0, 0, 0), h1 = h0, zi = h0, sm_ = h0; float4 zc = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned long long lx[PW], lt[PW], ln[PW];
+    if (lead) {
+#pragma unroll
+      for (int j = 0; j < AC; ++j) {
+        ai[j] = j < C.A ? S.aint[j * N + e] : make_int4(0, MSV_CAUSE_NONE, 0, 0);
+        srw[j] = S.sreward[j * N + e]; skl[j] = S.skills[j * N + e]; epr[j] = S.epret[j * N + e];
+      }
+      h0 = S.hdr0[e]; h1 = S.hdr1[e];
+#pragma unroll
+      for (int w = 0; w < PW; ++w) { lx[w] = S.pex[w * N + e]; lt[w] = S.ptc[w * N + e]; ln[w] = S.pen[w * N + e]; }
+      zc = S.zonecur[e]; zi = S.zoneint[e]; sm_ = S.smisc[e];
     }
-    for (int k = g; k < HC; k += G) { float2 h = S.heal[k * N + e]; HLP(0, k) = h.x; HLP(1, k) = h.y; }
+    // ---- shared-memory stores
+    if (mine) {
+      AG(F_CX, i) = k0.x; AG(F_CY, i) = k0.y; AG(F_A, i) = k0.z; AG(F_VX, i) = k0.w;
+      AG(F_VY, i) = k1.x; AG(F_W, i) = k1.y; AG(F_SLEEP, i) = k1.z; AGF(i) = __float_as_int(k1.w) & 3;
+      AG(F_FAT0, i) = ft.x; AG(F_FAT1, i) = ft.y; AG(F_FAT2, i) = ft.z; AG(F_FAT3, i) = ft.w;
+      AG(F_C0X, i) = k0.x; AG(F_C0Y, i) = k0.y; AG(F_A0, i) = k0.z; AG(F_ALPHA0, i) = 0.0f;
+      AG(F_QS, i) = 0.0f; AG(F_QC, i) = 1.0f;
+    } else AGF(i) = 0;
+#pragma unroll
+    for (int q = 0; q < BL; ++q) {
+      const int k = g + q * G;
+      if (k < BC) { put_box(k, b0[q], b1[q]); ITP(0, k) = it0[q].x; ITP(1, k) = it0[q].y; }
+    }
+#pragma unroll
+    for (int q = 0; q < HL; ++q) { const int k = g + q * G; if (k < HC) { HLP(0, k) = hl[q].x; HLP(1, k) = hl[q].y; } }
     nb = ni = nh = 0;
 #pragma unroll
     for (int w = 0; w < PW; ++w) { ex[w] = 0ull; tc[w] = 0ull; en[w] = 0ull; }
     if (lead) {
 #pragma unroll
-      for (int i = 0; i < AC; ++i) {
-        if (i < C.A) { int4 ai = S.aint[i * N + e]; LI(L_HEALTH + (i)) = ai.x; LI(L_CAUSE + (i)) = ai.y; LI(L_COOLDOWN + (i)) = ai.z; LI(L_INV + (i)) = ai.w; }
-        else { LI(L_HEALTH + (i)) = 0; LI(L_CAUSE + (i)) = MSV_CAUSE_NONE; LI(L_COOLDOWN + (i)) = 0; LI(L_INV + (i)) = 0; }
-        LF(L_SREW + (i)) = S.sreward[i * N + e]; LI(L_SKILLS + (i)) = S.skills[i * N + e];
-        LF(L_EPRET + (i)) = S.epret[i * N + e];
+      for (int j = 0; j < AC; ++j) {
+        LI(L_HEALTH + (j)) = ai[j].x; LI(L_CAUSE + (j)) = ai[j].y; LI(L_COOLDOWN + (j)) = ai[j].z; LI(L_INV + (j)) = ai[j].w;
+        LF(L_SREW + (j)) = srw[j]; LI(L_SKILLS + (j)) = skl[j]; LF(L_EPRET + (j)) = epr[j];
       }
-      int4 h0 = S.hdr0[e], h1 = S.hdr1[e];
       nb = h0.x & 255; ni = (h0.x >> 8) & 255; nh = (h0.x >> 16) & 255; LI(L_NP) = (h0.x >> 24) & 255;
       LI(L_STEPS) = h0.y; LI(L_EPISODE) = h0.z; LI(L_BODYSEQ) = h0.w;
       LI(L_CONTACTSEQ) = h1.x; LI(L_FIRST) = h1.y; LI(L_OVERFLOW) = h1.z; LI(L_NEWFIX) = h1.w;
 #pragma unroll
-      for (int w = 0; w < PW; ++w) { ex[w] = S.pex[w * N + e]; tc[w] = S.ptc[w * N + e]; en[w] = S.pen[w * N + e]; }
-      float4 zc = S.zonecur[e]; int4 zi = S.zoneint[e];
+      for (int w = 0; w < PW; ++w) { ex[w] = lx[w]; tc[w] = lt[w]; en[w] = ln[w]; }
       LF(L_ZX) = zc.x; LF(L_ZY) = zc.y; LF(L_ZR) = zc.z; LI(L_ZPHASE) = zi.x; LI(L_ZTCOOL) = zi.y; LI(L_ZTSHRINK) = zi.z; LI(L_ZEND) = zi.w;
-      int4 sm_ = S.smisc[e];
       LI(L_STSTEPS) = sm_.x; LI(L_STHEALS) = sm_.y; LI(L_STBOXES) = sm_.z; LI(L_STEPISODES) = sm_.w;
       NTC() = 0; OVF() = 0;
     }
     ntc = 0;
     gsync();
     share_counts(); share_bits();
-    prefetch_cold();
   }
-  // The cold per-pair / per-body words (contact sequence numbers, warm-start impulses, creation
-  // sequences, zone centres) are read in the middle of the step, one dependent load at a time; ask
-  // L2 for them now so that those loads do not wait for HBM.
-  DEV static void pf(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-  DEV void prefetch_cold() {
-#ifndef MSV_NO_PREFETCH
-#pragma unroll
-    for (int w = 0; w < PW; ++w) {
-      unsigned long long m = ex[w] & own[w];
-      while (m) {
-        int p = w * 64 + __ffsll((long long)m) - 1; m &= m - 1;
-        pf(&S.pseq[p * N + e]); pf(&S.pimp[p * N + e]);
-      }
-    }
-    for (int k = g; k < nb; k += G) pf(&S.boxseq[k * N + e]);
-    for (int k = g; k < ni; k += G) pf(&S.item1[k * N + e]);
-    for (int k = g; k < nh; k += G) pf(&S.healseq[k * N + e]);
-    if (lead) {
-      const int ph = LI(L_ZPHASE);
-      pf(&S.zonec[ph * N + e]); pf(&S.zonec[(ph + 1 < MSV_MAX_ZONES ? ph + 1 : ph) * N + e]);
-    }
-#endif
-  }
-  // read box at global slot `src` into shared slot `dst`
-  DEV void load_box(int dst, int src) {
-    float4 b0 = S.box0[src * N + e]; int4 b1 = S.box1[src * N + e];
+  // shared-memory record of a box (shape expanded, fat AABB computed once per box and step instead of once per pair test)
+  DEV void put_box(int dst, float4 b0, int4 b1) {
     BX(G_X, dst) = b0.x; BX(G_Y, dst) = b0.y;
     SBox t; sb_set_shape(t, b0.z, b0.w, (b1.y >> 1) & 1);
     BX(G_HX, dst) = t.hx; BX(G_HY, dst) = t.hy; BX(G_AX, dst) = t.ax; BX(G_AY, dst) = t.ay; BXROT(dst) = t.rot;
     t.px = b0.x; t.py = b0.y; t.qs = 0.0f; t.qc = 1.0f; t.ang = 0.0f;
-    float ft[4]; sb_fat(t, ft);                 // computed once per box and step instead of once per pair test
+    float ft[4]; sb_fat(t, ft);
     BX(G_F0, dst) = ft[0]; BX(G_F1, dst) = ft[1]; BX(G_F2, dst) = ft[2]; BX(G_F3, dst) = ft[3];
   }
+  // read box at global slot `src` into shared slot `dst`
+  DEV void load_box(int dst, int src) { put_box(dst, S.box0[src * N + e], S.box1[src * N + e]); }
   DEV void store() {
     gsync();
     for (int i = g; i < C.A; i += G) {
@@ -578,7 +581,19 @@ struct Env {
 #pragma unroll
     for (int w = 0; w < PW; ++w) { cand[w] = or64(cand[w]); any |= cand[w] != 0ull; }
     if (any) {                               // group-uniform
-      if (lead) { RARE_BEGIN(); unsigned long long cc[PW]; for (int w = 0; w < PW; ++w) cc[w] = cand[w]; MSV_COLDK(2, number_candidates(cc)); RARE_END(6); }
+      if (lead) {
+        int nset = 0;
+#pragma unroll
+        for (int w = 0; w < PW; ++w) nset += __popcll(cand[w]);
+        if (nset == 1) {                       // one new contact (the usual case): no ordering to do
+          int p = 0;
+#pragma unroll
+          for (int w = 0; w < PW; ++w) if (cand[w]) p = w * 64 + __ffsll((long long)cand[w]) - 1;
+          setb(ex, p); setb(en, p); clrb(tc, p);
+          S.pseq[p * N + e] = (uint32_t)(++LI(L_CONTACTSEQ));
+          S.pimp[p * N + e] = make_float2(0.0f, 0.0f);
+        } else { RARE_BEGIN(); unsigned long long cc[PW]; for (int w = 0; w < PW; ++w) cc[w] = cand[w]; MSV_COLDK(2, number_candidates(cc)); RARE_END(6); }
+      }
       share_bits();
     }
   }
@@ -1574,6 +1589,13 @@ struct Env {
     uint32_t a = o[(k & 1) * 2], b = o[(k & 1) * 2 + 1];
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
   }
+  // draws 2j and 2j+1 of a stream are the two halves of ONE Philox block: both at once (the reset path draws in order)
+  __device__ __noinline__ double2 philox_uniform2(uint32_t step, uint32_t stream, uint32_t blk) {
+    uint32_t o[4];
+    philox4x32(C.env_offset + (uint32_t)e, (uint32_t)LI(L_EPISODE), step, (stream << 16) | blk, C.seed_lo, C.seed_hi, o);
+    return make_double2(((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) / 9007199254740992.0,
+                        ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) / 9007199254740992.0);
+  }
 
   // Cameras._update_seen (sim:336-354), agent targets (the only ones the
   // omniscient observation reads, env:692-703)
@@ -1667,8 +1689,16 @@ struct Env {
   // [leader]
   __device__ __forceinline__ void post_step_boxes() {
     // boxes/Health.post_step (sem:429-435) + Object.pre_despawn (sem:858-861, 911-912)
-    for (int k = 0; k < nb;) {
-      int4 b1 = S.box1[k * N + e];
+    // (the health words of all boxes are fetched together: one memory latency instead of one per box)
+    int4 b1s[BC];
+#pragma unroll
+    for (int j = 0; j < BC; ++j) if (j < nb) b1s[j] = S.box1[j * N + e];
+    const int nb0 = nb; int removed = 0;
+#pragma unroll
+    for (int j = 0; j < BC; ++j) {
+      if (j >= nb0) continue;
+      const int k = j - removed;                  // current list position of the box that was at j
+      int4 b1 = b1s[j];
       if (!(b1.y & 1)) { b1.y |= 1; b1.x = C.box_health; S.box1[k * N + e] = b1; }
       if (b1.x <= 0) {
         if (LI(L_NP) < BC) {
@@ -1677,7 +1707,8 @@ struct Env {
           LI(L_NP)++;
         } else LI(L_OVERFLOW)++;
         { RARE_BEGIN(); MSV_COLDK(3, remove_box(k)); RARE_END(7); }
-      } else ++k;
+        removed++;
+      }
     }
   }
   // agents/Cameras.post_step (sim:333-334) runs between the two halves
@@ -1702,6 +1733,32 @@ struct Env {
     }
     for (int i = 0; i < C.A; ++i) if ((LU(L_DMASK) >> i) & 1u) LI(L_KCAUSE + (LI(L_NKILLS)++)) = LI(L_CAUSE + (i));  // TrackKills sem:628-629
     for (int i = 0; i < C.A; ++i) if ((LU(L_DMASK) >> i) & 1u) kill_agent(i);
+  }
+  // pairs that involve agent i (compile-time masks)
+  DEV static constexpr unsigned long long pairs_of(int i, int w) {
+    unsigned long long m = 0ull;
+    for (int j = 0; j < AC; ++j) if (j != i) { const int p = i < j ? j * (j - 1) / 2 + i : i * (i - 1) / 2 + j; if ((p >> 6) == w) m |= 1ull << (p & 63); }
+    for (int k = 0; k < BC + 4; ++k) { const int p = k < BC ? NAA + i * BC + k : NAA + AC * BC + i * 4 + (k - BC); if ((p >> 6) == w) m |= 1ull << (p & 63); }
+    return m;
+  }
+  // [leader] handle_deaths() for agents that carry nothing: TrackKills (sem:628-629) in index order, then
+  // b2World::DestroyBody for each (touching agent-agent contacts wake the partner), all with static pair masks
+  DEV void kill_agents_empty(unsigned dm) {
+#pragma unroll
+    for (int i = 0; i < AC; ++i) if ((dm >> i) & 1u) LI(L_KCAUSE + (LI(L_NKILLS)++)) = LI(L_CAUSE + (i));
+#pragma unroll
+    for (int i = 0; i < AC; ++i) {
+      if (!((dm >> i) & 1u)) continue;
+#pragma unroll
+      for (int j = 0; j < AC; ++j) {
+        if (j == i) continue;
+        const int p = i < j ? j * (j - 1) / 2 + i : i * (i - 1) / 2 + j;     // p_aa, static
+        if (((ex[0] & tc[0]) >> p) & 1ull) wake(j);
+      }
+#pragma unroll
+      for (int w = 0; w < PW; ++w) { const unsigned long long m = ~pairs_of(i, w); ex[w] &= m; tc[w] &= m; en[w] &= m; }
+      AGF(i) = 0;
+    }
   }
   // [leader] agents/AutoPickup.post_step (sem:278-283) for agent i: bodies in creation order
   COLD3 void pickup_agent(int i) {
@@ -1743,7 +1800,15 @@ struct Env {
       LU(L_DMASK) = 0; LI(L_NKILLS) = 0;
 #pragma unroll
       for (int i = 0; i < AC; ++i) if (i < C.A && alive(i) && LI(L_HEALTH + (i)) <= 0) LU(L_DMASK) |= 1u << i;
-      if (LU(L_DMASK)) { RARE_BEGIN(); MSV_COLDK(3, handle_deaths()); dflag = 1; RARE_END(3); }
+      if (LU(L_DMASK)) {
+        const unsigned dm = LU(L_DMASK);
+        int carried = 0;
+#pragma unroll
+        for (int i = 0; i < AC; ++i) if ((dm >> i) & 1u) carried += LI(L_INV + (i)) & 7;
+        if (carried == 0) kill_agents_empty(dm);      // nothing to drop (the usual case): TrackKills + DestroyBody only
+        else { RARE_BEGIN(); MSV_COLDK(3, handle_deaths()); RARE_END(3); }
+        dflag = 1;
+      }
     }
     dflag = bc(dflag);
     if (dflag) { gsync(); share_counts(); }   // drops changed the lists, deaths the flags
@@ -1917,10 +1982,15 @@ struct Env {
   COLD4 void reset() {
     LI(L_EPISODE) += 1; LI(L_STEPS) = 0;
     int n = C.grid_n;
-    unsigned char perm[64];
+    // (the shuffled cell list lives in the dead touching-contact list: byte-indexed shared memory instead of a local array)
+    unsigned char* perm = reinterpret_cast<unsigned char*>(&msv_sm[sb + W_TC]);
+    static_assert(K_COUNT * MAXC * 4 >= 64, "scratch too small for the spawn grid");
     for (int k = 0; k < n; ++k) perm[k] = (unsigned char)k;
+    double2 up = make_double2(0.0, 0.0);
     for (int i = n - 1; i >= 1; --i) {
-      double u = philox_uniform(0u, STREAM_SHUFFLE, (uint32_t)(n - 1 - i));
+      const uint32_t kd = (uint32_t)(n - 1 - i);
+      if (!(kd & 1u)) up = philox_uniform2(0u, STREAM_SHUFFLE, kd >> 1);
+      const double u = (kd & 1u) ? up.y : up.x;
       int j = (int)(u * (i + 1));
       unsigned char t = perm[i]; perm[i] = perm[j]; perm[j] = t;
     }
@@ -1934,8 +2004,8 @@ struct Env {
       if (C.box_randomized) {
         double z[2];
         for (int q = 0; q < 2; ++q) {
-          double u1 = philox_uniform(0u, STREAM_BOX, (uint32_t)(2 * (2 * b + q)));
-          double u2 = philox_uniform(0u, STREAM_BOX, (uint32_t)(2 * (2 * b + q) + 1));
+          const double2 ub = philox_uniform2(0u, STREAM_BOX, (uint32_t)(2 * b + q));
+          const double u1 = ub.x, u2 = ub.y;
           z[q] = sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);
         }
         double w = C.box_avg_w + C.box_std_w * z[0]; if (!(w > C.box_min_w)) w = C.box_min_w;
@@ -1973,8 +2043,8 @@ struct Env {
       int d = 0;
       for (int z = C.n_zones - 1; z >= 0; --z) {
         double L = C.floor_size - 2 * C.zone_radiuses[z];
-        double ux = philox_uniform(0u, STREAM_ZONE, (uint32_t)d); d++;
-        double uy = philox_uniform(0u, STREAM_ZONE, (uint32_t)d); d++;
+        const double2 uz = philox_uniform2(0u, STREAM_ZONE, (uint32_t)(d >> 1)); d += 2;
+        const double ux = uz.x, uy = uz.y;
         S.zonec[z * N + e] = make_float2((float)((ux * L) - L / 2), (float)((uy * L) - L / 2));
       }
     } else {
