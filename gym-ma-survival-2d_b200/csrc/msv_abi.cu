@@ -133,6 +133,7 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
   D->n_zones = c->zone_n_radiuses + 1; D->zone_centers_random = c->zone_centers_random;
   D->lidar_n = c->lidar_n; D->auto_reset = c->auto_reset; D->grid_n = c->grid_size * c->grid_size;
   D->immunity_cooldown = c->immunity_cooldown; D->battle_royale = c->battle_royale; D->b2_variant = c->b2_variant;
+  D->toi_max_count = (c->b2_variant & MSV_B2_SUBSTEPS_GE) ? 7 : 8;   // b2_maxSubSteps = 8: "toiCount > 8" vs "toiCount >= 8" skips the contact
   D->r_alive = c->r_alive; D->r_dead = c->r_dead; D->r_kill = c->r_kill; D->r_death = c->r_death;
   D->agent_r = (float)(c->agent_size / 2);          // semantics.py:16-18
   D->heal_r = (float)(c->heal_item_size / 2);       // semantics.py:24-25
@@ -359,6 +360,12 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
       cfg->zone_phases > cfg->zone_n_radiuses + 1 || cfg->lidar_n < 0 || cfg->lidar_n > MSV_MAX_LASERS ||
       cfg->zone_phases < 1 || env_offset < 0 || env_offset + (int64_t)num_envs > (int64_t)1 << 32)   // Philox counter word 0 is 32 bits
     return MSV_ERR_INVALID;
+  {  // b2PolygonShape::Set welds vertices closer than its tolerance: a box that small is not a box any more (Box2D asserts);
+     // the kernel treats every box analytically, so such configs are refused instead of simulated differently
+    const double tol2 = (cfg->b2_variant & MSV_B2_WELD_SQUARED) ? (0.5 * 0.005) * (0.5 * 0.005) : 0.5 * 0.005;   // compared with a SQUARED distance
+    const double wmin = cfg->box_randomized ? (cfg->box_min_w < cfg->box_min_h ? cfg->box_min_w : cfg->box_min_h) : cfg->box_size;
+    if (cfg->n_boxes > 0 && !(wmin * wmin >= tol2)) { g_err = "box edge below the b2PolygonShape::Set weld tolerance"; return MSV_ERR_INVALID; }
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
     g_err = "no CUDA device: libmasurv has no CPU fallback";
@@ -644,6 +651,17 @@ int64_t msv_debug_overflow(msv_handle* h) {
   int64_t tot = 0;
   for (int e = 0; e < h->C.n_real; ++e) tot += v[e].z;
   return tot;
+}
+
+/* debug: bounds-check violations counted by a `make CHECK=1` build since the library was loaded
+ * (-1: error, -2: this is not a checked build); *line = source line of the last violation */
+int64_t msv_debug_check_failures(msv_handle* h, int64_t* line) {
+  if (!h) return -1;
+  DevGuard g(h->device); cudaDeviceSynchronize();
+  unsigned long long v[2] = {0, 0};
+  if (msv_read_check(v) != cudaSuccess) return -1;
+  if (line) *line = (int64_t)v[1];
+  return v[0] == ~0ull ? -2 : (int64_t)v[0];
 }
 
 /* debug/bench: the two halves of msv_step separately, so that bench.py can put

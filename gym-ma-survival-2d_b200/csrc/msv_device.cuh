@@ -363,6 +363,22 @@ DEV f2 point_at(f2 c0, f2 c, float beta) { return vadd(vmul(1.0f - beta, c0), vm
 #define TOI_TOUCHING 3
 #define TOI_SEPARATED 4
 
+// make CHECK=1: every indexed access to the environment's shared-memory column (and the fixed-capacity lists
+// behind it) is bounds-checked; violations are counted (msv_debug_check_failures) and the index clamped.
+// compute-sanitizer is not available on the GPU pool, so this build is the memory-safety evidence.
+#ifdef MSV_CHECK
+__device__ unsigned long long g_chk[2];   // [0] violations, [1] line of the last one
+#define CHK(cond) do { if (!(cond)) { atomicAdd(&g_chk[0], 1ull); g_chk[1] = __LINE__; } } while (0)
+__device__ __forceinline__ int chk_idx_(int i, int n, int line) {
+  if ((unsigned)i < (unsigned)n) return i;
+  atomicAdd(&g_chk[0], 1ull); g_chk[1] = (unsigned long long)line;
+  return 0;
+}
+#define CHK_IDX(i, n) chk_idx_((i), (n), __LINE__)
+#else
+#define CHK(cond) do { } while (0)
+#define CHK_IDX(i, n) (i)
+#endif
 #ifdef MSV_PROFILE
 __device__ unsigned long long g_dbg[8];
 // rare-path census: [2k] number of calls, [2k+1] clock64() cycles spent in them (k: 0 generic island solve,

@@ -200,19 +200,19 @@ struct Env {
 #define MSV_COLDK(k, call) do { if ((MSV_INLINE_MASK >> (k)) & 1) { call; } else { Env c_(*this); c_.call; take(c_); } } while (0)
 
   // ---- shared-memory accessors
-  DEV float& AG(int f, int i) { return msv_sm[sb + (f * AC + i)]; }
-  DEV int& AGF(int i) { return reinterpret_cast<int*>(msv_sm)[sb + (F_FLAGS * AC + i)]; }
-  DEV float& BX(int f, int k) { return msv_sm[sb + (W_BOX + f * BC + k)]; }
-  DEV int& BXROT(int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_BOX + G_ROT * BC + k)]; }
-  DEV float& KF(int f, int k) { return msv_sm[sb + (W_TC + f * MAXC + k)]; }
-  DEV int& KI(int f, int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_TC + f * MAXC + k)]; }
+  DEV float& AG(int f, int i) { return msv_sm[sb + (CHK_IDX(f, F_COUNT) * AC + CHK_IDX(i, AC))]; }
+  DEV int& AGF(int i) { return reinterpret_cast<int*>(msv_sm)[sb + (F_FLAGS * AC + CHK_IDX(i, AC))]; }
+  DEV float& BX(int f, int k) { return msv_sm[sb + (W_BOX + CHK_IDX(f, G_COUNT) * BC + CHK_IDX(k, BC))]; }
+  DEV int& BXROT(int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_BOX + G_ROT * BC + CHK_IDX(k, BC))]; }
+  DEV float& KF(int f, int k) { return msv_sm[sb + (W_TC + CHK_IDX(f, K_COUNT) * MAXC + CHK_IDX(k, MAXC))]; }
+  DEV int& KI(int f, int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_TC + CHK_IDX(f, K_COUNT) * MAXC + CHK_IDX(k, MAXC))]; }
   DEV int& NTC() { return reinterpret_cast<int*>(msv_sm)[sb + (W_MISC + 0)]; }
-  DEV float& ITP(int c, int k) { return msv_sm[sb + (W_ITEM + c * BC + k)]; }
-  DEV float& HLP(int c, int k) { return msv_sm[sb + (W_HEAL + c * HC + k)]; }
-  DEV int& LI(int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_LEAD + k)]; }
-  DEV unsigned& LU(int k) { return reinterpret_cast<unsigned*>(msv_sm)[sb + (W_LEAD + k)]; }
-  DEV float& LF(int k) { return msv_sm[sb + (W_LEAD + k)]; }
-  DEV float& TOIA(int i, int k) { return msv_sm[sb + (W_TOI + i * (BC + 4) + k)]; }
+  DEV float& ITP(int c, int k) { return msv_sm[sb + (W_ITEM + CHK_IDX(c, 2) * BC + CHK_IDX(k, BC))]; }
+  DEV float& HLP(int c, int k) { return msv_sm[sb + (W_HEAL + CHK_IDX(c, 2) * HC + CHK_IDX(k, HC))]; }
+  DEV int& LI(int k) { return reinterpret_cast<int*>(msv_sm)[sb + (W_LEAD + CHK_IDX(k, L_COUNT))]; }
+  DEV unsigned& LU(int k) { return reinterpret_cast<unsigned*>(msv_sm)[sb + (W_LEAD + CHK_IDX(k, L_COUNT))]; }
+  DEV float& LF(int k) { return msv_sm[sb + (W_LEAD + CHK_IDX(k, L_COUNT))]; }
+  DEV float& TOIA(int i, int k) { return msv_sm[sb + (W_TOI + CHK_IDX(i, AC) * (BC + 4) + CHK_IDX(k, BC + 4))]; }
   DEV int& OVF() { return reinterpret_cast<int*>(msv_sm)[sb + (W_MISC + 1)]; }
   DEV bool alive(int i) { return AGF(i) & FL_ALIVE; }
   DEV bool awake(int i) { return AGF(i) & FL_AWAKE; }
@@ -242,6 +242,7 @@ struct Env {
   DEV static int p_aw(int i, int k) { return NAA + AC * BC + i * 4 + k; }
   // decode pair -> (a, sid, b)
   DEV static void decode(int p, int& a, int& sid, int& b) {
+    CHK((unsigned)p < (unsigned)P);
     if (p < NAA) {
       int j = 1; while (j * (j + 1) / 2 <= p) ++j;
       a = p - j * (j - 1) / 2; b = j; sid = -1;
@@ -626,6 +627,7 @@ struct Env {
 
   // append a touching contact to the environment's shared list (any lane)
   DEV void tcon_add(int p, int a, int sid, int b, const Manifold& m, float nimp, float timp) {
+    CHK((unsigned)p < (unsigned)P && (unsigned)b < (unsigned)AC && a < AC && sid < BC + 4);
     int k = atomicAdd(&NTC(), 1);
     if (k >= MAXC) { atomicAdd(&OVF(), 1); return; }
     KI(K_META, k) = meta_pack(p, a, sid, b); KI(K_SEQ, k) = (int)S.pseq[p * N + e];
@@ -993,6 +995,136 @@ struct Env {
   struct Ord { unsigned long long lo, hi; };   // island contact order: list slots, 5 bits each
   DEV static int ord_get(const Ord& o, int k) { return k < 12 ? (int)((o.lo >> (5 * k)) & 31ull) : (int)((o.hi >> (5 * (k - 12))) & 31ull); }
   DEV static void ord_put(Ord& o, int k, int v) { if (k < 12) o.lo |= (unsigned long long)v << (5 * k); else o.hi |= (unsigned long long)v << (5 * (k - 12)); }
+  // b2Island::Solve (after the damping) for an island of exactly TWO agents X < Y with at most NP
+  // contacts -- their agent-agent contact plus a few against static bodies -- with the bodies and the
+  // contact constants in registers (statically indexed, loops unrolled).  Same arithmetic, same order
+  // of operations as the general shared-memory loops of solve_island() below.
+  static constexpr int NP = 3;
+  DEV void island_pair(unsigned inisl, int nc, const Ord& ord, float h, float dtRatio) {
+    const int X = __ffs((int)inisl) - 1, Y = 31 - __clz((int)inisl);
+    f2 cX = apos(X), cY = apos(Y);
+    f2 vX = mk2(AG(F_VX, X), AG(F_VY, X)), vY = mk2(AG(F_VX, Y), AG(F_VY, Y));
+    float wX = AG(F_W, X), wY = AG(F_W, Y), aX = AG(F_A, X), aY = AG(F_A, Y);
+    const float mI = C.inv_mass, iI = C.inv_I;
+    int ty[NP], pr[NP];                          // 0: X-Y contact, 1: static body vs X, 2: static body vs Y
+    f2 nrm[NP], px[NP], rB[NP]; float nm[NP], tm[NP], ni_[NP], ti_[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      ty[k] = 0; pr[k] = 0; nrm[k] = mk2(0.f, 0.f); px[k] = nrm[k]; rB[k] = nrm[k]; nm[k] = tm[k] = ni_[k] = ti_[k] = 0.0f;
+      if (k >= nc) continue;
+      const int s = ord_get(ord, k);
+      int a_, sid, b_; meta_unpack(KI(K_META, s), pr[k], a_, sid, b_);
+      ni_[k] = dtRatio * KF(K_NI, s); ti_[k] = dtRatio * KF(K_TI, s);
+      if (a_ >= 0) {   // two dynamic circles (b2WorldManifold::Initialize, e_circles); body A = X, body B = Y
+        ty[k] = 0;
+        f2 normal = mk2(1.0f, 0.0f);
+        if (vlen2(vsub(cX, cY)) > B2_EPS * B2_EPS) { normal = vsub(cY, cX); vnormalize(normal); }
+        const f2 pA = vadd(cX, vmul(C.agent_r, normal)), pB = vsub(cY, vmul(C.agent_r, normal));
+        const f2 point = vmul(0.5f, vadd(pA, pB));
+        px[k] = vsub(point, cX); rB[k] = vsub(point, cY);                  // px := rA
+        const float rnA = vcross(px[k], normal), rnB = vcross(rB[k], normal);
+        const float kNormal = mI + mI + iI * rnA * rnA + iI * rnB * rnB;
+        nm[k] = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+        const f2 tangent = cross_vs(normal, 1.0f);
+        const float rtA = vcross(px[k], tangent), rtB = vcross(rB[k], tangent);
+        const float kTangent = mI + mI + iI * rtA * rtA + iI * rtB * rtB;
+        tm[k] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+        nrm[k] = normal;
+      } else {
+        ty[k] = b_ == X ? 1 : 2;
+        init_velocity_static(sid, mk2(KF(K_LNX, s), KF(K_LNY, s)), mk2(KF(K_LPX, s), KF(K_LPY, s)), b_ == X ? cX : cY,
+                             nrm[k], px[k], rB[k], nm[k], tm[k]);           // px := plane point
+      }
+    }
+    for (int it = -1; it < 10; ++it) {           // warm start, then 10 velocity iterations, contacts in island order
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        if (k >= nc) continue;
+        if (ty[k] != 0) {
+          f2 vB = ty[k] == 1 ? vX : vY; float wB = ty[k] == 1 ? wX : wY;
+          if (it < 0) warm_start_static(nrm[k], rB[k], ni_[k], ti_[k], vB, wB);
+          else solve_velocity_static(nrm[k], rB[k], nm[k], tm[k], ni_[k], ti_[k], vB, wB);
+          if (ty[k] == 1) { vX = vB; wX = wB; } else { vY = vB; wY = wB; }
+        } else {
+          const f2 normal = nrm[k], rA = px[k], rB_ = rB[k], tangent = cross_vs(normal, 1.0f);
+          if (it < 0) {   // b2ContactSolver::WarmStart
+            const f2 Pv = vadd(vmul(ni_[k], normal), vmul(ti_[k], tangent));
+            wX -= iI * vcross(rA, Pv); vX = vsub(vX, vmul(mI, Pv));
+            wY += iI * vcross(rB_, Pv); vY = vadd(vY, vmul(mI, Pv));
+          } else {        // b2ContactSolver::SolveVelocityConstraints: friction, then the normal constraint
+            {
+              const f2 dv = vsub(vsub(vadd(vY, cross_sv(wY, rB_)), vX), cross_sv(wX, rA));
+              const float vt = vdot(dv, tangent) - 0.0f;
+              float lambda = tm[k] * (-vt);
+              const float maxFriction = C.friction * ni_[k];
+              const float newImpulse = fclamp_(ti_[k] + lambda, -maxFriction, maxFriction);
+              lambda = newImpulse - ti_[k]; ti_[k] = newImpulse;
+              const f2 Pv = vmul(lambda, tangent);
+              vX = vsub(vX, vmul(mI, Pv)); wX -= iI * vcross(rA, Pv);
+              vY = vadd(vY, vmul(mI, Pv)); wY += iI * vcross(rB_, Pv);
+            }
+            {
+              const f2 dv = vsub(vsub(vadd(vY, cross_sv(wY, rB_)), vX), cross_sv(wX, rA));
+              const float vn = vdot(dv, normal);
+              float lambda = -nm[k] * (vn - 0.0f);
+              const float newImpulse = fmax_(ni_[k] + lambda, 0.0f);
+              lambda = newImpulse - ni_[k]; ni_[k] = newImpulse;
+              const f2 Pv = vmul(lambda, normal);
+              vX = vsub(vX, vmul(mI, Pv)); wX -= iI * vcross(rA, Pv);
+              vY = vadd(vY, vmul(mI, Pv)); wY += iI * vcross(rB_, Pv);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) if (k < nc) S.pimp[pr[k] * N + e] = make_float2(ni_[k], ti_[k]);   // b2ContactSolver::StoreImpulses
+    AG(F_VX, X) = vX.x; AG(F_VY, X) = vX.y; AG(F_W, X) = wX; AG(F_VX, Y) = vY.x; AG(F_VY, Y) = vY.y; AG(F_W, Y) = wY;
+    integrate_position(X, h); integrate_position(Y, h);
+    cX = apos(X); cY = apos(Y); aX = AG(F_A, X); aY = AG(F_A, Y);
+    bool ok = false;
+    for (int it = 0; it < 10 && !ok; ++it) {     // b2ContactSolver::SolvePositionConstraints
+      float minSep = 0.0f;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        if (k >= nc) continue;
+        float separation;
+        if (ty[k] == 1) separation = solve_position_static(nrm[k], px[k], cX, false);
+        else if (ty[k] == 2) separation = solve_position_static(nrm[k], px[k], cY, false);
+        else {         // circles: the manifold point is the midpoint, normal along the centres
+          f2 normal = vsub(cY, cX); vnormalize(normal);
+          const f2 point = vmul(0.5f, vadd(cX, cY));
+          separation = vdot(vsub(cY, cX), normal) - C.agent_r - C.agent_r;
+          const f2 rA = vsub(point, cX), rB_ = vsub(point, cY);
+          const float Cc = fclamp_(B2_BAUMGARTE * (separation + B2_LINEAR_SLOP), -B2_MAX_LIN_CORR, 0.0f);
+          const float rnA = vcross(rA, normal), rnB = vcross(rB_, normal);
+          const float K = mI + mI + iI * rnA * rnA + iI * rnB * rnB;
+          const float impulse = K > 0.0f ? -Cc / K : 0.0f;
+          const f2 Pv = vmul(impulse, normal);
+          cX = vsub(cX, vmul(mI, Pv)); aX -= iI * vcross(rA, Pv);
+          cY = vadd(cY, vmul(mI, Pv)); aY += iI * vcross(rB_, Pv);
+        }
+        minSep = fmin_(minSep, separation);
+      }
+      ok = minSep >= -3.0f * B2_LINEAR_SLOP;
+    }
+    AG(F_CX, X) = cX.x; AG(F_CY, X) = cX.y; AG(F_A, X) = aX; AG(F_CX, Y) = cY.x; AG(F_CY, Y) = cY.y; AG(F_A, Y) = aY;
+    {
+      const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
+      bool can_sleep = ok;                       // minSleepTime >= timeToSleep && positionSolved
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = q == 0 ? X : Y;
+        float w = AG(F_W, i); f2 v = mk2(AG(F_VX, i), AG(F_VY, i));
+        float st;
+        if (w * w > angTol || vdot(v, v) > linTol) st = 0.0f; else st = AG(F_SLEEP, i) + h;
+        AG(F_SLEEP, i) = st;
+        if (!(st >= B2_TIME_TO_SLEEP)) can_sleep = false;
+      }
+      if (can_sleep) { sleep_body(X); sleep_body(Y); }
+    }
+    synchronize_fixtures(X); synchronize_fixtures(Y);
+  }
   COLD0 void solve_island(int seed, float h, float dtRatio) {
     Ord ord; ord.lo = 0ull; ord.hi = 0ull;
     int nc = 0; unsigned taken = 0, inisl = 1u << seed;
@@ -1035,6 +1167,7 @@ struct Env {
       AG(F_VX, i) = C.damp * AG(F_VX, i); AG(F_VY, i) = C.damp * AG(F_VY, i);  // v *= 1/(1+h*damping)
       AG(F_W, i) *= C.damp;
     }
+    if (__popc(inisl) == 2 && nc <= NP) { island_pair(inisl, nc, ord, h, dtRatio); return; }   // two agents, <= NP contacts (the usual case)
     // b2ContactSolver::InitializeVelocityConstraints (+ the warm-start scaling of b2ContactSolver's constructor)
     for (int k = 0; k < nc; ++k) {
       const int s = ord_get(ord, k);
@@ -1222,7 +1355,7 @@ struct Env {
   static constexpr int SNAPW = F_COUNT + 6 * PW + 1;
   static constexpr int TOI_ISL = 8;
   static_assert(SNAPW <= K_COUNT * (MAXC - TOI_ISL), "snapshot does not fit the scratch slots");
-  DEV unsigned& SNAP(int q) { return reinterpret_cast<unsigned*>(msv_sm)[sb + (W_TC + (q / (MAXC - TOI_ISL)) * MAXC + TOI_ISL + q % (MAXC - TOI_ISL))]; }
+  DEV unsigned& SNAP(int q) { CHK((unsigned)q < (unsigned)SNAPW); return reinterpret_cast<unsigned*>(msv_sm)[sb + (W_TC + (q / (MAXC - TOI_ISL)) * MAXC + TOI_ISL + q % (MAXC - TOI_ISL))]; }
   COLD1 int toi_event(int minP, float minAlpha, float dt, int prevP) {
     int a, sid, b; decode(minP, a, sid, b);
     // backup the agent's sweep, advance to the TOI, re-evaluate the contact
@@ -1362,7 +1495,7 @@ struct Env {
 #pragma unroll
           for (int q = 1; q < SLOTS; ++q) if (i / G == q) { ec = evcnt[q]; cv = cvalid[q]; }
           const int cnt = (int)((ec >> (4 * k)) & 15ull);
-          if (cnt > B2_MAX_SUBSTEPS) continue;
+          if (cnt > C.toi_max_count) continue;       // b2_maxSubSteps (">=" under MSV_B2_SUBSTEPS_GE)
           float alpha = 1.0f; const bool have = (cv >> k) & 1u;
           if (have) alpha = TOIA(i, k);
           else {
@@ -1436,7 +1569,7 @@ struct Env {
           cvalid[q] = 0u;                      // "Invalidate all contact TOIs on this displaced body"
           if (r & 2) {                         // identical repeat: jump the contact's toiCount past b2_maxSubSteps
             unsigned long long c4 = (evcnt[q] >> (4 * ek)) & 15ull;
-            if (c4 <= (unsigned long long)B2_MAX_SUBSTEPS) evcnt[q] = (evcnt[q] & ~(15ull << (4 * ek))) | ((unsigned long long)(B2_MAX_SUBSTEPS + 1) << (4 * ek));
+            if (c4 <= (unsigned long long)C.toi_max_count) evcnt[q] = (evcnt[q] & ~(15ull << (4 * ek))) | ((unsigned long long)(C.toi_max_count + 1) << (4 * ek));
           }
         }
       }
@@ -1498,10 +1631,11 @@ struct Env {
         f2 off = mk2(qc * L + (-qs) * 0.0f, qs * L + qc * 0.0f);
         float x = AG(F_CX, i) + off.x, y = AG(F_CY, i) + off.y;
         int reh = __float_as_int(pl.w) & 1;
-        S.box0[nb * N + e] = make_float4(x, y, pl.x, pl.y);
-        S.box1[nb * N + e] = make_int4(0, reh << 1, MSV_CAUSE_NONE, C.box_ownership ? __float_as_int(pl.z) : MSV_CAUSE_NONE);
+        const float4 nb0 = make_float4(x, y, pl.x, pl.y);
+        const int4 nb1 = make_int4(0, reh << 1, MSV_CAUSE_NONE, C.box_ownership ? __float_as_int(pl.z) : MSV_CAUSE_NONE);
+        S.box0[nb * N + e] = nb0; S.box1[nb * N + e] = nb1;
         S.boxseq[nb * N + e] = LI(L_BODYSEQ)++;
-        load_box(nb, nb);
+        put_box(nb, nb0, nb1);                       // (not read back from global memory)
         for (int j = 0; j < C.A; ++j) { int p = p_ab(j, nb); clrb(ex, p); clrb(tc, p); clrb(en, p); }
         nb++; LI(L_NEWBOX) = 1; LI(L_NEWFIX) = 1;
       }
@@ -2013,10 +2147,11 @@ struct Env {
         hx = (float)(w / 2.); hy = (float)(h / 2.);
       }
       int cell = perm[--top];
-      S.box0[b * N + e] = make_float4(C.grid_px[cell], C.grid_py[cell], hx, hy);
-      S.box1[b * N + e] = make_int4(C.box_health, 1, MSV_CAUSE_NONE, MSV_CAUSE_NONE);
+      const float4 nb0 = make_float4(C.grid_px[cell], C.grid_py[cell], hx, hy);
+      const int4 nb1 = make_int4(C.box_health, 1, MSV_CAUSE_NONE, MSV_CAUSE_NONE);
+      S.box0[b * N + e] = nb0; S.box1[b * N + e] = nb1;
       S.boxseq[b * N + e] = LI(L_BODYSEQ)++;
-      load_box(b, b);
+      put_box(b, nb0, nb1);                          // (not read back from global memory)
       nb++;
     }
     for (int h = 0; h < C.H0; ++h) {
@@ -2039,21 +2174,27 @@ struct Env {
       } else { AGF(i) = 0; LI(L_HEALTH + (i)) = 0; }
       LI(L_CAUSE + (i)) = MSV_CAUSE_NONE; LI(L_COOLDOWN + (i)) = 0; LI(L_INV + (i)) = 0;
     }
+    float2 c0 = make_float2(0.0f, 0.0f);           // centre of phase 0 (kept: not read back from global memory)
     if (C.zone_centers_random) {
       int d = 0;
       for (int z = C.n_zones - 1; z >= 0; --z) {
         double L = C.floor_size - 2 * C.zone_radiuses[z];
         const double2 uz = philox_uniform2(0u, STREAM_ZONE, (uint32_t)(d >> 1)); d += 2;
         const double ux = uz.x, uy = uz.y;
-        S.zonec[z * N + e] = make_float2((float)((ux * L) - L / 2), (float)((uy * L) - L / 2));
+        const float2 cz = make_float2((float)((ux * L) - L / 2), (float)((uy * L) - L / 2));
+        S.zonec[z * N + e] = cz;
+        if (z == 0) c0 = cz;
       }
     } else {
-      for (int z = 0; z < C.n_zones; ++z)
-        S.zonec[z * N + e] = make_float2((float)C.zone_centers[z][0], (float)C.zone_centers[z][1]);
+      for (int z = 0; z < C.n_zones; ++z) {
+        const float2 cz = make_float2((float)C.zone_centers[z][0], (float)C.zone_centers[z][1]);
+        S.zonec[z * N + e] = cz;
+        if (z == 0) c0 = cz;
+      }
     }
     LI(L_ZTCOOL) = C.zone_cooldown; LI(L_ZTSHRINK) = 0; LI(L_ZPHASE) = 0; LI(L_ZEND) = 0;
     LF(L_ZR) = C.zone_r32[0];
-    float2 c0 = S.zonec[e]; LF(L_ZX) = c0.x; LF(L_ZY) = c0.y;
+    LF(L_ZX) = c0.x; LF(L_ZY) = c0.y;
     LU(L_DMASK) = 0; LI(L_NKILLS) = 0; LI(L_USEHEAL) = 0; LI(L_USEBOX) = 0;
     for (int i = 0; i < AC; ++i) LF(L_EPRET + (i)) = 0.0f;
   }

@@ -559,6 +559,15 @@ cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* ski
   return cudaPeekAtLastError();
 }
 
+cudaError_t msv_read_check(unsigned long long out[2]) {
+#ifdef MSV_CHECK
+  return cudaMemcpyFromSymbol(out, g_chk, sizeof(unsigned long long) * 2);
+#else
+  out[0] = ~0ull; out[1] = 0;      // not a checked build
+  return cudaSuccess;
+#endif
+}
+
 cudaError_t msv_read_profile(unsigned long long out[64], int reset) {
   cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 64);
   if (e != cudaSuccess) return e;

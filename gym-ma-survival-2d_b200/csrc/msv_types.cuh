@@ -20,6 +20,7 @@ struct DevConst {
   int zone_phases, zone_cooldown, zone_damage, n_zones, zone_centers_random;
   int lidar_n, auto_reset, grid_n;  // grid_n = grid_size^2
   int immunity_cooldown, battle_royale, b2_variant;
+  int toi_max_count;     // a contact takes part in SolveTOI while toiCount <= this (b2_maxSubSteps, or one less under MSV_B2_SUBSTEPS_GE)
   float r_alive, r_dead, r_kill, r_death;
   float agent_r, heal_r, item_r, box_h;
   float inv_mass, inv_I, friction, dt, dt_ratio1, damp;

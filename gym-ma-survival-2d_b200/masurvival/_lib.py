@@ -84,6 +84,8 @@ def load():
     L.msv_debug_obs_kernel.argtypes = [vp, vp]
     L.msv_debug_overflow.argtypes = [vp]
     L.msv_debug_overflow.restype = i64
+    L.msv_debug_check_failures.argtypes = [vp, ctypes.POINTER(i64)]
+    L.msv_debug_check_failures.restype = i64
     if L.msv_abi_version() != 2:
         raise MasurvError('libmasurv.so ABI version mismatch')
     for name, dt in (('msv_sizeof_config', CONFIG_DT), ('msv_sizeof_env_state', STATE_DT),
@@ -208,6 +210,13 @@ class Handle:
 
     def overflow_events(self):
         return int(load().msv_debug_overflow(self.h))
+
+    def check_failures(self):
+        """(violations, source line of the last one) counted by a bounds-checked build (make CHECK=1);
+        violations == -2 when the loaded library is not a checked build"""
+        line = ctypes.c_int64()
+        n = int(load().msv_debug_check_failures(self.h, ctypes.byref(line)))
+        return n, int(line.value)
 
     def bytes_per_env_step(self):
         return int(load().msv_bytes_per_env_step(self.h))

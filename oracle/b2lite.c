@@ -98,6 +98,13 @@ void b2l_set_as_box(b2l_shape* s, float hx, float hy) {
 
 /* b2PolygonShape::Set (2.3.0): weld, gift-wrap from the right-most (lowest on
  * ties) point, normals = normalize(cross(edge, 1)). */
+/* Details that differ between Box2D 2.3.x builds (masurv.h MSV_B2_*): the real pybox2d cannot be run in
+ * this image, so the choices it would pin are switchable.  Process-global: the oracle sets it from the
+ * env's config at every entry point. */
+static int g_b2_variant = 0;
+void b2l_set_variant(int v) { g_b2_variant = v; }
+int b2l_get_variant(void) { return g_b2_variant; }
+
 int b2l_polygon_set(b2l_shape* s, const v2* vertices, int count) {
   memset(s, 0, sizeof *s);
   s->type = B2L_POLYGON; s->radius = b2_polygonRadius;
@@ -106,7 +113,8 @@ int b2l_polygon_set(b2l_shape* s, const v2* vertices, int count) {
   for (int i = 0; i < n; ++i) {
     v2 v = vertices[i]; int unique = 1;
     for (int j = 0; j < tempCount; ++j)
-      if (vlen2(vsub(v, ps[j])) < 0.5f * b2_linearSlop) { unique = 0; break; }
+      /* 2.3.0 compares the SQUARED distance with 0.5*linearSlop; later releases square the tolerance */
+      if (vlen2(vsub(v, ps[j])) < ((g_b2_variant & 2) ? (0.5f * b2_linearSlop) * (0.5f * b2_linearSlop) : 0.5f * b2_linearSlop)) { unique = 0; break; }
     if (unique) ps[tempCount++] = v;
   }
   n = tempCount;
@@ -734,8 +742,13 @@ static void island_solve(b2l_world* w, island_t* is, float h, float dtRatio, int
       /* gravity 0, no forces: v += h * (0 + invMass * 0) */
       v = vadd(v, vmul(h, vadd(vmul(1.0f, V(0.0f, 0.0f)), vmul(b->invMass, V(0.0f, 0.0f)))));
       wv += h * b->invI * 0.0f;
-      v = vmul(1.0f / (1.0f + h * b->linDamp), v);
-      wv *= 1.0f / (1.0f + h * b->angDamp);
+      if (g_b2_variant & 1) {   /* Box2D <= 2.2: v *= b2Clamp(1 - h * damping, 0, 1) */
+        v = vmul(fclamp(1.0f - h * b->linDamp, 0.0f, 1.0f), v);
+        wv *= fclamp(1.0f - h * b->angDamp, 0.0f, 1.0f);
+      } else {                  /* 2.3.x: Pade approximation */
+        v = vmul(1.0f / (1.0f + h * b->linDamp), v);
+        wv *= 1.0f / (1.0f + h * b->angDamp);
+      }
     }
     is->st[i].c = c; is->st[i].a = a; is->st[i].v = v; is->st[i].w = wv;
   }
@@ -1256,7 +1269,7 @@ static void world_solve_toi(b2l_world* w, float dt, int velIters) {
     for (int k = 0; k < nco; ++k) {
       b2l_contact* c = &w->contacts[corder[k]];
       if (!(c->flags & B2L_ENABLED)) continue;
-      if (c->toiCount > b2_maxSubSteps) continue;
+      if ((g_b2_variant & 4) ? c->toiCount >= b2_maxSubSteps : c->toiCount > b2_maxSubSteps) continue;
       float alpha = 1.0f;
       if (c->flags & B2L_TOI) alpha = c->toi;
       else {

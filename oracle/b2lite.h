@@ -111,6 +111,10 @@ int  b2l_shape_raycast(const b2l_shape* s, b2l_vec2 p, float qs, float qc,
                        float* fraction, b2l_vec2* normal);
 void b2l_rot(float angle, float* s, float* c); /* b2Rot::Set */
 
+/* Box2D build variant (masurv.h MSV_B2_* bits), process-global */
+void b2l_set_variant(int v);
+int  b2l_get_variant(void);
+
 /* world */
 b2l_world* b2l_world_new(void);
 void b2l_world_free(b2l_world* w);

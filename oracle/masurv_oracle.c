@@ -180,6 +180,7 @@ oracle_env* orc_create(const msv_config* cfg, uint64_t seed, int64_t env_id) {
   oracle_env* e = (oracle_env*)calloc(1, sizeof *e);
   e->cfg = *cfg; e->seed = seed; e->env_id = env_id;
   e->w = b2l_world_new();
+  b2l_set_variant(cfg->b2_variant);
   e->agent_r = (float)(cfg->agent_size / 2);       /* sem:16-18 */
   e->heal_r = (float)(cfg->heal_item_size / 2);    /* sem:24-25 */
   e->item_r = (float)(cfg->box_item_size / 2);
@@ -231,6 +232,7 @@ static void lidar_update(oracle_env* e);
 /* BaseEnv.reset (env:59-74) */
 void orc_reset(oracle_env* e, orc_out* out) {
   const msv_config* c = &e->cfg;
+  b2l_set_variant(c->b2_variant);
   e->episode += 1; e->steps = 0;
   memset(e->ep_return, 0, sizeof e->ep_return);
   b2l_world_clear(e->w);
@@ -423,6 +425,7 @@ static void box_change_health(oracle_env* e, int k, int delta, int cause) {
 /* ----------------------------------------------------------------- step --- */
 void orc_step(oracle_env* e, const uint8_t* actions, orc_out* out) {
   const msv_config* c = &e->cfg;
+  b2l_set_variant(c->b2_variant);
   const int A = c->n_agents;
   b2l_world* w = e->w;
   static const double dtab[3] = {-1., 0., 1.};

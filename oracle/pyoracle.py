@@ -24,9 +24,10 @@ STATS_DT = STRUCTS['msv_stats']
 
 
 def build(force=False):
-    so = os.path.join(_HERE, 'liboracle.so')
+    name = os.environ.get('ORACLE_LIB', 'liboracle.so')      # ORACLE_LIB=liboracle_asan.so: the sanitizer build (make asan)
+    so = os.path.join(_HERE, name)
     if force or not os.path.exists(so):
-        subprocess.check_call(['make', '-C', _HERE, 'liboracle.so'])
+        subprocess.check_call(['make', '-C', _HERE, name])
     return so
 
 

@@ -41,6 +41,14 @@ class _V2(ctypes.Structure):
 
 
 _L.b2l_world_new.restype = _vp
+_L.b2l_set_variant.argtypes = [_i]
+
+
+def set_variant(v):
+    """Box2D build variant of the restated subset (include/masurv.h MSV_B2_* bits); process-global"""
+    _L.b2l_set_variant(int(v))
+
+
 _L.b2l_world_free.argtypes = [_vp]
 _L.b2l_circle.argtypes = [_vp, _f]
 _L.b2l_set_as_box.argtypes = [_vp, _f, _f]

@@ -190,3 +190,67 @@ def test_box_item_cycle_and_vertex_order():
     ang = float(before['angle'][0])
     assert abs(float(st['box_x'][3]) - (float(before['x'][0]) + 0.75 * math.cos(ang))) < 1e-5
     assert st['box_has_health'][3] == 1 and st['box_health'][3] == 20
+
+
+# ---- Box2D build variants (masurv.h MSV_B2_*): each switchable detail has its own known answer --------
+def test_b2_variant_clamp_damping():
+    """bit 0: Box2D <= 2.2 damping v *= clamp(1 - h*d, 0, 1) instead of the Pade form of 2.3.x"""
+    out = {}
+    for var in (0, 1):
+        rec, o = fresh(box2d={'variant': var})
+        s = clear_world(o.get_state().copy())
+        place(s, 0, 0.0, 0.0, 0.0, vx=1.0, vy=-2.0, w=0.5); place(s, 1, 5.0, 5.0)
+        o.set_state(s)
+        o.step([NOOP, NOOP])
+        out[var] = o.get_state()
+    clampd = f32(1.0) - DT * f32(0.8)
+    assert out[0]['vx'][0] == f32(1.0) * DAMP * DAMP
+    assert out[1]['vx'][0] == f32(1.0) * clampd * clampd and out[1]['omega'][0] == f32(0.5) * clampd * clampd
+    assert out[0]['vx'][0] != out[1]['vx'][0]
+
+
+def test_b2_variant_weld_tolerance():
+    """bit 1: b2PolygonShape::Set welds vertices whose SQUARED distance is below 0.5*linearSlop in 2.3.0
+    (so below 0.05 apart), below (0.5*linearSlop)^2 in later releases"""
+    import ctypes
+    L = po.lib()
+    L.b2l_set_variant.argtypes = [ctypes.c_int]
+    L.b2l_polygon_set.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    L.b2l_polygon_set.restype = ctypes.c_int
+    shape = np.zeros(256, dtype=np.uint8)                       # opaque b2l_shape
+    tiny = np.array([[-0.02, -0.02], [0.02, -0.02], [0.02, 0.02], [-0.02, 0.02]], dtype=np.float32)   # 0.04 edges
+    normal = np.array([[-0.5, -0.5], [0.5, -0.5], [0.5, 0.5], [-0.5, 0.5]], dtype=np.float32)
+    try:
+        L.b2l_set_variant(0)
+        assert L.b2l_polygon_set(shape.ctypes.data, tiny.ctypes.data, 4) == -1      # welded down to < 3 vertices
+        assert L.b2l_polygon_set(shape.ctypes.data, normal.ctypes.data, 4) == 0
+        L.b2l_set_variant(2)
+        assert L.b2l_polygon_set(shape.ctypes.data, tiny.ctypes.data, 4) == 0       # 0.04 > 0.0025: kept
+    finally:
+        L.b2l_set_variant(0)
+
+
+def test_b2_variant_toi_substeps():
+    """bit 2: a contact leaves SolveTOI at toiCount >= b2_maxSubSteps instead of > : replaying the recorded
+    actions of the g_ffa_hoard fixture (an agent gets wedged at record 275), the default reproduces the
+    reference-recorded trajectory with 84 TOI events, the variant departs from it at the wedge"""
+    import test_cpu_golden as tg
+    path = [p for p in tg.GOLDEN if 'g_ffa_hoard' in p][0]
+    g = np.load(path)
+    variant, over = tg.CASE_CFG['g_ffa_hoard']
+    seed, env_id, _ = [int(v) for v in g['meta']]
+    res = {}
+    for var in (0, 4):
+        o2 = {k: dict(v) for k, v in over.items()}
+        o2['box2d'] = {'variant': var}
+        orc = po.OracleEnv(parity.make_config(variant, auto_reset=False, **o2), seed=seed, env_id=env_id)
+        n, first = 0, None
+        for r in range(400):
+            if g['kind'][r] == 0:
+                out = orc.reset()
+            else:
+                out = orc.step(g['actions'][r]); n += out['n_toi_events']
+            if first is None and not np.array_equal(out['agent'], g['agent'][r]):
+                first = r
+        res[var] = (n, first)
+    assert res[0][1] is None and res[4][1] == 275 and res[4][0] < res[0][0]

@@ -408,3 +408,61 @@ def test_unwired_modules_and_episode_stats():
                          immunity_phase={'cooldown': 0}, safe_zone={'cooldown': 6}, health={'health': 9}, gameover={'mode': 'lastalive'})
     _assert_clean(r)
     assert r['episode_stats_checked'] > 20
+
+
+def test_lockstep_box2d_variants():
+    """the switchable Box2D build details (clamp damping, toiCount >= maxSubSteps) are honoured identically
+    by the oracle and the kernel"""
+    import gpu_lockstep
+    r = gpu_lockstep.run('2v2', 48, 150, verbose=False, box2d={'variant': 5})
+    _assert_clean(r)
+    r = gpu_lockstep.run('ffa', 16, 120, verbose=False, box2d={'variant': 7}, spawn_grid={'grid_size': 8, 'floor_size': 14},
+                         safe_zone={'cooldown': 80, 'radiuses': [7, 4, 2, 1]})
+    _assert_clean(r)
+    assert r['toi_events'] > 0
+
+
+CHECKED_CHILD = r"""
+import numpy as np, torch
+import parity
+from masurvival import _lib
+assert _lib.LIB_PATH.endswith('libmasurv_check.so')
+rng = np.random.default_rng(0)
+for name, n, steps, over, fwd in (('2v2', 4096, 500, {}, False),
+                                  ('ffa', 1024, 300, {'spawn_grid': {'grid_size': 8, 'floor_size': 14}, 'inventory': {'slots': 1},
+                                                      'safe_zone': {'cooldown': 60, 'radiuses': [7, 4, 2, 1]}}, True),
+                                  ('1v1', 2048, 300, {'boxes': {'ownership': True}, 'observation': {'omniscent': False}}, False),
+                                  ('ffa_lidar', 512, 100, {}, True)):
+    rec = parity.make_config(name, auto_reset=True, **over)
+    A = int(rec['n_agents'])
+    h = _lib.Handle(rec, n, 0, 3, 0)
+    h.reset()
+    for t in range(steps):
+        a = parity.random_actions(rng, n, A, 0.7, 0.4, 0.3)
+        if fwd:
+            a[..., 0] = 2                       # everybody pushes forward: pile-ups, wedges, long TOI chains
+        h.step(torch.as_tensor(a).cuda().data_ptr())
+    torch.cuda.synchronize()
+    bad, line = h.check_failures()
+    assert bad == 0, (name, bad, line)
+    assert h.overflow_events() == 0, name
+    st = h.flush_stats()
+    assert int(st['steps']) == n * steps and int(st['episodes']) > 0
+    h.close()
+print('CHECKED-BUILD-CLEAN')
+"""
+
+
+def test_checked_build():
+    """compute-sanitizer is closed on the GPU pool: the bounds-checked twin of the library (make CHECK=1: every
+    indexed access to the shared-memory state column and the fixed-capacity lists is range-checked) runs crowded
+    roll-outs of all three capacity classes in a child process and must count zero violations and zero overflows"""
+    import os
+    import subprocess
+    import sys
+    lib = os.path.join(parity.ROOT, 'gym-ma-survival-2d_b200', 'masurvival', 'libmasurv_check.so')
+    assert os.path.exists(lib), 'build it with __graft_entry__.build()'
+    env = dict(os.environ, MSV_LIB=lib, PYTHONPATH=os.pathsep.join(
+        [os.path.join(parity.ROOT, 'tests'), os.path.join(parity.ROOT, 'oracle'), os.path.join(parity.ROOT, 'gym-ma-survival-2d_b200')]))
+    p = subprocess.run([sys.executable, '-c', CHECKED_CHILD], env=env, capture_output=True, text=True, timeout=1200)
+    assert p.returncode == 0 and 'CHECKED-BUILD-CLEAN' in p.stdout, (p.stdout[-2000:], p.stderr[-4000:])
