@@ -283,10 +283,20 @@ def run_ours(args):
         envs[t % ROT].step_host_async(acts_host[abatch(t)], rew_host[t % ROT], done_host[t % ROT])
         envs[t % ROT].step_host_wait()
 
+    def e2e_pipelined():  # the same per-step copies, the ROT env groups in flight: a trainer that drives several env
+        t = tick[0]; tick[0] += 1   # groups collects group r's rewards/dones while the other groups' steps run
+        envs[t % ROT].step_host_wait()
+        envs[t % ROT].step_host_async(acts_host[abatch(t)], rew_host[t % ROT], done_host[t % ROT])
+
     for _ in range(max(3, args.warmup)):
         e2e_sync()
     Re = int(max(5, min(R, 200)))
-    e2e_ms = float(np.median([timed(e2e_sync, args.steps) for _ in range(Re)])) / args.steps
+    e2e_sync_ms = float(np.median([timed(e2e_sync, args.steps) for _ in range(Re)])) / args.steps
+    for _ in range(max(3, args.warmup)):
+        e2e_pipelined()
+    e2e_ms = float(np.median([timed(e2e_pipelined, args.steps) for _ in range(Re)])) / args.steps
+    for e_ in envs:
+        e_.step_host_wait()
     e2e_value = n_gpus * N * A / (e2e_ms * 1e-3)
     checksum = float(sum(float(r.sum()) for r in rew_host))
 
@@ -313,9 +323,9 @@ def run_ours(args):
         e_.step_host_wait()
     obs_checksum = float(obs_bufs[0][1]['agent'][:, :, -6:].astype(np.float64).sum())
 
-    bytes_env = env.bytes_per_env_step()            # whole step (k_step + k_obs [+ k_lidar])
-    obs_bytes = env.obs_bytes_per_env()             # written by k_obs
-    kstep_bytes = bytes_env - obs_bytes + 8         # k_step: state r/w, actions, rewards, dones, 8 B mask word for k_obs
+    bytes_env = env.bytes_per_env_step()            # whole step (k_step + k_obs2 [+ k_lidar])
+    kstep_bytes = env._h.kernel_bytes_per_env(0)    # k_step: state read + written, actions, rewards, dones, camera words
+    kbytes = [env._h.kernel_bytes_per_env(w) for w in range(3)]
     peak, peak_src = measured_peak()
     kavg_ms = float(k_ms[0])
     achieved = kstep_bytes * N / (kavg_ms * 1e-3) / 1e9
@@ -344,7 +354,11 @@ def run_ours(args):
         'env_steps_per_sec': value / A,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': N * A * 6, 'd2h_bytes_per_step': N * A * 4 + N,
                 'ms_per_step': e2e_ms, 'repeats': Re,
-                'api': 'MaSurvivalVec.step_host_async + step_host_wait -> msv_step_host_async/_wait (pinned host buffers; returns when rewards/dones are in host memory)',
+                'api': f'MaSurvivalVec.step_host_async / step_host_wait -> msv_step_host_async/_wait, pinned host buffers: every step copies its '
+                       f'actions in and its rewards/dones out; the {ROT} env groups are kept in flight (the host waits for a group\'s results right '
+                       'before submitting that group\'s next step)',
+                'sync': {'value': n_gpus * N * A / (e2e_sync_ms * 1e-3), 'ms_per_step': e2e_sync_ms,
+                         'how': 'one group at a time: submit, then block until its rewards/dones are in host memory'},
                 'reward_checksum': checksum},
         'e2e_obs': {'value': n_gpus * N * A / (e2e_obs_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': N * A * 6,
                     'd2h_bytes_per_step': N * A * 4 + N + obs_bytes_host, 'ms_per_step': e2e_obs_ms,
@@ -359,6 +373,8 @@ def run_ours(args):
                      'traffic': ctr.get('dram_bytes_per_launch'), 'kernel': W['kernel'], 'kernel_ms': kavg_ms,
                      'kernel_ms_all': {'k_step': float(k_ms[0]), 'k_obs': float(k_ms[1]), 'k_lidar': float(k_ms[2])},
                      'kernel_share_of_step': float(k_ms[0] / max(k_ms.sum(), 1e-9)),
+                     'kernel_gbs_all': {n: (kbytes[j] * N / (k_ms[j] * 1e-3) / 1e9 if k_ms[j] > 0.004 else None) for j, n in enumerate(('k_step', 'k_obs', 'k_lidar'))},
+                     'algorithmic_bytes_per_env_step_all': dict(zip(('k_step', 'k_obs', 'k_lidar'), kbytes)),
                      'algorithmic_bytes_per_env_step': kstep_bytes, 'whole_step_bytes_per_env_step': bytes_env,
                      'whole_step_gbs': bytes_env * N / (ms_per_step * 1e-3) / 1e9, 'peak_source': peak_src,
                      'issue': issue,

@@ -49,6 +49,9 @@ struct msv_handle {
   char* arena = nullptr; size_t arena_bytes = 0, obs_begin = 0, obs_end = 0;
   size_t device_bytes = 0;
   bool zombie = false;           // msv_destroy was called while DLPack exports were alive
+  // k_spare (pre-drawn reset records) runs on a side stream beside the observation kernels and is joined
+  // back into the caller's stream before msv_step returns (fork/join inside the call: graph-capture safe)
+  cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // debug: CUDA-event timing of the kernels of msv_step (bench.py's roofline numerator)
   bool timing = false; std::vector<cudaEvent_t> tev; size_t tev_used = 0;
   double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
@@ -399,6 +402,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   rc |= dalloc(h, &S.sreward, AC * N); rc |= dalloc(h, &S.skills, AC * N); rc |= dalloc(h, &S.smisc, N);
   const size_t A = cfg->n_agents, B = cfg->n_boxes, H = cfg->n_heals, Sw = h->C.S, L = cfg->lidar_n;
   rc |= dalloc(h, &S.epret, AC * N);
+  rc |= dalloc(h, &S.spare, N * (size_t)MSV_SPARE_W); rc |= dalloc(h, &S.spare_ep, N);
   {  // one arena for every output tensor, so that msv_step_host_obs reads the observations back in ONE copy
     struct Slot { void** p; size_t bytes; };
     const size_t f = sizeof(float);
@@ -432,6 +436,8 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   {  // episode counter starts at -1 so that the first reset is episode 0
     std::vector<int4> hd(N, make_int4(0, 0, -1, 0));
     cudaMemcpy(S.hdr0, hd.data(), N * sizeof(int4), cudaMemcpyHostToDevice);
+    std::vector<int> se(N, INT32_MIN);              // no reset record drawn yet
+    cudaMemcpy(S.spare_ep, se.data(), N * sizeof(int), cudaMemcpyHostToDevice);
   }
   {  // observation element table for k_obs (env:391-447 shapes, env:510-657 contents)
     std::vector<ObsDesc> D;
@@ -542,6 +548,9 @@ static void really_destroy(msv_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_step) cudaEventDestroy(h->ev_step);
   if (h->ev_obs) cudaEventDestroy(h->ev_obs);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
@@ -632,11 +641,33 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
     if (which == 0) { int rc = readback(h, st); if (rc) return rc; }
   }
   if (timed) tmark(h, st);
+  const bool spare = which == 1 || (which == 0 && h->cfg.auto_reset != 0);
+  if (spare) {                                  // the step / reset left finished environments without a record for their next episode
+    if (!h->side_stream) {
+      CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    CK(msv_launch_spare(h->C, h->S, h->O.dones, 0, h->side_stream));   // every env whose record is stale (two 4-byte loads each for the others)
+    CK(cudaEventRecord(h->ev_join, h->side_stream));
+    h->launches += 1;
+  }
   CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, nullptr, st));   // fetch_observations
   h->launches += 1;
   if (timed) tmark(h, st);
-  if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, (cudaStream_t)stream)); h->launches++; }
+  if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, h->HC, (cudaStream_t)stream)); h->launches++; }
   if (timed) tmark(h, st);
+  if (spare) {
+    // The record kernel is NOT joined back in normal operation: it overlaps the observation kernels and the next
+    // step, and nothing on `st` ever waits for it.  That is safe by construction -- a record is published by
+    // writing its episode number last (after a fence); a reset that does not find the number it expects draws
+    // the record itself -- and msv_get_state / msv_set_state / msv_destroy synchronise the device.  Only while
+    // the caller is capturing `st` into a CUDA graph must the fork be joined inside the call.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
   if (which == 0) { int rc = readback_obs(h, st); if (rc) return rc; }
   return MSV_OK;
 }
@@ -987,23 +1018,32 @@ int msv_flush_stats(msv_handle* h, msv_stats* out) {
   return MSV_OK;
 }
 
-// Algorithmic HBM bytes of one step for one env: every live state word is read
-// once, the words a step can change are written once, plus actions in and
-// observations / rewards / dones out.  (DESIGN.md "roofline numerator".)
-int64_t msv_bytes_per_env_step(msv_handle* h) {
+// Algorithmic HBM bytes per environment and step, per kernel (DESIGN.md "roofline numerator"): every state
+// word a kernel touches in EVERY step is counted once per direction; the cold per-contact words (pseq/pimp, read
+// and written only for live contacts) and the lists touched only on spawn/despawn are left out.
+//   which 0: k_step   reads  agents (akin0, akin1, afat, aint, sreward, skills, epret) 76*A, boxes (box0, box1) 32*B,
+//                            floor items (item0) 16*B, heals 8*H, zone (zonecur, zoneint) 32, header (hdr0, hdr1) 32,
+//                            pair bit-matrices 24*PW, stats word 16, actions 6*A
+//                     writes agents 76*A, zone 32, header 32, pair bit-matrices 24*PW, stats 16, camera words
+//                            (obm 8, + omask 4*A when not omniscient), rewards 4*A, done 1
+//   which 1: k_obs2   reads  agents (akin0, akin1, aint) 48*A, obm 8 (+ omask 4*A), hdr0 16, boxes 32*B, items 16*B,
+//                            heals 8*H, zone 32 + next centre 8;   writes the observation tensors
+//   which 2: k_lidar  reads  hdr0 16, boxes 32*B, items 16*B, heals 8*H, agents (akin0, akin1) 32*A;  writes 8*A*L
+int64_t msv_kernel_bytes_per_env(msv_handle* h, int32_t which) {
   if (!h) return 0;
-  const int64_t A = h->C.A, B = h->C.B0, H = h->C.H0, S = h->C.S, L = h->C.lidar_n, Z = h->C.n_zones, PW = h->PW;
-  int64_t agents_rw = A * (16 + 16 + 16 + 16);            // akin0, akin1, afat, aint
-  int64_t boxes_r = B * (16 + 16), items_r = 0, heals_r = H * 8;  // static geometry read for ray casts
-  int64_t zone_rw = 16 + 16, zone_r = Z * 8 > 16 ? 16 : Z * 8;     // current + next centre
-  int64_t hdr_rw = 16 + 16 + PW * 8 * 3, stats_rw = A * 8 + 16;
-  int64_t state_r = agents_rw + boxes_r + items_r + heals_r + zone_rw + zone_r + hdr_rw + stats_rw;
-  int64_t state_w = agents_rw + zone_rw + hdr_rw + stats_rw;
-  int64_t obs = 4 * (A * S + A * (A - 1) * S + A * (A - 1) + 6);
-  if (H > 0) obs += 4 * (H * 2 + A * H + 2 * A);
-  if (B > 0) obs += 4 * (B * 11 + A * B + B * 10 + A * B + A * 8 + A);
-  if (L > 0) obs += 8 * A * L;
-  return state_r + state_w + A * 6 + obs + 4 * A + 1;
+  const int64_t A = h->C.A, B = h->C.B0, H = h->C.H0, L = h->C.lidar_n, PW = h->PW;
+  const int64_t om = h->C.omniscient ? 0 : 4 * A;
+  if (which == 0) {
+    const int64_t rd = 76 * A + 32 * B + 16 * B + 8 * H + 32 + 32 + 24 * PW + 16 + 6 * A;
+    const int64_t wr = 76 * A + 32 + 32 + 24 * PW + 16 + 8 + om + 4 * A + 1;
+    return rd + wr;
+  }
+  if (which == 1) return 48 * A + 8 + om + 16 + 32 * B + 16 * B + 8 * H + 40 + (int64_t)h->obs.n_elems * 4;
+  if (which == 2) return L > 0 ? 16 + 32 * B + 16 * B + 8 * H + 32 * A + 8 * A * L : 0;
+  return 0;
+}
+int64_t msv_bytes_per_env_step(msv_handle* h) {
+  return msv_kernel_bytes_per_env(h, 0) + msv_kernel_bytes_per_env(h, 1) + msv_kernel_bytes_per_env(h, 2);
 }
 int64_t msv_obs_bytes_per_env(msv_handle* h) { return h ? (int64_t)h->obs.n_elems * 4 : 0; }
 int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }

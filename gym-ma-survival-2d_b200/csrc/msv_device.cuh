@@ -384,11 +384,16 @@ __device__ unsigned long long g_dbg[8];
 // rare-path census: [2k] number of calls, [2k+1] clock64() cycles spent in them (k: 0 generic island solve,
 // 1 TOI event, 2 reset, 3 deaths, 4 pickups, 5 use/give, 6 contact numbering, 7 box removal)
 __device__ unsigned long long g_cnt[16];
+__device__ unsigned long long g_sub[16];   // sub-phase cycle sums inside toi_event (development)
+#define SUB_BEGIN() long long sub_t_ = clock64()
+#define SUB(k) do { long long n_ = clock64(); atomicAdd(&g_sub[k], (unsigned long long)(n_ - sub_t_)); sub_t_ = n_; } while (0)
 #define RARE_BEGIN() long long rare_t0_ = clock64()
 #define RARE_END(k) do { atomicAdd(&g_cnt[2 * (k)], 1ull); atomicAdd(&g_cnt[2 * (k) + 1], (unsigned long long)(clock64() - rare_t0_)); } while (0)
 #else
 #define RARE_BEGIN() do { } while (0)
 #define RARE_END(k) do { } while (0)
+#define SUB_BEGIN() do { } while (0)
+#define SUB(k) do { } while (0)
 #endif
 // b2TimeOfImpact(proxyA = box, proxyB = circle centre), tMax = 1
 struct ToiOut { int state; float t; };

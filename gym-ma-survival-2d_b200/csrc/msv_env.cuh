@@ -104,6 +104,61 @@ extern __shared__ float msv_sm[];
 #define COLD4 __device__ __noinline__
 #endif
 
+// Counter-based Philox draws of (global env id, episode, step, stream, block): two uniform doubles per block
+__device__ __noinline__ double2 philox_uniform2_of(const DevConst& C, uint32_t genv, uint32_t episode, uint32_t step, uint32_t stream, uint32_t blk) {
+  uint32_t o[4];
+  philox4x32(genv, episode, step, (stream << 16) | blk, C.seed_lo, C.seed_hi, o);
+  return make_double2(((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) / 9007199254740992.0,
+                      ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) / 9007199254740992.0);
+}
+
+// Everything BaseEnv.reset (env:59-74) takes from the random generator, for episode `episode` of global env
+// `genv`, as one record (layout MSV_SP_*): SpawnGrid shuffle (sem:59-79) -> the cells ResetSpawns hands to boxes,
+// heals and agents (sem:82-94), RandomizeBoxShapes (sem:97-120), SafeZone centres (sem:739-756).  A pure function
+// of (seed, env, episode): k_spare evaluates it ahead of time, the step kernel only when no record is ready.
+__device__ __noinline__ void draw_reset(const DevConst& C, uint32_t genv, uint32_t episode, float* rec) {
+  const int n = C.grid_n;
+  unsigned char perm[64];
+  for (int k = 0; k < n; ++k) perm[k] = (unsigned char)k;
+  double2 up = make_double2(0.0, 0.0);
+  for (int i = n - 1; i >= 1; --i) {
+    const uint32_t kd = (uint32_t)(n - 1 - i);
+    if (!(kd & 1u)) up = philox_uniform2_of(C, genv, episode, 0u, STREAM_SHUFFLE, kd >> 1);
+    const double u = (kd & 1u) ? up.y : up.x;
+    const int j = (int)(u * (i + 1));
+    const unsigned char t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+  }
+  int top = n;
+  for (int b = 0; b < C.B0; ++b) {
+    float hx = C.box_h, hy = C.box_h;
+    if (C.box_randomized) {
+      double z[2];
+      for (int q = 0; q < 2; ++q) {
+        const double2 ub = philox_uniform2_of(C, genv, episode, 0u, STREAM_BOX, (uint32_t)(2 * b + q));
+        z[q] = sqrt(-2.0 * log(1.0 - ub.x)) * cos(6.283185307179586 * ub.y);
+      }
+      double w = C.box_avg_w + C.box_std_w * z[0]; if (!(w > C.box_min_w)) w = C.box_min_w;
+      double h = C.box_avg_h + C.box_std_h * z[1]; if (!(h > C.box_min_h)) h = C.box_min_h;
+      hx = (float)(w / 2.); hy = (float)(h / 2.);
+    }
+    const int cell = perm[--top];
+    rec[MSV_SP_BOX + 4 * b + 0] = C.grid_px[cell]; rec[MSV_SP_BOX + 4 * b + 1] = C.grid_py[cell];
+    rec[MSV_SP_BOX + 4 * b + 2] = hx; rec[MSV_SP_BOX + 4 * b + 3] = hy;
+  }
+  for (int h = 0; h < C.H0; ++h) { const int cell = perm[--top]; rec[MSV_SP_HEAL + 2 * h] = C.grid_px[cell]; rec[MSV_SP_HEAL + 2 * h + 1] = C.grid_py[cell]; }
+  for (int i = 0; i < C.A; ++i) { const int cell = perm[--top]; rec[MSV_SP_AGENT + 2 * i] = C.grid_px[cell]; rec[MSV_SP_AGENT + 2 * i + 1] = C.grid_py[cell]; }
+  if (C.zone_centers_random) {
+    int d = 0;
+    for (int z = C.n_zones - 1; z >= 0; --z) {
+      const double L = C.floor_size - 2 * C.zone_radiuses[z];
+      const double2 uz = philox_uniform2_of(C, genv, episode, 0u, STREAM_ZONE, (uint32_t)(d >> 1)); d += 2;
+      rec[MSV_SP_ZONE + 2 * z] = (float)((uz.x * L) - L / 2); rec[MSV_SP_ZONE + 2 * z + 1] = (float)((uz.y * L) - L / 2);
+    }
+  } else {
+    for (int z = 0; z < C.n_zones; ++z) { rec[MSV_SP_ZONE + 2 * z] = (float)C.zone_centers[z][0]; rec[MSV_SP_ZONE + 2 * z + 1] = (float)C.zone_centers[z][1]; }
+  }
+}
+
 template <int AC, int BC, int HC, int G>
 struct Env {
   using PL = PairLayout<AC, BC>;
@@ -1195,20 +1250,37 @@ struct Env {
       KF(KS_NX, s) = normal.x; KF(KS_NY, s) = normal.y; KF(KS_PX, s) = px.x; KF(KS_PY, s) = px.y;
       KF(KS_RBX, s) = rB.x; KF(KS_RBY, s) = rB.y; KF(K_NM, s) = nm; KF(K_TM, s) = tm;
     }
-    // warm start, then 10 velocity iterations, contacts in island order
+    // warm start, then 10 velocity iterations, contacts in island order.  The bodies' velocities (then positions)
+    // live in REGISTERS -- one record per agent slot, picked with statically unrolled selects -- because the
+    // Gauss-Seidel sweep is one long dependent chain through them: a shared-memory store/load round trip per
+    // contact and iteration is what made a 4-agent pile-up cost ~100k cycles.  The per-contact constants, which
+    // are off that chain, stay in shared memory.
+    f2 bv[AC]; float bw[AC];
+#pragma unroll
+    for (int q = 0; q < AC; ++q) { bv[q] = mk2(AG(F_VX, q), AG(F_VY, q)); bw[q] = AG(F_W, q); }
+    auto getv = [&](int i, f2& v, float& w) {
+      v = bv[0]; w = bw[0];
+#pragma unroll
+      for (int q = 1; q < AC; ++q) if (i == q) { v = bv[q]; w = bw[q]; }
+    };
+    auto setv = [&](int i, f2 v, float w) {
+#pragma unroll
+      for (int q = 0; q < AC; ++q) if (i == q) { bv[q] = v; bw[q] = w; }
+    };
     for (int it = -1; it < 10; ++it) {
       for (int k = 0; k < nc; ++k) {
         const int s = ord_get(ord, k);
         int p, a_, sid, b_; meta_unpack(KI(K_META, s), p, a_, sid, b_);
         const f2 normal = mk2(KF(KS_NX, s), KF(KS_NY, s)), rB = mk2(KF(KS_RBX, s), KF(KS_RBY, s));
+        const float nm_ = KF(K_NM, s), tm_ = KF(K_TM, s);
         float ni_ = KF(K_NI, s), ti_ = KF(K_TI, s);
-        f2 vB = mk2(AG(F_VX, b_), AG(F_VY, b_)); float wB = AG(F_W, b_);
+        f2 vB; float wB; getv(b_, vB, wB);
         if (a_ < 0) {
           if (it < 0) warm_start_static(normal, rB, ni_, ti_, vB, wB);
-          else solve_velocity_static(normal, rB, KF(K_NM, s), KF(K_TM, s), ni_, ti_, vB, wB);
+          else solve_velocity_static(normal, rB, nm_, tm_, ni_, ti_, vB, wB);
         } else {
           const f2 rA = mk2(KF(KS_PX, s), KF(KS_PY, s)), tangent = cross_vs(normal, 1.0f);
-          f2 vA = mk2(AG(F_VX, a_), AG(F_VY, a_)); float wA = AG(F_W, a_);
+          f2 vA; float wA; getv(a_, vA, wA);
           const float mA = C.inv_mass, iA = C.inv_I, mB = C.inv_mass, iB = C.inv_I;
           if (it < 0) {   // b2ContactSolver::WarmStart
             const f2 Pv = vadd(vmul(ni_, normal), vmul(ti_, tangent));
@@ -1218,7 +1290,7 @@ struct Env {
             {
               const f2 dv = vsub(vsub(vadd(vB, cross_sv(wB, rB)), vA), cross_sv(wA, rA));
               const float vt = vdot(dv, tangent) - 0.0f;
-              float lambda = KF(K_TM, s) * (-vt);
+              float lambda = tm_ * (-vt);
               const float maxFriction = C.friction * ni_;
               const float newImpulse = fclamp_(ti_ + lambda, -maxFriction, maxFriction);
               lambda = newImpulse - ti_; ti_ = newImpulse;
@@ -1229,7 +1301,7 @@ struct Env {
             {
               const f2 dv = vsub(vsub(vadd(vB, cross_sv(wB, rB)), vA), cross_sv(wA, rA));
               const float vn = vdot(dv, normal);
-              float lambda = -KF(K_NM, s) * (vn - 0.0f);
+              float lambda = -nm_ * (vn - 0.0f);
               const float newImpulse = fmax_(ni_ + lambda, 0.0f);
               lambda = newImpulse - ni_; ni_ = newImpulse;
               const f2 Pv = vmul(lambda, normal);
@@ -1237,29 +1309,34 @@ struct Env {
               vB = vadd(vB, vmul(mB, Pv)); wB += iB * vcross(rB, Pv);
             }
           }
-          AG(F_VX, a_) = vA.x; AG(F_VY, a_) = vA.y; AG(F_W, a_) = wA;
+          setv(a_, vA, wA);
         }
-        AG(F_VX, b_) = vB.x; AG(F_VY, b_) = vB.y; AG(F_W, b_) = wB;
+        setv(b_, vB, wB);
         KF(K_NI, s) = ni_; KF(K_TI, s) = ti_;
       }
     }
+#pragma unroll
+    for (int q = 0; q < AC; ++q) if ((inisl >> q) & 1u) { AG(F_VX, q) = bv[q].x; AG(F_VY, q) = bv[q].y; AG(F_W, q) = bw[q]; }
     for (int k = 0; k < nc; ++k) {   // b2ContactSolver::StoreImpulses
       const int s = ord_get(ord, k);
       S.pimp[(KI(K_META, s) & 255) * N + e] = make_float2(KF(K_NI, s), KF(K_TI, s));
     }
     for (int i = 0; i < C.A; ++i) if ((inisl >> i) & 1u) integrate_position(i, h);
+    // positions: the same register scheme (bv := centre, bw := angle)
+#pragma unroll
+    for (int q = 0; q < AC; ++q) { bv[q] = mk2(AG(F_CX, q), AG(F_CY, q)); bw[q] = AG(F_A, q); }
     bool ok = false;
     for (int it = 0; it < 10 && !ok; ++it) {   // b2ContactSolver::SolvePositionConstraints
       float minSep = 0.0f;
       for (int k = 0; k < nc; ++k) {
         const int s = ord_get(ord, k);
         int p, a_, sid, b_; meta_unpack(KI(K_META, s), p, a_, sid, b_);
-        f2 cB = apos(b_);
+        f2 cB; float aB; getv(b_, cB, aB);
         float separation;
         if (a_ < 0) {
           separation = solve_position_static(mk2(KF(KS_NX, s), KF(KS_NY, s)), mk2(KF(KS_PX, s), KF(KS_PY, s)), cB, false);
         } else {       // circles: the manifold point is the midpoint, normal along the centres
-          f2 cA = apos(a_); float aA = AG(F_A, a_), aB = AG(F_A, b_);
+          f2 cA; float aA; getv(a_, cA, aA);
           const float mA = C.inv_mass, iA = C.inv_I, mB = C.inv_mass, iB = C.inv_I;
           f2 normal = vsub(cB, cA); vnormalize(normal);
           const f2 point = vmul(0.5f, vadd(cA, cB));
@@ -1272,13 +1349,15 @@ struct Env {
           const f2 Pv = vmul(impulse, normal);
           cA = vsub(cA, vmul(mA, Pv)); aA -= iA * vcross(rA, Pv);
           cB = vadd(cB, vmul(mB, Pv)); aB += iB * vcross(rB, Pv);
-          AG(F_CX, a_) = cA.x; AG(F_CY, a_) = cA.y; AG(F_A, a_) = aA; AG(F_A, b_) = aB;
+          setv(a_, cA, aA);
         }
-        AG(F_CX, b_) = cB.x; AG(F_CY, b_) = cB.y;
+        setv(b_, cB, aB);
         minSep = fmin_(minSep, separation);
       }
       ok = minSep >= -3.0f * B2_LINEAR_SLOP;
     }
+#pragma unroll
+    for (int q = 0; q < AC; ++q) if ((inisl >> q) & 1u) { AG(F_CX, q) = bv[q].x; AG(F_CY, q) = bv[q].y; AG(F_A, q) = bw[q]; }
     {
       const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
       bool can_sleep = ok;                       // minSleepTime >= timeToSleep && positionSolved
@@ -1357,6 +1436,7 @@ struct Env {
   static_assert(SNAPW <= K_COUNT * (MAXC - TOI_ISL), "snapshot does not fit the scratch slots");
   DEV unsigned& SNAP(int q) { CHK((unsigned)q < (unsigned)SNAPW); return reinterpret_cast<unsigned*>(msv_sm)[sb + (W_TC + (q / (MAXC - TOI_ISL)) * MAXC + TOI_ISL + q % (MAXC - TOI_ISL))]; }
   COLD1 int toi_event(int minP, float minAlpha, float dt, int prevP) {
+    SUB_BEGIN();
     int a, sid, b; decode(minP, a, sid, b);
     // backup the agent's sweep, advance to the TOI, re-evaluate the contact
     const float bk0 = AG(F_C0X, b), bk1 = AG(F_C0Y, b), bk2 = AG(F_CX, b), bk3 = AG(F_CY, b), bk4 = AG(F_A0, b), bk5 = AG(F_A, b), bk6 = AG(F_ALPHA0, b);
@@ -1381,6 +1461,7 @@ struct Env {
       wake(b);
       isl_add(sid, m_min);
     }
+    SUB(0);
     {
       // the agent's other existing contacts against static bodies, newest (largest creation sequence) first;
       // the sequence numbers are fetched together (one memory latency), then ranked in registers
@@ -1405,6 +1486,7 @@ struct Env {
         if (t2) isl_add(best, m);
       }
     }
+    SUB(1);
     const float subdt = (1.0f - minAlpha) * dt;
     // b2Island::SolveTOI -- every contact of the mini island has a static body A
     {
@@ -1418,6 +1500,7 @@ struct Env {
       AG(F_CX, b) = cB.x; AG(F_CY, b) = cB.y;
     }
     AG(F_C0X, b) = AG(F_CX, b); AG(F_C0Y, b) = AG(F_CY, b); AG(F_A0, b) = AG(F_A, b);
+    SUB(2);
     {
       // b2ContactSolver::InitializeVelocityConstraints at the corrected position (impulses start at zero, no warm start)
       const f2 cB = apos(b);
@@ -1445,10 +1528,12 @@ struct Env {
         }
       AG(F_VX, b) = vB.x; AG(F_VY, b) = vB.y; AG(F_W, b) = wB;
     }
+    SUB(3);
     integrate_position(b, subdt);
     AGF(b) &= ~FL_MOVED;
     synchronize_fixtures(b);
     if (AGF(b) & FL_MOVED) find_new_contacts_of(b);
+    SUB(4);
     // A TOI event is a pure function of (agent b's sweep/velocity/AABB words, the pair
     // bit-matrices, the contact counter).  If this event left all of them exactly as the
     // previous event on the same contact did, every further event on it would repeat
@@ -1464,6 +1549,7 @@ struct Env {
       snap(F_COUNT + 6 * w + 4, (unsigned)en[w]); snap(F_COUNT + 6 * w + 5, (unsigned)(en[w] >> 32));
     }
     snap(SNAPW - 1, (unsigned)LI(L_CONTACTSEQ));
+    SUB(5);
     return 1 | (same ? 2 : 0);
   }
 
@@ -1722,13 +1808,6 @@ struct Env {
     philox4x32(C.env_offset + (uint32_t)e, (uint32_t)LI(L_EPISODE), step, (stream << 16) | (k >> 1), C.seed_lo, C.seed_hi, o);
     uint32_t a = o[(k & 1) * 2], b = o[(k & 1) * 2 + 1];
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
-  }
-  // draws 2j and 2j+1 of a stream are the two halves of ONE Philox block: both at once (the reset path draws in order)
-  __device__ __noinline__ double2 philox_uniform2(uint32_t step, uint32_t stream, uint32_t blk) {
-    uint32_t o[4];
-    philox4x32(C.env_offset + (uint32_t)e, (uint32_t)LI(L_EPISODE), step, (stream << 16) | blk, C.seed_lo, C.seed_hi, o);
-    return make_double2(((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) / 9007199254740992.0,
-                        ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6)) / 9007199254740992.0);
   }
 
   // Cameras._update_seen (sim:336-354), agent targets (the only ones the
@@ -2115,56 +2194,43 @@ struct Env {
   // Philox4x32-10 keyed by (seed, global env id, episode).          [leader]
   COLD4 void reset() {
     LI(L_EPISODE) += 1; LI(L_STEPS) = 0;
-    int n = C.grid_n;
-    // (the shuffled cell list lives in the dead touching-contact list: byte-indexed shared memory instead of a local array)
-    unsigned char* perm = reinterpret_cast<unsigned char*>(&msv_sm[sb + W_TC]);
-    static_assert(K_COUNT * MAXC * 4 >= 64, "scratch too small for the spawn grid");
-    for (int k = 0; k < n; ++k) perm[k] = (unsigned char)k;
-    double2 up = make_double2(0.0, 0.0);
-    for (int i = n - 1; i >= 1; --i) {
-      const uint32_t kd = (uint32_t)(n - 1 - i);
-      if (!(kd & 1u)) up = philox_uniform2(0u, STREAM_SHUFFLE, kd >> 1);
-      const double u = (kd & 1u) ? up.y : up.x;
-      int j = (int)(u * (i + 1));
-      unsigned char t = perm[i]; perm[i] = perm[j]; perm[j] = t;
-    }
-    int top = n;
+    // the episode's random draws: the record k_spare prepared, or (no record for this episode yet) drawn now.
+    // It is staged in the dead touching-contact list of the environment's shared-memory column.
+    float* rec = &msv_sm[sb + W_TC];
+    static_assert(K_COUNT * MAXC >= MSV_SPARE_W, "scratch too small for a reset record");
+    if (S.spare_ep[e] == LI(L_EPISODE)) {
+      const float4* src = reinterpret_cast<const float4*>(S.spare + (size_t)e * MSV_SPARE_W);
+      float4 v[MSV_SPARE_W / 4];
+#pragma unroll
+      for (int q = 0; q < MSV_SPARE_W / 4; ++q) v[q] = src[q];         // one memory latency
+#pragma unroll
+      for (int q = 0; q < MSV_SPARE_W / 4; ++q) { rec[4 * q] = v[q].x; rec[4 * q + 1] = v[q].y; rec[4 * q + 2] = v[q].z; rec[4 * q + 3] = v[q].w; }
+    } else draw_reset(C, C.env_offset + (uint32_t)e, (uint32_t)LI(L_EPISODE), rec);
     LI(L_BODYSEQ) = 0; LI(L_CONTACTSEQ) = 0; LI(L_FIRST) = 1; LI(L_NEWFIX) = 1;
     nb = 0; ni = 0; nh = 0; LI(L_NP) = 0;
 #pragma unroll
     for (int w = 0; w < PW; ++w) { ex[w] = 0ull; tc[w] = 0ull; en[w] = 0ull; }
+#pragma unroll 1
     for (int b = 0; b < C.B0; ++b) {
-      float hx = C.box_h, hy = C.box_h;
-      if (C.box_randomized) {
-        double z[2];
-        for (int q = 0; q < 2; ++q) {
-          const double2 ub = philox_uniform2(0u, STREAM_BOX, (uint32_t)(2 * b + q));
-          const double u1 = ub.x, u2 = ub.y;
-          z[q] = sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);
-        }
-        double w = C.box_avg_w + C.box_std_w * z[0]; if (!(w > C.box_min_w)) w = C.box_min_w;
-        double h = C.box_avg_h + C.box_std_h * z[1]; if (!(h > C.box_min_h)) h = C.box_min_h;
-        hx = (float)(w / 2.); hy = (float)(h / 2.);
-      }
-      int cell = perm[--top];
-      const float4 nb0 = make_float4(C.grid_px[cell], C.grid_py[cell], hx, hy);
+      const float4 nb0 = make_float4(rec[MSV_SP_BOX + 4 * b], rec[MSV_SP_BOX + 4 * b + 1], rec[MSV_SP_BOX + 4 * b + 2], rec[MSV_SP_BOX + 4 * b + 3]);
       const int4 nb1 = make_int4(C.box_health, 1, MSV_CAUSE_NONE, MSV_CAUSE_NONE);
       S.box0[b * N + e] = nb0; S.box1[b * N + e] = nb1;
       S.boxseq[b * N + e] = LI(L_BODYSEQ)++;
       put_box(b, nb0, nb1);                          // (not read back from global memory)
       nb++;
     }
+#pragma unroll 1
     for (int h = 0; h < C.H0; ++h) {
-      int cell = perm[--top];
-      S.heal[h * N + e] = make_float2(C.grid_px[cell], C.grid_py[cell]); HLP(0, h) = C.grid_px[cell]; HLP(1, h) = C.grid_py[cell];
+      const float x = rec[MSV_SP_HEAL + 2 * h], y = rec[MSV_SP_HEAL + 2 * h + 1];
+      S.heal[h * N + e] = make_float2(x, y); HLP(0, h) = x; HLP(1, h) = y;
       S.healseq[h * N + e] = LI(L_BODYSEQ)++;
       nh++;
     }
     LI(L_BODYSEQ) += 4;  // walls
+#pragma unroll 1
     for (int i = 0; i < AC; ++i) {
       if (i < C.A) {
-        int cell = perm[--top];
-        float x = C.grid_px[cell], y = C.grid_py[cell], r = C.agent_r;
+        const float x = rec[MSV_SP_AGENT + 2 * i], y = rec[MSV_SP_AGENT + 2 * i + 1], r = C.agent_r;
         AG(F_CX, i) = x; AG(F_CY, i) = y; AG(F_A, i) = 0.0f; AG(F_VX, i) = 0.0f; AG(F_VY, i) = 0.0f; AG(F_W, i) = 0.0f;
         AG(F_C0X, i) = x; AG(F_C0Y, i) = y; AG(F_A0, i) = 0.0f; AG(F_ALPHA0, i) = 0.0f; AG(F_SLEEP, i) = 0.0f;
         AG(F_FAT0, i) = (x - r) - B2_AABB_EXT; AG(F_FAT1, i) = (y - r) - B2_AABB_EXT;
@@ -2173,30 +2239,14 @@ struct Env {
         LI(L_HEALTH + (i)) = C.health; LI(L_BODYSEQ)++;
       } else { AGF(i) = 0; LI(L_HEALTH + (i)) = 0; }
       LI(L_CAUSE + (i)) = MSV_CAUSE_NONE; LI(L_COOLDOWN + (i)) = 0; LI(L_INV + (i)) = 0;
+      LF(L_EPRET + (i)) = 0.0f;
     }
-    float2 c0 = make_float2(0.0f, 0.0f);           // centre of phase 0 (kept: not read back from global memory)
-    if (C.zone_centers_random) {
-      int d = 0;
-      for (int z = C.n_zones - 1; z >= 0; --z) {
-        double L = C.floor_size - 2 * C.zone_radiuses[z];
-        const double2 uz = philox_uniform2(0u, STREAM_ZONE, (uint32_t)(d >> 1)); d += 2;
-        const double ux = uz.x, uy = uz.y;
-        const float2 cz = make_float2((float)((ux * L) - L / 2), (float)((uy * L) - L / 2));
-        S.zonec[z * N + e] = cz;
-        if (z == 0) c0 = cz;
-      }
-    } else {
-      for (int z = 0; z < C.n_zones; ++z) {
-        const float2 cz = make_float2((float)C.zone_centers[z][0], (float)C.zone_centers[z][1]);
-        S.zonec[z * N + e] = cz;
-        if (z == 0) c0 = cz;
-      }
-    }
+#pragma unroll 1
+    for (int z = 0; z < C.n_zones; ++z) S.zonec[z * N + e] = make_float2(rec[MSV_SP_ZONE + 2 * z], rec[MSV_SP_ZONE + 2 * z + 1]);
     LI(L_ZTCOOL) = C.zone_cooldown; LI(L_ZTSHRINK) = 0; LI(L_ZPHASE) = 0; LI(L_ZEND) = 0;
     LF(L_ZR) = C.zone_r32[0];
-    LF(L_ZX) = c0.x; LF(L_ZY) = c0.y;
+    LF(L_ZX) = rec[MSV_SP_ZONE]; LF(L_ZY) = rec[MSV_SP_ZONE + 1];
     LU(L_DMASK) = 0; LI(L_NKILLS) = 0; LI(L_USEHEAL) = 0; LI(L_USEBOX) = 0;
-    for (int i = 0; i < AC; ++i) LF(L_EPRET + (i)) = 0.0f;
   }
   // ImmunityPhase (sem:652-674): Health.immune is True from reset until max(cooldown, 1) steps have run  [leader]
   DEV void store_immune(DevOut& O) {

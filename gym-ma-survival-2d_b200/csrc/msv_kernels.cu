@@ -94,23 +94,33 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   env.share_counts();
   PROF(6);
   PHASE_SYNC(4);
-  env.cameras();
-  PROF(7);
-  PHASE_SYNC(5);
+  // Cameras run on the post-physics state, before this step's deaths (env:325,330).  An environment that
+  // finishes and is reset in place needs them once more for the first observation of its new episode: that
+  // second evaluation goes through the SAME code (one copy of the camera / ray-cast program, already warm in
+  // the instruction cache) instead of a second inlined copy that only reset environments would ever fetch.
   int again = 0;
-  env.post_step_rest();                    // sim:241-242
-  PROF(8);
-  PHASE_SYNC(7);
-  if (env.lead) {
-    bool done = env.rewards_done(O);       // env:85-89
-    if (done && C.auto_reset) {            // vector-env extension: the observation returned is the new episode's first
-      env.LI(env.L_STEPISODES)++;
-      { RARE_BEGIN(); MSV_COLD_ON(env, reset()); RARE_END(2); }
-      again = 1;
+#pragma unroll 1
+  for (int pass = 0;; ++pass) {
+    env.cameras();
+    if (pass) break;
+    PROF(7);
+    PHASE_SYNC(5);
+    env.post_step_rest();                  // sim:241-242
+    PROF(8);
+    PHASE_SYNC(7);
+    if (env.lead) {
+      bool done = env.rewards_done(O);     // env:85-89
+      if (done && C.auto_reset) {          // vector-env extension: the observation returned is the new episode's first
+        env.LI(env.L_STEPISODES)++;
+        { RARE_BEGIN(); MSV_COLD_ON(env, reset()); RARE_END(2); }
+        again = 1;
+      }
+      env.store_immune(O);
     }
-    env.store_immune(O);
+    again = env.bc(again);
+    if (!again) break;                     // group-uniform
+    env.share_counts();
   }
-  if (env.bc(again)) { env.share_counts(); env.cameras(); }
   PROF(9);
   PHASE_SYNC(8);
   if (env.lead) env.store_obm();           // env:84: the observation tensors are gathered by k_obs
@@ -276,19 +286,19 @@ k_obs(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, co
 __global__ void __launch_bounds__(1024)
 k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC) {
   extern __shared__ float stage[];
-  __shared__ int koff[MSV_OBS_KEYS + 1];
   const int A = C.A, B = C.B0, H = C.H0, Sw = C.S, N = C.N;
   const int e0 = blockIdx.x * OBS2_E, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
+  // this lane's row of every tensor slice in the stage (registers: the key is a compile-time constant at every use)
+  int koff[MSV_OBS_KEYS], kbase[MSV_OBS_KEYS];
+  {
     int o = 0;
-    for (int k = 0; k < MSV_OBS_KEYS; ++k) { koff[k] = o; o += OBS2_E * Tb.keys[k].chunk; }
-    koff[MSV_OBS_KEYS] = o;
+#pragma unroll
+    for (int k = 0; k < MSV_OBS_KEYS; ++k) { koff[k] = o; kbase[k] = o + lane * Tb.keys[k].chunk; o += OBS2_E * Tb.keys[k].chunk; }
   }
-  __syncthreads();
   const int e = e0 + lane;
   const bool live = e < N;                       // rows past the padded batch do not exist
   const int n_items = A + 2 * B + H + 1;
-  auto put = [&](int key, int off, float v) { stage[koff[key] + lane * Tb.keys[key].chunk + off] = v; };
+  auto put = [&](int key, int off, float v) { stage[kbase[key] + off] = v; };
   auto vert = [&](float hx, float hy, int rot, int comp) {   // b2PolygonShape vertex order (Q8)
     int j = ((comp >> 1) + rot) & 3;
     return (comp & 1) ? ((j >= 2) ? hy : -hy) : ((j == 1 || j == 2) ? hx : -hx);
@@ -384,89 +394,174 @@ k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, c
   }
 }
 
-// Lidars._update (simulation.py:377-392) as an extension observation block,
-// scanned on the state the observation describes.  ONE WARP PER AGENT: the
-// rays go across the lanes; when there are fewer than 32 rays each ray is
-// shared by 32/R' lanes (R' = rays rounded up to a power of two) that split
-// the body list, and the nearest hit is reduced with warp shuffles on a packed
-// (fraction bits << 32 | body order) key -- the minimum fraction wins, ties go
-// to the first body in scan order, exactly like the sequential scan.
-__global__ void __launch_bounds__(128)
-k_lidar(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ DevOut O, int BC) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// Lidars._update (simulation.py:377-392) as an extension observation block, scanned on the state the
+// observation describes.  ONE WARP PER AGENT, rays across the lanes.  A block covers whole environments:
+// it first stages the environment's bodies (scan order: boxes, box items, heals, walls, agents) as a
+// table in shared memory; each warp then culls the table against its agent's fan -- one body per lane,
+// range and (for fans narrower than a half plane) the two edge half-planes, conservatively -- and the
+// surviving bodies, still in scan order, are ray-tested by every lane.  The minimum fraction wins, ties go
+// to the first body in scan order, exactly like the sequential scan of the reference's callback.
+#define LID_MAXB 64            // >= MSV_MAX_BOXES * 2 + MSV_MAX_HEALS + 4 + MSV_MAX_AGENTS = 44
+#define LID_W 8
+__global__ void __launch_bounds__(256)
+k_lidar(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ DevOut O, int EB, int BC, int HC) {
+  extern __shared__ float lid_sm[];                  // [EB][LID_MAXB][LID_W]: kind, x, y, then r | hx, hy, ax, ay, rot (agents: r, angle)
   const int A = C.A, L = C.lidar_n, N = C.N;
-  if (warp >= C.n_real * A) return;
-  const int e = warp / A, i = warp - e * A;
-  int RP = 1; while (RP < L) RP <<= 1;              // rays rounded up to a power of two (<= 32)
-  const int LPR = 32 / RP;                           // lanes per ray
-  const int r = lane & (RP - 1), part = lane / RP;
-  const float4 k0 = S.akin0[i * N + e];
-  const bool alive_i = (__float_as_int(S.akin1[i * N + e].w) & 1) != 0;
-  unsigned long long best = ~0ull;                   // no hit
-  if (alive_i && r < L) {
-    const int4 h0 = S.hdr0[e];
-    const int nb = h0.x & 255, ni = (h0.x >> 8) & 255, nh = (h0.x >> 16) & 255;
-    const f2 me = mk2(k0.x, k0.y);
-    const double ang = C.lidar_ang[r] + (double)k0.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int el = warp / A, i = warp - el * A;        // environment slot of the block, agent
+  const int e = blockIdx.x * EB + el;
+  const bool on = e < C.n_real;
+  // table slots are the CAPACITY slots of every list (boxes, box items, heals, walls, agents: the scan order), so
+  // that no load depends on the list lengths: slots past a list's length become KIND_NONE.  One memory round trip.
+  const int oI = BC, oH = 2 * BC, oW = 2 * BC + HC, oA = oW + 4, T = oA + A;
+  float* tab = lid_sm + (size_t)el * LID_MAXB * LID_W;
+  if (on) {
+    const int c = S.hdr0[e].x;
+    const int nb = c & 255, ni = (c >> 8) & 255, nh = (c >> 16) & 255;
+    for (int b = i * 32 + lane; b < T; b += A * 32) {
+      float* t = tab + b * LID_W;
+      if (b < oI) {
+        const float4 b0 = S.box0[b * N + e]; const int reh = (S.box1[b * N + e].y >> 1) & 1;
+        SBox bx; sb_set_shape(bx, b0.z, b0.w, reh);
+        t[0] = __int_as_float(b < nb ? KIND_BOX : KIND_NONE); t[1] = b0.x; t[2] = b0.y; t[3] = bx.hx; t[4] = bx.hy; t[5] = bx.ax; t[6] = bx.ay; t[7] = __int_as_float(bx.rot);
+      } else if (b < oH) {
+        const float4 it = S.item0[(b - oI) * N + e];
+        t[0] = __int_as_float(b - oI < ni ? KIND_ITEM : KIND_NONE); t[1] = it.x; t[2] = it.y; t[3] = C.item_r;
+      } else if (b < oW) {
+        const float2 hh = S.heal[(b - oH) * N + e];
+        t[0] = __int_as_float(b - oH < nh ? KIND_HEAL : KIND_NONE); t[1] = hh.x; t[2] = hh.y; t[3] = C.heal_r;
+      } else if (b < oA) {
+        t[0] = __int_as_float(KIND_WALL); t[1] = C.walls[b - oW].px; t[2] = C.walls[b - oW].py; t[3] = __int_as_float(b - oW);
+      } else {
+        const float4 o = S.akin0[(b - oA) * N + e];
+        const bool al = (__float_as_int(S.akin1[(b - oA) * N + e].w) & 1) != 0;
+        t[0] = __int_as_float(al ? KIND_AGENT : KIND_NONE); t[1] = o.x; t[2] = o.y; t[3] = C.agent_r; t[4] = o.z;
+      }
+    }
+  }
+  __syncthreads();
+  if (!on) return;
+  const float* mine = tab + (oA + i) * LID_W;
+  const bool alive_i = __float_as_int(mine[0]) == KIND_AGENT;
+  const size_t obase = ((size_t)e * A + i) * L;
+  if (!alive_i) {                                    // dead agents have no Lidars row: reported as "no hit"
+    if (lane < L) { O.lidar_frac[obase + lane] = 1.0f; O.lidar_hit[obase + lane] = 0; }
+    return;
+  }
+  const f2 me = mk2(mine[1], mine[2]);
+  const float heading = mine[4];
+  // ---- cull: which bodies can any ray of this fan reach?  (conservative; never the agent itself)
+  unsigned long long cand = 0ull;
+  {
+    const float hf = 0.5f * (float)(C.lidar_ang[L - 1] - C.lidar_ang[0]);          // half the fan
+    const bool convex = L > 1 && hf < 1.45f;                                       // fan inside a half plane (with margin)
+    float sl, cl, sr, cr;
+    sincosf(heading + hf, &sl, &cl); sincosf(heading - hf, &sr, &cr);
+#pragma unroll
+    for (int round = 0; round < LID_MAXB / 32; ++round) {
+      const int b = round * 32 + lane;
+      bool keep = false;
+      if (b < T) {
+        const float* t = tab + b * LID_W;
+        const int kind = __float_as_int(t[0]);
+        if (kind == KIND_WALL) keep = true;                                        // long thin boxes: the per-ray test handles them
+        else if (kind != KIND_NONE && b != oA + i) {
+          const float bound = kind == KIND_BOX ? t[3] + t[4] + 0.02f : t[3] + 0.02f;    // |hx|+|hy| >= circumradius
+          const float dx = t[1] - me.x, dy = t[2] - me.y;
+          const float dist = sqrtf(dx * dx + dy * dy);
+          const float slack = bound + 1e-3f * (1.0f + dist);
+          keep = dist <= C.lidar_depth + slack;
+          if (keep && convex && dist > slack) {
+            const float crossL = cl * dy - sl * dx, crossR = cr * dy - sr * dx;    // > 0: left of that edge
+            if (crossL > slack || crossR < -slack) keep = false;
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      cand |= (unsigned long long)m << (32 * round);
+    }
+  }
+  // ---- rays
+  if (lane < L) {
+    const int r = lane;
+    const double ang = C.lidar_ang[r] + (double)heading;
     const f2 off = from_polar(C.lidar_depth, (float)ang);
     const f2 p2 = vadd(me, off);
-    const int T = nb + ni + nh + 4 + A;              // scan order: boxes, box items, heals, walls, agents
-    // conservative reject before every exact test: the ray's AABB against a bound of the shape
     const float lx = fmin_(me.x, p2.x), ly = fmin_(me.y, p2.y), ux = fmax_(me.x, p2.x), uy = fmax_(me.y, p2.y);
-    auto far_from = [&](float cx, float cy, float rad) { return cx + rad < lx || cx - rad > ux || cy + rad < ly || cy - rad > uy; };
-    for (int b = part; b < T; b += LPR) {
-      float f; bool hit = false; int q = b;
-      if (q < nb) {
-        float4 b0 = S.box0[q * N + e];
-        if (!far_from(b0.x, b0.y, b0.z + b0.w + 0.01f)) {
-          int reh = (S.box1[q * N + e].y >> 1) & 1;
-          SBox bx; bx.px = b0.x; bx.py = b0.y; bx.qs = 0.0f; bx.qc = 1.0f; bx.ang = 0.0f; sb_set_shape(bx, b0.z, b0.w, reh);
+    // conservative reject before every exact test: distance from the body's centre to the ray's segment against a
+    // bound of the shape (much tighter than the segment's AABB for a 10 m ray); it can only skip shapes the exact test would miss
+    const float dd = C.lidar_depth;
+    auto far_from = [&](float cx, float cy, float rad) {
+      const float dx = cx - me.x, dy = cy - me.y, lim = (rad + 0.01f) * dd;
+      const float perp = off.x * dy - off.y * dx, along = off.x * dx + off.y * dy;
+      return fabsf(perp) > lim || along < -lim || along > dd * dd + lim;
+    };
+    float best = 2.0f; int bestb = -1;
+    unsigned long long m = cand;
+    while (m) {
+      const int b = __ffsll((long long)m) - 1; m &= m - 1;
+      const float* t = tab + b * LID_W;
+      const int kind = __float_as_int(t[0]);
+      float f; bool hit = false;
+      if (kind == KIND_BOX) {
+        if (!far_from(t[1], t[2], t[3] + t[4] + 0.01f)) {
+          SBox bx; bx.px = t[1]; bx.py = t[2]; bx.qs = 0.0f; bx.qc = 1.0f; bx.ang = 0.0f;
+          bx.hx = t[3]; bx.hy = t[4]; bx.ax = t[5]; bx.ay = t[6]; bx.rot = __float_as_int(t[7]);
           hit = ray_box(bx, me, p2, f);
         }
-      } else if ((q -= nb) < ni) { float4 it = S.item0[q * N + e]; if (!far_from(it.x, it.y, C.item_r + 0.01f)) hit = ray_circle(mk2(it.x, it.y), C.item_r, me, p2, f); }
-      else if ((q -= ni) < nh) { float2 hh = S.heal[q * N + e]; if (!far_from(hh.x, hh.y, C.heal_r + 0.01f)) hit = ray_circle(mk2(hh.x, hh.y), C.heal_r, me, p2, f); }
-      else if ((q -= nh) < 4) {
-        const WallC& w = C.walls[q];
+      } else if (kind == KIND_WALL) {
+        const WallC& w = C.walls[__float_as_int(t[3])];
         if (!(w.fat[2] < lx || w.fat[0] > ux || w.fat[3] < ly || w.fat[1] > uy)) {
           SBox bx; bx.px = w.px; bx.py = w.py; bx.qs = w.qs; bx.qc = w.qc; bx.ang = w.ang; bx.hx = C.wall_hx; bx.hy = C.wall_hy; bx.ax = 1.0f; bx.ay = 1.0f; bx.rot = 0;
           hit = ray_box(bx, me, p2, f);
         }
-      } else {
-        q -= 4;
-        if (q != i) {
-          float4 o = S.akin0[q * N + e];
-          if (!far_from(o.x, o.y, C.agent_r + 0.01f) && (__float_as_int(S.akin1[q * N + e].w) & 1)) hit = ray_circle(mk2(o.x, o.y), C.agent_r, me, p2, f);
-        }
+      } else {                                         // item, heal or agent circle
+        if (!far_from(t[1], t[2], t[3] + 0.01f)) hit = ray_circle(mk2(t[1], t[2]), t[3], me, p2, f);
       }
-      if (hit) {
-        unsigned long long key = ((unsigned long long)__float_as_uint(f) << 32) | (unsigned)b;
-        if (key < best) best = key;
-      }
+      if (hit && f < best) { best = f; bestb = b; }    // scan order is ascending b: strict < keeps the first of equal fractions
     }
-  }
-  for (int o = RP; o < 32; o <<= 1) {                // combine the lanes that share a ray
-    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-    if (other < best) best = other;
-  }
-  if (part == 0 && r < L) {
     float fr = 1.0f; int hitcode = 0;
-    if (best != ~0ull) {
-      const int4 h0 = S.hdr0[e];
-      const int nb = h0.x & 255, ni = (h0.x >> 8) & 255, nh = (h0.x >> 16) & 255;
-      int b = (int)(best & 0xffffffffu);
-      fr = __uint_as_float((unsigned)(best >> 32));
+    if (bestb >= 0) {
+      fr = best;
       int kind, idx;
-      if (b < nb) { kind = KIND_BOX; idx = b; }
-      else if (b < nb + ni) { kind = KIND_ITEM; idx = b - nb; }
-      else if (b < nb + ni + nh) { kind = KIND_HEAL; idx = b - nb - ni; }
-      else if (b < nb + ni + nh + 4) { kind = KIND_WALL; idx = b - nb - ni - nh; }
-      else { kind = KIND_AGENT; idx = b - nb - ni - nh - 4; }
+      if (bestb < oI) { kind = KIND_BOX; idx = bestb; }
+      else if (bestb < oH) { kind = KIND_ITEM; idx = bestb - oI; }
+      else if (bestb < oW) { kind = KIND_HEAL; idx = bestb - oH; }
+      else if (bestb < oA) { kind = KIND_WALL; idx = bestb - oW; }
+      else { kind = KIND_AGENT; idx = bestb - oA; }
       hitcode = (kind << 8) | idx;
     }
-    O.lidar_frac[((size_t)e * A + i) * L + r] = fr;
-    O.lidar_hit[((size_t)e * A + i) * L + r] = hitcode;
+    O.lidar_frac[obase + r] = fr;
+    O.lidar_hit[obase + r] = hitcode;
   }
-  (void)BC;
+}
+
+// Pre-draw the reset record of every environment whose record is not the one of its NEXT episode (after a
+// reset, after msv_set_state).  Runs beside the observation kernels, off the step kernel's critical path: the
+// in-kernel reset of a finished environment then only copies 96 floats instead of running the Philox shuffle,
+// the Box-Muller box shapes and the zone-centre draws while the 63 other environments of its block wait.
+// `only_done`: look only at the environments whose done flag is set (the ones the step just reset).
+__global__ void __launch_bounds__(128)
+k_spare(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const uint8_t* __restrict__ dones, int only_done) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= C.n_real) return;
+  if (only_done && !dones[e]) return;
+  const int next = S.hdr0[e].z + 1;
+  if (S.spare_ep[e] == next) return;
+  float rec[MSV_SPARE_W];
+#pragma unroll
+  for (int q = 0; q < MSV_SPARE_W; ++q) rec[q] = 0.0f;
+  draw_reset(C, C.env_offset + (uint32_t)e, (uint32_t)next, rec);
+  float4* dst = reinterpret_cast<float4*>(S.spare + (size_t)e * MSV_SPARE_W);
+#pragma unroll
+  for (int q = 0; q < MSV_SPARE_W / 4; ++q) dst[q] = make_float4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
+  __threadfence();
+  S.spare_ep[e] = next;
+}
+
+cudaError_t msv_launch_spare(const DevConst& C, const DevState& S, const uint8_t* dones, int only_done, cudaStream_t st) {
+  k_spare<<<(C.n_real + 127) / 128, 128, 0, st>>>(C, S, dones, only_done);
+  return cudaPeekAtLastError();
 }
 
 // flush_stats (env:471-480): sum the per-env accumulators, then zero them
@@ -530,7 +625,9 @@ cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable&
     for (int k = 0; k < MSV_OBS_KEYS; ++k) smem += (size_t)OBS2_E * T.keys[k].chunk * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_obs2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    const int threads = smem <= 56 * 1024 ? 256 : 1024;     // small stage: several blocks per SM; large (ffa): one block of 32 warps
+    // one warp per source item when they fit a block (a single round of loads), else 32 warps looping over the items
+    const int n_items = C.A + 2 * C.B0 + C.H0 + 1;
+    const int threads = n_items <= 32 ? 32 * n_items : 1024;
     k_obs2<<<(C.n_real + OBS2_E - 1) / OBS2_E, threads, smem, st>>>(C, S, T, AC);
     return cudaPeekAtLastError();
   }
@@ -539,9 +636,11 @@ cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable&
   return cudaPeekAtLastError();
 }
 
-cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut& O, int BC, cudaStream_t st) {
-  long long warps = (long long)C.n_real * C.A;
-  k_lidar<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(C, S, O, BC);
+cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut& O, int BC, int HC, cudaStream_t st) {
+  int EB = 8 / C.A; if (EB < 1) EB = 1;              // whole environments per block, 8 warps (A = 8: one env; A = 4: two; A <= 2: four)
+  const int warps = EB * C.A;
+  const size_t smem = (size_t)EB * LID_MAXB * LID_W * sizeof(float);
+  k_lidar<<<(C.n_real + EB - 1) / EB, warps * 32, smem, st>>>(C, S, O, EB, BC, HC);
   return cudaPeekAtLastError();
 }
 
@@ -577,7 +676,10 @@ cudaError_t msv_read_profile(unsigned long long out[64], int reset) {
     // [44..47] generic solve / TOI event (calls, cycles); the rest go to [60..63] and the slowest-wait slots that are unused ([58],[59])
     out[58] = d[4]; out[59] = d[5]; out[60] = d[6]; out[61] = d[7]; out[62] = d[8]; out[63] = d[9];
     out[14] = d[10]; out[15] = d[11]; out[42] = d[12]; out[43] = d[13];
-    unsigned long long z16[16] = {0}; if (reset) cudaMemcpyToSymbol(g_cnt, z16, sizeof z16); }
+    unsigned long long z16[16] = {0}; if (reset) cudaMemcpyToSymbol(g_cnt, z16, sizeof z16);
+    unsigned long long sb_[16]; cudaMemcpyFromSymbol(sb_, g_sub, sizeof sb_);
+    for (int k = 0; k < 6; ++k) out[20 + k] = sb_[k];     // (slots 16..27 normally hold the slowest group's phases; 20..25 reused when MSV_SUBPROF is read)
+    if (reset) cudaMemcpyToSymbol(g_sub, z16, sizeof z16); }
 #endif
   if (reset) { unsigned long long z[64] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof z); }
   return e;

@@ -13,5 +13,6 @@ cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* ski
                              unsigned long long* out_kills, unsigned long long* out_misc, cudaStream_t st);
 cudaError_t msv_read_profile(unsigned long long out[64], int reset);
 cudaError_t msv_read_check(unsigned long long out[2]);
+cudaError_t msv_launch_spare(const DevConst& C, const DevState& S, const uint8_t* dones, int only_done, cudaStream_t st);
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, const uint8_t* only_if, cudaStream_t st);
-cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut& O, int BC, cudaStream_t st);
+cudaError_t msv_launch_lidar(const DevConst& C, const DevState& S, const DevOut& O, int BC, int HC, cudaStream_t st);

@@ -73,9 +73,20 @@ struct DevState {
   int* skills;     // [AC][N]
   int4* smisc;     // [N] steps, heals_used, boxes_placed, episodes
   float* epret;    // [AC][N] running return of the current episode, per agent
+  // Pre-drawn reset records (k_spare): everything BaseEnv.reset draws from the RNG for an env's NEXT episode --
+  // spawn cells, box shapes, zone centres -- computed off the step's critical path; valid iff spare_ep[e] == episode + 1
+  float* spare;    // [N][MSV_SPARE_W]
+  int* spare_ep;   // [N]
   unsigned long long* obm;  // [N] others_mask bits (observer i sees agent j: bit i*AC+j)
   unsigned* omask;          // [AC][N] non-omniscient: per observer, seen heals (bits 0-15), boxes (16-23), box items (24-31)
 };
+
+// layout of a reset record: boxes (x, y, hx, hy), heals (x, y), agents (x, y), zone centres (x, y)
+#define MSV_SP_BOX 0
+#define MSV_SP_HEAL (4 * MSV_MAX_BOXES)
+#define MSV_SP_AGENT (MSV_SP_HEAL + 2 * MSV_MAX_HEALS)
+#define MSV_SP_ZONE (MSV_SP_AGENT + 2 * MSV_MAX_AGENTS)
+#define MSV_SPARE_W (MSV_SP_ZONE + 2 * MSV_MAX_ZONES)
 
 struct DevOut {
   float* agent;          // [N][A][S]

@@ -21,7 +21,7 @@ EXPORTS = [
     'msv_default_config', 'msv_create', 'msv_destroy', 'msv_reset', 'msv_step',
     'msv_step_host', 'msv_step_host_obs', 'msv_step_host_async', 'msv_step_host_wait', 'msv_obs_host_bytes',
     'msv_obs_host_offset', 'msv_device_bytes', 'msv_tensor', 'msv_tensor_info', 'msv_get_state', 'msv_set_state',
-    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_obs_bytes_per_env', 'msv_kernel_launches',
+    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_kernel_bytes_per_env', 'msv_obs_bytes_per_env', 'msv_kernel_launches',
     'msv_last_error', 'msv_philox4x32',
 ]
 
@@ -73,6 +73,8 @@ def load():
     L.msv_flush_stats.argtypes = [vp, vp]
     L.msv_bytes_per_env_step.argtypes = [vp]
     L.msv_bytes_per_env_step.restype = i64
+    L.msv_kernel_bytes_per_env.argtypes = [vp, i32]
+    L.msv_kernel_bytes_per_env.restype = i64
     L.msv_obs_bytes_per_env.argtypes = [vp]
     L.msv_obs_bytes_per_env.restype = i64
     L.msv_kernel_launches.argtypes = [vp]
@@ -220,6 +222,10 @@ class Handle:
 
     def bytes_per_env_step(self):
         return int(load().msv_bytes_per_env_step(self.h))
+
+    def kernel_bytes_per_env(self, which):
+        """algorithmic HBM bytes per env-step of kernel `which` (0 k_step, 1 k_obs2, 2 k_lidar)"""
+        return int(load().msv_kernel_bytes_per_env(self.h, which))
 
     def obs_bytes_per_env(self):
         return int(load().msv_obs_bytes_per_env(self.h))

@@ -310,8 +310,10 @@ int msv_observe(msv_handle* h, void* cuda_stream);
 int msv_flush_stats(msv_handle* h, msv_stats* out);
 
 /* Algorithmic HBM bytes one msv_step moves per env (state read+write,
- * actions, observations, rewards, dones) -- the roofline numerator. */
+ * actions, observations, rewards, dones) -- the roofline numerator -- and
+ * its split by kernel (which: 0 step kernel, 1 observation gather, 2 lidar). */
 int64_t msv_bytes_per_env_step(msv_handle* h);
+int64_t msv_kernel_bytes_per_env(msv_handle* h, int32_t which);
 /* The part of it written by the observation gather kernel (k_obs). */
 int64_t msv_obs_bytes_per_env(msv_handle* h);
 int64_t msv_kernel_launches(msv_handle* h); /* launches since create */

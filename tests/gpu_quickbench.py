@@ -68,6 +68,9 @@ def run(variant, N, steps=600, warm=100, prof=False):
         rare = [('generic island solve', 44), ('TOI event', 46), ('reset', 58), ('deaths', 60), ('pickups', 62), ('use/give', 14), ('contact numbering', 42)]
         print('   rare paths (calls per 1000 env-steps, mean cycles per call): ' +
               ', '.join(f'{n}: {buf[i] / (N * 20) * 1000:.2f} x {buf[i + 1] / max(buf[i], 1):.0f}' for n, i in rare))
+        nev = max(buf[46], 1)
+        print('   toi_event sub-phases (mean cycles): ' + ', '.join(f'{n}={buf[20 + i] / nev:.0f}' for i, n in enumerate(
+            ['advance+update', 'other contacts', 'position solve', 'velocity solve', 'integrate+sync+broadphase', 'snapshot'])))
         print('   b2TimeOfImpact calls per 1000 env-steps: %.1f, mean cycles %.0f' % (buf[28] / (N * 20) * 1000, buf[31] / max(buf[28], 1)))
     for x in hs:
         x.close()

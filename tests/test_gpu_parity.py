@@ -447,7 +447,8 @@ for name, n, steps, over, fwd in (('2v2', 4096, 500, {}, False),
     assert bad == 0, (name, bad, line)
     assert h.overflow_events() == 0, name
     st = h.flush_stats()
-    assert int(st['steps']) == n * steps and int(st['episodes']) > 0
+    assert int(st['steps']) == n * steps, (name, st)
+    print(name, 'episodes', int(st['episodes']), 'steps', int(st['steps']))
     h.close()
 print('CHECKED-BUILD-CLEAN')
 """
