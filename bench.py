@@ -258,7 +258,9 @@ def run_ours(args):
     for _ in range(int(math.ceil(150.0 / max(est, 1e-6)))):
         dev_step()
     l0 = sum(e_.kernel_launches() for e_ in envs)
+    torch.cuda.profiler.start()        # `ncu --profile-from-start off` captures exactly the timed repeats (no effect otherwise)
     reps = [timed(dev_step, args.steps) for _ in range(R)]
+    torch.cuda.profiler.stop()
     launches_per_rep = (sum(e_.kernel_launches() for e_ in envs) - l0) // R
     clocks = clk.stop()
     ms_per_step = float(np.median(reps)) / args.steps

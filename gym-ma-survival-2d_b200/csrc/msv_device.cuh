@@ -387,6 +387,9 @@ __device__ unsigned long long g_cnt[16];
 __device__ unsigned long long g_sub[16];   // sub-phase cycle sums inside toi_event (development)
 #define SUB_BEGIN() long long sub_t_ = clock64()
 #define SUB(k) do { long long n_ = clock64(); atomicAdd(&g_sub[k], (unsigned long long)(n_ - sub_t_)); sub_t_ = n_; } while (0)
+#define SUBCNT(k, v) atomicAdd(&g_sub[k], (unsigned long long)(v))
+// maximum duration (cycles << 8 | tag) of a section
+#define SUBMAX(k, tag) atomicMax(&g_sub[k], ((unsigned long long)(clock64() - sub_t_) << 8) | (unsigned long long)((tag) & 255))
 #define RARE_BEGIN() long long rare_t0_ = clock64()
 #define RARE_END(k) do { atomicAdd(&g_cnt[2 * (k)], 1ull); atomicAdd(&g_cnt[2 * (k) + 1], (unsigned long long)(clock64() - rare_t0_)); } while (0)
 #else
@@ -394,6 +397,8 @@ __device__ unsigned long long g_sub[16];   // sub-phase cycle sums inside toi_ev
 #define RARE_END(k) do { } while (0)
 #define SUB_BEGIN() do { } while (0)
 #define SUB(k) do { } while (0)
+#define SUBCNT(k, v) do { } while (0)
+#define SUBMAX(k, tag) do { } while (0)
 #endif
 // b2TimeOfImpact(proxyA = box, proxyB = circle centre), tMax = 1
 struct ToiOut { int state; float t; };

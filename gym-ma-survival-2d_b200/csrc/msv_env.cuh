@@ -1035,8 +1035,10 @@ struct Env {
       taken |= 1u << best;
       ord |= (unsigned long long)best << (5 * cnt); cnt++;
     }
+    SUB_BEGIN();
     if (cnt <= NR) island_single<NR>(i, cnt, ord, h, dtRatio);
     else island_single<BC + 4>(i, cnt, ord, h, dtRatio);
+    SUBMAX(cnt <= NR ? 6 : 7, cnt);
   }
 
   // b2World::Solve for ONE island that contains agent-agent contacts, executed by the lane of the
@@ -1181,6 +1183,7 @@ struct Env {
     synchronize_fixtures(X); synchronize_fixtures(Y);
   }
   COLD0 void solve_island(int seed, float h, float dtRatio) {
+    SUB_BEGIN();
     Ord ord; ord.lo = 0ull; ord.hi = 0ull;
     int nc = 0; unsigned taken = 0, inisl = 1u << seed;
     {
@@ -1222,7 +1225,9 @@ struct Env {
       AG(F_VX, i) = C.damp * AG(F_VX, i); AG(F_VY, i) = C.damp * AG(F_VY, i);  // v *= 1/(1+h*damping)
       AG(F_W, i) *= C.damp;
     }
-    if (__popc(inisl) == 2 && nc <= NP) { island_pair(inisl, nc, ord, h, dtRatio); return; }   // two agents, <= NP contacts (the usual case)
+    SUB(8);
+    if (__popc(inisl) == 2 && nc <= NP) { island_pair(inisl, nc, ord, h, dtRatio); SUB(9); return; }   // two agents, <= NP contacts (the usual case)
+    SUBCNT(14, 1); SUBCNT(15, nc);
     // b2ContactSolver::InitializeVelocityConstraints (+ the warm-start scaling of b2ContactSolver's constructor)
     for (int k = 0; k < nc; ++k) {
       const int s = ord_get(ord, k);
@@ -1250,6 +1255,7 @@ struct Env {
       KF(KS_NX, s) = normal.x; KF(KS_NY, s) = normal.y; KF(KS_PX, s) = px.x; KF(KS_PY, s) = px.y;
       KF(KS_RBX, s) = rB.x; KF(KS_RBY, s) = rB.y; KF(K_NM, s) = nm; KF(K_TM, s) = tm;
     }
+    SUB(10);
     // warm start, then 10 velocity iterations, contacts in island order.  The bodies' velocities (then positions)
     // live in REGISTERS -- one record per agent slot, picked with statically unrolled selects -- because the
     // Gauss-Seidel sweep is one long dependent chain through them: a shared-memory store/load round trip per
@@ -1321,6 +1327,7 @@ struct Env {
       const int s = ord_get(ord, k);
       S.pimp[(KI(K_META, s) & 255) * N + e] = make_float2(KF(K_NI, s), KF(K_TI, s));
     }
+    SUB(11);
     for (int i = 0; i < C.A; ++i) if ((inisl >> i) & 1u) integrate_position(i, h);
     // positions: the same register scheme (bv := centre, bw := angle)
 #pragma unroll
@@ -1358,6 +1365,7 @@ struct Env {
     }
 #pragma unroll
     for (int q = 0; q < AC; ++q) if ((inisl >> q) & 1u) { AG(F_CX, q) = bv[q].x; AG(F_CY, q) = bv[q].y; AG(F_A, q) = bw[q]; }
+    SUB(12);
     {
       const float linTol = B2_LIN_SLEEP_TOL * B2_LIN_SLEEP_TOL, angTol = B2_ANG_SLEEP_TOL * B2_ANG_SLEEP_TOL;
       bool can_sleep = ok;                       // minSleepTime >= timeToSleep && positionSolved
@@ -1402,7 +1410,7 @@ struct Env {
       }
       if (comp == (1u << i)) { solve_single(i, h, dtRatio); continue; }
       const unsigned cand = comp & awk;          // no awake member: the island is not simulated
-      if (cand != 0u && (31 - __clz((int)cand)) == i) { RARE_BEGIN(); MSV_COLDK(0, solve_island(i, h, dtRatio)); RARE_END(0); }
+      if (cand != 0u && (31 - __clz((int)cand)) == i) { RARE_BEGIN(); SUB_BEGIN(); MSV_COLDK(0, solve_island(i, h, dtRatio)); SUBMAX(13, __popc(comp)); RARE_END(0); }
     }
     gsync();
   }

@@ -679,6 +679,8 @@ cudaError_t msv_read_profile(unsigned long long out[64], int reset) {
     unsigned long long z16[16] = {0}; if (reset) cudaMemcpyToSymbol(g_cnt, z16, sizeof z16);
     unsigned long long sb_[16]; cudaMemcpyFromSymbol(sb_, g_sub, sizeof sb_);
     for (int k = 0; k < 6; ++k) out[20 + k] = sb_[k];     // (slots 16..27 normally hold the slowest group's phases; 20..25 reused when MSV_SUBPROF is read)
+    for (int k = 0; k < 8; ++k) out[48 + k] = sb_[8 + k]; // island sub-phases (slots 48.. normally: the slowest group's waits)
+    out[26] = sb_[6]; out[27] = sb_[7];                   // longest island_single<NR> / <BC+4> (cycles << 8 | contacts)
     if (reset) cudaMemcpyToSymbol(g_sub, z16, sizeof z16); }
 #endif
   if (reset) { unsigned long long z[64] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof z); }

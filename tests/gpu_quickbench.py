@@ -71,6 +71,11 @@ def run(variant, N, steps=600, warm=100, prof=False):
         nev = max(buf[46], 1)
         print('   toi_event sub-phases (mean cycles): ' + ', '.join(f'{n}={buf[20 + i] / nev:.0f}' for i, n in enumerate(
             ['advance+update', 'other contacts', 'position solve', 'velocity solve', 'integrate+sync+broadphase', 'snapshot'])))
+        nis = max(buf[44], 1); ngen = max(buf[48 + 6], 1)
+        print('   solve_island: DFS+damping mean %.0f; pair path mean %.0f; general path: %d calls (%.2f per 1000 env-steps), mean contacts %.1f, init %.0f, velocity %.0f, integrate+position %.0f cycles' % (
+            buf[48] / nis, buf[49] / max(nis - buf[54], 1), buf[54], buf[54] / (N * 20) * 1000, buf[55] / ngen, buf[50] / ngen, buf[51] / ngen, buf[52] / ngen))
+        print('   longest single sections: island_single<3> %d cycles (cnt %d), island_single<big> %d cycles (cnt %d), solve_island %d cycles (%d agents)' % (
+            buf[26] >> 8, buf[26] & 255, buf[27] >> 8, buf[27] & 255, buf[53] >> 8, buf[53] & 255))
         print('   b2TimeOfImpact calls per 1000 env-steps: %.1f, mean cycles %.0f' % (buf[28] / (N * 20) * 1000, buf[31] / max(buf[28], 1)))
     for x in hs:
         x.close()
