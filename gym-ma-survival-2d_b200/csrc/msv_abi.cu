@@ -1058,6 +1058,14 @@ int msv_debug_profile(msv_handle* h, int enable, unsigned long long out[64]) {
   return MSV_OK;
 }
 
+/* debug (profile build): per-block timeline of the last k_step launch, 24 words per block */
+int msv_debug_blocks(msv_handle* h, unsigned long long* out, int n_words) {
+  if (!h || !out) return MSV_ERR_INVALID;
+  DevGuard g(h->device); CK(cudaDeviceSynchronize());
+  CK(msv_read_blocks(out, n_words));
+  return MSV_OK;
+}
+
 void msv_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
   for (int r = 0; r < 10; ++r) {

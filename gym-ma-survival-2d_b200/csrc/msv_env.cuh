@@ -78,6 +78,12 @@ extern __shared__ float msv_sm[];
 #ifndef MSV_INLINE_MASK
 #define MSV_INLINE_MASK 0
 #endif
+#ifndef MSV_TOI_COOP
+#define MSV_TOI_COOP 0   // deal the b2TimeOfImpact calls of SolveTOI out to the group's lanes (0: every lane its own agent's)
+#endif
+#ifndef MSV_FIXPOINT
+#define MSV_FIXPOINT 1   // stop Gauss-Seidel sweeps at a bitwise fixed point (exact); 0 = always run every iteration (development A/B)
+#endif
 #if (MSV_INLINE_MASK >> 0) & 1
 #define COLD0 __device__ __forceinline__
 #else
@@ -984,9 +990,18 @@ struct Env {
       }
 #pragma unroll (NRr <= NR ? NRr : 1)
       for (int k = 0; k < NRr; ++k) if (k < cnt) warm_start_static(nrm[k], rB[k], ni_[k], ti_[k], vB, wB);
+      // A sweep is a pure function of (velocity, accumulated impulses): after one that changed none of those bits
+      // every further sweep is a no-op, so the loop stops there (the usual case after 1-4 sweeps) -- FIXPOINT_EXIT
       for (int it = 0; it < 10; ++it) {
+        const f2 v_in = vB; const float w_in = wB; bool changed = false;
 #pragma unroll (NRr <= NR ? NRr : 1)
-        for (int k = 0; k < NRr; ++k) if (k < cnt) solve_velocity_static(nrm[k], rB[k], nm[k], tm[k], ni_[k], ti_[k], vB, wB);
+        for (int k = 0; k < NRr; ++k) if (k < cnt) {
+          const float n0 = ni_[k], t0 = ti_[k];
+          solve_velocity_static(nrm[k], rB[k], nm[k], tm[k], ni_[k], ti_[k], vB, wB);
+          changed |= (__float_as_uint(ni_[k]) != __float_as_uint(n0)) | (__float_as_uint(ti_[k]) != __float_as_uint(t0));
+        }
+        if (MSV_FIXPOINT && !changed && __float_as_uint(vB.x) == __float_as_uint(v_in.x) && __float_as_uint(vB.y) == __float_as_uint(v_in.y) &&
+            __float_as_uint(wB) == __float_as_uint(w_in)) break;
       }
 #pragma unroll (NRr <= NR ? NRr : 1)
       for (int k = 0; k < NRr; ++k) if (k < cnt) S.pimp[pr[k] * N + e] = make_float2(ni_[k], ti_[k]);
@@ -1094,9 +1109,11 @@ struct Env {
       }
     }
     for (int it = -1; it < 10; ++it) {           // warm start, then 10 velocity iterations, contacts in island order
+      const f2 vX_in = vX, vY_in = vY; const float wX_in = wX, wY_in = wY; bool changed = false;   // FIXPOINT_EXIT (see island_single)
 #pragma unroll
       for (int k = 0; k < NP; ++k) {
         if (k >= nc) continue;
+        const float n0_ = ni_[k], t0_ = ti_[k];
         if (ty[k] != 0) {
           f2 vB = ty[k] == 1 ? vX : vY; float wB = ty[k] == 1 ? wX : wY;
           if (it < 0) warm_start_static(nrm[k], rB[k], ni_[k], ti_[k], vB, wB);
@@ -1132,7 +1149,11 @@ struct Env {
             }
           }
         }
+        changed |= (__float_as_uint(ni_[k]) != __float_as_uint(n0_)) | (__float_as_uint(ti_[k]) != __float_as_uint(t0_));
       }
+      if (MSV_FIXPOINT && it >= 0 && !changed &&
+          __float_as_uint(vX.x) == __float_as_uint(vX_in.x) && __float_as_uint(vX.y) == __float_as_uint(vX_in.y) && __float_as_uint(wX) == __float_as_uint(wX_in) &&
+          __float_as_uint(vY.x) == __float_as_uint(vY_in.x) && __float_as_uint(vY.y) == __float_as_uint(vY_in.y) && __float_as_uint(wY) == __float_as_uint(wY_in)) break;
     }
 #pragma unroll
     for (int k = 0; k < NP; ++k) if (k < nc) S.pimp[pr[k] * N + e] = make_float2(ni_[k], ti_[k]);   // b2ContactSolver::StoreImpulses
@@ -1498,12 +1519,16 @@ struct Env {
     const float subdt = (1.0f - minAlpha) * dt;
     // b2Island::SolveTOI -- every contact of the mini island has a static body A
     {
+      // A sweep is a pure function of the centre: one that leaves it bitwise unchanged (an agent wedged between
+      // opposing faces: the corrections cancel exactly) would repeat verbatim until the iteration limit -> stop there.
       f2 cB = apos(b);
       for (int it = 0; it < 20; ++it) {
+        const f2 c_in = cB;
         float minSep = 0.0f;
         for (int k = 0; k < nisl; ++k)
           minSep = fmin_(minSep, solve_position_static(mk2(KF(KS_NX, k), KF(KS_NY, k)), mk2(KF(KS_PX, k), KF(KS_PY, k)), cB, true));
         if (minSep >= -1.5f * B2_LINEAR_SLOP) break;
+        if (__float_as_uint(cB.x) == __float_as_uint(c_in.x) && __float_as_uint(cB.y) == __float_as_uint(c_in.y)) break;
       }
       AG(F_CX, b) = cB.x; AG(F_CY, b) = cB.y;
     }
@@ -1527,13 +1552,21 @@ struct Env {
         KF(K_NM, k) = kNormal > 0.0f ? 1.0f / kNormal : 0.0f; KF(K_TM, k) = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
         KF(K_NI, k) = 0.0f; KF(K_TI, k) = 0.0f;
       }
+      // Gauss-Seidel sweeps are a pure function of (velocity, accumulated impulses): after a sweep that changed none
+      // of those bits every further sweep is a no-op -> stop (the usual case after 1-3 sweeps)
       f2 vB = mk2(AG(F_VX, b), AG(F_VY, b)); float wB = AG(F_W, b);
-      for (int it = 0; it < 10; ++it)
+      for (int it = 0; it < 10; ++it) {
+        const f2 v_in = vB; const float w_in = wB; bool changed = false;
         for (int k = 0; k < nisl; ++k) {
-          float ni_ = KF(K_NI, k), ti_ = KF(K_TI, k);
+          const float ni0 = KF(K_NI, k), ti0 = KF(K_TI, k);
+          float ni_ = ni0, ti_ = ti0;
           solve_velocity_static(mk2(KF(KS_NX, k), KF(KS_NY, k)), mk2(KF(KS_RBX, k), KF(KS_RBY, k)), KF(K_NM, k), KF(K_TM, k), ni_, ti_, vB, wB);
           KF(K_NI, k) = ni_; KF(K_TI, k) = ti_;
+          changed |= __float_as_uint(ni_) != __float_as_uint(ni0) || __float_as_uint(ti_) != __float_as_uint(ti0);
         }
+        if (!changed && __float_as_uint(vB.x) == __float_as_uint(v_in.x) && __float_as_uint(vB.y) == __float_as_uint(v_in.y) &&
+            __float_as_uint(wB) == __float_as_uint(w_in)) break;
+      }
       AG(F_VX, b) = vB.x; AG(F_VY, b) = vB.y; AG(F_W, b) = wB;
     }
     SUB(3);
@@ -1566,64 +1599,92 @@ struct Env {
   // Every lane evaluates b2TimeOfImpact for the contacts of its own agents;
   // the group picks the minimum; the leader runs the event.
   DEV void solve_toi(float dt) {
-    for (int i = g; i < C.A; i += G) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
-    // Per (own agent, static body k): the contact's toiCount (4 bits each) and the validity bit of
-    // its cached TOI (b2Contact::e_toiFlag / m_toi, the value sits in shared memory); both are
-    // only ever needed by the lane that owns the agent.
-    unsigned long long evcnt[SLOTS]; unsigned cvalid[SLOTS];
-#pragma unroll
-    for (int q = 0; q < SLOTS; ++q) { evcnt[q] = 0ull; cvalid[q] = 0u; }
+    static_assert(SLOTS == 1, "solve_toi: one agent per lane");
+    const int i = g;                           // this lane's agent
+    if (i < C.A) { AGF(i) &= ~FL_ISLAND; AG(F_ALPHA0, i) = 0.0f; }
+    // Per static body k of the lane's agent: the contact's toiCount (4 bits each) and the validity bit of
+    // its cached TOI (b2Contact::e_toiFlag / m_toi, the value sits in shared memory); both are only ever
+    // needed by the lane that owns the agent.
+    unsigned long long evcnt = 0ull; unsigned cvalid = 0u;
     int prevP = -1;                            // leader: contact of the previous event that ran (its state snapshot sits in shared memory)
+    // b2TimeOfImpact(static body k, agent j) as SolveTOI evaluates it for a contact without a cached TOI
+    auto toi_alpha = [&](int j, int k) {
+      const SBox sbx = static_box(k);
+      const f2 q0 = mk2(AG(F_C0X, j), AG(F_C0Y, j)), q1 = apos(j);
+      float beta = 1.0f;
+      const int state = time_of_impact(sbx, q0, q1, C.agent_r, beta);
+      const float alpha0 = AG(F_ALPHA0, j);
+      return state == TOI_TOUCHING ? fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f) : 1.0f;
+    };
+    TOIPROF(long long tp0 = clock64(); long long tp_ev = 0; int tp_it = 0; int tp_ran = 0; int tp_not = 0; int tp_same = 0; int tp_calls = 0;)
     for (int guard = 0; guard < 64; ++guard) {
+      TOIPROF(tp_it++;)
+      // ---- (1) every lane: the existing, enabled agent-vs-static contacts of its agent that still take part.
+      // Cached TOIs enter the minimum directly; the contacts whose TOI must be computed are collected in `need`
+      // (bit k = static body k).
+      unsigned need = 0u;
       int minP = -1, minSeq = -1; float minAlpha = 1.0f;
+      // the world contact list is newest first and the scan keeps the FIRST minimum:
+      // on equal alpha the contact with the larger creation sequence wins
+      auto consider = [&](int p, float alpha) {
+        if (alpha < 1.0f) {
+          const int sq = (int)S.pseq[p * N + e];
+          if (alpha < minAlpha || (alpha == minAlpha && sq > minSeq)) { minAlpha = alpha; minP = p; minSeq = sq; }
+        }
+      };
+      if (i < C.A && alive(i) && awake(i)) {
 #pragma unroll
-      for (int w = 0; w < PW; ++w) {
-        // existing, enabled agent-vs-static contacts (pair index >= NAA) of my agents
-        unsigned long long mbits = ex[w] & en[w] & own[w];
-        if (w == 0) mbits &= ~((1ull << NAA) - 1ull);
-        while (mbits) {
-          int p = w * 64 + __ffsll((long long)mbits) - 1; mbits &= mbits - 1;
-          int a_, k, i; decode(p, a_, k, i);
-          if (!alive(i) || !awake(i)) continue;
-          unsigned long long ec = evcnt[0]; unsigned cv = cvalid[0];
-#pragma unroll
-          for (int q = 1; q < SLOTS; ++q) if (i / G == q) { ec = evcnt[q]; cv = cvalid[q]; }
-          const int cnt = (int)((ec >> (4 * k)) & 15ull);
-          if (cnt > C.toi_max_count) continue;       // b2_maxSubSteps (">=" under MSV_B2_SUBSTEPS_GE)
-          float alpha = 1.0f; const bool have = (cv >> k) & 1u;
-          if (have) alpha = TOIA(i, k);
-          else {
-            float beta;
-            const SBox sbx = static_box(k);
-            const f2 q0 = mk2(AG(F_C0X, i), AG(F_C0Y, i)), q1 = apos(i);
+        for (int w = 0; w < PW; ++w) {
+          unsigned long long mbits = ex[w] & en[w] & own[w];
+          if (w == 0) mbits &= ~((1ull << NAA) - 1ull);     // pair index >= NAA: against static bodies
+          while (mbits) {
+            int p = w * 64 + __ffsll((long long)mbits) - 1; mbits &= mbits - 1;
+            int a_, k, i_; decode(p, a_, k, i_);
+            const int cnt = (int)((evcnt >> (4 * k)) & 15ull);
+            if (cnt > C.toi_max_count) continue;       // b2_maxSubSteps (">=" under MSV_B2_SUBSTEPS_GE)
+            if ((cvalid >> k) & 1u) { consider(p, TOIA(i, k)); continue; }
             // b2TimeOfImpact can only report e_touching at a time where the true distance
             // between the core shapes is below target + tolerance (0.49625).  The sweep is a
             // straight segment against a static box, so if a lower bound of the segment-box
             // distance (largest per-axis gap in the box frame) clears that with margin, the
             // outcome is alpha = 1 whatever path the root finder takes: skip the call.
-            bool may_touch = true;
-            {
-              f2 l0 = sb_mulT(sbx, q0), l1 = sb_mulT(sbx, q1);
-              float gx = fmax_(fmin_(l0.x, l1.x) - sbx.hx, -sbx.hx - fmax_(l0.x, l1.x));
-              float gy = fmax_(fmin_(l0.y, l1.y) - sbx.hy, -sbx.hy - fmax_(l0.y, l1.y));
-              if (fmax_(gx, gy) > (B2_POLY_RADIUS + C.agent_r - 3.0f * B2_LINEAR_SLOP) + 0.25f * B2_LINEAR_SLOP + 0.004f) may_touch = false;
-            }
-            int state = 0; beta = 1.0f;
-            if (may_touch) state = time_of_impact(sbx, q0, q1, C.agent_r, beta);
-            float alpha0 = AG(F_ALPHA0, i);
-            if (state == TOI_TOUCHING) alpha = fmin_(alpha0 + (1.0f - alpha0) * beta, 1.0f);
-            TOIA(i, k) = alpha;
-#pragma unroll
-            for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || i / G == q) cvalid[q] |= 1u << k;
-          }
-          // the world contact list is newest first and the scan keeps the FIRST minimum:
-          // on equal alpha the contact with the larger creation sequence wins
-          if (alpha < 1.0f) {
-            int sq = (int)S.pseq[p * N + e];
-            if (alpha < minAlpha || (alpha == minAlpha && sq > minSeq)) { minAlpha = alpha; minP = p; minSeq = sq; }
+            const SBox sbx = static_box(k);
+            const f2 l0 = sb_mulT(sbx, mk2(AG(F_C0X, i), AG(F_C0Y, i))), l1 = sb_mulT(sbx, apos(i));
+            const float gx = fmax_(fmin_(l0.x, l1.x) - sbx.hx, -sbx.hx - fmax_(l0.x, l1.x));
+            const float gy = fmax_(fmin_(l0.y, l1.y) - sbx.hy, -sbx.hy - fmax_(l0.y, l1.y));
+            if (fmax_(gx, gy) > (B2_POLY_RADIUS + C.agent_r - 3.0f * B2_LINEAR_SLOP) + 0.25f * B2_LINEAR_SLOP + 0.004f) { TOIA(i, k) = 1.0f; cvalid |= 1u << k; }
+            else if (MSV_TOI_COOP) need |= 1u << k;
+            else { const float al = toi_alpha(i, k); TOIA(i, k) = al; cvalid |= 1u << k; consider(p, al); }
           }
         }
       }
+      // ---- (2) the group computes the missing TOIs together: the calls are dealt out to the lanes in
+      // (agent, static body) order, so an agent wedged between several bodies does not serialise them on
+      // its own lane while the others idle.  Any lane can evaluate any pair: the inputs sit in shared memory.
+      if (MSV_TOI_COOP && __any_sync(gmask, need != 0u)) {          // group-uniform
+        unsigned ms[G]; int T = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) { ms[j] = from(need, j); T += __popc(ms[j]); }
+        TOIPROF(tp_calls += T;)
+        for (int r0 = 0; r0 < T; r0 += G) {
+          const int t = r0 + g;
+          int fj = -1, fk = 0, base = 0;
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int c = __popc(ms[j]);
+            if (t >= base && t < base + c) { fj = j; fk = (int)__fns(ms[j], 0u, t - base + 1); }
+            base += c;
+          }
+          if (fj >= 0) TOIA(fj, fk) = toi_alpha(fj, fk);
+        }
+        gsync();
+        cvalid |= need;
+        while (need) {
+          const int k = __ffs((int)need) - 1; need &= need - 1u;
+          consider(k < BC ? p_ab(i, k) : p_aw(i, k - BC), TOIA(i, k));
+        }
+      }
+      // ---- (3) minimum over the group
 #pragma unroll
       for (int o = 1; o < G; o <<= 1) {        // group minimum (alpha ascending, creation sequence descending)
         float oa = __shfl_xor_sync(gmask, minAlpha, o, G);
@@ -1632,13 +1693,11 @@ struct Env {
       }
       if (minP < 0 || 1.0f - 10.0f * B2_EPS < minAlpha) break;   // group-uniform
       int ea, ek, eb; decode(minP, ea, ek, eb);   // the event's contact: static body ek, agent eb
-      const bool mine = (eb % G) == g;
-      if (mine) {
-#pragma unroll
-        for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || eb / G == q) cvalid[q] &= ~(1u << ek);
-      }
+      const bool mine = eb == g;
+      if (mine) cvalid &= ~(1u << ek);
       gsync();
       int r = 0;
+      TOIPROF(long long tpe = clock64();)
       if (lead) {
         RARE_BEGIN();
         if ((MSV_INLINE_MASK >> 1) & 1) r = toi_event(minP, minAlpha, dt, prevP);
@@ -1648,27 +1707,26 @@ struct Env {
       }
       gsync();
       r = bc(r);
+      TOIPROF(tp_ev += clock64() - tpe; if (r & 1) tp_ran++; else tp_not++; if (r & 2) tp_same++;)
       share_bits();
       if (mine) {                              // toiCount of the event's contact (saturating at 15 > b2_maxSubSteps)
-#pragma unroll
-        for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || eb / G == q) {
-          unsigned long long c4 = (evcnt[q] >> (4 * ek)) & 15ull;
-          if (c4 < 15ull) evcnt[q] += 1ull << (4 * ek);
-        }
+        const unsigned long long c4 = (evcnt >> (4 * ek)) & 15ull;
+        if (c4 < 15ull) evcnt += 1ull << (4 * ek);
       }
       if (!(r & 1)) continue;
       if (mine) {
-#pragma unroll
-        for (int q = 0; q < SLOTS; ++q) if (SLOTS == 1 || eb / G == q) {
-          cvalid[q] = 0u;                      // "Invalidate all contact TOIs on this displaced body"
-          if (r & 2) {                         // identical repeat: jump the contact's toiCount past b2_maxSubSteps
-            unsigned long long c4 = (evcnt[q] >> (4 * ek)) & 15ull;
-            if (c4 <= (unsigned long long)C.toi_max_count) evcnt[q] = (evcnt[q] & ~(15ull << (4 * ek))) | ((unsigned long long)(C.toi_max_count + 1) << (4 * ek));
-          }
-        }
+        if (r & 2) {
+          // identical repeat: every further event on this contact would repeat verbatim -> jump its toiCount past
+          // b2_maxSubSteps.  The agent's state is exactly what it was after the previous event, so the TOIs of its
+          // other contacts, computed from that state, are still the ones SolveTOI would recompute: keep them.
+          const unsigned long long c4 = (evcnt >> (4 * ek)) & 15ull;
+          if (c4 <= (unsigned long long)C.toi_max_count) evcnt = (evcnt & ~(15ull << (4 * ek))) | ((unsigned long long)(C.toi_max_count + 1) << (4 * ek));
+        } else cvalid = 0u;                    // "Invalidate all contact TOIs on this displaced body"
       }
     }
     gsync();
+    TOIPROF(if (lead) { unsigned long long tot = (unsigned long long)(clock64() - tp0); unsigned long long old = atomicMax(&g_toi[0], tot);
+      if (tot > old) { g_toi[1] = tp_it; g_toi[2] = tp_ran; g_toi[3] = tp_not; g_toi[4] = tp_same; g_toi[5] = (unsigned long long)tp_ev; g_toi[6] = tot - (unsigned long long)tp_ev; g_toi[7] = tp_calls; g_toi[8] = (unsigned long long)e; } })
   }
 
   // ======================================================================

@@ -21,11 +21,18 @@
 // [32+k] time spent waiting at phase barrier k (sum), [48+k] the slowest group's waits
 __device__ unsigned long long g_prof[64];
 #ifdef MSV_PROFILE
+// per-block timeline of the last launch: clock64() of thread 0 at kernel entry, after every phase barrier and at exit
+// ([block][0] = number of stamps).  The barriers make these the block's phase durations; tests/gpu_quickbench.py --blocks
+#define MSV_BLK_MAX 2048
+#define MSV_BLK_STAMPS 24
+__device__ unsigned long long g_blk[MSV_BLK_MAX * MSV_BLK_STAMPS];
+#define BLK_STAMP() do { if (C.profile && threadIdx.x == 0 && blockIdx.x < MSV_BLK_MAX && blk_n < MSV_BLK_STAMPS) { g_blk[blockIdx.x * MSV_BLK_STAMPS + blk_n] = (unsigned long long)clock64(); blk_n++; } } while (0)
 #define PROF(k) do { if (C.profile) { long long _t = clock64(); ph[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
 #define PROFW(k) do { if (C.profile) { long long _t = clock64(); wt[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
 #else
 #define PROF(k) do { } while (0)
 #define PROFW(k) do { } while (0)
+#define BLK_STAMP() do { } while (0)
 #endif
 
 // thread -> (environment slot of the block, lane of the group)
@@ -37,7 +44,7 @@ __device__ unsigned long long g_prof[64];
 #ifdef MSV_NO_PHASE_SYNC
 #define PHASE_SYNC(k) do { } while (0)
 #else
-#define PHASE_SYNC(k) do { if ((MSV_SYNC_MASK >> (k)) & 1) __syncthreads(); PROFW(k); } while (0)
+#define PHASE_SYNC(k) do { if ((MSV_SYNC_MASK >> (k)) & 1) __syncthreads(); PROFW(k); BLK_STAMP(); } while (0)
 #endif
 #define MSV_GROUP_SETUP(G)                                                                       \
   const int es = threadIdx.x / (G), g = threadIdx.x % (G);                                       \
@@ -56,6 +63,8 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   const long long t_begin = t_last;
   unsigned long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long wt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int blk_n = 1;
+  BLK_STAMP();
 #endif
   env.load();
   const bool real = e < C.n_real;   // padding envs (N rounded up to the block size) get the no-op action
@@ -128,6 +137,9 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   env.store();
   PROF(11);
 #ifdef MSV_PROFILE
+  __syncthreads();
+  BLK_STAMP();
+  if (C.profile && threadIdx.x == 0 && blockIdx.x < MSV_BLK_MAX) g_blk[blockIdx.x * MSV_BLK_STAMPS] = (unsigned long long)blk_n;
   if (C.profile && env.lead) {
     for (int k = 0; k < 12; ++k) { atomicAdd(&g_prof[k], ph[k]); atomicAdd(&g_prof[32 + k], wt[k]); }
     unsigned long long tot = (unsigned long long)(clock64() - t_begin);
@@ -664,6 +676,20 @@ cudaError_t msv_read_check(unsigned long long out[2]) {
 #else
   out[0] = ~0ull; out[1] = 0;      // not a checked build
   return cudaSuccess;
+#endif
+}
+
+cudaError_t msv_read_blocks(unsigned long long* out, int n_words) {   // development: the per-block timeline of the last k_step launch
+#ifdef MSV_PROFILE
+  if (n_words > MSV_BLK_MAX * MSV_BLK_STAMPS) n_words = MSV_BLK_MAX * MSV_BLK_STAMPS;
+  cudaError_t e_ = cudaMemcpyFromSymbol(out, g_blk, sizeof(unsigned long long) * (size_t)n_words);
+  if (e_ == cudaSuccess && n_words >= MSV_BLK_MAX * MSV_BLK_STAMPS) {   // the last row: the longest solve_toi call (g_toi), then cleared
+    e_ = cudaMemcpyFromSymbol(out + (MSV_BLK_MAX - 1) * MSV_BLK_STAMPS, g_toi, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_toi, z, sizeof z);
+  }
+  return e_;
+#else
+  (void)out; (void)n_words; return cudaErrorNotSupported;
 #endif
 }
 

@@ -12,6 +12,7 @@ void msv_capacity(int cap, int* AC, int* BC, int* HC, int* P, int* PW, int* sm_w
 cudaError_t msv_launch_stats(int N, int stride, int AC, float* sreward, int* skills, int4* smisc, double* out_reward,
                              unsigned long long* out_kills, unsigned long long* out_misc, cudaStream_t st);
 cudaError_t msv_read_profile(unsigned long long out[64], int reset);
+cudaError_t msv_read_blocks(unsigned long long* out, int n_words);
 cudaError_t msv_read_check(unsigned long long out[2]);
 cudaError_t msv_launch_spare(const DevConst& C, const DevState& S, const uint8_t* dones, int only_done, cudaStream_t st);
 cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable& T, int AC, const uint8_t* only_if, cudaStream_t st);

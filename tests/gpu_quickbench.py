@@ -18,6 +18,60 @@ PHASES = ['load', 'pre_step', 'find_new', 'collide', 'solve', 'toi', 'post_boxes
           'rewards+reset', 'observe', 'store']
 
 
+BLK_PHASES = ['load', 'motors+use/give', 'melee(+find_new)', 'collide#1', 'solve#1', 'find_new#1', 'toi#1', 'collide#2', 'solve#2',
+              'find_new#2', 'toi#2+box deaths', 'cameras', 'post_rest', 'rewards+reset', 'store']
+
+
+def blocks(variant, N, warm=1500, launches=40):
+    """per-block timeline (profile build): which phase makes the slowest block of a launch slow"""
+    import ctypes
+    import numpy as np
+    rec = make_config(variant, auto_reset=True)
+    A = int(rec['n_agents'])
+    h = _lib.Handle(rec, N, 0, 1, 0)
+    h.reset()
+    torch.manual_seed(1234)
+    NB = 61
+    acts = torch.randint(0, 2, (NB, N, A, 6), dtype=torch.uint8, device='cuda')
+    acts[..., 0:3] = torch.randint(0, 3, (NB, N, A, 3), dtype=torch.uint8, device='cuda')
+    for t in range(warm):
+        h.step(acts[(t * 7) % NB].data_ptr())
+    L = _lib.load()
+    L.msv_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.msv_debug_blocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    L.msv_debug_profile(h.h, 1, None)
+    W = 24
+    buf = np.zeros(2048 * W, dtype=np.uint64)
+    tot_mean, tot_max, ph_mean, ph_max, ph_maxany, toi_rows = [], [], [], [], [], []
+    for t in range(launches):
+        h.step(acts[((warm + t) * 7) % NB].data_ptr())
+        rc = L.msv_debug_blocks(h.h, buf.ctypes.data, buf.size)
+        assert rc == 0, rc
+        b = buf.reshape(2048, W).astype(np.int64)
+        toi_rows.append(b[2047, :9].copy()); b[2047] = 0
+        nb = int((b[:, 0] > 0).sum())
+        b = b[:nb]
+        n = int(b[0, 0])
+        d = np.diff(b[:, 1:n], axis=1)          # [blocks, phases]
+        tot = d.sum(axis=1)
+        k = int(tot.argmax())
+        tot_mean.append(tot.mean()); tot_max.append(tot.max())
+        ph_mean.append(d.mean(axis=0)); ph_max.append(d[k]); ph_maxany.append(d.max(axis=0))
+        b[:, 0] = 0
+    L.msv_debug_profile(h.h, 0, None)
+    ph_mean, ph_max, ph_maxany = np.mean(ph_mean, axis=0), np.mean(ph_max, axis=0), np.mean(ph_maxany, axis=0)
+    print(f'{variant} N={N}: {nb} blocks; block time mean {np.mean(tot_mean):.0f} cycles, slowest block of a launch {np.mean(tot_max):.0f} '
+          f'(x{np.mean(tot_max) / np.mean(tot_mean):.2f}); worst launch {np.max(tot_max):.0f}, best {np.min(tot_max):.0f}')
+    print('   %-20s %10s %14s %16s' % ('phase', 'mean block', 'slowest block', 'max over blocks'))
+    for i in range(len(ph_mean)):
+        nm = BLK_PHASES[i] if i < len(BLK_PHASES) else str(i)
+        print('   %-20s %10.0f %14.0f %16.0f' % (nm, ph_mean[i], ph_max[i], ph_maxany[i]))
+    print('   longest solve_toi call of each launch: cycles, loop iterations, events run, not touching, identical repeats, cycles in events, cycles in scans, TOI calls, env')
+    for r in toi_rows[:16]:
+        print('     ', ' '.join(str(int(x)) for x in r))
+    h.close()
+
+
 def run(variant, N, steps=600, warm=100, prof=False):
     rec = make_config(variant, auto_reset=True)
     A = int(rec['n_agents'])
@@ -89,6 +143,8 @@ if __name__ == '__main__':
     elif a and a[0] == '--all':
         for v, N in (('2v2', 16384), ('1v1_heal_only', 4096), ('1v1', 16384), ('ffa', 32768), ('ffa_lidar', 32768)):
             run(v, N, steps=500)
+    elif a and a[0] == '--blocks':
+        blocks(a[1] if len(a) > 1 else '2v2', int(a[2]) if len(a) > 2 else 16384)
     elif a and a[0] == '--prof':
         run(a[1] if len(a) > 1 else '2v2', int(a[2]) if len(a) > 2 else 16384, steps=400, warm=1500, prof=True)   # stationary episode mix
     else:
