@@ -52,6 +52,7 @@ struct msv_handle {
   // k_spare (pre-drawn reset records) runs on a side stream beside the observation kernels and is joined
   // back into the caller's stream before msv_step returns (fork/join inside the call: graph-capture safe)
   cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  uint32_t tq_ticket = 0, tq_base = 0; bool handoff = true;   // k_step -> k_obs2 tile hand-off (MSV_NO_HANDOFF=1 turns it off)
   // debug: CUDA-event timing of the kernels of msv_step (bench.py's roofline numerator)
   bool timing = false; std::vector<cudaEvent_t> tev; size_t tev_used = 0;
   double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
@@ -223,28 +224,29 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
 // = lanes per environment).  All blocks should be resident at once (the step is one long dependent
 // chain per environment, so a second wave would double the time): take the largest tile for which
 // ceil(blocks / SMs) blocks fit on an SM (registers, shared memory).  MSV_EPB overrides (development).
+// Tile size of k_step.  A block's warps run the step in phase lock-step (block barriers between the phases)
+// and so share one pass over its ~570 KB of instructions; two blocks on an SM sit in different phases and evict
+// each other's lines from the instruction caches.  Measured on the stationary 2v2 workload (16 384 envs,
+// profiles/r02_tiles.txt): two 64-env blocks of 256 threads per SM 124.9 us/step; ONE block of 512 threads per SM
+// with 128 envs 112.5, 120 envs 113.0, 112 envs (147 blocks: every SM busy) 109.8.  So: one block per SM, as few
+// waves as the block capacity allows, and within that the smallest tile that still covers the batch (a block lasts
+// as long as its slowest environment in every phase, so spreading the batch over all SMs shortens every block).
 static void plan_blocks(msv_handle* h, int device) {
-  cudaDeviceProp pr; int sms = 148; size_t smem_sm = 227 * 1024, regs_sm = 65536;
-  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) { sms = pr.multiProcessorCount; smem_sm = pr.sharedMemPerMultiprocessor; regs_sm = (size_t)pr.regsPerMultiprocessor; }
-  const int G = h->AC, wpe = 32 / G, epb_max = MSV_TPB / G, n = h->C.n_real;
-  int best = epb_max; long best_load = -1;
-  for (int epb = epb_max; epb >= wpe; epb -= wpe) {
-    const long blocks = (n + epb - 1) / epb;
-    const size_t smem_blk = (size_t)h->sm_words * epb * sizeof(float) + 1024;
-    long res = (long)(smem_sm / smem_blk);
-    const long by_regs = (long)(regs_sm / (128 * (size_t)epb * G));
-    if (by_regs < res) res = by_regs;
-    if (res > 32) res = 32;
-    if (res < 1) continue;
-    const long per_sm = (blocks + sms - 1) / sms;
-    if (per_sm > res) continue;                    // would need a second wave
-    (void)best_load;
-    best = epb; break;                             // the largest tile that still runs as a single wave (measured, 2v2 16 384 envs,
-  }                                                // stationary mix: 64 envs/block 222 us, 56: 225, 40: 247, 32: 271, 16: 314 -- the
-                                                   // warps of a block share the instruction stream, so bigger tiles win over a balanced grid)
-  if (const char* ov = getenv("MSV_EPB")) { int v = atoi(ov); if (v >= wpe && v <= epb_max && v % wpe == 0) best = v; }
-  h->C.epb = best;
-  h->C.N = (n + best - 1) / best * best;
+  cudaDeviceProp pr; int sms = 148; size_t smem_blk_max = 227 * 1024;
+  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) { sms = pr.multiProcessorCount; smem_blk_max = pr.sharedMemPerBlockOptin; }
+  const int G = h->AC, wpe = 32 / G, n = h->C.n_real;
+  long cap = MSV_TPB / G;                                          // by threads (128 registers each: 512 fill the register file)
+  const long by_smem = (long)(smem_blk_max / ((size_t)h->sm_words * sizeof(float)));
+  if (by_smem < cap) cap = by_smem;
+  cap = cap / wpe * wpe; if (cap < wpe) cap = wpe;
+  const long waves = (n + cap * sms - 1) / (cap * sms);
+  long best = (n + waves * sms - 1) / (waves * sms);
+  best = (best + wpe - 1) / wpe * wpe;
+  if (best > cap) best = cap;
+  if (best < wpe) best = wpe;
+  if (const char* ov = getenv("MSV_EPB")) { int v = atoi(ov); if (v >= wpe && v <= cap && v % wpe == 0) best = v; }
+  h->C.epb = (int)best;
+  h->C.N = (int)((n + best - 1) / best * best);
 }
 
 template <typename T> static int dalloc(msv_handle* h, T** p, size_t count) {
@@ -383,6 +385,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
          : (cfg->n_agents <= 4 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 1 : 2;
   msv_capacity(h->cap, &h->AC, &h->BC, &h->HC, &h->P, &h->PW, &h->sm_words);
   plan_blocks(h, device);
+  if (const char* nh = getenv("MSV_NO_HANDOFF")) h->handoff = atoi(nh) == 0;   // development A/B: plain stream-ordered launches
   if (msv_launch(h->cap, 3, h->C, h->S, h->O, nullptr, 0) != cudaSuccess) {
     g_err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; delete h; return MSV_ERR_CUDA;
   }
@@ -429,6 +432,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
     if (!rc) for (int k = 0; k < n_slots; ++k) *slots[k].p = h->arena + offs[k];
   }
   rc |= dalloc(h, &S.obm, N); rc |= dalloc(h, &S.omask, AC * N);
+  rc |= dalloc(h, &S.tq, N / (size_t)h->C.epb); rc |= dalloc(h, &S.tq_tail, 4);
   rc |= dalloc(h, &h->d_actions, N * A * 6);
   rc |= dalloc(h, &h->d_stat_reward, (size_t)MSV_MAX_AGENTS); rc |= dalloc(h, &h->d_stat_kills, (size_t)MSV_MAX_AGENTS);
   rc |= dalloc(h, &h->d_stat_misc, (size_t)4);
@@ -626,6 +630,19 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
   }
   const bool timed = h->timing && which == 0;
   if (timed) tmark(h, st);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+  // Tile hand-off (DevConst::tq_ticket): the observation kernel is launched programmatically dependent on the
+  // step kernel and consumes the step kernel's blocks in the order they finish, so the observation of a finished
+  // tile is written while the step's slow blocks (a wedged agent, a multi-agent island, a reset) still run.
+  // Needs the two launches adjacent in the stream: off under kernel timing, stream capture and terminal capture.
+  DevConst Cq = h->C;
+  const bool handoff = which == 0 && h->cfg.auto_reset != 2 && !timed && !capturing && h->handoff;
+  if (handoff) {
+    if (++h->tq_ticket == 0u) h->tq_ticket = 1u;
+    Cq.tq_ticket = h->tq_ticket; Cq.tq_base = h->tq_base;
+    h->tq_base += (uint32_t)(h->C.N / h->C.epb);
+  }
   if (which == 0 && h->cfg.auto_reset == 2) {
     // step without the in-kernel reset, keep the finished episodes' last observation, then
     // reset exactly the envs that finished (same Philox streams as the in-kernel reset)
@@ -636,10 +653,16 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
     CK(msv_launch(h->cap, 4, h->C, h->S, h->O, nullptr, st));
     h->launches += 3;
   } else {
-    CK(msv_launch(h->cap, which, h->C, h->S, h->O, actions, st));
+    CK(msv_launch(h->cap, which, Cq, h->S, h->O, actions, st));
     h->launches += 1;
-    if (which == 0) { int rc = readback(h, st); if (rc) return rc; }
+    if (which == 0 && !handoff) { int rc = readback(h, st); if (rc) return rc; }
   }
+  if (timed) tmark(h, st);
+  CK(msv_launch_obs(Cq, h->S, h->obs, h->AC, nullptr, st));   // fetch_observations
+  h->launches += 1;
+  if (which == 0 && handoff) { int rc = readback(h, st); if (rc) return rc; }   // (an event between the two launches would serialise them)
+  if (timed) tmark(h, st);
+  if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, h->HC, (cudaStream_t)stream)); h->launches++; }
   if (timed) tmark(h, st);
   const bool spare = which == 1 || (which == 0 && h->cfg.auto_reset != 0);
   if (spare) {                                  // the step / reset left finished environments without a record for their next episode
@@ -648,25 +671,17 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
       CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
+    // The record kernel runs on a side stream, forked after the observation kernels and NOT joined back in normal
+    // operation: it overlaps the next step, and nothing on `st` ever waits for it.  That is safe by construction --
+    // a record is published by writing its episode number last (after a fence); a reset that does not find the
+    // number it expects draws the record itself -- and msv_get_state / msv_set_state / msv_destroy synchronise
+    // the device.  Only while the caller is capturing `st` into a CUDA graph must the fork be joined inside the call.
     CK(cudaEventRecord(h->ev_fork, st));
     CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     CK(msv_launch_spare(h->C, h->S, h->O.dones, 0, h->side_stream));   // every env whose record is stale (two 4-byte loads each for the others)
     CK(cudaEventRecord(h->ev_join, h->side_stream));
     h->launches += 1;
-  }
-  CK(msv_launch_obs(h->C, h->S, h->obs, h->AC, nullptr, st));   // fetch_observations
-  h->launches += 1;
-  if (timed) tmark(h, st);
-  if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, h->HC, (cudaStream_t)stream)); h->launches++; }
-  if (timed) tmark(h, st);
-  if (spare) {
-    // The record kernel is NOT joined back in normal operation: it overlaps the observation kernels and the next
-    // step, and nothing on `st` ever waits for it.  That is safe by construction -- a record is published by
-    // writing its episode number last (after a fence); a reset that does not find the number it expects draws
-    // the record itself -- and msv_get_state / msv_set_state / msv_destroy synchronise the device.  Only while
-    // the caller is capturing `st` into a CUDA graph must the fork be joined inside the call.
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    if (capturing) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   if (which == 0) { int rc = readback_obs(h, st); if (rc) return rc; }
   return MSV_OK;
@@ -681,6 +696,9 @@ int64_t msv_debug_overflow(msv_handle* h) {
   if (cudaMemcpy(v.data(), h->S.hdr1, v.size() * sizeof(int4), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   int64_t tot = 0;
   for (int e = 0; e < h->C.n_real; ++e) tot += v[e].z;
+  unsigned tq[4] = {0, 0, 0, 0};                  // [2]: an observation tile gave up waiting for its completion-queue entry
+  if (cudaMemcpy(tq, h->S.tq_tail, sizeof tq, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (tq[2]) tot += 1000000;
   return tot;
 }
 
@@ -1063,6 +1081,14 @@ int msv_debug_blocks(msv_handle* h, unsigned long long* out, int n_words) {
   if (!h || !out) return MSV_ERR_INVALID;
   DevGuard g(h->device); CK(cudaDeviceSynchronize());
   CK(msv_read_blocks(out, n_words));
+  return MSV_OK;
+}
+
+/* debug (profile build): %globaltimer trace of the k_step -> k_obs2 hand-off of the last step, 5 rows of 4096 words */
+int msv_debug_trace(msv_handle* h, unsigned long long* out, int n_words) {
+  if (!h || !out) return MSV_ERR_INVALID;
+  DevGuard g(h->device); CK(cudaDeviceSynchronize());
+  CK(msv_read_trace(out, n_words));
   return MSV_OK;
 }
 

@@ -12,6 +12,7 @@
 #define MSV_SYNC_MASK 0x3FF
 #endif
 #endif
+#include <cstdlib>
 #include "msv_env.cuh"
 #include "msv_launch.h"
 
@@ -25,6 +26,12 @@ __device__ unsigned long long g_prof[64];
 // ([block][0] = number of stamps).  The barriers make these the block's phase durations; tests/gpu_quickbench.py --blocks
 #define MSV_BLK_MAX 2048
 #define MSV_BLK_STAMPS 24
+// hand-off trace of the last step (%globaltimer, ns): [0] k_step block start, [1] its queue entry published,
+// [2] observation tile resident, [3] its entry acquired, [4] tile written; tests/gpu_quickbench.py --trace
+#define MSV_TR_MAX 4096
+__device__ unsigned long long g_tr[5 * MSV_TR_MAX];
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TRACE(row, idx) do { if (threadIdx.x == 0 && (idx) < MSV_TR_MAX) g_tr[(row) * MSV_TR_MAX + (idx)] = gtime_ns(); } while (0)
 __device__ unsigned long long g_blk[MSV_BLK_MAX * MSV_BLK_STAMPS];
 #define BLK_STAMP() do { if (C.profile && threadIdx.x == 0 && blockIdx.x < MSV_BLK_MAX && blk_n < MSV_BLK_STAMPS) { g_blk[blockIdx.x * MSV_BLK_STAMPS + blk_n] = (unsigned long long)clock64(); blk_n++; } } while (0)
 #define PROF(k) do { if (C.profile) { long long _t = clock64(); ph[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
@@ -33,6 +40,7 @@ __device__ unsigned long long g_blk[MSV_BLK_MAX * MSV_BLK_STAMPS];
 #define PROF(k) do { } while (0)
 #define PROFW(k) do { } while (0)
 #define BLK_STAMP() do { } while (0)
+#define TRACE(row, idx) do { } while (0)
 #endif
 
 // thread -> (environment slot of the block, lane of the group)
@@ -57,6 +65,10 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
        const __grid_constant__ DevOut Oc, const uint8_t* __restrict__ actions) {
   MSV_GROUP_SETUP(G);
   DevOut O = Oc;
+  // Let the observation kernel (launched programmatically dependent, see msv_abi.cu launch()) become resident as
+  // soon as every block of this grid has started: its blocks wait for entries of the completion queue below.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  TRACE(0, blockIdx.x);
   Env<AC, BC, HC, G> env(C, S, es, g, gmask, e);
 #ifdef MSV_PROFILE
   long long t_last = C.profile ? clock64() : 0;
@@ -136,6 +148,16 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   PROF(10);
   env.store();
   PROF(11);
+  if (C.tq_ticket) {                       // publish this tile: every store of the block, then (release) its queue entry
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned slot = atomicAdd(S.tq_tail, 1u) - C.tq_base;
+      const unsigned long long v = ((unsigned long long)C.tq_ticket << 32) | (unsigned long long)blockIdx.x;
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(S.tq + slot), "l"(v) : "memory");
+      TRACE(1, blockIdx.x);
+    }
+  }
 #ifdef MSV_PROFILE
   __syncthreads();
   BLK_STAMP();
@@ -299,7 +321,39 @@ __global__ void __launch_bounds__(1024)
 k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ ObsTable Tb, int AC) {
   extern __shared__ float stage[];
   const int A = C.A, B = C.B0, H = C.H0, Sw = C.S, N = C.N;
-  const int e0 = blockIdx.x * OBS2_E, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // A tile is (part of) the environments of one k_step block: block `kb`, sub-tile `sub` of up to OBS2_E rows.
+  // With the hand-off on (C.tq_ticket != 0) `kb` is the (blockIdx.x / spb)-th block of the running step kernel
+  // to finish, read from its completion queue; otherwise tiles are taken in index order.
+  const int spb = (C.epb + OBS2_E - 1) / OBS2_E;
+  int kb = blockIdx.x / spb; const int sub = blockIdx.x - kb * spb;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  TRACE(2, blockIdx.x);
+  if (C.tq_ticket) {
+    __shared__ int s_kb;
+    if (threadIdx.x == 0) {
+      const unsigned long long* q = S.tq + kb;
+      unsigned long long v;
+      int spins = 0;
+      // Poll with relaxed loads and fence once at the end: an acquire load is LDG.STRONG + CCTL.IVALL, and
+      // invalidating the SM's L1 on every poll would take the local-memory lines of the step-kernel block that
+      // shares the SM with it.
+      for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+        if ((unsigned)(v >> 32) == C.tq_ticket) break;
+        // (never seen: ~4 s without the entry -> record a fault for msv_debug_overflow and take the tile by index, so
+        // that a broken hand-off shows up as a failing test instead of a hung device)
+        if (++spins > (1 << 22)) { S.tq_tail[2] = 1u; v = (unsigned long long)kb; break; }
+        __nanosleep(1000);
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      s_kb = (int)(unsigned)(v & 0xffffffffull);
+    }
+    __syncthreads();
+    kb = s_kb;
+  }
+  TRACE(3, blockIdx.x);
+  const int e0 = kb * C.epb + sub * OBS2_E, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int rows = C.epb - sub * OBS2_E; if (rows > OBS2_E) rows = OBS2_E;   // a multiple of 32 / G >= 4: every run below is a whole number of float4
   // this lane's row of every tensor slice in the stage (registers: the key is a compile-time constant at every use)
   int koff[MSV_OBS_KEYS], kbase[MSV_OBS_KEYS];
   {
@@ -308,8 +362,10 @@ k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, c
     for (int k = 0; k < MSV_OBS_KEYS; ++k) { koff[k] = o; kbase[k] = o + lane * Tb.keys[k].chunk; o += OBS2_E * Tb.keys[k].chunk; }
   }
   const int e = e0 + lane;
-  const bool live = e < N;                       // rows past the padded batch do not exist
+  const bool live = lane < rows;                 // (e < N: the padded batch is a whole number of k_step blocks)
   const int n_items = A + 2 * B + H + 1;
+  // (state loads below bypass L1 -- __ldcg: each word is read once, and with the hand-off on it was written by a
+  // block of the still-running step kernel on another SM)
   auto put = [&](int key, int off, float v) { stage[kbase[key] + off] = v; };
   auto vert = [&](float hx, float hy, int rot, int comp) {   // b2PolygonShape vertex order (Q8)
     int j = ((comp >> 1) + rot) & 3;
@@ -323,13 +379,13 @@ k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, c
       float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
       float r_id = 0.f, r_team = 0.f, r_hp = 0.f, r_x = 0.f, r_y = 0.f, r_a = 0.f, r_vx = 0.f, r_vy = 0.f, r_w = 0.f;   // env:659-691
       if (live) {
-        const float4 k0 = S.akin0[j * N + e], k1 = S.akin1[j * N + e]; const int4 ai = S.aint[j * N + e];
-        al = (__float_as_int(k1.w) & 1) != 0; inv = ai.w; obm = S.obm[e]; cnts = S.hdr0[e].x;
-        if (!C.omniscient) om = S.omask[j * N + e];
+        const float4 k0 = __ldcg(&S.akin0[j * N + e]), k1 = __ldcg(&S.akin1[j * N + e]); const int4 ai = __ldcg(&S.aint[j * N + e]);
+        al = (__float_as_int(k1.w) & 1) != 0; inv = ai.w; obm = __ldcg(&S.obm[e]); cnts = __ldcg(&S.hdr0[e].x);
+        if (!C.omniscient) om = __ldcg(&S.omask[j * N + e]);
         r_id = (float)j; r_team = (float)(j < A / 2 ? 0 : 1);
         if (al) { r_hp = (float)ai.x; r_x = k0.x; r_y = k0.y; r_a = k0.z; r_vx = k0.w; r_vy = k1.x; r_w = k1.y; }
         const int n = inv & 7;
-        if (al && n > 0 && ((inv >> (4 + 2 * (n - 1))) & 3) == MSV_ITEM_BOX) pl = S.ainv[(j * 4 + n - 1) * N + e];
+        if (al && n > 0 && ((inv >> (4 + 2 * (n - 1))) & 3) == MSV_ITEM_BOX) pl = __ldcg(&S.ainv[(j * 4 + n - 1) * N + e]);
       }
       const int tm = C.teams ? 1 : 0;
       auto emit = [&](int key, int base) {         // [id, (team), health, x, y, angle, vx, vy, omega]
@@ -370,32 +426,31 @@ k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, c
     } else if (it < A + B) {                     // ---- box k (env:570-591)
       const int k = it - A;
       float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f); int rot = 0; bool on = false;
-      if (live && k < (S.hdr0[e].x & 255)) { b0 = S.box0[k * N + e]; rot = (S.box1[k * N + e].y >> 1) & 1; on = true; }
+      if (live && k < (__ldcg(&S.hdr0[e].x) & 255)) { b0 = __ldcg(&S.box0[k * N + e]); rot = (__ldcg(&S.box1[k * N + e].y) >> 1) & 1; on = true; }
       for (int c = 0; c < 8; ++c) put(8, k * 11 + c, on ? vert(b0.z, b0.w, rot, c) : 0.0f);
       put(8, k * 11 + 8, on ? b0.x : 0.0f); put(8, k * 11 + 9, on ? b0.y : 0.0f); put(8, k * 11 + 10, 0.0f);
     } else if (it < A + 2 * B) {                 // ---- floor box item k (env:593-619)
       const int k = it - A - B;
       float4 i0 = make_float4(0.f, 0.f, 0.f, 0.f); bool on = false;
-      if (live && k < ((S.hdr0[e].x >> 8) & 255)) { i0 = S.item0[k * N + e]; on = true; }
+      if (live && k < ((__ldcg(&S.hdr0[e].x) >> 8) & 255)) { i0 = __ldcg(&S.item0[k * N + e]); on = true; }
       for (int c = 0; c < 8; ++c) put(10, k * 10 + c, on ? vert(i0.z, i0.w, 1, c) : 0.0f);
       put(10, k * 10 + 8, on ? i0.x : 0.0f); put(10, k * 10 + 9, on ? i0.y : 0.0f);
     } else if (it < A + 2 * B + H) {             // ---- heal k (env:552-568)
       const int k = it - A - 2 * B;
       float2 hh = make_float2(0.f, 0.f);
-      if (live && k < ((S.hdr0[e].x >> 16) & 255)) hh = S.heal[k * N + e];
+      if (live && k < ((__ldcg(&S.hdr0[e].x) >> 16) & 255)) hh = __ldcg(&S.heal[k * N + e]);
       put(4, 2 * k, hh.x); put(4, 2 * k + 1, hh.y);
     } else {                                     // ---- zone (env:537-550)
       float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (live) {
-        const float4 zc = S.zonecur[e]; const int ph = S.zoneint[e].x;
+        const float4 zc = __ldcg(&S.zonecur[e]); const int ph = __ldcg(&S.zoneint[e].x);
         z[0] = zc.x; z[1] = zc.y; z[2] = zc.z;
-        if (ph < C.zone_phases - 1) { const float2 c2 = S.zonec[(ph + 1) * N + e]; z[3] = c2.x; z[4] = c2.y; z[5] = C.zone_r32[ph + 1]; }
+        if (ph < C.zone_phases - 1) { const float2 c2 = __ldcg(&S.zonec[(ph + 1) * N + e]); z[3] = c2.x; z[4] = c2.y; z[5] = C.zone_r32[ph + 1]; }
       }
       for (int c = 0; c < 6; ++c) put(3, c, z[c]);
     }
   }
   __syncthreads();
-  int rows = N - e0; if (rows > OBS2_E) rows = OBS2_E;         // N is a multiple of 4: every run below is a whole number of float4
   for (int k = 0; k < MSV_OBS_KEYS; ++k) {
     const int chunk = Tb.keys[k].chunk;
     if (chunk <= 0 || (k >= 4 && k <= 7 && H == 0) || (k >= 8 && B == 0)) continue;   // key groups the config does not have
@@ -403,6 +458,17 @@ k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, c
     const float4* src = reinterpret_cast<const float4*>(stage + koff[k]);
     float4* dst = reinterpret_cast<float4*>(Tb.keys[k].base + (size_t)e0 * chunk);
     for (int q = threadIdx.x; q < n4; q += blockDim.x) dst[q] = src[q];
+  }
+  TRACE(4, blockIdx.x);
+  if (C.tq_ticket) {
+    // The last tile to finish waits for the step kernel's grid to have completed, so that "this grid is complete"
+    // implies "the step kernel is complete" for whatever follows in the stream, whichever way the runtime orders
+    // a third kernel after a programmatic pair.  (Every other block has already seen its tile's release.)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned d = atomicAdd(S.tq_tail + 1, 1u);
+      if (d == gridDim.x - 1) { S.tq_tail[1] = 0u; asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    }
   }
 }
 
@@ -607,7 +673,8 @@ static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, con
   const int epb = C.epb;                             // environments per block (runtime: msv_plan_blocks)
   const int blocks = C.N / epb, tpb = epb * G;
   size_t smem = (size_t)Env<AC, BC, HC, G>::SM_WORDS * epb * sizeof(float);
-  const size_t smem_max = (size_t)Env<AC, BC, HC, G>::SM_WORDS * (MSV_TPB / G) * sizeof(float);
+  size_t smem_max = (size_t)Env<AC, BC, HC, G>::SM_WORDS * (MSV_TPB / G) * sizeof(float);
+  if (smem_max > 227 * 1024) smem_max = 227 * 1024;   // (plan_blocks keeps the tile within the per-block limit)
   if (which == 3) {  // one-time: allow the dynamic shared memory the kernels need
     cudaError_t e = cudaFuncSetAttribute(k_step<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
@@ -636,12 +703,25 @@ cudaError_t msv_launch_obs(const DevConst& C, const DevState& S, const ObsTable&
     size_t smem = 0;
     for (int k = 0; k < MSV_OBS_KEYS; ++k) smem += (size_t)OBS2_E * T.keys[k].chunk * sizeof(float);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_obs2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_obs2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      // same L1/shared split as the step kernel, so that a tile can become resident on an SM that still runs one of its blocks
+      const char* cv = getenv("MSV_OBS_CARVEOUT");
+      if (!cv || atoi(cv) != 0) cudaFuncSetAttribute(k_obs2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      attr_set = true;
+    }
     // one warp per source item when they fit a block (a single round of loads), else 32 warps looping over the items
     const int n_items = C.A + 2 * C.B0 + C.H0 + 1;
     const int threads = n_items <= 32 ? 32 * n_items : 1024;
-    k_obs2<<<(C.n_real + OBS2_E - 1) / OBS2_E, threads, smem, st>>>(C, S, T, AC);
-    return cudaPeekAtLastError();
+    const int spb = (C.epb + OBS2_E - 1) / OBS2_E;                       // tiles per k_step block
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((C.N / C.epb) * spb)); cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;                // may start before the step kernel has finished
+    cfg.attrs = at; cfg.numAttrs = C.tq_ticket ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_obs2, C, S, T, AC);
   }
 #endif
   k_obs<<<(C.n_real + OBS_EPB - 1) / OBS_EPB, 256, (size_t)OBS_EPB * T.n_elems * sizeof(float), st>>>(C, S, T, AC, only_if);
@@ -687,6 +767,17 @@ cudaError_t msv_read_blocks(unsigned long long* out, int n_words) {   // develop
     e_ = cudaMemcpyFromSymbol(out + (MSV_BLK_MAX - 1) * MSV_BLK_STAMPS, g_toi, sizeof(unsigned long long) * 16);
     unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_toi, z, sizeof z);
   }
+  return e_;
+#else
+  (void)out; (void)n_words; return cudaErrorNotSupported;
+#endif
+}
+
+cudaError_t msv_read_trace(unsigned long long* out, int n_words) {     // development: hand-off trace of the last step
+#ifdef MSV_PROFILE
+  if (n_words > 5 * MSV_TR_MAX) n_words = 5 * MSV_TR_MAX;
+  cudaError_t e_ = cudaMemcpyFromSymbol(out, g_tr, sizeof(unsigned long long) * (size_t)n_words);
+  if (e_ == cudaSuccess) { static unsigned long long z[5 * MSV_TR_MAX]; e_ = cudaMemcpyToSymbol(g_tr, z, sizeof z); }
   return e_;
 #else
   (void)out; (void)n_words; return cudaErrorNotSupported;

@@ -39,6 +39,11 @@ struct DevConst {
   uint32_t seed_lo, seed_hi;
   uint32_t env_offset;       // global index of env 0 (Philox counter word 0); msv_create rejects ids >= 2^32
   int profile;           // debug: accumulate per-phase clock64() deltas into g_prof
+  // Tile hand-off from k_step to the observation kernel (set per launch by the host, 0 = off): a k_step block
+  // that has stored its environments appends its index to the completion queue DevState::tq; the observation
+  // kernel, launched programmatically dependent on k_step, consumes the queue in order while k_step's slower
+  // blocks are still running.  Entries are (ticket << 32 | block); slot = atomicAdd(tq_tail, 1) - tq_base.
+  uint32_t tq_ticket, tq_base;
 };
 
 // All per-environment state, structure-of-arrays: every array is
@@ -79,6 +84,8 @@ struct DevState {
   int* spare_ep;   // [N]
   unsigned long long* obm;  // [N] others_mask bits (observer i sees agent j: bit i*AC+j)
   unsigned* omask;          // [AC][N] non-omniscient: per observer, seen heals (bits 0-15), boxes (16-23), box items (24-31)
+  unsigned long long* tq;   // [N / epb] completion queue of the current step's k_step blocks (see DevConst::tq_ticket)
+  unsigned* tq_tail;        // [2] entries appended since the handle was created (mod 2^32); observation blocks finished
 };
 
 // layout of a reset record: boxes (x, y, hx, hy), heals (x, y), agents (x, y), zone centres (x, y)

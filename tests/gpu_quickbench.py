@@ -72,6 +72,43 @@ def blocks(variant, N, warm=1500, launches=40):
     h.close()
 
 
+def trace(variant, N, warm=1500, launches=12):
+    """hand-off trace (profile build): when do the observation tiles run relative to the step kernel's blocks"""
+    import ctypes
+    import numpy as np
+    rec = make_config(variant, auto_reset=True)
+    A = int(rec['n_agents'])
+    h = _lib.Handle(rec, N, 0, 1, 0)
+    h.reset()
+    torch.manual_seed(1234)
+    NB = 61
+    acts = torch.randint(0, 2, (NB, N, A, 6), dtype=torch.uint8, device='cuda')
+    acts[..., 0:3] = torch.randint(0, 3, (NB, N, A, 3), dtype=torch.uint8, device='cuda')
+    for t in range(warm):
+        h.step(acts[(t * 7) % NB].data_ptr())
+    L = _lib.load()
+    L.msv_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    M = 4096
+    buf = np.zeros(5 * M, dtype=np.uint64)
+    L.msv_debug_trace(h.h, buf.ctypes.data, buf.size)     # clear
+    for t in range(launches):
+        h.step(acts[((warm + t) * 7) % NB].data_ptr())
+        rc = L.msv_debug_trace(h.h, buf.ctypes.data, buf.size)
+        assert rc == 0, rc
+        b = buf.reshape(5, M).astype(np.int64)
+        nk = int((b[0] > 0).sum()); no = int((b[2] > 0).sum())
+        t0 = b[0, :nk].min()
+        ks0, ks1 = b[0, :nk] - t0, b[1, :nk] - t0
+        o_res, o_acq, o_done = b[2, :no] - t0, b[3, :no] - t0, b[4, :no] - t0
+        kend = ks1.max()
+        q = lambda x, p: float(np.percentile(x, p)) / 1e3
+        print(f'{variant} N={N} launch {t}: k_step {nk} blocks, start spread {q(ks0, 100):.1f} us, block end p10/p50/p90/max = '
+              f'{q(ks1, 10):.1f}/{q(ks1, 50):.1f}/{q(ks1, 90):.1f}/{kend / 1e3:.1f} us | obs {no} tiles: resident p10/p50/p90 = '
+              f'{q(o_res, 10):.1f}/{q(o_res, 50):.1f}/{q(o_res, 90):.1f} us, acquired->written median {q(o_done - o_acq, 50):.1f} us, '
+              f'written before k_step end: {int((o_done <= kend).sum())}/{no}, last tile written {(o_done.max() - kend) / 1e3:+.1f} us after k_step end')
+    h.close()
+
+
 def run(variant, N, steps=600, warm=100, prof=False):
     rec = make_config(variant, auto_reset=True)
     A = int(rec['n_agents'])
@@ -84,19 +121,23 @@ def run(variant, N, steps=600, warm=100, prof=False):
     NB = 61   # prime: every batch sees all of them in a scrambled order (see bench.py)
     acts = torch.randint(0, 2, (NB, N, A, 6), dtype=torch.uint8, device='cuda')
     acts[..., 0:3] = torch.randint(0, 3, (NB, N, A, 3), dtype=torch.uint8, device='cuda')
+    # QB_STREAM=1: a non-blocking stream of our own instead of the legacy default stream
+    strm = torch.cuda.Stream() if os.environ.get('QB_STREAM', '0') == '1' else torch.cuda.current_stream()
+    sp = strm.cuda_stream
+    torch.cuda.synchronize()
     for t in range(warm * ROT):
-        hs[t % ROT].step(acts[((t // ROT) * 7 + (t % ROT) * 13) % NB].data_ptr())
+        hs[t % ROT].step(acts[((t // ROT) * 7 + (t % ROT) * 13) % NB].data_ptr(), sp)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(strm)
     for t in range(steps):
-        hs[t % ROT].step(acts[((t // ROT) * 7 + (t % ROT) * 13) % NB].data_ptr())
-    e1.record()
+        hs[t % ROT].step(acts[((t // ROT) * 7 + (t % ROT) * 13) % NB].data_ptr(), sp)
+    e1.record(strm)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     bps = h.bytes_per_env_step()
     st = h.flush_stats()
-    tag = os.environ.get('MSV_LIB', 'default').split('/')[-1] + (' EPB=' + os.environ['MSV_EPB'] if 'MSV_EPB' in os.environ else '') + f' rot={ROT}'
+    tag = os.environ.get('MSV_LIB', 'default').split('/')[-1] + (' EPB=' + os.environ['MSV_EPB'] if 'MSV_EPB' in os.environ else '') + f' rot={ROT}' + (' own-stream' if sp else ' stream0') + (' NO_HANDOFF' if os.environ.get('MSV_NO_HANDOFF', '0') == '1' else '')
     print(f'[{tag}] {variant} N={N}: {ms*1e3:.1f} us/step, {N/ms*1e3:.3e} env-steps/s, {N*A/ms*1e3:.3e} agent-steps/s, '
           f'{bps} B/env-step -> {N*bps/ms/1e6:.1f} GB/s, episodes={int(st["episodes"])}')
     if prof:
@@ -143,6 +184,8 @@ if __name__ == '__main__':
     elif a and a[0] == '--all':
         for v, N in (('2v2', 16384), ('1v1_heal_only', 4096), ('1v1', 16384), ('ffa', 32768), ('ffa_lidar', 32768)):
             run(v, N, steps=500)
+    elif a and a[0] == '--trace':
+        trace(a[1] if len(a) > 1 else '2v2', int(a[2]) if len(a) > 2 else 16384)
     elif a and a[0] == '--blocks':
         blocks(a[1] if len(a) > 1 else '2v2', int(a[2]) if len(a) > 2 else 16384)
     elif a and a[0] == '--prof':
