@@ -344,6 +344,7 @@ def run_ours(args):
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': config_block(args.workload, n_gpus, N),
+        'tile_plan': env._h.tile_plan(),
         'l2': f'{ROT} batches of {N} envs stepped round-robin ({ROT} x {batch_bytes / 1e6:.0f} MB of state+outputs > 126 MB L2): inputs larger than L2, no flush',
         'timing': {'method': 'median over repeats of K steps; each repeat: barrier+sync, CUDA events, max over ranks',
                    'repeats': R, 'timed_ms_total': float(np.sum(reps)), 'rep_ms_min': float(np.min(reps)), 'rep_ms_max': float(np.max(reps)),

@@ -53,6 +53,7 @@ struct msv_handle {
   // back into the caller's stream before msv_step returns (fork/join inside the call: graph-capture safe)
   cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint32_t tq_ticket = 0, tq_base = 0; bool handoff = true;   // k_step -> k_obs2 tile hand-off (MSV_NO_HANDOFF=1 turns it off)
+  bool step_pdl = true, last_was_step = false, no_spare = false; cudaStream_t last_stream = nullptr;   // k_step programmatically dependent on the previous step's observation kernel (MSV_STEP_PDL=0 turns it off)
   // debug: CUDA-event timing of the kernels of msv_step (bench.py's roofline numerator)
   bool timing = false; std::vector<cudaEvent_t> tev; size_t tev_used = 0;
   double* d_stat_reward; unsigned long long* d_stat_kills; unsigned long long* d_stat_misc;
@@ -240,8 +241,9 @@ static void plan_blocks(msv_handle* h, int device) {
   if (by_smem < cap) cap = by_smem;
   cap = cap / wpe * wpe; if (cap < wpe) cap = wpe;
   const long waves = (n + cap * sms - 1) / (cap * sms);
-  long best = (n + waves * sms - 1) / (waves * sms);
+  long best = (n + sms - 1) / sms;                                  // one wave: spread the batch over every SM
   best = (best + wpe - 1) / wpe * wpe;
+  if (waves > 1) best = cap;   // several waves (blocks are handed out as SMs free up): the largest tile -- ffa + lidar, 32 768 envs: 64 envs 1 239 us, 56 (four even waves) 1 288, 48: 1 327
   if (best > cap) best = cap;
   if (best < wpe) best = wpe;
   if (const char* ov = getenv("MSV_EPB")) { int v = atoi(ov); if (v >= wpe && v <= cap && v % wpe == 0) best = v; }
@@ -386,6 +388,8 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   msv_capacity(h->cap, &h->AC, &h->BC, &h->HC, &h->P, &h->PW, &h->sm_words);
   plan_blocks(h, device);
   if (const char* nh = getenv("MSV_NO_HANDOFF")) h->handoff = atoi(nh) == 0;   // development A/B: plain stream-ordered launches
+  if (const char* sp = getenv("MSV_STEP_PDL")) h->step_pdl = atoi(sp) != 0;
+  if (const char* ns = getenv("MSV_NO_SPARE")) h->no_spare = atoi(ns) != 0;    // development: no record kernel (resets draw their own)
   if (msv_launch(h->cap, 3, h->C, h->S, h->O, nullptr, 0) != cudaSuccess) {
     g_err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"; delete h; return MSV_ERR_CUDA;
   }
@@ -641,6 +645,7 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
   if (handoff) {
     if (++h->tq_ticket == 0u) h->tq_ticket = 1u;
     Cq.tq_ticket = h->tq_ticket; Cq.tq_base = h->tq_base;
+    Cq.pdl_wait = (h->step_pdl && h->last_was_step && h->last_stream == st) ? 1u : 0u;   // the previous call on this stream ended with this handle's observation kernels
     h->tq_base += (uint32_t)(h->C.N / h->C.epb);
   }
   if (which == 0 && h->cfg.auto_reset == 2) {
@@ -664,7 +669,7 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
   if (timed) tmark(h, st);
   if (h->C.lidar_n > 0) { CK(msv_launch_lidar(h->C, h->S, h->O, h->BC, h->HC, (cudaStream_t)stream)); h->launches++; }
   if (timed) tmark(h, st);
-  const bool spare = which == 1 || (which == 0 && h->cfg.auto_reset != 0);
+  const bool spare = (which == 1 || (which == 0 && h->cfg.auto_reset != 0)) && !h->no_spare;
   if (spare) {                                  // the step / reset left finished environments without a record for their next episode
     if (!h->side_stream) {
       CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -684,6 +689,7 @@ static int launch(msv_handle* h, int which, const uint8_t* actions, void* stream
     if (capturing) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   if (which == 0) { int rc = readback_obs(h, st); if (rc) return rc; }
+  h->last_was_step = handoff; h->last_stream = st;
   return MSV_OK;
 }
 
@@ -1065,6 +1071,11 @@ int64_t msv_bytes_per_env_step(msv_handle* h) {
 }
 int64_t msv_obs_bytes_per_env(msv_handle* h) { return h ? (int64_t)h->obs.n_elems * 4 : 0; }
 int64_t msv_kernel_launches(msv_handle* h) { return h ? h->launches : 0; }
+int msv_tile_plan(msv_handle* h, int32_t out[4]) {
+  if (!h || !out) return MSV_ERR_INVALID;
+  out[0] = h->C.epb; out[1] = h->C.N / h->C.epb; out[2] = h->C.epb * h->AC; out[3] = (h->handoff && h->cfg.auto_reset != 2) ? 1 : 0;
+  return MSV_OK;
+}
 
 /* debug: enable / read the per-phase cycle profile of k_step (not part of
  * the stable ABI; used by tests/gpu_quickbench.py) */

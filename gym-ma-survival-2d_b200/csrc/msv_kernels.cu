@@ -7,11 +7,6 @@
 // k_reset : BaseEnv.reset (env:59-74) for every environment.
 // k_observe: fetch_observations only (after msv_set_state).
 // k_stats : flush_stats reduction.
-#ifndef MSV_NO_PHASE_SYNC
-#ifndef MSV_SYNC_MASK
-#define MSV_SYNC_MASK 0x3FF
-#endif
-#endif
 #include <cstdlib>
 #include "msv_env.cuh"
 #include "msv_launch.h"
@@ -29,9 +24,9 @@ __device__ unsigned long long g_prof[64];
 // hand-off trace of the last step (%globaltimer, ns): [0] k_step block start, [1] its queue entry published,
 // [2] observation tile resident, [3] its entry acquired, [4] tile written; tests/gpu_quickbench.py --trace
 #define MSV_TR_MAX 4096
-__device__ unsigned long long g_tr[5 * MSV_TR_MAX];
+__device__ unsigned long long g_tr[2 * 5 * MSV_TR_MAX];   // two steps (ticket parity), so that the gap between consecutive steps can be read
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define TRACE(row, idx) do { if (threadIdx.x == 0 && (idx) < MSV_TR_MAX) g_tr[(row) * MSV_TR_MAX + (idx)] = gtime_ns(); } while (0)
+#define TRACE(row, idx) do { if (threadIdx.x == 0 && (idx) < MSV_TR_MAX) g_tr[((C.tq_ticket & 1u) * 5 + (row)) * MSV_TR_MAX + (idx)] = gtime_ns(); } while (0)
 __device__ unsigned long long g_blk[MSV_BLK_MAX * MSV_BLK_STAMPS];
 #define BLK_STAMP() do { if (C.profile && threadIdx.x == 0 && blockIdx.x < MSV_BLK_MAX && blk_n < MSV_BLK_STAMPS) { g_blk[blockIdx.x * MSV_BLK_STAMPS + blk_n] = (unsigned long long)clock64(); blk_n++; } } while (0)
 #define PROF(k) do { if (C.profile) { long long _t = clock64(); ph[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
@@ -46,13 +41,20 @@ __device__ unsigned long long g_blk[MSV_BLK_MAX * MSV_BLK_STAMPS];
 // thread -> (environment slot of the block, lane of the group)
 // keep the warps of a block in the same phase: they then share instruction-cache lines
 #define MSV_COLD_ON(env, call) do { if ((MSV_INLINE_MASK >> 4) & 1) { env.call; } else { auto c_ = env; c_.call; env.take(c_); } } while (0)
-#ifndef MSV_SYNC_MASK
-#define MSV_SYNC_MASK 0x3FF
+// Which of the ten phase barriers are kept (bit k = PHASE_SYNC(k)), per capacity class.  Measured on the stationary
+// workloads with one 512-thread block per SM (profiles/r02_barriers.txt): without any barrier the step is 50 % slower
+// (163 against 109 us, 2v2); dropping single ones moves it by +-1 %; for the 2- and 4-lane classes dropping the two
+// between solve, FindNewContacts and SolveTOI (3 and 9: the lanes flow from the island solver into the TOI scan)
+// gains 2.5 % (108.7 -> 106.0 us), while the 8-lane class is fastest with all ten (345 against 349 us).
+#ifndef MSV_SYNC_MASK_ALL
+#define MSV_SYNC_MASK(G) ((G) >= 8 ? 0x3FF : 0x1F7)
+#else
+#define MSV_SYNC_MASK(G) (MSV_SYNC_MASK_ALL)     // development: make SYNCMASK=0x... (one mask for every class)
 #endif
 #ifdef MSV_NO_PHASE_SYNC
 #define PHASE_SYNC(k) do { } while (0)
 #else
-#define PHASE_SYNC(k) do { if ((MSV_SYNC_MASK >> (k)) & 1) __syncthreads(); PROFW(k); BLK_STAMP(); } while (0)
+#define PHASE_SYNC(k) do { if ((MSV_SYNC_MASK(G) >> (k)) & 1) __syncthreads(); PROFW(k); BLK_STAMP(); } while (0)
 #endif
 #define MSV_GROUP_SETUP(G)                                                                       \
   const int es = threadIdx.x / (G), g = threadIdx.x % (G);                                       \
@@ -68,6 +70,9 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   // Let the observation kernel (launched programmatically dependent, see msv_abi.cu launch()) become resident as
   // soon as every block of this grid has started: its blocks wait for entries of the completion queue below.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Launched programmatically dependent on the previous step's observation kernel (its launch latency and block
+  // start-up then overlap that kernel's tail): nothing of the state may be read or written before that grid is complete.
+  if (C.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
   TRACE(0, blockIdx.x);
   Env<AC, BC, HC, G> env(C, S, es, g, gmask, e);
 #ifdef MSV_PROFILE
@@ -484,6 +489,7 @@ k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, c
 __global__ void __launch_bounds__(256)
 k_lidar(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, const __grid_constant__ DevOut O, int EB, int BC, int HC) {
   extern __shared__ float lid_sm[];                  // [EB][LID_MAXB][LID_W]: kind, x, y, then r | hx, hy, ax, ay, rot (agents: r, angle)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // (the next step's k_step may be waiting to become resident)
   const int A = C.A, L = C.lidar_n, N = C.N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int el = warp / A, i = warp - el * A;        // environment slot of the block, agent
@@ -681,6 +687,15 @@ static cudaError_t launch_t(int which, const DevConst& C, const DevState& S, con
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_observe<AC, BC, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     return e;
   }
+  if (which == 0 && C.pdl_wait) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3((unsigned)tpb); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_step<AC, BC, HC, G>, C, S, O, actions);
+  }
   if (which == 0) k_step<AC, BC, HC, G><<<blocks, tpb, smem, st>>>(C, S, O, actions);
   else if (which == 1) k_reset<AC, BC, HC, G><<<blocks, tpb, smem, st>>>(C, S, O, 0);
   else if (which == 4) k_reset<AC, BC, HC, G><<<blocks, tpb, smem, st>>>(C, S, O, 1);
@@ -775,9 +790,9 @@ cudaError_t msv_read_blocks(unsigned long long* out, int n_words) {   // develop
 
 cudaError_t msv_read_trace(unsigned long long* out, int n_words) {     // development: hand-off trace of the last step
 #ifdef MSV_PROFILE
-  if (n_words > 5 * MSV_TR_MAX) n_words = 5 * MSV_TR_MAX;
+  if (n_words > 2 * 5 * MSV_TR_MAX) n_words = 2 * 5 * MSV_TR_MAX;
   cudaError_t e_ = cudaMemcpyFromSymbol(out, g_tr, sizeof(unsigned long long) * (size_t)n_words);
-  if (e_ == cudaSuccess) { static unsigned long long z[5 * MSV_TR_MAX]; e_ = cudaMemcpyToSymbol(g_tr, z, sizeof z); }
+  if (e_ == cudaSuccess) { static unsigned long long z[2 * 5 * MSV_TR_MAX]; e_ = cudaMemcpyToSymbol(g_tr, z, sizeof z); }
   return e_;
 #else
   (void)out; (void)n_words; return cudaErrorNotSupported;

@@ -44,6 +44,7 @@ struct DevConst {
   // kernel, launched programmatically dependent on k_step, consumes the queue in order while k_step's slower
   // blocks are still running.  Entries are (ticket << 32 | block); slot = atomicAdd(tq_tail, 1) - tq_base.
   uint32_t tq_ticket, tq_base;
+  uint32_t pdl_wait;     // k_step was launched programmatically dependent on the previous step's last kernel: wait for it before touching state
 };
 
 // All per-environment state, structure-of-arrays: every array is

@@ -21,7 +21,7 @@ EXPORTS = [
     'msv_default_config', 'msv_create', 'msv_destroy', 'msv_reset', 'msv_step',
     'msv_step_host', 'msv_step_host_obs', 'msv_step_host_async', 'msv_step_host_wait', 'msv_obs_host_bytes',
     'msv_obs_host_offset', 'msv_device_bytes', 'msv_tensor', 'msv_tensor_info', 'msv_get_state', 'msv_set_state',
-    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_kernel_bytes_per_env', 'msv_obs_bytes_per_env', 'msv_kernel_launches',
+    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_kernel_bytes_per_env', 'msv_obs_bytes_per_env', 'msv_kernel_launches', 'msv_tile_plan',
     'msv_last_error', 'msv_philox4x32',
 ]
 
@@ -79,6 +79,7 @@ def load():
     L.msv_obs_bytes_per_env.restype = i64
     L.msv_kernel_launches.argtypes = [vp]
     L.msv_kernel_launches.restype = i64
+    L.msv_tile_plan.argtypes = [vp, vp]
     L.msv_last_error.argtypes = [vp]
     L.msv_last_error.restype = ctypes.c_char_p
     L.msv_philox4x32.argtypes = [vp, vp, vp]
@@ -232,3 +233,10 @@ class Handle:
 
     def kernel_launches(self):
         return int(load().msv_kernel_launches(self.h))
+
+    def tile_plan(self):
+        """how the batch is tiled onto the GPU (msv_tile_plan)"""
+        out = (ctypes.c_int32 * 4)()
+        check(load().msv_tile_plan(self.h, out), self.h)
+        return {'envs_per_block': int(out[0]), 'blocks': int(out[1]), 'threads_per_block': int(out[2]),
+                'observation_hand_off': bool(out[3])}

@@ -317,6 +317,12 @@ int64_t msv_kernel_bytes_per_env(msv_handle* h, int32_t which);
 /* The part of it written by the observation gather kernel (k_obs). */
 int64_t msv_obs_bytes_per_env(msv_handle* h);
 int64_t msv_kernel_launches(msv_handle* h); /* launches since create */
+/* How the batch is tiled onto the GPU: out[0] environments per thread block of
+ * the step kernel, out[1] its blocks, out[2] its threads per block, out[3] 1 when
+ * the observation kernels are launched programmatically dependent on the step
+ * kernel and consume its tiles as they finish (the vectorised counterpart of
+ * env:76-90 has no analogue in the reference: it steps one env at a time). */
+int msv_tile_plan(msv_handle* h, int32_t out[4]);
 int64_t msv_device_bytes(msv_handle* h);    /* HBM allocated by the handle */
 
 const char* msv_last_error(msv_handle* h);

@@ -181,6 +181,50 @@ def test_full_size_properties():
         e.close()
 
 
+@pytest.mark.parametrize('vname,N,steps', [('2v2', 4100, 260), ('ffa_lidar', 1030, 60)])
+def test_tile_hand_off_equals_plain_launches(vname, N, steps, monkeypatch):
+    """The observation kernel consumes k_step's tiles in the order they finish (completion queue +
+    programmatic dependent launch, k_step itself dependent on the previous step's observation kernel).
+    The outputs must be bit-identical to plain stream-ordered launches, on a ragged batch (padding
+    environments in the last tile), on a stream of our own, with episode ends and in-kernel resets."""
+    import torch
+    from masurvival.envs import MaSurvivalVec
+    from masurvival.config import variant
+    A = 4 if vname == '2v2' else 8
+    over = {'safe_zone': {'cooldown': 10}, 'health': {'health': 20}}
+    cfg = parity.apply_overrides(variant(vname), over)
+    monkeypatch.delenv('MSV_NO_HANDOFF', raising=False)
+    e1 = MaSurvivalVec(cfg, N, seed=11)
+    monkeypatch.setenv('MSV_NO_HANDOFF', '1')
+    e2 = MaSurvivalVec(cfg, N, seed=11)
+    monkeypatch.delenv('MSV_NO_HANDOFF', raising=False)
+    p1, p2 = e1._h.tile_plan(), e2._h.tile_plan()
+    assert p1['observation_hand_off'] and not p2['observation_hand_off']
+    assert p1['envs_per_block'] * p1['blocks'] >= N and p1['threads_per_block'] <= 512
+    assert p1['blocks'] <= 148 or p1['threads_per_block'] == 512    # one wave of one block per SM, else full tiles
+    g = torch.Generator(device='cuda'); g.manual_seed(2)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        o1 = e1.reset(); o2 = e2.reset()
+        dones = 0
+        for t in range(steps):
+            a = torch.empty((N, A, 6), dtype=torch.uint8, device='cuda')
+            a[..., :3] = torch.randint(0, 3, (N, A, 3), dtype=torch.uint8, device='cuda', generator=g)
+            a[..., 3:] = torch.randint(0, 2, (N, A, 3), dtype=torch.uint8, device='cuda', generator=g)
+            o1, r1, d1, _ = e1.step(a)
+            o2, r2, d2, _ = e2.step(a)
+            if t % 7 == 0 or t == steps - 1:
+                for k in o1:
+                    assert torch.equal(o1[k], o2[k]), (t, k)
+                assert torch.equal(r1, r2) and torch.equal(d1, d2)
+            dones += int(d1.sum())
+    st.synchronize()
+    assert dones > N // 4
+    assert e1.get_state().tobytes() == e2.get_state().tobytes()
+    assert e1._h.overflow_events() == 0 and e2._h.overflow_events() == 0   # (includes the hand-off's own fault flag)
+    e1.close(); e2.close()
+
+
 def test_golden_fixtures_on_gpu():
     """the committed golden vectors (recorded from the reference's own Python,
     tests/golden/make_golden.py) replayed through the C ABI on the GPU"""
