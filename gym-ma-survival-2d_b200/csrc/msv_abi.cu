@@ -43,6 +43,10 @@ struct msv_handle {
   // msv_step_host* read rewards/dones back on a second stream as soon as the step kernel is done
   // (overlapping the copy with the observation kernels) and the observation arena after them
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_step = nullptr, ev_obs = nullptr, ev_copy = nullptr;
+  // msv_step_host*: the actions go up on a stream of their own, so that with several handles driven through one
+  // launch stream (env groups in flight) a group's upload overlaps the other groups' kernels instead of sitting
+  // in stream order in front of its own step kernel
+  cudaStream_t up_stream = nullptr; cudaEvent_t ev_up = nullptr, ev_done = nullptr; bool done_valid = false;
   float* host_rewards = nullptr; uint8_t* host_dones = nullptr; void* host_obs = nullptr;   // destinations of the pending read-back (one step)
   bool copy_pending = false;     // ev_copy was recorded and nobody waited for it yet
   // every output tensor lives in ONE device arena: [rewards | dones | observation keys | lidar]
@@ -562,6 +566,9 @@ static void really_destroy(msv_handle* h) {
   if (h->ev_step) cudaEventDestroy(h->ev_step);
   if (h->ev_obs) cudaEventDestroy(h->ev_obs);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->ev_up) cudaEventDestroy(h->ev_up);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  if (h->up_stream) cudaStreamDestroy(h->up_stream);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   delete h;
 }
@@ -587,6 +594,9 @@ static int copy_setup(msv_handle* h) {
   CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_obs, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   return MSV_OK;
 }
 // rewards and dones are final once the step kernel has run: copy them to the host buffers of a
@@ -752,16 +762,22 @@ int msv_step_host_async(msv_handle* h, const uint8_t* actions_host, float* rewar
     h->copy_pending = false;
     CK(cudaStreamWaitEvent(st, h->ev_copy, 0));
   }
-  cudaError_t ce = cudaMemcpyAsync(h->d_actions, actions_host, N * A * 6, cudaMemcpyHostToDevice, st);
+  // upload on up_stream: after this handle's previous step (whose step kernel read d_actions), before this one's
+  if (h->done_valid) CK(cudaStreamWaitEvent(h->up_stream, h->ev_done, 0));
+  cudaError_t ce = cudaMemcpyAsync(h->d_actions, actions_host, N * A * 6, cudaMemcpyHostToDevice, h->up_stream);
   int rc = MSV_OK;
   if (ce != cudaSuccess) { h->err = std::string("cudaMemcpyAsync(actions): ") + cudaGetErrorString(ce); rc = MSV_ERR_CUDA; }
+  if (!rc && (cudaEventRecord(h->ev_up, h->up_stream) != cudaSuccess || cudaStreamWaitEvent(st, h->ev_up, 0) != cudaSuccess)) {
+    h->err = "cudaEventRecord/cudaStreamWaitEvent(upload) failed"; rc = MSV_ERR_CUDA;
+  }
   if (!rc) {
     h->host_rewards = rewards_host; h->host_dones = dones_host; h->host_obs = obs_host;
     rc = launch(h, 0, h->d_actions, stream);
     h->host_rewards = nullptr; h->host_dones = nullptr; h->host_obs = nullptr;
   }
+  if (!rc) { if (cudaEventRecord(h->ev_done, st) == cudaSuccess) h->done_valid = true; else { h->err = "cudaEventRecord(step done) failed"; rc = MSV_ERR_CUDA; } }
   if (rc) {                    // nothing may still be writing into the caller's buffers after an error return
-    cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(st);
+    cudaStreamSynchronize(h->up_stream); cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(st);
     h->copy_pending = false;
   }
   return rc;
