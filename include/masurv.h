@@ -276,7 +276,12 @@ int msv_step_host_obs(msv_handle* h, const uint8_t* actions_host,
  * env groups): _async enqueues copy-in, kernels and copy-out and returns;
  * _wait blocks (spinning on an event, no stream synchronize) until the host
  * buffers of the last _async call are complete.  The next step on the same
- * handle is ordered after the copy-out by the library.  obs_host may be NULL. */
+ * handle is ordered after the copy-out by the library.  obs_host may be NULL.
+ * The actions go up on an internal upload stream (ordered after this handle's
+ * previous step, before this one's step kernel), so with several handles driven
+ * through one launch stream a group's upload overlaps the other groups' kernels;
+ * actions_host must stay unchanged until the step kernel has consumed it
+ * (msv_step_host_wait of this call is sufficient). */
 int msv_step_host_async(msv_handle* h, const uint8_t* actions_host,
                         float* rewards_host, uint8_t* dones_host, void* obs_host,
                         void* cuda_stream);
