@@ -27,6 +27,21 @@ def test_lockstep_rollout(variant, n, steps):
     _assert_clean(r)
 
 
+@pytest.mark.parametrize('variant,n,epb,steps', [('2v2', 224, 112, 130), ('ffa', 112, 56, 60), ('1v1', 512, 160, 100)])
+def test_lockstep_production_tiles(variant, n, epb, steps, monkeypatch):
+    """the tile shapes the planner picks for the BASELINE batch sizes (one block of up to 512 threads per SM:
+    112 envs x 4 lanes, 56 x 8, and the largest 2-lane tile), in lock-step with the oracle"""
+    import gpu_lockstep
+    from masurvival import _lib
+    monkeypatch.setenv('MSV_EPB', str(epb))
+    h = _lib.Handle(make_config(variant, auto_reset=True), n, device=0, seed=1, env_offset=0)
+    plan = h.tile_plan(); h.close()
+    assert plan['envs_per_block'] == epb and plan['threads_per_block'] in (448, 320)
+    r = gpu_lockstep.run(variant, n, steps, verbose=False, safe_zone={'cooldown': 15}, health={'health': 25})
+    _assert_clean(r)
+    assert r['dones'] > 0 and r['overflow_events'] == 0
+
+
 def test_lockstep_fast_zone_and_resets():
     """short safe-zone phases: every env runs through shrink, endgame, death,
     death-drop and in-kernel auto-reset several times"""
