@@ -155,8 +155,7 @@ k_step(const __grid_constant__ DevConst C, const __grid_constant__ DevState S,
   PROF(11);
   if (C.tq_ticket) {                       // publish this tile: every store of the block, then (release) its queue entry
     __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
+    if (threadIdx.x == 0) {           // (st.release.gpu is the fence: cumulative over the block's stores ordered before it by the barrier)
       const unsigned slot = atomicAdd(S.tq_tail, 1u) - C.tq_base;
       const unsigned long long v = ((unsigned long long)C.tq_ticket << 32) | (unsigned long long)blockIdx.x;
       asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(S.tq + slot), "l"(v) : "memory");
