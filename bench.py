@@ -251,6 +251,10 @@ def run_ours(args):
         clk.start()
     est = timed(dev_step, max(args.warmup, 3)) / max(args.warmup, 3)     # the W warm-up steps double as the duration estimate
     R = int(max(args.repeats, math.ceil(60.0 / max(est * args.steps, 1e-6))))
+    # The step time of this workload drifts by up to +-20 % over a few hundred steps (it follows the longest TOI chain /
+    # largest island among the batch, and wedged agents stay wedged for a while): identical from run to run -- the
+    # roll-out is deterministic -- but a median over a short window lands in a slow or a fast stretch.  Time >= 3 000 steps.
+    R = int(max(R, math.ceil(3000.0 / max(args.steps, 1))))
     R = min(R, 2000)
     # The host-side pauses above (stats read-back, sampler start) let the GPU idle for a few ms, after which
     # the first ~40 ms of work run up to 35 % slower (measured: 20-step repeats of 4.0, 3.5, 3.4, 3.1, 2.9, 2.9 ...
@@ -296,7 +300,8 @@ def run_ours(args):
     e2e_sync_ms = float(np.median([timed(e2e_sync, args.steps) for _ in range(Re)])) / args.steps
     for _ in range(max(3, args.warmup)):
         e2e_pipelined()
-    e2e_ms = float(np.median([timed(e2e_pipelined, args.steps) for _ in range(Re)])) / args.steps
+    e2e_reps = [timed(e2e_pipelined, args.steps) for _ in range(Re)]
+    e2e_ms = float(np.median(e2e_reps)) / args.steps
     for e_ in envs:
         e_.step_host_wait()
     e2e_value = n_gpus * N * A / (e2e_ms * 1e-3)
@@ -404,7 +409,7 @@ def run_ours(args):
         'ms_per_step_by_episode_phase': phase_ms,
         'env_steps_per_sec': value / A,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': N * A * 6, 'd2h_bytes_per_step': N * A * 4 + N,
-                'ms_per_step': e2e_ms, 'repeats': Re,
+                'ms_per_step': e2e_ms, 'repeats': Re, 'rep_ms': [round(float(x), 4) for x in e2e_reps[:32]],
                 'api': f'MaSurvivalVec.step_host_async / step_host_wait -> msv_step_host_async/_wait, pinned host buffers: every step copies its '
                        f'actions in and its rewards/dones out; the {ROT} env groups are kept in flight (the host waits for a group\'s results right '
                        'before submitting that group\'s next step)',
@@ -542,7 +547,7 @@ def main():
     ap.add_argument('--envs', type=int, default=0, help='environments per GPU (default: the workload\'s BASELINE count)')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--preroll', type=int, default=1500, help='untimed steps per batch before the timed region (stationary episode mix)')
-    ap.add_argument('--repeats', type=int, default=5, help='minimum number of timed repeats of K steps (median reported)')
+    ap.add_argument('--repeats', type=int, default=15, help='minimum number of timed repeats of K steps (median reported; the step time drifts by a few % over hundreds of steps as wedged agents come and go, so the median wants more than a handful)')
     ap.add_argument('--rotate', type=int, default=0, help='independent env batches stepped round-robin (0: enough to exceed L2)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-phase', action='store_true', help='skip the per-episode-phase timing')

@@ -15,12 +15,12 @@ def load(w):
 
 def main():
     out = ['<!-- MEASURED_TABLE begin (profiles/make_table.py) -->',
-           '| workload (`bench.py --workload`) | envs/GPU | ms/step | agent-steps/s (device) | `e2e` (rewards+dones) | `e2e_obs` sync / pipelined | k_step / k_obs2 / k_lidar ms | k_step GB/s (frac of 6 534) | C port, 16 threads | GPU/CPU |',
-           '|---|---|---|---|---|---|---|---|---|---|']
+           '| workload (`bench.py --workload`) | envs/GPU | ms/step | agent-steps/s (device) | `e2e` (rewards+dones) | `concurrent_groups` device / e2e | `e2e_obs` sync / pipelined | k_step / k_obs2 / k_lidar ms | k_step GB/s (frac of 6 534) | C port, 16 threads | GPU/CPU |',
+           '|---|---|---|---|---|---|---|---|---|---|---|']
     for w in W:
         d = load(w); r = d['roofline']; k = r['kernel_ms_all']
         cpu = d.get('cpu_baseline', {}).get('value')
-        out.append(f"| {w} | {d['config']['envs_per_gpu']} | {d['ms_per_step']:.4f} | {d['value']:.3e} | {d['e2e']['value']:.3e} | "
+        out.append(f"| {w} | {d['config']['envs_per_gpu']} | {d['ms_per_step']:.4f} | {d['value']:.3e} | {d['e2e']['value']:.3e} | {d['concurrent_groups']['value']:.3e} / {d['concurrent_groups']['e2e']['value']:.3e} | "
                    f"{d['e2e_obs']['value']:.3e} / {d['e2e_obs']['pipelined']['value']:.3e} | {k['k_step']:.4f} / {k['k_obs']:.4f} / {k['k_lidar']:.4f} | "
                    f"{r['achieved']:.0f} ({r['frac']:.4f}) | {cpu:.3e} | {d['value'] / cpu:.0f}x |" if cpu else '| %s | n/a |' % w)
     d = load('2v2')
