@@ -22,11 +22,12 @@ __device__ unsigned long long g_prof[64];
 #define MSV_BLK_MAX 2048
 #define MSV_BLK_STAMPS 24
 // hand-off trace of the last step (%globaltimer, ns): [0] k_step block start, [1] its queue entry published,
-// [2] observation tile resident, [3] its entry acquired, [4] tile written; tests/gpu_quickbench.py --trace
+// [2] observation tile resident, [3] its entry acquired, [4] tile written, [5] tile staged in shared memory; tests/gpu_quickbench.py --trace
 #define MSV_TR_MAX 4096
-__device__ unsigned long long g_tr[2 * 5 * MSV_TR_MAX];   // two steps (ticket parity), so that the gap between consecutive steps can be read
+#define MSV_TR_ROWS 6
+__device__ unsigned long long g_tr[2 * MSV_TR_ROWS * MSV_TR_MAX];   // two steps (ticket parity), so that the gap between consecutive steps can be read
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define TRACE(row, idx) do { if (threadIdx.x == 0 && (idx) < MSV_TR_MAX) g_tr[((C.tq_ticket & 1u) * 5 + (row)) * MSV_TR_MAX + (idx)] = gtime_ns(); } while (0)
+#define TRACE(row, idx) do { if (threadIdx.x == 0 && (idx) < MSV_TR_MAX) g_tr[((C.tq_ticket & 1u) * MSV_TR_ROWS + (row)) * MSV_TR_MAX + (idx)] = gtime_ns(); } while (0)
 __device__ unsigned long long g_blk[MSV_BLK_MAX * MSV_BLK_STAMPS];
 #define BLK_STAMP() do { if (C.profile && threadIdx.x == 0 && blockIdx.x < MSV_BLK_MAX && blk_n < MSV_BLK_STAMPS) { g_blk[blockIdx.x * MSV_BLK_STAMPS + blk_n] = (unsigned long long)clock64(); blk_n++; } } while (0)
 #define PROF(k) do { if (C.profile) { long long _t = clock64(); ph[k] += (unsigned long long)(_t - t_last); t_last = _t; } } while (0)
@@ -455,6 +456,7 @@ k_obs2(const __grid_constant__ DevConst C, const __grid_constant__ DevState S, c
     }
   }
   __syncthreads();
+  TRACE(5, blockIdx.x);
   for (int k = 0; k < MSV_OBS_KEYS; ++k) {
     const int chunk = Tb.keys[k].chunk;
     if (chunk <= 0 || (k >= 4 && k <= 7 && H == 0) || (k >= 8 && B == 0)) continue;   // key groups the config does not have
@@ -789,9 +791,9 @@ cudaError_t msv_read_blocks(unsigned long long* out, int n_words) {   // develop
 
 cudaError_t msv_read_trace(unsigned long long* out, int n_words) {     // development: hand-off trace of the last step
 #ifdef MSV_PROFILE
-  if (n_words > 2 * 5 * MSV_TR_MAX) n_words = 2 * 5 * MSV_TR_MAX;
+  if (n_words > 2 * MSV_TR_ROWS * MSV_TR_MAX) n_words = 2 * MSV_TR_ROWS * MSV_TR_MAX;
   cudaError_t e_ = cudaMemcpyFromSymbol(out, g_tr, sizeof(unsigned long long) * (size_t)n_words);
-  if (e_ == cudaSuccess) { static unsigned long long z[2 * 5 * MSV_TR_MAX]; e_ = cudaMemcpyToSymbol(g_tr, z, sizeof z); }
+  if (e_ == cudaSuccess) { static unsigned long long z[2 * MSV_TR_ROWS * MSV_TR_MAX]; e_ = cudaMemcpyToSymbol(g_tr, z, sizeof z); }
   return e_;
 #else
   (void)out; (void)n_words; return cudaErrorNotSupported;

@@ -89,27 +89,27 @@ def trace(variant, N, warm=1500, launches=12):
     L = _lib.load()
     L.msv_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     M = 4096
-    buf = np.zeros(2 * 5 * M, dtype=np.uint64)
+    buf = np.zeros(2 * 6 * M, dtype=np.uint64)
     L.msv_debug_trace(h.h, buf.ctypes.data, buf.size)     # clear
     for t in range(launches):
         for r in range(2):                                # two steps back to back: the trace keeps both (ticket parity)
             h.step(acts[((warm + 2 * t + r) * 7) % NB].data_ptr())
         rc = L.msv_debug_trace(h.h, buf.ctypes.data, buf.size)
         assert rc == 0, rc
-        two = buf.reshape(2, 5, M).astype(np.int64)
+        two = buf.reshape(2, 6, M).astype(np.int64)
         first = 0 if two[0, 0][two[0, 0] > 0].min() < two[1, 0][two[1, 0] > 0].min() else 1
         prev_end = None
         for b in (two[first], two[1 - first]):
             nk = int((b[0] > 0).sum()); no = int((b[2] > 0).sum())
             t0 = b[0, :nk].min()
             ks0, ks1 = b[0, :nk] - t0, b[1, :nk] - t0
-            o_res, o_acq, o_done = b[2, :no] - t0, b[3, :no] - t0, b[4, :no] - t0
+            o_res, o_acq, o_done, o_stg = b[2, :no] - t0, b[3, :no] - t0, b[4, :no] - t0, b[5, :no] - t0
             kend = ks1.max()
             q = lambda x, p: float(np.percentile(x, p)) / 1e3
             gap = '' if prev_end is None else f', first block starts {(t0 - prev_end) / 1e3:+.1f} us after the previous step\'s last tile'
             print(f'{variant} N={N} launch {t}: k_step {nk} blocks, start spread {q(ks0, 100):.1f} us, block end p10/p50/p90/max = '
                   f'{q(ks1, 10):.1f}/{q(ks1, 50):.1f}/{q(ks1, 90):.1f}/{kend / 1e3:.1f} us | obs {no} tiles: resident p10/p50/p90 = '
-                  f'{q(o_res, 10):.1f}/{q(o_res, 50):.1f}/{q(o_res, 90):.1f} us, acquired->written median {q(o_done - o_acq, 50):.1f} us, '
+                  f'{q(o_res, 10):.1f}/{q(o_res, 50):.1f}/{q(o_res, 90):.1f} us, acquired->staged->written median {q(o_stg - o_acq, 50):.1f} + {q(o_done - o_stg, 50):.1f} us (last 8 tiles: {q((o_stg - o_acq)[np.argsort(o_done)[-8:]], 50):.1f} + {q((o_done - o_stg)[np.argsort(o_done)[-8:]], 50):.1f}), '
                   f'written before k_step end: {int((o_done <= kend).sum())}/{no}, last tile written {(o_done.max() - kend) / 1e3:+.1f} us after k_step end{gap}')
             prev_end = t0 + o_done.max()
     h.close()
