@@ -225,34 +225,59 @@ static int build_const(const msv_config* c, int N, uint64_t seed, int64_t env_of
   return 0;
 }
 
-// Grid shape of k_step: a block is a tile of `epb` environments (epb * G threads, G = agent capacity
-// = lanes per environment).  All blocks should be resident at once (the step is one long dependent
-// chain per environment, so a second wave would double the time): take the largest tile for which
-// ceil(blocks / SMs) blocks fit on an SM (registers, shared memory).  MSV_EPB overrides (development).
-// Tile size of k_step.  A block's warps run the step in phase lock-step (block barriers between the phases)
-// and so share one pass over its ~570 KB of instructions; two blocks on an SM sit in different phases and evict
-// each other's lines from the instruction caches.  Measured on the stationary 2v2 workload (16 384 envs,
-// profiles/r02_tiles.txt): two 64-env blocks of 256 threads per SM 124.9 us/step; ONE block of 512 threads per SM
-// with 128 envs 112.5, 120 envs 113.0, 112 envs (147 blocks: every SM busy) 109.8.  So: one block per SM, as few
-// waves as the block capacity allows, and within that the smallest tile that still covers the batch (a block lasts
-// as long as its slowest environment in every phase, so spreading the batch over all SMs shortens every block).
+// Tile size of k_step: a block is a tile of `epb` environments (epb * G threads, G = agent capacity = lanes per
+// environment).  A block's warps run the step in phase lock-step (block barriers between the phases) and so share
+// one pass over its ~560 KB of instructions; two blocks on an SM sit in different phases and evict each other's
+// lines from the instruction caches.  Measured on the stationary 2v2 workload (16 384 envs, profiles/r02_tiles.txt):
+// two 64-env blocks of 256 threads per SM 124.9 us/step; ONE block of 512 threads per SM with 128 envs 112.5,
+// 120 envs 113.0, 112 envs (147 blocks: every SM busy) 109.8.  So: one block per SM, as few waves as the block
+// capacity allows; a batch that fits one wave is spread over every SM (a block lasts as long as its slowest
+// environment in every phase, so smaller tiles shorten every block), a batch that needs several waves takes the
+// largest tile (blocks are handed out as SMs free up; ffa + lidar, 32 768 envs: 64-env tiles 1 239 us, 56 -- four
+// even waves -- 1 288, 48: 1 327).
+static long plan_tile(int G, int sm_words, long n, long sms, size_t smem_blk_max) {
+  const long wpe = 32 / G;
+  long cap = MSV_TPB / G;                                          // by threads (128 registers each: 512 fill the register file)
+  const long by_smem = (long)(smem_blk_max / ((size_t)sm_words * sizeof(float)));
+  if (by_smem < cap) cap = by_smem;
+  cap = cap / wpe * wpe; if (cap < wpe) cap = wpe;
+  if (sms < 1) sms = 1;
+  if (n < 1) n = 1;
+  const long waves = (n + cap * sms - 1) / (cap * sms);
+  long best = (n + sms - 1) / sms;                                  // one wave: spread the batch over every SM
+  best = (best + wpe - 1) / wpe * wpe;
+  if (waves > 1) best = cap;
+  if (best > cap) best = cap;
+  if (best < wpe) best = wpe;
+  return best;
+}
+static int capacity_class(const msv_config* cfg) {
+  return (cfg->n_agents <= 2 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 0
+       : (cfg->n_agents <= 4 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 1 : 2;
+}
 static void plan_blocks(msv_handle* h, int device) {
   cudaDeviceProp pr; int sms = 148; size_t smem_blk_max = 227 * 1024;
   if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) { sms = pr.multiProcessorCount; smem_blk_max = pr.sharedMemPerBlockOptin; }
   const int G = h->AC, wpe = 32 / G, n = h->C.n_real;
-  long cap = MSV_TPB / G;                                          // by threads (128 registers each: 512 fill the register file)
-  const long by_smem = (long)(smem_blk_max / ((size_t)h->sm_words * sizeof(float)));
-  if (by_smem < cap) cap = by_smem;
-  cap = cap / wpe * wpe; if (cap < wpe) cap = wpe;
-  const long waves = (n + cap * sms - 1) / (cap * sms);
-  long best = (n + sms - 1) / sms;                                  // one wave: spread the batch over every SM
-  best = (best + wpe - 1) / wpe * wpe;
-  if (waves > 1) best = cap;   // several waves (blocks are handed out as SMs free up): the largest tile -- ffa + lidar, 32 768 envs: 64 envs 1 239 us, 56 (four even waves) 1 288, 48: 1 327
-  if (best > cap) best = cap;
-  if (best < wpe) best = wpe;
-  if (const char* ov = getenv("MSV_EPB")) { int v = atoi(ov); if (v >= wpe && v <= cap && v % wpe == 0) best = v; }
+  long best = plan_tile(G, h->sm_words, n, sms, smem_blk_max);
+  if (const char* ov = getenv("MSV_EPB")) {                         // development override
+    const long cap = plan_tile(G, h->sm_words, (long)1 << 40, 1, smem_blk_max);   // (many waves -> the capacity)
+    int v = atoi(ov); if (v >= wpe && v <= cap && v % wpe == 0) best = v;
+  }
   h->C.epb = (int)best;
   h->C.N = (int)((n + best - 1) / best * best);
+}
+/* The same planner without a device (host logic only): how `num_envs` environments of `cfg` would be tiled onto a
+ * GPU with `sm_count` SMs and `smem_per_block` bytes of opt-in shared memory per block.
+ * out = {envs per block, blocks, threads per block, capacity class}. */
+int msv_plan_tile(const msv_config* cfg, int32_t num_envs, int32_t sm_count, int64_t smem_per_block, int32_t out[4]) {
+  if (!cfg || !out || num_envs < 1 || sm_count < 1 || smem_per_block < 1024) return MSV_ERR_INVALID;
+  const int cap = capacity_class(cfg);
+  int AC, BC, HC, P, PW, smw;
+  msv_capacity(cap, &AC, &BC, &HC, &P, &PW, &smw);
+  const long epb = plan_tile(AC, smw, num_envs, sm_count, (size_t)smem_per_block);
+  out[0] = (int32_t)epb; out[1] = (int32_t)((num_envs + epb - 1) / epb); out[2] = (int32_t)(epb * AC); out[3] = cap;
+  return MSV_OK;
 }
 
 template <typename T> static int dalloc(msv_handle* h, T** p, size_t count) {
@@ -387,8 +412,7 @@ int msv_create(const msv_config* cfg, int32_t num_envs, int32_t device, uint64_t
   DevGuard guard(device);
   { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != device) { delete h; return MSV_ERR_CUDA; } }
   build_const(cfg, num_envs, seed, env_offset, &h->C);
-  h->cap = (cfg->n_agents <= 2 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 0
-         : (cfg->n_agents <= 4 && cfg->n_boxes <= 4 && cfg->n_heals <= 4) ? 1 : 2;
+  h->cap = capacity_class(cfg);
   msv_capacity(h->cap, &h->AC, &h->BC, &h->HC, &h->P, &h->PW, &h->sm_words);
   plan_blocks(h, device);
   if (const char* nh = getenv("MSV_NO_HANDOFF")) h->handoff = atoi(nh) == 0;   // development A/B: plain stream-ordered launches

@@ -21,7 +21,7 @@ EXPORTS = [
     'msv_default_config', 'msv_create', 'msv_destroy', 'msv_reset', 'msv_step',
     'msv_step_host', 'msv_step_host_obs', 'msv_step_host_async', 'msv_step_host_wait', 'msv_obs_host_bytes',
     'msv_obs_host_offset', 'msv_device_bytes', 'msv_tensor', 'msv_tensor_info', 'msv_get_state', 'msv_set_state',
-    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_kernel_bytes_per_env', 'msv_obs_bytes_per_env', 'msv_kernel_launches', 'msv_tile_plan',
+    'msv_observe', 'msv_flush_stats', 'msv_bytes_per_env_step', 'msv_kernel_bytes_per_env', 'msv_obs_bytes_per_env', 'msv_kernel_launches', 'msv_tile_plan', 'msv_plan_tile',
     'msv_last_error', 'msv_philox4x32',
 ]
 
@@ -80,6 +80,7 @@ def load():
     L.msv_kernel_launches.argtypes = [vp]
     L.msv_kernel_launches.restype = i64
     L.msv_tile_plan.argtypes = [vp, vp]
+    L.msv_plan_tile.argtypes = [vp, i32, i32, i64, vp]
     L.msv_last_error.argtypes = [vp]
     L.msv_last_error.restype = ctypes.c_char_p
     L.msv_philox4x32.argtypes = [vp, vp, vp]

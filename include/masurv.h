@@ -328,6 +328,12 @@ int64_t msv_kernel_launches(msv_handle* h); /* launches since create */
  * kernel and consume its tiles as they finish (the vectorised counterpart of
  * env:76-90 has no analogue in the reference: it steps one env at a time). */
 int msv_tile_plan(msv_handle* h, int32_t out[4]);
+/* The planner behind it, without a device (pure host logic): how num_envs
+ * environments of cfg would be tiled onto a GPU with sm_count SMs and
+ * smem_per_block bytes of opt-in shared memory per block (B200: 148, 232448).
+ * out = {envs per block, blocks, threads per block, capacity class 0..2}. */
+int msv_plan_tile(const msv_config* cfg, int32_t num_envs, int32_t sm_count,
+                  int64_t smem_per_block, int32_t out[4]);
 int64_t msv_device_bytes(msv_handle* h);    /* HBM allocated by the handle */
 
 const char* msv_last_error(msv_handle* h);

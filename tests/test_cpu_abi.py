@@ -126,3 +126,38 @@ def test_create_rejects_bad_arguments_before_touching_the_device():
         assert fn(None, None) == -1
     assert L.msv_step(None, None, None) == -1 and L.msv_destroy(None) == -1
     assert L.msv_bytes_per_env_step(None) == 0 and L.msv_kernel_launches(None) == 0
+
+
+def test_tile_planner_host_logic():
+    """msv_plan_tile: the k_step tile planner without a device.  One block of <= 512 threads per SM; a batch that
+    fits one wave is spread over every SM, one that needs several waves takes the largest tile."""
+    L = _lib.load()
+    SMS, SMEM = 148, 232448                       # B200: multiProcessorCount, sharedMemPerBlockOptin
+
+    def plan(variant, n, sms=SMS, smem=SMEM):
+        rec = parity.make_config(variant, auto_reset=True)
+        out = (ctypes.c_int32 * 4)()
+        assert L.msv_plan_tile(rec.ctypes.data, n, sms, smem, out) == 0
+        return tuple(int(x) for x in out)
+
+    # the BASELINE.json batch sizes (what bench.py reports as tile_plan on a B200)
+    assert plan('2v2', 16384) == (112, 147, 448, 1)
+    assert plan('ffa', 8192) == (56, 147, 448, 2)
+    assert plan('1v1_heal_only', 4096) == (32, 128, 64, 0)
+    assert plan('ffa_lidar', 32768) == (64, 512, 512, 2)      # several waves: the largest tile
+    assert plan('2v2', 1) == (8, 1, 32, 1) and plan('ffa', 3) == (4, 1, 32, 2)
+    lanes = {0: 2, 1: 4, 2: 8}
+    rng = np.random.default_rng(0)
+    for variant in ('1v1', '2v2', 'ffa'):
+        for n in [int(x) for x in rng.integers(1, 200000, size=40)] + [147 * 112, 148 * 128, 148 * 128 + 1]:
+            epb, blocks, threads, cap = plan(variant, n)
+            G = lanes[cap]
+            assert threads == epb * G and 32 <= threads <= 512 and threads % 32 == 0     # whole warps, whole groups
+            assert epb * blocks >= n > epb * (blocks - 1)
+            if blocks > SMS:                                                              # several waves -> full tiles
+                assert plan(variant, 10 ** 7)[0] == epb
+    # a GPU with less shared memory per block gets smaller tiles; invalid arguments are rejected
+    assert plan('2v2', 16384, smem=100 * 1024)[0] < 112
+    out = (ctypes.c_int32 * 4)()
+    rec = parity.make_config('2v2')
+    assert L.msv_plan_tile(None, 16, SMS, SMEM, out) != 0 and L.msv_plan_tile(rec.ctypes.data, 0, SMS, SMEM, out) != 0
