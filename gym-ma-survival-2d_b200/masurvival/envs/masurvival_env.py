@@ -251,6 +251,12 @@ class MaSurvivalVec:
         self._h.observe(self._stream())
         return self._obs()
 
+    def tile_plan(self):
+        """How this batch is tiled onto the GPU (msv_tile_plan): envs per thread block of the step
+        kernel, its blocks and threads per block, and whether the observation kernel consumes the step
+        kernel's tiles as they finish.  No counterpart in the reference (it steps one env at a time)."""
+        return self._h.tile_plan()
+
     # ---- stats (env:471-508) -------------------------------------------------
     def flush_stats(self):
         """Sum of the reference's per-env flush_stats() dict over all envs."""
